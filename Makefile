@@ -1,0 +1,34 @@
+# Builds the product: ebwt2indel_b200/libe2i.so (C ABI, include/e2i.h) and bin/ebwt2InDel (host CLI).
+# sm_100a only; no CPU fallback.  `make oracle` builds the test-only CPU oracle.
+NVCC ?= /usr/local/cuda/bin/nvcc
+CXX ?= g++
+ARCH := -gencode arch=compute_100a,code=sm_100a
+NVFLAGS := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC,-Wall,-Wno-unused-function -Iinclude -Iebwt2indel_b200/csrc
+CSRC := ebwt2indel_b200/csrc
+OBJ := build/context.o build/index.o build/navigate.o build/call.o build/snp_format.o
+LIB := ebwt2indel_b200/libe2i.so
+BIN := bin/ebwt2InDel
+
+all: $(LIB) $(BIN)
+
+build/%.o: $(CSRC)/%.cu $(CSRC)/common.cuh $(CSRC)/lookback.cuh include/e2i.h
+	@mkdir -p build
+	$(NVCC) $(NVFLAGS) -c $< -o $@
+
+build/snp_format.o: $(CSRC)/snp_format.cpp $(CSRC)/common.cuh include/e2i.h
+	@mkdir -p build
+	$(NVCC) $(NVFLAGS) -x cu -c $< -o $@
+
+$(LIB): $(OBJ)
+	$(NVCC) $(ARCH) -shared -o $@ $(OBJ)
+
+$(BIN): $(CSRC)/main.cpp include/e2i.h $(LIB)
+	@mkdir -p bin
+	$(CXX) -O2 -std=c++17 -Wall -Iinclude $(CSRC)/main.cpp -o $@ -Lebwt2indel_b200 -le2i -Wl,-rpath,'$$ORIGIN/../ebwt2indel_b200'
+
+oracle:
+	$(MAKE) -C oracle
+
+clean:
+	rm -rf build $(LIB) $(BIN)
+.PHONY: all oracle clean

@@ -1,0 +1,554 @@
+// call.cu -- a16-a20: phase 4 on the device.
+//
+// Replaces the cluster scans of run_one_dataset / run_two_datasets / run_two_datasets_da
+// (/root/reference/ebwt2InDel.cpp:1609-1655, 1395-1445, 1510-1560) and the three find_variants
+// (:840-934, 941-1005, 1013-1096) with extract_consensus (:265-319) and extract_dna (:325-342).
+//
+// Three kernels per slab of suffix-array positions:
+//   1. scan_clusters: streams the 3n bits, finds maximal runs of  LCP_threshold[2i] & !LCP_minima[i],
+//      keeps runs of length >= 2*mcov_out that are closed before n, builds the per-individual
+//      symbol histograms (rank differences in modes -1/-2, a DA-guided walk in mode -d; TERM counts
+//      as 'A', include.hpp:275-289) and appends the clusters that pass the frequent-allele filter
+//      to a candidate list in SA order (ordered append by decoupled look-back).
+//   2. consensus: one thread per (candidate, allele): LF(range, c), then k_left-1 steps of 4-way LF
+//      following the largest child (ties -> A,C,G,T order).
+//   3. right_context: first position of the cluster with LCP >= k_right, then k_right FL steps.
+// Classification and text formatting (a21-a23) run on the host in snp_format.cpp.
+#include <algorithm>
+
+#include "common.cuh"
+#include "lookback.cuh"
+
+namespace e2i {
+
+constexpr int kScanThreads = 256;
+constexpr int kScanTile = kScanThreads * 64;     // positions per tile
+constexpr int kMaxCand = 22;                     // clusters of length >= 2 that can start inside one 64-bit word
+
+struct Candidate {
+    uint64_t begin, end;        // merged SA range [begin, end)
+    uint64_t b1, e1, b2, e2;    // range in BWT 1 / BWT 2 (mode -2); modes -1/-d: b1,e1 = begin,end
+    uint32_t mask0, mask1;      // frequent alleles of individual 0 / 1 (bit c = A,C,G,T)
+    uint32_t pad0, pad1;
+};
+
+struct CallCtl {
+    uint32_t ticket;
+    uint32_t pad;
+    unsigned long long n_cand;
+    unsigned long long n_clusters, clust_size, rank_q;
+    unsigned long long hist[201];
+};
+
+struct CallArgs {
+    DevIndex ix1, ix2;
+    const uint32_t *thr, *minima, *da;
+    const uint64_t *da_rank512;
+    uint64_t n;                 // merged length
+    uint64_t pos_begin, pos_end;// clusters starting in [pos_begin, pos_end) belong to this launch
+    uint64_t first_tile;        // pos_begin / kScanTile
+    uint32_t n_tiles;
+    uint32_t mcov, q;
+    int mode;                   // 1, 2, 3
+    int k_left, k_right;
+    Candidate *cand;
+    uint64_t cand_cap;
+    unsigned long long *desc;
+    uint32_t epoch;
+    CallCtl *ctl;
+};
+
+__device__ __forceinline__ uint32_t even_bits(uint32_t x) {
+    x &= 0x55555555u;
+    x = (x | (x >> 1)) & 0x33333333u;
+    x = (x | (x >> 2)) & 0x0f0f0f0fu;
+    x = (x | (x >> 4)) & 0x00ff00ffu;
+    x = (x | (x >> 8)) & 0x0000ffffu;
+    return x;
+}
+
+// flagged positions [64w, 64w+64): LCP_threshold[2i] && !LCP_minima[i]  (ebwt2InDel.cpp:1611)
+__device__ __forceinline__ uint64_t flag_word(const CallArgs &a, uint64_t w) {
+    if (w * 64 >= a.n) return 0;
+    const uint4 t = __ldg(reinterpret_cast<const uint4 *>(a.thr) + w);
+    const uint2 m = __ldg(reinterpret_cast<const uint2 *>(a.minima) + w);
+    const uint64_t lo = even_bits(t.x) | (even_bits(t.y) << 16), hi = even_bits(t.z) | (even_bits(t.w) << 16);
+    uint64_t f = (lo | (hi << 32)) & ~((uint64_t)m.x | ((uint64_t)m.y << 32));
+    const uint64_t rem = a.n - w * 64;
+    if (rem < 64) f &= (1ull << rem) - 1;
+    return f;
+}
+
+__device__ __forceinline__ int bit_at(const uint32_t *words, uint64_t i) { return (int)((__ldg(words + (i >> 5)) >> (i & 31)) & 1u); }
+
+// number of 1s of the DA in [0, i)
+__device__ __forceinline__ uint64_t da_rank1(const CallArgs &a, uint64_t i) {
+    const uint64_t g = i >> 9;
+    uint64_t r = __ldg(a.da_rank512 + g);
+    const uint32_t *w = a.da + g * 16;
+    const int full = (int)((i & 511) >> 5), rem = (int)(i & 31);
+    for (int k = 0; k < full; ++k) r += __popc(__ldg(w + k));
+    if (rem) r += __popc(__ldg(w + full) & ((1u << rem) - 1u));
+    return r;
+}
+
+__device__ __forceinline__ uint32_t frequent_mask(const uint64_t cnt[4], uint32_t mcov) {
+    uint32_t m = 0;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) if (cnt[c] >= mcov) m |= 1u << c;
+    return m;
+}
+
+// Kernel 1.  Persistent CTAs take tiles by ticket (ordered append needs tile order).
+__global__ void __launch_bounds__(kScanThreads)
+scan_clusters_kernel(const CallArgs a) {
+    __shared__ uint32_t s_tile;
+    __shared__ uint32_t s_wcnt[kScanThreads / 32];
+    __shared__ unsigned long long s_base;
+    __shared__ unsigned int s_hist[201];
+    __shared__ unsigned long long s_stat[3];
+    for (int i = threadIdx.x; i < 201; i += kScanThreads) s_hist[i] = 0;
+    if (threadIdx.x < 3) s_stat[threadIdx.x] = 0;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned long long t_clusters = 0, t_size = 0, t_rank = 0;
+    while (true) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_tile = atomicAdd(&a.ctl->ticket, 1u);
+        __syncthreads();
+        const uint32_t tile = s_tile;
+        if (tile >= a.n_tiles) break;
+        const uint64_t w = (a.first_tile + tile) * kScanThreads + threadIdx.x;   // 64-bit word of flags
+        const uint64_t f = flag_word(a, w);
+        uint64_t prev = 0;
+        if (w > 0 && f) prev = flag_word(a, w - 1) >> 63;
+        uint64_t starts = f & ~((f << 1) | prev);
+        // local candidate store
+        uint64_t c_begin[kMaxCand], c_end[kMaxCand];
+        uint64_t c_r[kMaxCand][4];
+        uint32_t c_mask[kMaxCand];
+        int nc = 0;
+        while (starts) {
+            const int b = __ffsll((long long)starts) - 1;
+            starts &= starts - 1;
+            const uint64_t begin = w * 64 + b;
+            if (begin < a.pos_begin || begin >= a.pos_end) continue;
+            // end = first unflagged position after begin
+            uint64_t end;
+            {
+                uint64_t inv = ~f & (b == 63 ? 0ull : (~0ull << (b + 1)));
+                uint64_t ww = w;
+                while (!inv) { ++ww; inv = ~flag_word(a, ww); }
+                end = ww * 64 + (__ffsll((long long)inv) - 1);
+            }
+            if (end >= a.n) continue;                      // a run still open at i = n is never closed (:1609-1655)
+            const uint64_t len = end - begin;
+            t_size += len;
+            if (len <= 200) atomicAdd(&s_hist[len], 1u);
+            if (len < 2ull * a.mcov) continue;             // :1629
+            t_clusters++;
+            uint64_t cnt0[4] = {0, 0, 0, 0}, cnt1[4] = {0, 0, 0, 0};
+            uint64_t b1 = begin, e1 = end, b2 = 0, e2 = 0;
+            if (a.mode == 1) {
+                uint64_t rb[4], re[4];
+                rank4(a.ix1, begin, rb);
+                rank4(a.ix1, end, re);
+                t_rank += 2;
+                uint64_t acgt = 0;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) { cnt0[c] = re[c] - rb[c]; acgt += cnt0[c]; }
+                cnt0[0] += len - acgt;                     // TERM counted as 'A'
+            } else if (a.mode == 3) {
+                for (uint64_t i = begin; i < end; ++i) {
+                    int c = access_code(a.ix1, i);
+                    if (c == 4) c = 0;
+                    if (bit_at(a.da, i)) cnt1[c]++; else cnt0[c]++;
+                }
+            } else {
+                const uint64_t ob = da_rank1(a, begin), oe = da_rank1(a, end);
+                b2 = ob; e2 = oe; b1 = begin - ob; e1 = end - oe;
+                uint64_t rb[4], re[4], acgt = 0;
+                rank4(a.ix1, b1, rb); rank4(a.ix1, e1, re);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) { cnt0[c] = re[c] - rb[c]; acgt += cnt0[c]; }
+                cnt0[0] += (e1 - b1) - acgt;
+                rank4(a.ix2, b2, rb); rank4(a.ix2, e2, re);
+                acgt = 0;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) { cnt1[c] = re[c] - rb[c]; acgt += cnt1[c]; }
+                cnt1[0] += (e2 - b2) - acgt;
+                t_rank += 4;
+            }
+            const uint32_t m0 = frequent_mask(cnt0, a.mcov), m1 = frequent_mask(cnt1, a.mcov);
+            const int n0 = __popc(m0), n1 = __popc(m1);
+            bool pass;
+            if (a.mode == 1) pass = n0 >= 2 && !(a.q > 0 && (uint32_t)n0 > a.q);                         // :961-966
+            else pass = n0 > 0 && n1 > 0 && !(a.q > 0 && ((uint32_t)n0 > a.q || (uint32_t)n1 > a.q));    // :870-880
+            if (pass && nc < kMaxCand) {
+                c_begin[nc] = begin; c_end[nc] = end;
+                c_r[nc][0] = b1; c_r[nc][1] = e1; c_r[nc][2] = b2; c_r[nc][3] = e2;
+                c_mask[nc] = m0 | (m1 << 8);
+                nc++;
+            }
+        }
+        // ordered append: thread order inside the tile, tile order across tiles
+        const uint32_t bal_incl = [&] {
+            uint32_t x = (uint32_t)nc;
+#pragma unroll
+            for (int s = 1; s < 32; s <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, s); if (lane >= s) x += y; }
+            return x;
+        }();
+        if (lane == 31) s_wcnt[warp] = bal_incl;
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t x = lane < kScanThreads / 32 ? s_wcnt[lane] : 0u;
+            const uint32_t own = x;
+#pragma unroll
+            for (int s = 1; s < 8; s <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, s); if (lane >= s) x += y; }
+            const uint32_t tot = __shfl_sync(0xffffffffu, x, 7);
+            if (lane < kScanThreads / 32) s_wcnt[lane] = x - own;
+            unsigned long long agg[1] = {tot}, excl[1];
+            lookback_exclusive<1>(a.desc, a.epoch, tile, agg, excl);
+            if (lane == 0) {
+                s_base = excl[0];
+                if (tile == a.n_tiles - 1) a.ctl->n_cand = excl[0] + tot;
+            }
+        }
+        __syncthreads();
+        unsigned long long slot = s_base + s_wcnt[warp] + (bal_incl - (uint32_t)nc);
+        for (int k = 0; k < nc; ++k, ++slot) {
+            if (slot < a.cand_cap) {
+                Candidate cd;
+                cd.begin = c_begin[k]; cd.end = c_end[k];
+                cd.b1 = c_r[k][0]; cd.e1 = c_r[k][1]; cd.b2 = c_r[k][2]; cd.e2 = c_r[k][3];
+                cd.mask0 = c_mask[k] & 0xffu; cd.mask1 = c_mask[k] >> 8; cd.pad0 = cd.pad1 = 0;
+                a.cand[slot] = cd;
+            }
+        }
+    }
+    // flush statistics once per CTA
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+        t_clusters += __shfl_xor_sync(0xffffffffu, t_clusters, s);
+        t_size += __shfl_xor_sync(0xffffffffu, t_size, s);
+        t_rank += __shfl_xor_sync(0xffffffffu, t_rank, s);
+    }
+    if (lane == 0) {
+        atomicAdd(&s_stat[0], t_clusters);
+        atomicAdd(&s_stat[1], t_size);
+        atomicAdd(&s_stat[2], t_rank);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (s_stat[0]) atomicAdd(&a.ctl->n_clusters, s_stat[0]);
+        if (s_stat[1]) atomicAdd(&a.ctl->clust_size, s_stat[1]);
+        if (s_stat[2]) atomicAdd(&a.ctl->rank_q, s_stat[2]);
+    }
+    for (int i = threadIdx.x; i < 201; i += kScanThreads)
+        if (s_hist[i]) atomicAdd(&a.ctl->hist[i], (unsigned long long)s_hist[i] * (unsigned long long)i);
+}
+
+// Kernel 2: consensus left contexts (extract_consensus, ebwt2InDel.cpp:265-319; consensus_letter :243-261).
+// One thread per (candidate, slot); slots 0-3 = alleles of individual 0, 4-7 = individual 1.
+__global__ void consensus_kernel(const CallArgs a, uint64_t n_cand, char *__restrict__ left,
+                                 int32_t *__restrict__ support, uint8_t *__restrict__ reached,
+                                 unsigned long long *rank_q) {
+    const uint64_t gid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= n_cand * 8) return;
+    const uint64_t ci = gid >> 3;
+    const int slot = (int)(gid & 7), ind = slot >> 2, c = slot & 3;
+    const Candidate cd = a.cand[ci];
+    const uint32_t mask = ind ? cd.mask1 : cd.mask0;
+    reached[gid] = 0;
+    if (!((mask >> c) & 1u)) return;
+    const bool second = a.mode == 2 && ind == 1;
+    const DevIndex &ix = second ? a.ix2 : a.ix1;
+    uint64_t first = second ? cd.b2 : cd.b1, last = second ? cd.e2 : cd.e1;
+    if (a.mode == 3) { first = cd.begin; last = cd.end; }
+    char *out = left + gid * (uint64_t)a.k_left;
+    uint64_t rb[4], re[4];
+    unsigned nq = 0;
+    // LF(range, c) (dna_bwt.hpp:168-192)
+    rank4(ix, first, rb);
+    nq++;
+    if (last > first) { rank4(ix, last, re); nq++; } else { re[0] = rb[0]; re[1] = rb[1]; re[2] = rb[2]; re[3] = rb[3]; }
+    uint64_t lo = ix.F[c] + rb[c], hi = ix.F[c] + re[c];
+    support[gid] = (int32_t)(hi - lo);
+    int k = 0;
+    out[a.k_left - 1 - k] = "ACGT"[c];
+    k++;
+    for (int rem = a.k_left - 1; rem > 0; --rem) {
+        rank4(ix, lo, rb);
+        nq++;
+        if (hi > lo) { rank4(ix, hi, re); nq++; } else { re[0] = rb[0]; re[1] = rb[1]; re[2] = rb[2]; re[3] = rb[3]; }
+        int best = 0;
+        uint64_t bs = re[0] - rb[0];
+#pragma unroll
+        for (int x = 1; x < 4; ++x) { const uint64_t sz = re[x] - rb[x]; if (sz > bs) { bs = sz; best = x; } }
+        if (bs == 0) break;
+        out[a.k_left - 1 - k] = "ACGT"[best];
+        k++;
+        lo = ix.F[best] + rb[best];
+        hi = ix.F[best] + re[best];
+    }
+    reached[gid] = (k == a.k_left);
+    atomicAdd(rank_q + (gid & 63), (unsigned long long)nq);
+}
+
+// Kernel 3: right context (find_variants' scan for LCP >= k_right + extract_dna, :325-342, 979-988, 901-912)
+__global__ void right_context_kernel(const CallArgs a, uint64_t n_cand, char *__restrict__ right,
+                                     uint8_t *__restrict__ right_len, uint8_t *__restrict__ has_right,
+                                     unsigned long long *rank_q) {
+    const uint64_t ci = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (ci >= n_cand) return;
+    const Candidate cd = a.cand[ci];
+    uint64_t i = cd.begin, i0 = cd.b1, i1 = cd.b2;
+    while (i < cd.end && !bit_at(a.thr, 2 * i + 1)) {
+        if (a.mode == 2) { if (bit_at(a.da, i)) i1++; else i0++; }
+        ++i;
+    }
+    has_right[ci] = 0;
+    right_len[ci] = 0;
+    if (!(i < cd.end)) return;
+    const bool second = a.mode == 2 && bit_at(a.da, i);
+    const DevIndex &ix = second ? a.ix2 : a.ix1;
+    uint64_t pos = a.mode == 2 ? (second ? i1 : i0) : i;
+    char *out = right + ci * (uint64_t)a.k_right;
+    int k = 0, len = a.k_right;
+    int c = f_code(ix, pos);
+    unsigned nq = 0;
+    while (c != 4 && len > 0) {
+        out[k++] = "ACGT"[c];
+        pos = fl_map(ix, pos, c);
+        nq++;
+        c = f_code(ix, pos);
+        len--;
+    }
+    has_right[ci] = 1;
+    right_len[ci] = (uint8_t)k;
+    atomicAdd(rank_q + (ci & 63), (unsigned long long)nq);
+}
+
+// popcount of every 512-bit group of the DA, then an in-place exclusive scan (one CTA)
+__global__ void da_group_popc_kernel(const uint32_t *__restrict__ words, uint64_t n_groups, uint64_t *__restrict__ out) {
+    const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_groups) return;
+    const uint4 *p = reinterpret_cast<const uint4 *>(words) + g * 4;
+    uint32_t c = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { const uint4 v = __ldg(p + k); c += __popc(v.x) + __popc(v.y) + __popc(v.z) + __popc(v.w); }
+    out[g] = c;
+}
+
+__global__ void __launch_bounds__(1024) scan_u64_kernel(uint64_t *data, uint64_t n) {
+    __shared__ unsigned long long s_warp[32];
+    __shared__ unsigned long long s_carry;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (uint64_t base = 0; base < n; base += 1024) {
+        const uint64_t i = base + threadIdx.x;
+        const unsigned long long v = i < n ? data[i] : 0ull;
+        unsigned long long x = v;
+#pragma unroll
+        for (int s = 1; s < 32; s <<= 1) { const unsigned long long y = __shfl_up_sync(0xffffffffu, x, s); if (lane >= s) x += y; }
+        if (lane == 31) s_warp[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            unsigned long long y = s_warp[lane];
+#pragma unroll
+            for (int s = 1; s < 32; s <<= 1) { const unsigned long long z = __shfl_up_sync(0xffffffffu, y, s); if (lane >= s) y += z; }
+            s_warp[lane] = y;
+        }
+        __syncthreads();
+        const unsigned long long ex = s_carry + (warp ? s_warp[warp - 1] : 0ull) + x - v;
+        if (i < n) data[i] = ex;
+        __syncthreads();
+        if (threadIdx.x == 0) s_carry += s_warp[31];
+        __syncthreads();
+    }
+}
+
+}  // namespace e2i
+
+using namespace e2i;
+
+static int build_da_rank(e2i_ctx *ctx, e2i_bits *da) {
+    if (da->rank512) return E2I_OK;
+    const uint64_t n_groups = da->n_words32 / 16;
+    E2I_CUDA_TRY(cudaMalloc(&da->rank512, (n_groups + 1) * 8));
+    da_group_popc_kernel<<<(unsigned)((n_groups + 255) / 256), 256, 0, ctx->stream>>>(da->words, n_groups, da->rank512);
+    scan_u64_kernel<<<1, 1024, 0, ctx->stream>>>(da->rank512, n_groups);
+    E2I_CUDA_TRY(cudaGetLastError());
+    return E2I_OK;
+}
+
+extern "C" int e2i_call(e2i_ctx *ctx, const e2i_index *b1, const e2i_index *b2, const e2i_bits *da,
+                        const e2i_lcpbits *l, const e2i_params *p, uint64_t pos_begin, uint64_t pos_end,
+                        e2i_calls **out, e2i_stats *st) {
+    if (!ctx || !b1 || !l || !p || !out || !st) { set_error("e2i_call: null argument"); return E2I_ERR_ARG; }
+    if (b2 && !da) { set_error("e2i_call: two BWTs need the document array produced by e2i_navigate"); return E2I_ERR_ARG; }
+    if (p->k_left < 1 || p->k_left > 255 || p->k_right < 1 || p->k_right > 255) { set_error("e2i_call: k_left and k_right must be in [1,255]"); return E2I_ERR_ARG; }
+    if (p->mcov_out < 1) { set_error("e2i_call: mcov_out must be >= 1"); return E2I_ERR_ARG; }
+    const int mode = b2 ? 2 : (da ? 3 : 1);
+    const uint64_t n = b1->n + (b2 ? b2->n : 0);
+    if (l->n != n || (da && da->n != n)) { set_error("e2i_call: bitvector length does not match the BWT length"); return E2I_ERR_ARG; }
+    E2I_CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    if (mode == 2) E2I_TRY(build_da_rank(ctx, const_cast<e2i_bits *>(da)));
+    pos_end = std::min<uint64_t>(pos_end, n);
+
+    e2i_calls *calls = new e2i_calls();
+    calls->ctx = ctx;
+    calls->k_left = p->k_left;
+    calls->k_right = p->k_right;
+
+    CallArgs a{};
+    a.ix1 = b1->dev();
+    a.ix2 = b2 ? b2->dev() : b1->dev();
+    a.thr = l->thr;
+    a.minima = l->minima;
+    a.da = da ? da->words : nullptr;
+    a.da_rank512 = da ? da->rank512 : nullptr;
+    a.n = n;
+    a.mcov = (uint32_t)p->mcov_out;
+    a.q = (uint32_t)std::max(0, p->max_variants_per_position);
+    a.mode = mode;
+    a.k_left = p->k_left;
+    a.k_right = p->k_right;
+
+    CallCtl *dctl = nullptr;
+    unsigned long long *rank_q = nullptr;
+    Candidate *cand = nullptr;
+    char *d_left = nullptr, *d_right = nullptr;
+    int32_t *d_support = nullptr;
+    uint8_t *d_reached = nullptr, *d_rlen = nullptr, *d_has = nullptr;
+    auto cleanup = [&] { cudaFree(dctl); cudaFree(rank_q); cudaFree(cand); cudaFree(d_left); cudaFree(d_right); cudaFree(d_support); cudaFree(d_reached); cudaFree(d_rlen); cudaFree(d_has); };
+    auto fail = [&](int rc) { cleanup(); delete calls; return rc; };
+#define TRYF(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { set_error("CUDA error %s at %s:%d: %s", cudaGetErrorName(_e), __FILE__, __LINE__, cudaGetErrorString(_e)); return fail(E2I_ERR_CUDA); } } while (0)
+    TRYF(cudaMalloc(&dctl, sizeof(CallCtl)));
+    TRYF(cudaMalloc(&rank_q, 64 * 8));
+    TRYF(cudaMemsetAsync(rank_q, 0, 64 * 8, s));
+    TRYF(cudaEventRecord(ctx->ev[4], s));
+
+    const uint64_t slab = 1ull << 28;   // positions per slab: bounds the candidate list
+    const uint64_t cand_cap = slab / (2ull * a.mcov + 1) + kMaxCand + 2;
+    TRYF(cudaMalloc(&cand, cand_cap * sizeof(Candidate)));
+    a.cand = cand;
+    a.cand_cap = cand_cap;
+    CallCtl hctl;
+    std::vector<uint8_t> h_reached, h_rlen, h_has;
+    std::vector<int32_t> h_support;
+    std::vector<char> h_left, h_right;
+    std::vector<Candidate> h_cand;
+    for (uint64_t sb = pos_begin / kScanTile * kScanTile; sb < pos_end; sb += slab) {
+        const uint64_t se = std::min<uint64_t>(sb + slab, (pos_end + kScanTile - 1) / kScanTile * kScanTile);
+        a.pos_begin = std::max(sb, pos_begin);
+        a.pos_end = std::min(se, pos_end);
+        a.first_tile = sb / kScanTile;
+        a.n_tiles = (uint32_t)((se - sb + kScanTile - 1) / kScanTile);
+        if ((size_t)a.n_tiles > ctx->desc_words) {
+            cudaFree(ctx->desc);
+            ctx->desc = nullptr;
+            ctx->desc_words = (size_t)a.n_tiles + 1024;
+            TRYF(cudaMalloc(&ctx->desc, ctx->desc_words * 8));
+            TRYF(cudaMemsetAsync(ctx->desc, 0, ctx->desc_words * 8, s));
+            ctx->epoch = 0;
+        }
+        if (++ctx->epoch >= 0xffffu) { TRYF(cudaMemsetAsync(ctx->desc, 0, ctx->desc_words * 8, s)); ctx->epoch = 1; }
+        a.desc = ctx->desc;
+        a.epoch = ctx->epoch;
+        a.ctl = dctl;
+        TRYF(cudaMemsetAsync(dctl, 0, sizeof(CallCtl), s));
+        const int grid = (int)std::min<uint64_t>(a.n_tiles, (uint64_t)ctx->sm_count * 8);
+        scan_clusters_kernel<<<grid, kScanThreads, 0, s>>>(a);
+        TRYF(cudaGetLastError());
+        TRYF(cudaMemcpyAsync(&hctl, dctl, sizeof(CallCtl), cudaMemcpyDeviceToHost, s));
+        TRYF(cudaStreamSynchronize(s));
+        st->n_clusters += hctl.n_clusters;
+        st->clust_size += hctl.clust_size;
+        st->rank_call += hctl.rank_q;
+        for (int i = 0; i <= 200; ++i) st->clust_sizes[i] += hctl.hist[i];
+        const uint64_t nc = hctl.n_cand;
+        if (nc > cand_cap) { set_error("e2i_call: candidate list overflow (%llu > %llu)", (unsigned long long)nc, (unsigned long long)cand_cap); return fail(E2I_ERR_MEMORY); }
+        st->candidates += nc;
+        if (nc == 0) continue;
+        TRYF(cudaMalloc(&d_left, nc * 8 * (size_t)p->k_left));
+        TRYF(cudaMalloc(&d_right, nc * (size_t)p->k_right));
+        TRYF(cudaMalloc(&d_support, nc * 8 * sizeof(int32_t)));
+        TRYF(cudaMalloc(&d_reached, nc * 8));
+        TRYF(cudaMalloc(&d_rlen, nc));
+        TRYF(cudaMalloc(&d_has, nc));
+        TRYF(cudaMemsetAsync(d_support, 0, nc * 8 * sizeof(int32_t), s));
+        consensus_kernel<<<(unsigned)((nc * 8 + 127) / 128), 128, 0, s>>>(a, nc, d_left, d_support, d_reached, rank_q);
+        right_context_kernel<<<(unsigned)((nc + 127) / 128), 128, 0, s>>>(a, nc, d_right, d_rlen, d_has, rank_q);
+        TRYF(cudaGetLastError());
+        h_cand.resize(nc); h_left.resize(nc * 8 * (size_t)p->k_left); h_right.resize(nc * (size_t)p->k_right);
+        h_support.resize(nc * 8); h_reached.resize(nc * 8); h_rlen.resize(nc); h_has.resize(nc);
+        TRYF(cudaMemcpyAsync(h_cand.data(), cand, nc * sizeof(Candidate), cudaMemcpyDeviceToHost, s));
+        TRYF(cudaMemcpyAsync(h_left.data(), d_left, h_left.size(), cudaMemcpyDeviceToHost, s));
+        TRYF(cudaMemcpyAsync(h_right.data(), d_right, h_right.size(), cudaMemcpyDeviceToHost, s));
+        TRYF(cudaMemcpyAsync(h_support.data(), d_support, nc * 8 * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+        TRYF(cudaMemcpyAsync(h_reached.data(), d_reached, nc * 8, cudaMemcpyDeviceToHost, s));
+        TRYF(cudaMemcpyAsync(h_rlen.data(), d_rlen, nc, cudaMemcpyDeviceToHost, s));
+        TRYF(cudaMemcpyAsync(h_has.data(), d_has, nc, cudaMemcpyDeviceToHost, s));
+        TRYF(cudaStreamSynchronize(s));
+        cudaFree(d_left); cudaFree(d_right); cudaFree(d_support); cudaFree(d_reached); cudaFree(d_rlen); cudaFree(d_has);
+        d_left = d_right = nullptr; d_support = nullptr; d_reached = d_rlen = d_has = nullptr;
+        // compact on the host: keep clusters with a right context; pack reached contexts per individual
+        const size_t kl = (size_t)p->k_left, kr = (size_t)p->k_right;
+        for (uint64_t ci = 0; ci < nc; ++ci) {
+            if (!h_has[ci]) continue;
+            e2i_call_rec rec{};
+            rec.begin = h_cand[ci].begin;
+            rec.end = h_cand[ci].end;
+            rec.right_len = h_rlen[ci];
+            const size_t base = calls->left.size();
+            calls->left.resize(base + 8 * kl, 0);
+            for (int ind = 0; ind < 2; ++ind) {
+                int k = 0;
+                for (int c = 0; c < 4; ++c) {
+                    const size_t src = ci * 8 + ind * 4 + c;
+                    if (!h_reached[src]) continue;
+                    std::memcpy(&calls->left[base + (ind * 4 + k) * kl], &h_left[src * kl], kl);
+                    rec.support[ind * 4 + k] = h_support[src];
+                    k++;
+                }
+                if (ind == 0) rec.n0 = (uint8_t)k; else rec.n1 = (uint8_t)k;
+            }
+            const size_t rb = calls->right.size();
+            calls->right.resize(rb + kr, 0);
+            std::memcpy(&calls->right[rb], &h_right[ci * kr], rec.right_len);
+            calls->recs.push_back(rec);
+        }
+    }
+    unsigned long long hq[64];
+    TRYF(cudaMemcpyAsync(hq, rank_q, sizeof hq, cudaMemcpyDeviceToHost, s));
+    TRYF(cudaEventRecord(ctx->ev[5], s));
+    TRYF(cudaStreamSynchronize(s));
+    for (int i = 0; i < 64; ++i) st->rank_call += hq[i];
+    float ms = 0;
+    TRYF(cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5]));
+    st->ms_call += ms;
+#undef TRYF
+    cleanup();
+    *out = calls;
+    return E2I_OK;
+}
+
+extern "C" uint64_t e2i_calls_count(const e2i_calls *c) { return c ? c->recs.size() : 0; }
+
+extern "C" int e2i_calls_fetch(const e2i_calls *c, e2i_call_rec *host_recs, char *host_left, char *host_right,
+                               uint64_t cap, uint64_t *n) {
+    if (!c || !n) { set_error("e2i_calls_fetch: null argument"); return E2I_ERR_ARG; }
+    const uint64_t k = std::min<uint64_t>(cap, c->recs.size());
+    if (k && (!host_recs || !host_left || !host_right)) { set_error("e2i_calls_fetch: null buffer"); return E2I_ERR_ARG; }
+    if (k) {
+        std::memcpy(host_recs, c->recs.data(), k * sizeof(e2i_call_rec));
+        std::memcpy(host_left, c->left.data(), k * 8 * (size_t)c->k_left);
+        std::memcpy(host_right, c->right.data(), k * (size_t)c->k_right);
+    }
+    *n = k;
+    return E2I_OK;
+}
+
+extern "C" void e2i_calls_free(e2i_calls *c) { delete c; }

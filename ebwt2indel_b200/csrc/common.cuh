@@ -1,0 +1,223 @@
+// common.cuh -- shared host/device definitions of libe2i (B200 / sm_100a).
+//
+// HBM layout of the rank-indexed BWT (replaces dna_string, /root/reference/internal/dna_string.hpp):
+//   one 64-byte block per 128 symbols = 4 x uint4:
+//     [0] four u32 counts of A,C,G,T before the block, relative to the 2^32-symbol superblock
+//     [1] plane 0 (bit 0 of the code)   [2] plane 1 (bit 1 of the code)   [3] TERM plane
+//   symbol j of the block sits at bit j%32 of word j/32 of each plane (A=00, C=01, G=10, T=11;
+//   TERM has its TERM-plane bit set and 00 in the others).  A superblock table (4 x u64 absolute
+//   counts per 2^32 symbols) lifts the u32 counters to 64-bit positions.  One rank query =
+//   one aligned 64-byte fetch (two 32-byte sectors) + 16 popcounts.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "e2i.h"
+
+namespace e2i {
+
+constexpr int kBlockSyms = 128;          // symbols per index block
+constexpr int kBlockShift = 7;
+constexpr int kSuperShift = 32;          // symbols per superblock = 2^32
+constexpr int kTileSyms = 16384;         // symbols per index-build tile (128 blocks)
+constexpr int kTileShift = 14;
+constexpr int kSuperTileShift = kSuperShift - kTileShift;
+
+struct DevIndex {
+    const uint4 *blocks;      // 4 x uint4 per block
+    const uint64_t *super;    // 4 x u64 per superblock
+    uint64_t n;
+    uint64_t F[4];            // F_A, F_C, F_G, F_T (dna_bwt.hpp:412-415)
+};
+
+void set_error(const char *fmt, ...);
+
+#define E2I_CUDA_TRY(expr)                                                                   \
+    do {                                                                                     \
+        cudaError_t _e = (expr);                                                             \
+        if (_e != cudaSuccess) {                                                             \
+            e2i::set_error("CUDA error %s at %s:%d: %s", cudaGetErrorName(_e), __FILE__,     \
+                           __LINE__, cudaGetErrorString(_e));                                \
+            return E2I_ERR_CUDA;                                                             \
+        }                                                                                    \
+    } while (0)
+
+#define E2I_TRY(expr)                 \
+    do {                              \
+        int _rc = (expr);             \
+        if (_rc != E2I_OK) return _rc; \
+    } while (0)
+
+// Size-class caching allocator for frontier frames (sizes change every sweep; cudaMalloc per
+// sweep would serialise the device).  Classes are {1, 1.25, 1.5, 1.75} x 2^k bytes.
+class DevicePool {
+  public:
+    ~DevicePool() { release(); }
+    int alloc(void **p, size_t bytes);
+    void free(void *p);
+    void release();
+    size_t bytes_live() const { return live_; }
+    size_t bytes_reserved() const { return reserved_; }
+    void set_limit(size_t bytes) { limit_ = bytes; }
+
+  private:
+    struct Blk { void *p; size_t cls; bool used; };
+    std::vector<Blk> blks_;
+    size_t live_ = 0, reserved_ = 0, limit_ = 0;
+};
+
+}  // namespace e2i
+
+struct e2i_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev[8] = {};
+    int sm_count = 148;
+    uint64_t frontier_budget = 0;
+    e2i::DevicePool pool;
+    // look-back descriptors shared by all ordered-compaction kernels
+    unsigned long long *desc = nullptr;
+    size_t desc_words = 0;
+    uint32_t epoch = 0;
+    void *ctl = nullptr;        // device control block (ticket + counters), see navigate.cu
+    void *ctl_host = nullptr;   // pinned mirror
+};
+
+struct e2i_index {
+    e2i_ctx *ctx = nullptr;
+    uint4 *blocks = nullptr;
+    uint64_t *super = nullptr;
+    uint64_t n = 0, n_blocks = 0, n_super = 0, bytes = 0;
+    uint64_t F[4] = {0, 0, 0, 0};
+    uint8_t term = '#';
+    e2i::DevIndex dev() const {
+        e2i::DevIndex d;
+        d.blocks = blocks;
+        d.super = super;
+        d.n = n;
+        for (int i = 0; i < 4; ++i) d.F[i] = F[i];
+        return d;
+    }
+};
+
+struct e2i_bits {
+    e2i_ctx *ctx = nullptr;
+    uint32_t *words = nullptr;    // packed bits, zero-padded to a multiple of 64 u32 words
+    uint64_t n = 0, n_words32 = 0;
+    uint64_t *rank512 = nullptr;  // popcount before every 512-bit group (built on demand, mode -2)
+};
+
+struct e2i_lcpbits {
+    e2i_ctx *ctx = nullptr;
+    uint32_t *thr = nullptr;      // 2n bits: bit 2i = LCP[i] >= K, bit 2i+1 = LCP[i] >= k_right
+    uint32_t *minima = nullptr;   // n bits
+    uint64_t n = 0, thr_words32 = 0, min_words32 = 0;
+};
+
+struct e2i_calls {
+    e2i_ctx *ctx = nullptr;
+    std::vector<e2i_call_rec> recs;
+    std::vector<char> left, right;
+    int k_left = 0, k_right = 0;
+};
+
+#ifdef __CUDACC__
+namespace e2i {
+
+__device__ __forceinline__ uint32_t prefix_mask32(int off, int word) {
+    // bits of `word` (32 symbols) that lie before block offset `off`
+    int k = off - 32 * word;
+    return k >= 32 ? 0xffffffffu : (k <= 0 ? 0u : ((1u << k) - 1u));
+}
+
+// a2: parallel_rank (dna_string.hpp:140-152): #A,#C,#G,#T in [0, i), 0 <= i <= n.
+__device__ __forceinline__ void rank4(const DevIndex &ix, uint64_t i, uint64_t out[4]) {
+    const uint4 *p = ix.blocks + (i >> kBlockShift) * 4;
+    const uint4 cnt = __ldg(p), a = __ldg(p + 1), b = __ldg(p + 2), t = __ldg(p + 3);
+    const uint64_t *sb = ix.super + (i >> kSuperShift) * 4;
+    const int off = (int)(i & (kBlockSyms - 1));
+    const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w}, tw[4] = {t.x, t.y, t.z, t.w};
+    uint32_t nN = 0, nC = 0, nG = 0, nT = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const uint32_t nt = ~tw[k] & prefix_mask32(off, k);
+        nN += __popc(nt);
+        nC += __popc(nt & aw[k]);
+        nG += __popc(nt & bw[k]);
+        nT += __popc(nt & aw[k] & bw[k]);
+    }
+    nC -= nT;
+    nG -= nT;
+    out[0] = sb[0] + cnt.x + (nN - nC - nG - nT);
+    out[1] = sb[1] + cnt.y + nC;
+    out[2] = sb[2] + cnt.z + nG;
+    out[3] = sb[3] + cnt.w + nT;
+}
+
+// single-symbol count before block `blk` (absolute)
+__device__ __forceinline__ uint64_t block_count(const DevIndex &ix, uint64_t blk, int c) {
+    const uint32_t *cnt = reinterpret_cast<const uint32_t *>(ix.blocks + blk * 4);
+    return ix.super[(blk >> (kSuperShift - kBlockShift)) * 4 + c] + __ldg(cnt + c);
+}
+
+// a3: operator[] (dna_string.hpp:113-135): code 0..3 = A,C,G,T, 4 = TERM
+__device__ __forceinline__ int access_code(const DevIndex &ix, uint64_t i) {
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(ix.blocks + (i >> kBlockShift) * 4);
+    const int off = (int)(i & (kBlockSyms - 1)), k = off >> 5, sh = off & 31;
+    const uint32_t a = (__ldg(w + 4 + k) >> sh) & 1u, b = (__ldg(w + 8 + k) >> sh) & 1u, t = (__ldg(w + 12 + k) >> sh) & 1u;
+    return t ? 4 : (int)(a | (b << 1));
+}
+
+// F column (dna_bwt.hpp:100-110): code of the first symbol of suffix i
+__device__ __forceinline__ int f_code(const DevIndex &ix, uint64_t i) {
+    return i < ix.F[0] ? 4 : i < ix.F[1] ? 0 : i < ix.F[2] ? 1 : i < ix.F[3] ? 2 : 3;
+}
+
+// a4: select (dna_string.hpp:182-188, 254-272): position of the r-th (0-based) symbol c.
+// Binary search on the interleaved block counters, then a bit select inside the block.
+__device__ __forceinline__ uint64_t select_sym(const DevIndex &ix, uint64_t r, int c) {
+    uint64_t lo = 0, hi = ix.n >> kBlockShift;  // last block whose count <= r lies in [lo, hi]
+    while (lo < hi) {
+        const uint64_t mid = (lo + hi + 1) >> 1;
+        if (block_count(ix, mid, c) <= r) lo = mid; else hi = mid - 1;
+    }
+    uint32_t k = (uint32_t)(r - block_count(ix, lo, c));  // k-th occurrence inside block lo
+    const uint4 *p = ix.blocks + lo * 4;
+    const uint4 a = __ldg(p + 1), b = __ldg(p + 2), t = __ldg(p + 3);
+    const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w}, tw[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+        const uint32_t m = ~tw[w] & ((c & 1) ? aw[w] : ~aw[w]) & ((c & 2) ? bw[w] : ~bw[w]);
+        const uint32_t pc = __popc(m);
+        if (k < pc) return (lo << kBlockShift) + 32 * w + __fns(m, 0, (int)k + 1);
+        k -= pc;
+    }
+    return ~0ull;  // unreachable for r < #c
+}
+
+// FL (dna_bwt.hpp:115-133); the caller guarantees F(i) != TERM
+__device__ __forceinline__ uint64_t fl_map(const DevIndex &ix, uint64_t i, int c) {
+    return select_sym(ix, i - ix.F[c], c);
+}
+
+__device__ __forceinline__ uint64_t shfl_u64(uint64_t v, int src, int width = 32) {
+    return __shfl_sync(0xffffffffu, v, src, width);
+}
+__device__ __forceinline__ uint64_t shfl_down_u64(uint64_t v, int d, int width = 32) {
+    return __shfl_down_sync(0xffffffffu, v, d, width);
+}
+__device__ __forceinline__ uint64_t shfl_up_u64(uint64_t v, int d, int width = 32) {
+    return __shfl_up_sync(0xffffffffu, v, d, width);
+}
+
+}  // namespace e2i
+#endif

@@ -1,0 +1,244 @@
+// context.cu -- device context, error reporting, parameter defaults, the frame allocator and the
+// whole-path entry points e2i_run / e2i_run_device.
+//
+// e2i_run replaces run_one_dataset / run_two_datasets / run_two_datasets_da
+// (/root/reference/ebwt2InDel.cpp:1584-1674, 1344-1465, 1471-1579): load + index the eBWT(s),
+// traverse (phases 2-3), scan clusters and extract contexts (phase 4), format the .snp text.
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace e2i {
+
+static thread_local std::string g_last_error;
+
+void set_error(const char *fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+}
+
+// ---- DevicePool ------------------------------------------------------------------------------
+static size_t size_class(size_t bytes) {
+    if (bytes < 4096) bytes = 4096;
+    size_t p = 4096;
+    while (p * 2 <= bytes) p *= 2;         // p <= bytes < 2p
+    if (bytes == p) return p;
+    for (int q = 5; q <= 8; ++q) {          // 1.25p, 1.5p, 1.75p, 2p
+        const size_t c = p / 4 * q;
+        if (bytes <= c) return c;
+    }
+    return 2 * p;
+}
+
+int DevicePool::alloc(void **out, size_t bytes) {
+    const size_t cls = size_class(bytes);
+    for (Blk &b : blks_)
+        if (!b.used && b.cls == cls) { b.used = true; live_ += cls; *out = b.p; return E2I_OK; }
+    if (limit_ && reserved_ + cls > limit_) {
+        // drop cached blocks of other classes before giving up
+        for (size_t i = 0; i < blks_.size();) {
+            if (!blks_[i].used) { cudaFree(blks_[i].p); reserved_ -= blks_[i].cls; blks_[i] = blks_.back(); blks_.pop_back(); }
+            else ++i;
+        }
+        if (reserved_ + cls > limit_) return E2I_ERR_MEMORY;
+    }
+    void *p = nullptr;
+    cudaError_t e = cudaMalloc(&p, cls);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        for (size_t i = 0; i < blks_.size();) {
+            if (!blks_[i].used) { cudaFree(blks_[i].p); reserved_ -= blks_[i].cls; blks_[i] = blks_.back(); blks_.pop_back(); }
+            else ++i;
+        }
+        e = cudaMalloc(&p, cls);
+        if (e != cudaSuccess) { cudaGetLastError(); return E2I_ERR_MEMORY; }
+    }
+    blks_.push_back({p, cls, true});
+    reserved_ += cls;
+    live_ += cls;
+    *out = p;
+    return E2I_OK;
+}
+
+void DevicePool::free(void *p) {
+    for (Blk &b : blks_)
+        if (b.p == p) { b.used = false; live_ -= b.cls; return; }
+}
+
+void DevicePool::release() {
+    for (Blk &b : blks_) cudaFree(b.p);
+    blks_.clear();
+    live_ = reserved_ = 0;
+}
+
+}  // namespace e2i
+
+using namespace e2i;
+
+extern "C" const char *e2i_last_error(void) { return g_last_error.c_str(); }
+extern "C" const char *e2i_version(void) { return "ebwt2indel_b200 0.1.0 (sm_100a)"; }
+
+// globals of ebwt2InDel.cpp:20-74
+extern "C" void e2i_params_default(e2i_params *p) {
+    if (!p) return;
+    p->k_left = 31; p->k_right = 30; p->K = 16; p->max_gap = 10; p->max_snvs = 2; p->mcov_out = 3;
+    p->complexity = 20;          // complexity_def = k_right_def - 10, computed from the DEFAULT -R (:64)
+    p->max_variants_per_position = 0;
+    p->term = '#';
+}
+
+// "0 means default" (ebwt2InDel.cpp:1740-1746); -q and -t are taken as given
+extern "C" void e2i_params_resolve(e2i_params *p) {
+    if (!p) return;
+    e2i_params d;
+    e2i_params_default(&d);
+    if (p->complexity == 0) p->complexity = d.complexity;
+    if (p->K == 0) p->K = d.K;
+    if (p->max_gap == 0) p->max_gap = d.max_gap;
+    if (p->k_left == 0) p->k_left = d.k_left;
+    if (p->k_right == 0) p->k_right = d.k_right;
+    if (p->max_snvs == 0) p->max_snvs = d.max_snvs;
+    if (p->mcov_out == 0) p->mcov_out = d.mcov_out;
+}
+
+extern "C" int e2i_create(int device, e2i_ctx **out) {
+    if (!out) { set_error("e2i_create: null argument"); return E2I_ERR_ARG; }
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        set_error("e2i_create: no CUDA device available (%s); this library has no CPU fallback",
+                  e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+        return E2I_ERR_CUDA;
+    }
+    if (device < 0 || device >= count) { set_error("e2i_create: device %d out of range [0,%d)", device, count); return E2I_ERR_ARG; }
+    E2I_CUDA_TRY(cudaSetDevice(device));
+    e2i_ctx *ctx = new e2i_ctx();
+    ctx->device = device;
+    cudaDeviceProp prop;
+    E2I_CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    ctx->sm_count = prop.multiProcessorCount;
+    E2I_CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    E2I_CUDA_TRY(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    for (auto &ev : ctx->ev) E2I_CUDA_TRY(cudaEventCreate(&ev));
+    E2I_CUDA_TRY(cudaMalloc(&ctx->ctl, 4096));
+    E2I_CUDA_TRY(cudaMallocHost(&ctx->ctl_host, 4096));
+    *out = ctx;
+    return E2I_OK;
+}
+
+extern "C" void e2i_destroy(e2i_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    ctx->pool.release();
+    cudaFree(ctx->desc);
+    cudaFree(ctx->ctl);
+    cudaFreeHost(ctx->ctl_host);
+    for (auto &ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    delete ctx;
+}
+
+extern "C" int e2i_set_frontier_budget(e2i_ctx *ctx, uint64_t bytes) {
+    if (!ctx) { set_error("e2i_set_frontier_budget: null context"); return E2I_ERR_ARG; }
+    ctx->frontier_budget = bytes;
+    return E2I_OK;
+}
+
+// ---- whole path ------------------------------------------------------------------------------
+static int run_on_device(e2i_ctx *ctx, const uint8_t *dev_bwt1, uint64_t n1, const uint8_t *dev_bwt2, uint64_t n2,
+                         const uint8_t *dev_da, const e2i_params *p, char **snp, size_t *snp_len, e2i_stats *st,
+                         void (*release_inputs)(void *), void *release_arg) {
+    e2i_index *b1 = nullptr, *b2 = nullptr;
+    e2i_bits *da = nullptr, *da_nav = nullptr;
+    e2i_lcpbits *lcp = nullptr;
+    e2i_calls *calls = nullptr;
+    auto cleanup = [&] {
+        e2i_calls_free(calls); e2i_lcpbits_free(lcp); e2i_bits_free(da); e2i_bits_free(da_nav);
+        e2i_index_free(b1); e2i_index_free(b2);
+    };
+    cudaStream_t s = ctx->stream;
+    cudaEventRecord(ctx->ev[6], s);
+    uint64_t bad = 0;
+    int rc = e2i_index_build_device(ctx, dev_bwt1, n1, (uint8_t)p->term, &b1, &bad);
+    if (rc == E2I_OK && dev_bwt2) rc = e2i_index_build_device(ctx, dev_bwt2, n2, (uint8_t)p->term, &b2, &bad);
+    if (rc == E2I_OK && dev_da) rc = e2i_da_load_device(ctx, dev_da, n1, &da);
+    cudaEventRecord(ctx->ev[7], s);
+    if (rc == E2I_OK) {
+        cudaEventSynchronize(ctx->ev[7]);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, ctx->ev[6], ctx->ev[7]);
+        st->ms_index += ms;
+    }
+    if (release_inputs) release_inputs(release_arg);   // the ASCII copies are dead once the index exists
+    if (rc == E2I_OK) rc = e2i_navigate(ctx, b1, b2, p, &lcp, b2 ? &da_nav : nullptr, st);
+    if (rc == E2I_OK) rc = e2i_call(ctx, b1, b2, b2 ? da_nav : da, lcp, p, 0, UINT64_MAX, &calls, st);
+    if (rc == E2I_OK)
+        rc = e2i_snp_format(calls->recs.data(), calls->left.data(), calls->right.data(), calls->recs.size(), p,
+                            (b2 || da) ? 1 : 0, 1, snp, snp_len, st);
+    cleanup();
+    return rc;
+}
+
+extern "C" int e2i_run_device(e2i_ctx *ctx, const uint8_t *dev_bwt1, uint64_t n1, const uint8_t *dev_bwt2, uint64_t n2,
+                              const uint8_t *dev_da, const e2i_params *p, char **snp, size_t *snp_len, e2i_stats *st) {
+    if (!ctx || !dev_bwt1 || !p || !snp || !snp_len || !st) { set_error("e2i_run_device: null argument"); return E2I_ERR_ARG; }
+    if (dev_bwt2 && dev_da) { set_error("Document array (-d) can only be used with one input BWT file (-1)"); return E2I_ERR_ARG; }
+    E2I_CUDA_TRY(cudaSetDevice(ctx->device));
+    return run_on_device(ctx, dev_bwt1, n1, dev_bwt2, n2, dev_da, p, snp, snp_len, st, nullptr, nullptr);
+}
+
+namespace {
+struct HostInputs {
+    uint8_t *d1 = nullptr, *d2 = nullptr, *dd = nullptr;
+};
+void free_inputs(void *arg) {
+    HostInputs *h = static_cast<HostInputs *>(arg);
+    cudaFree(h->d1); cudaFree(h->d2); cudaFree(h->dd);
+    h->d1 = h->d2 = h->dd = nullptr;
+}
+}  // namespace
+
+extern "C" int e2i_run(e2i_ctx *ctx, const uint8_t *host_bwt1, uint64_t n1, const uint8_t *host_bwt2, uint64_t n2,
+                       const uint8_t *host_da, const e2i_params *p, char **snp, size_t *snp_len, e2i_stats *st) {
+    if (!ctx || !host_bwt1 || !p || !snp || !snp_len || !st) { set_error("e2i_run: null argument"); return E2I_ERR_ARG; }
+    if (host_bwt2 && host_da) { set_error("Document array (-d) can only be used with one input BWT file (-1)"); return E2I_ERR_ARG; }
+    E2I_CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    HostInputs in;
+    auto fail = [&](cudaError_t e) { set_error("e2i_run: %s", cudaGetErrorString(e)); free_inputs(&in); return E2I_ERR_CUDA; };
+    cudaError_t e = cudaEventRecord(ctx->ev[6], s);
+    if (e == cudaSuccess) e = cudaMalloc(&in.d1, n1 + 16);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(in.d1, host_bwt1, n1, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess && host_bwt2) {
+        e = cudaMalloc(&in.d2, n2 + 16);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(in.d2, host_bwt2, n2, cudaMemcpyHostToDevice, s);
+    }
+    if (e == cudaSuccess && host_da) {
+        e = cudaMalloc(&in.dd, n1 + 16);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(in.dd, host_da, n1, cudaMemcpyHostToDevice, s);
+    }
+    if (e == cudaSuccess) e = cudaEventRecord(ctx->ev[7], s);
+    if (e == cudaSuccess) e = cudaEventSynchronize(ctx->ev[7]);
+    if (e != cudaSuccess) return fail(e);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ctx->ev[6], ctx->ev[7]);
+    st->ms_h2d += ms;
+    const int rc = run_on_device(ctx, in.d1, n1, in.d2, n2, in.dd, p, snp, snp_len, st, free_inputs, &in);
+    free_inputs(&in);
+    return rc;
+}
+
+extern "C" int e2i_host_alloc(uint64_t bytes, void **out) {
+    if (!out) { set_error("e2i_host_alloc: null argument"); return E2I_ERR_ARG; }
+    cudaError_t e = cudaMallocHost(out, bytes ? bytes : 1);
+    if (e != cudaSuccess) { cudaGetLastError(); set_error("e2i_host_alloc(%llu bytes): %s", (unsigned long long)bytes, cudaGetErrorString(e)); return E2I_ERR_CUDA; }
+    return E2I_OK;
+}
+
+extern "C" void e2i_host_free(void *p) { if (p) cudaFreeHost(p); }

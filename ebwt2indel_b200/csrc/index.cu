@@ -1,0 +1,473 @@
+// index.cu -- a1/a5: ASCII BWT -> rank-indexed blocks in HBM, and the batched test hooks.
+//
+// Replaces dna_string(path, TERM) + build_rank_support (/root/reference/internal/dna_string.hpp:
+// 55-110, 275-315, 320-369) and the F-array scan of dna_bwt(path, TERM) (dna_bwt.hpp:36-62).
+// Three streaming kernels: count symbols per 16384-symbol tile, scan the tile totals, pack
+// (second read of the ASCII, one write of the 64-byte blocks).  HBM traffic: 2n read + n/2 write.
+#include "common.cuh"
+
+namespace e2i {
+
+// ---- symbol classification -------------------------------------------------------------------
+// code: 0..3 = A,C,G,T; 4 = TERM; 5 = forbidden
+__device__ __forceinline__ int classify(uint32_t ch, uint32_t term) {
+    if (ch == term) return 4;
+    if (ch == 'A') return 0;
+    if (ch == 'C') return 1;
+    if (ch == 'G') return 2;
+    if (ch == 'T') return 3;
+    return 5;
+}
+
+struct Piece {               // 16 symbols
+    uint32_t p0, p1, pt;     // 16 plane bits each
+    uint32_t cnt;            // 4 x 8-bit counts A,C,G,T
+    int bad;                 // index (0..15) of the first forbidden symbol, or -1
+};
+
+__device__ __forceinline__ Piece encode_piece(uint4 v, uint64_t pos0, uint64_t n, uint32_t term) {
+    Piece pc{0, 0, 0, 0, -1};
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const uint32_t ch = (w[j >> 2] >> (8 * (j & 3))) & 0xffu;
+        if (pos0 + j < n) {
+            const int c = classify(ch, term);
+            if (c == 5) {
+                if (pc.bad < 0) pc.bad = j;
+            } else if (c == 4) {
+                pc.pt |= 1u << j;
+            } else {
+                pc.p0 |= (uint32_t)(c & 1) << j;
+                pc.p1 |= (uint32_t)(c >> 1) << j;
+                pc.cnt += 1u << (8 * c);
+            }
+        }
+    }
+    return pc;
+}
+
+__device__ __forceinline__ uint4 load_piece(const uint8_t *ascii, uint64_t pos0, uint64_t n) {
+    // 16-byte aligned vector load when the whole piece is inside the buffer, bytewise tail otherwise
+    if (pos0 + 16 <= n) return __ldg(reinterpret_cast<const uint4 *>(ascii + pos0));
+    uint32_t w[4] = {0, 0, 0, 0};
+    for (int j = 0; j < 16; ++j)
+        if (pos0 + j < n) w[j >> 2] |= (uint32_t)ascii[pos0 + j] << (8 * (j & 3));
+    return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+constexpr int kBuildThreads = 256;
+constexpr int kPiecesPerTile = kTileSyms / 16;                       // 1024
+constexpr int kPiecesPerThread = kPiecesPerTile / kBuildThreads;     // 4
+
+// Kernel 1: per-tile symbol totals.  Grid-stride over tiles; coalesced 16-byte loads.
+__global__ void __launch_bounds__(kBuildThreads)
+count_tiles_kernel(const uint8_t *__restrict__ ascii, uint64_t n, uint32_t term, uint64_t n_tiles,
+                   uint4 *__restrict__ tile_cnt, unsigned long long *bad_pos) {
+    __shared__ unsigned long long s_part[kBuildThreads / 32];
+    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        unsigned long long acc = 0;  // 4 x 16-bit fields
+#pragma unroll
+        for (int it = 0; it < kPiecesPerThread; ++it) {
+            const uint64_t pos0 = (tile << kTileShift) + (uint64_t)(it * kBuildThreads + threadIdx.x) * 16;
+            if (pos0 < n) {
+                const Piece pc = encode_piece(load_piece(ascii, pos0, n), pos0, n, term);
+                if (pc.bad >= 0) atomicMin(bad_pos, (unsigned long long)(pos0 + pc.bad));
+                acc += (unsigned long long)(pc.cnt & 0xffu) | ((unsigned long long)((pc.cnt >> 8) & 0xffu) << 16) |
+                       ((unsigned long long)((pc.cnt >> 16) & 0xffu) << 32) | ((unsigned long long)(pc.cnt >> 24) << 48);
+            }
+        }
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+        if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned long long t = 0;
+            for (int w = 0; w < kBuildThreads / 32; ++w) t += s_part[w];
+            tile_cnt[tile] = make_uint4((uint32_t)(t & 0xffff), (uint32_t)((t >> 16) & 0xffff),
+                                        (uint32_t)((t >> 32) & 0xffff), (uint32_t)(t >> 48));
+        }
+        __syncthreads();
+    }
+}
+
+// Kernel 2: exclusive scan of the tile totals (one CTA, coalesced chunks of 1024 tiles).
+constexpr int kScanThreads = 1024;
+__global__ void __launch_bounds__(kScanThreads)
+scan_tiles_kernel(const uint4 *__restrict__ tile_cnt, uint64_t n_tiles, ulonglong4 *__restrict__ tile_prefix,
+                  unsigned long long *__restrict__ totals) {
+    __shared__ unsigned long long s_warp[32][4];
+    __shared__ unsigned long long s_carry[4];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x < 4) s_carry[threadIdx.x] = 0;
+    __syncthreads();
+    for (uint64_t base = 0; base < n_tiles; base += kScanThreads) {
+        const uint64_t t = base + threadIdx.x;
+        uint4 c = t < n_tiles ? tile_cnt[t] : make_uint4(0, 0, 0, 0);
+        unsigned long long v[4] = {c.x, c.y, c.z, c.w}, incl[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            unsigned long long x = v[k];
+#pragma unroll
+            for (int s = 1; s < 32; s <<= 1) {
+                const unsigned long long y = __shfl_up_sync(0xffffffffu, x, s);
+                if (lane >= s) x += y;
+            }
+            incl[k] = x;
+            if (lane == 31) s_warp[warp][k] = x;
+        }
+        __syncthreads();
+        if (warp == 0) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                unsigned long long x = s_warp[lane][k];
+#pragma unroll
+                for (int s = 1; s < 32; s <<= 1) {
+                    const unsigned long long y = __shfl_up_sync(0xffffffffu, x, s);
+                    if (lane >= s) x += y;
+                }
+                s_warp[lane][k] = x;  // inclusive over warps
+            }
+        }
+        __syncthreads();
+        unsigned long long ex[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            ex[k] = s_carry[k] + (warp ? s_warp[warp - 1][k] : 0ull) + incl[k] - v[k];
+        if (t < n_tiles) tile_prefix[t] = make_ulonglong4(ex[0], ex[1], ex[2], ex[3]);
+        __syncthreads();
+        if (threadIdx.x < 4) s_carry[threadIdx.x] += s_warp[31][threadIdx.x];
+        __syncthreads();
+    }
+    if (threadIdx.x < 4) totals[threadIdx.x] = s_carry[threadIdx.x];
+}
+
+// Kernel 3: pack one tile (128 blocks) per CTA iteration.
+__global__ void __launch_bounds__(kBuildThreads)
+pack_tiles_kernel(const uint8_t *__restrict__ ascii, uint64_t n, uint32_t term, uint64_t n_tiles,
+                  const ulonglong4 *__restrict__ tile_prefix, uint4 *__restrict__ blocks,
+                  unsigned long long *__restrict__ super) {
+    __shared__ uint16_t s_plane[3][kPiecesPerTile];
+    __shared__ uint32_t s_cnt[kPiecesPerTile];
+    __shared__ unsigned long long s_blk[kTileSyms / kBlockSyms];      // exclusive per-block prefix, 4 x 16 bit
+    __shared__ unsigned long long s_wsum[4];
+    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+#pragma unroll
+        for (int it = 0; it < kPiecesPerThread; ++it) {
+            const int piece = it * kBuildThreads + threadIdx.x;
+            const uint64_t pos0 = (tile << kTileShift) + (uint64_t)piece * 16;
+            Piece pc{0, 0, 0, 0, -1};
+            if (pos0 < n) pc = encode_piece(load_piece(ascii, pos0, n), pos0, n, term);
+            s_plane[0][piece] = (uint16_t)pc.p0;
+            s_plane[1][piece] = (uint16_t)pc.p1;
+            s_plane[2][piece] = (uint16_t)pc.pt;
+            s_cnt[piece] = pc.cnt;
+        }
+        __syncthreads();
+        // per-block totals (8 pieces each) and their exclusive scan over the 128 blocks of the tile
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        unsigned long long mine = 0, incl = 0;
+        if (threadIdx.x < 128) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const uint32_t c = s_cnt[threadIdx.x * 8 + k];
+                mine += (unsigned long long)(c & 0xffu) | ((unsigned long long)((c >> 8) & 0xffu) << 16) |
+                        ((unsigned long long)((c >> 16) & 0xffu) << 32) | ((unsigned long long)(c >> 24) << 48);
+            }
+            incl = mine;
+#pragma unroll
+            for (int s = 1; s < 32; s <<= 1) {
+                const unsigned long long y = __shfl_up_sync(0xffffffffu, incl, s);
+                if (lane >= s) incl += y;
+            }
+            if (lane == 31) s_wsum[warp] = incl;
+        }
+        __syncthreads();
+        if (threadIdx.x < 128) {
+            unsigned long long off = 0;
+            for (int w = 0; w < warp; ++w) off += s_wsum[w];
+            s_blk[threadIdx.x] = off + incl - mine;
+        }
+        __syncthreads();
+        const ulonglong4 tp = tile_prefix[tile];
+        const ulonglong4 sp = tile_prefix[(tile >> kSuperTileShift) << kSuperTileShift];
+        if (threadIdx.x == 0 && (tile & ((1ull << kSuperTileShift) - 1)) == 0) {
+            unsigned long long *s = super + (tile >> kSuperTileShift) * 4;
+            s[0] = tp.x; s[1] = tp.y; s[2] = tp.z; s[3] = tp.w;
+        }
+        // 128 blocks x 4 uint4 = 512 uint4 per tile, written coalesced
+        uint4 *out = blocks + (tile << (kTileShift - kBlockShift)) * 4;
+#pragma unroll
+        for (int it = 0; it < 2; ++it) {
+            const int q = it * kBuildThreads + threadIdx.x;
+            const int blk = q >> 2, part = q & 3;
+            uint4 v;
+            if (part == 0) {
+                const unsigned long long e = s_blk[blk];
+                v.x = (uint32_t)(tp.x - sp.x) + (uint32_t)(e & 0xffff);
+                v.y = (uint32_t)(tp.y - sp.y) + (uint32_t)((e >> 16) & 0xffff);
+                v.z = (uint32_t)(tp.z - sp.z) + (uint32_t)((e >> 32) & 0xffff);
+                v.w = (uint32_t)(tp.w - sp.w) + (uint32_t)(e >> 48);
+            } else {
+                const uint16_t *pl = s_plane[part - 1] + blk * 8;
+                v.x = pl[0] | ((uint32_t)pl[1] << 16);
+                v.y = pl[2] | ((uint32_t)pl[3] << 16);
+                v.z = pl[4] | ((uint32_t)pl[5] << 16);
+                v.w = pl[6] | ((uint32_t)pl[7] << 16);
+            }
+            out[q] = v;
+        }
+        __syncthreads();
+    }
+}
+
+// ---- batched test hooks ------------------------------------------------------------------------
+__global__ void rank_batch_kernel(DevIndex ix, const uint64_t *__restrict__ pos, uint64_t m, uint64_t *__restrict__ out4) {
+    const uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= m) return;
+    uint64_t r[4];
+    rank4(ix, pos[q], r);
+    reinterpret_cast<ulonglong2 *>(out4)[2 * q] = make_ulonglong2(r[0], r[1]);
+    reinterpret_cast<ulonglong2 *>(out4)[2 * q + 1] = make_ulonglong2(r[2], r[3]);
+}
+
+__global__ void access_batch_kernel(DevIndex ix, const uint64_t *__restrict__ pos, uint64_t m, uint8_t *__restrict__ out, uint8_t term) {
+    const uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= m) return;
+    const int c = access_code(ix, pos[q]);
+    out[q] = c == 4 ? term : (uint8_t)"ACGT"[c];
+}
+
+__global__ void fl_batch_kernel(DevIndex ix, const uint64_t *__restrict__ pos, uint64_t m, uint64_t *__restrict__ out) {
+    const uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= m) return;
+    const uint64_t i = pos[q];
+    const int c = f_code(ix, i);
+    out[q] = c == 4 ? ~0ull : fl_map(ix, i, c);
+}
+
+// document array: ASCII '1' -> 1, anything else -> 0 (ebwt2InDel.cpp:1503-1508); 32 positions per thread
+__global__ void da_pack_kernel(const uint8_t *__restrict__ ascii, uint64_t n, uint32_t *__restrict__ words, uint64_t n_words) {
+    const uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= n_words) return;
+    uint32_t bits = 0;
+    const uint64_t base = w * 32;
+    if (base + 32 <= n) {
+        const uint4 a = __ldg(reinterpret_cast<const uint4 *>(ascii + base));
+        const uint4 b = __ldg(reinterpret_cast<const uint4 *>(ascii + base + 16));
+        const uint32_t v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int j = 0; j < 32; ++j) bits |= (uint32_t)(((v[j >> 2] >> (8 * (j & 3))) & 0xffu) == '1') << j;
+    } else {
+        for (int j = 0; j < 32; ++j) if (base + j < n) bits |= (uint32_t)(ascii[base + j] == '1') << j;
+    }
+    words[w] = bits;
+}
+
+}  // namespace e2i
+
+using namespace e2i;
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+extern "C" int e2i_index_build_device(e2i_ctx *ctx, const uint8_t *dev_ascii, uint64_t n, uint8_t term,
+                                      e2i_index **out, uint64_t *bad_pos) {
+    if (!ctx || !out || (n && !dev_ascii)) { set_error("e2i_index_build_device: null argument"); return E2I_ERR_ARG; }
+    if (reinterpret_cast<uintptr_t>(dev_ascii) & 15) { set_error("e2i_index_build_device: input must be 16-byte aligned"); return E2I_ERR_ARG; }
+    E2I_CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    e2i_index *ix = new e2i_index();
+    ix->ctx = ctx;
+    ix->n = n;
+    ix->term = term;
+    ix->n_blocks = n / kBlockSyms + 1;                       // rank(n) must be addressable (dna_string.hpp:62)
+    const uint64_t n_tiles = (ix->n_blocks + 127) / 128;
+    ix->n_super = (n >> kSuperShift) + 1;
+    const size_t blk_bytes = n_tiles * 128 * 64;
+    ix->bytes = blk_bytes + ix->n_super * 32;
+    uint4 *tile_cnt = nullptr;
+    ulonglong4 *tile_prefix = nullptr;
+    unsigned long long *scal = nullptr;  // [0..3] totals, [4] bad position
+    auto fail = [&](int rc) { cudaFree(tile_cnt); cudaFree(tile_prefix); cudaFree(scal); e2i_index_free(ix); return rc; };
+#define TRYF(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { set_error("CUDA error %s at %s:%d: %s", cudaGetErrorName(_e), __FILE__, __LINE__, cudaGetErrorString(_e)); return fail(E2I_ERR_CUDA); } } while (0)
+    TRYF(cudaMalloc(&ix->blocks, blk_bytes));
+    TRYF(cudaMalloc(&ix->super, ix->n_super * 32));
+    TRYF(cudaMalloc(&tile_cnt, n_tiles * sizeof(uint4)));
+    TRYF(cudaMalloc(&tile_prefix, n_tiles * sizeof(ulonglong4)));
+    TRYF(cudaMalloc(&scal, 5 * sizeof(unsigned long long)));
+    unsigned long long init[5] = {0, 0, 0, 0, ~0ull};
+    TRYF(cudaMemcpyAsync(scal, init, sizeof init, cudaMemcpyHostToDevice, s));
+    const int grid = (int)std::min<uint64_t>(n_tiles, (uint64_t)ctx->sm_count * 16);
+    count_tiles_kernel<<<grid, kBuildThreads, 0, s>>>(dev_ascii, n, term, n_tiles, tile_cnt, scal + 4);
+    scan_tiles_kernel<<<1, kScanThreads, 0, s>>>(tile_cnt, n_tiles, tile_prefix, scal);
+    pack_tiles_kernel<<<grid, kBuildThreads, 0, s>>>(dev_ascii, n, term, n_tiles, tile_prefix, ix->blocks,
+                                                     reinterpret_cast<unsigned long long *>(ix->super));
+    TRYF(cudaGetLastError());
+    unsigned long long res[5];
+    TRYF(cudaMemcpyAsync(res, scal, sizeof res, cudaMemcpyDeviceToHost, s));
+    TRYF(cudaStreamSynchronize(s));
+#undef TRYF
+    cudaFree(tile_cnt); cudaFree(tile_prefix); cudaFree(scal);
+    tile_cnt = nullptr; tile_prefix = nullptr; scal = nullptr;
+    if (res[4] != ~0ull) {
+        if (bad_pos) *bad_pos = res[4];
+        set_error("forbidden character at position %llu: only A,C,G,T and the terminator (ASCII %d) are admitted in the input BWT",
+                  res[4], (int)term);
+        e2i_index_free(ix);
+        return E2I_ERR_SYMBOL;
+    }
+    const uint64_t acgt = res[0] + res[1] + res[2] + res[3];
+    ix->F[0] = n - acgt;                                      // dna_bwt.hpp:51-60
+    ix->F[1] = ix->F[0] + res[0];
+    ix->F[2] = ix->F[1] + res[1];
+    ix->F[3] = ix->F[2] + res[2];
+    *out = ix;
+    return E2I_OK;
+}
+
+extern "C" int e2i_index_build(e2i_ctx *ctx, const uint8_t *host_ascii, uint64_t n, uint8_t term,
+                               e2i_index **out, uint64_t *bad_pos) {
+    if (!ctx || !out || (n && !host_ascii)) { set_error("e2i_index_build: null argument"); return E2I_ERR_ARG; }
+    E2I_CUDA_TRY(cudaSetDevice(ctx->device));
+    uint8_t *d = nullptr;
+    E2I_CUDA_TRY(cudaMalloc(&d, n + 16));
+    cudaError_t e = cudaMemcpyAsync(d, host_ascii, n, cudaMemcpyHostToDevice, ctx->stream);
+    if (e != cudaSuccess) { cudaFree(d); set_error("H2D copy failed: %s", cudaGetErrorString(e)); return E2I_ERR_CUDA; }
+    const int rc = e2i_index_build_device(ctx, d, n, term, out, bad_pos);
+    cudaFree(d);
+    return rc;
+}
+
+extern "C" void e2i_index_free(e2i_index *ix) {
+    if (!ix) return;
+    cudaFree(ix->blocks);
+    cudaFree(ix->super);
+    delete ix;
+}
+
+extern "C" uint64_t e2i_index_size(const e2i_index *ix) { return ix ? ix->n : 0; }
+extern "C" uint64_t e2i_index_bytes(const e2i_index *ix) { return ix ? ix->bytes : 0; }
+extern "C" int e2i_index_F(const e2i_index *ix, uint64_t F[4]) {
+    if (!ix || !F) { set_error("e2i_index_F: null argument"); return E2I_ERR_ARG; }
+    for (int i = 0; i < 4; ++i) F[i] = ix->F[i];
+    return E2I_OK;
+}
+
+namespace {
+template <typename TOut, typename Launch>
+int batch_hook(e2i_ctx *ctx, const uint64_t *host_pos, uint64_t m, TOut *host_out, size_t out_per, Launch launch) {
+    if (!ctx || (m && (!host_pos || !host_out))) { set_error("batch hook: null argument"); return E2I_ERR_ARG; }
+    if (m == 0) return E2I_OK;
+    E2I_CUDA_TRY(cudaSetDevice(ctx->device));
+    uint64_t *dpos = nullptr;
+    TOut *dout = nullptr;
+    E2I_CUDA_TRY(cudaMalloc(&dpos, m * sizeof(uint64_t)));
+    cudaError_t e = cudaMalloc(&dout, m * out_per * sizeof(TOut));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dpos, host_pos, m * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) { launch(dpos, dout); e = cudaGetLastError(); }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(host_out, dout, m * out_per * sizeof(TOut), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(dpos);
+    cudaFree(dout);
+    if (e != cudaSuccess) { set_error("batch hook failed: %s", cudaGetErrorString(e)); return E2I_ERR_CUDA; }
+    return E2I_OK;
+}
+}  // namespace
+
+extern "C" int e2i_rank_batch(e2i_ctx *ctx, const e2i_index *ix, const uint64_t *host_pos, uint64_t m, uint64_t *host_out4) {
+    if (!ix) { set_error("e2i_rank_batch: null index"); return E2I_ERR_ARG; }
+    for (uint64_t k = 0; k < m; ++k) if (host_pos[k] > ix->n) { set_error("e2i_rank_batch: position %llu > n", (unsigned long long)host_pos[k]); return E2I_ERR_ARG; }
+    return batch_hook<uint64_t>(ctx, host_pos, m, host_out4, 4, [&](uint64_t *dp, uint64_t *dout) {
+        rank_batch_kernel<<<(unsigned)((m + 255) / 256), 256, 0, ctx->stream>>>(ix->dev(), dp, m, dout);
+    });
+}
+
+extern "C" int e2i_rank_batch_device(e2i_ctx *ctx, const e2i_index *ix, const uint64_t *dev_pos, uint64_t m,
+                                     uint64_t *dev_out4, float *ms) {
+    if (!ctx || !ix || !dev_pos || !dev_out4) { set_error("e2i_rank_batch_device: null argument"); return E2I_ERR_ARG; }
+    E2I_CUDA_TRY(cudaSetDevice(ctx->device));
+    E2I_CUDA_TRY(cudaEventRecord(ctx->ev[0], ctx->stream));
+    rank_batch_kernel<<<(unsigned)((m + 255) / 256), 256, 0, ctx->stream>>>(ix->dev(), dev_pos, m, dev_out4);
+    E2I_CUDA_TRY(cudaGetLastError());
+    E2I_CUDA_TRY(cudaEventRecord(ctx->ev[1], ctx->stream));
+    E2I_CUDA_TRY(cudaEventSynchronize(ctx->ev[1]));
+    if (ms) E2I_CUDA_TRY(cudaEventElapsedTime(ms, ctx->ev[0], ctx->ev[1]));
+    return E2I_OK;
+}
+
+extern "C" int e2i_access_batch(e2i_ctx *ctx, const e2i_index *ix, const uint64_t *host_pos, uint64_t m, uint8_t *host_out) {
+    if (!ix) { set_error("e2i_access_batch: null index"); return E2I_ERR_ARG; }
+    for (uint64_t k = 0; k < m; ++k) if (host_pos[k] >= ix->n) { set_error("e2i_access_batch: position out of range"); return E2I_ERR_ARG; }
+    return batch_hook<uint8_t>(ctx, host_pos, m, host_out, 1, [&](uint64_t *dp, uint8_t *dout) {
+        access_batch_kernel<<<(unsigned)((m + 255) / 256), 256, 0, ctx->stream>>>(ix->dev(), dp, m, dout, ix->term);
+    });
+}
+
+extern "C" int e2i_fl_batch(e2i_ctx *ctx, const e2i_index *ix, const uint64_t *host_pos, uint64_t m, uint64_t *host_out) {
+    if (!ix) { set_error("e2i_fl_batch: null index"); return E2I_ERR_ARG; }
+    for (uint64_t k = 0; k < m; ++k) if (host_pos[k] >= ix->n) { set_error("e2i_fl_batch: position out of range"); return E2I_ERR_ARG; }
+    return batch_hook<uint64_t>(ctx, host_pos, m, host_out, 1, [&](uint64_t *dp, uint64_t *dout) {
+        fl_batch_kernel<<<(unsigned)((m + 255) / 256), 256, 0, ctx->stream>>>(ix->dev(), dp, m, dout);
+    });
+}
+
+// ---- document array ----------------------------------------------------------------------------
+static uint64_t padded_words32(uint64_t bits) { return ((bits + 31) / 32 + 63) / 64 * 64 + 64; }
+
+extern "C" int e2i_da_load_device(e2i_ctx *ctx, const uint8_t *dev_ascii01, uint64_t n, e2i_bits **out) {
+    if (!ctx || !out || (n && !dev_ascii01)) { set_error("e2i_da_load_device: null argument"); return E2I_ERR_ARG; }
+    E2I_CUDA_TRY(cudaSetDevice(ctx->device));
+    e2i_bits *b = new e2i_bits();
+    b->ctx = ctx;
+    b->n = n;
+    b->n_words32 = padded_words32(n);
+    cudaError_t e = cudaMalloc(&b->words, b->n_words32 * 4);
+    if (e == cudaSuccess) e = cudaMemsetAsync(b->words, 0, b->n_words32 * 4, ctx->stream);
+    const uint64_t nw = (n + 31) / 32;
+    if (e == cudaSuccess && nw) {
+        da_pack_kernel<<<(unsigned)((nw + 255) / 256), 256, 0, ctx->stream>>>(dev_ascii01, n, b->words, nw);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) { set_error("e2i_da_load_device: %s", cudaGetErrorString(e)); e2i_bits_free(b); return E2I_ERR_CUDA; }
+    *out = b;
+    return E2I_OK;
+}
+
+extern "C" int e2i_da_load(e2i_ctx *ctx, const uint8_t *host_ascii01, uint64_t n, e2i_bits **out) {
+    if (!ctx || !out || (n && !host_ascii01)) { set_error("e2i_da_load: null argument"); return E2I_ERR_ARG; }
+    E2I_CUDA_TRY(cudaSetDevice(ctx->device));
+    uint8_t *d = nullptr;
+    E2I_CUDA_TRY(cudaMalloc(&d, n + 16));
+    cudaError_t e = cudaMemcpyAsync(d, host_ascii01, n, cudaMemcpyHostToDevice, ctx->stream);
+    if (e != cudaSuccess) { cudaFree(d); set_error("H2D copy failed: %s", cudaGetErrorString(e)); return E2I_ERR_CUDA; }
+    const int rc = e2i_da_load_device(ctx, d, n, out);
+    cudaFree(d);
+    return rc;
+}
+
+extern "C" int e2i_bits_fetch(e2i_ctx *ctx, const e2i_bits *b, uint64_t *host_words, uint64_t n_words) {
+    if (!ctx || !b || !host_words) { set_error("e2i_bits_fetch: null argument"); return E2I_ERR_ARG; }
+    const uint64_t have = b->n_words32 / 2;
+    const uint64_t k = n_words < have ? n_words : have;
+    E2I_CUDA_TRY(cudaMemcpy(host_words, b->words, k * 8, cudaMemcpyDeviceToHost));
+    for (uint64_t i = k; i < n_words; ++i) host_words[i] = 0;
+    return E2I_OK;
+}
+
+extern "C" uint64_t e2i_bits_size(const e2i_bits *b) { return b ? b->n : 0; }
+
+extern "C" int e2i_bits_device(const e2i_bits *b, void **dev_words, uint64_t *words32) {
+    if (!b) { set_error("e2i_bits_device: null argument"); return E2I_ERR_ARG; }
+    if (dev_words) *dev_words = b->words;
+    if (words32) *words32 = b->n_words32;
+    return E2I_OK;
+}
+
+extern "C" void e2i_bits_free(e2i_bits *b) {
+    if (!b) return;
+    cudaFree(b->words);
+    cudaFree(b->rank512);
+    delete b;
+}

@@ -1,0 +1,701 @@
+// navigate.cu -- a6-a15: phases 2+3 of the hot path as frontier sweeps over the index in HBM.
+//
+// Replaces navigate_one_bwt (/root/reference/ebwt2InDel.cpp:555-676) and navigate_two_bwts
+// (:679-831): the two explicit-stack DFS loops over suffix-tree leaves and right-maximal internal
+// nodes, with dna_bwt::LF(sa_node) / next_nodes / next_leaves (internal/dna_bwt.hpp:323-404),
+// update_LCP_leaf (:344-355), update_lcp_threshold (internal/include.hpp:826-860),
+// update_lcp_minima (:357-391), update_DA (:394-449) and find_leaves (:474-527).
+//
+// B200 design.  Every LCP / DA bit has exactly one writer, so traversal order is free.  The
+// frontier is swept breadth-first, and every sweep keeps its nodes SORTED BY SUFFIX-ARRAY
+// POSITION: the children cW of a sorted frontier are appended, in tile order, to four queues
+// (one per c); A-queue ++ C-queue ++ G-queue ++ T-queue is again sorted because LF is monotone
+// per symbol.  A sorted frontier turns the reference's random rank gathers into one
+// near-sequential pass over the 64-byte index blocks per sweep (neighbouring nodes share blocks
+// and DRAM pages) and makes the bit updates land in neighbouring words.  Ordered appends use a
+// single-pass decoupled look-back (lookback.cuh).  When a sweep would not fit the frontier budget
+// it is cut into position-contiguous chunks that are finished depth-first (bounded memory).
+//
+// Work mapping.  Internal nodes: 8 lanes per node (16 per node pair in mode -2): lane j < 6 owns
+// boundary j (first_TERM .. last), fetches its 64-byte block and computes the four ranks; child c
+// is valid iff >= 2 of the 5 boundary gaps are non-empty for c (number_of_children >= 2), found
+// with one ballot per symbol.  Leaves: one thread per leaf (two ranks per BWT).
+#include <algorithm>
+#include <memory>
+
+#include "common.cuh"
+#include "lookback.cuh"
+
+namespace e2i {
+
+constexpr int kNavThreads = 256;
+constexpr int kNodeIter = 4;            // node groups per lane-group per tile
+constexpr int kStripes = 128;           // striped statistics counters (avoid single-address atomics)
+enum { C_LCP = 0, C_NMIN, C_RANK, C_BITUPD, C_DA, C_NCOUNTERS = 8 };
+
+struct LaunchCtl {
+    uint32_t ticket;
+    uint32_t pad;
+    unsigned long long out_count[4];
+};
+
+struct Segs {                 // a position-sorted run of records given as <= 4 segments
+    const uint64_t *p[4];
+    uint32_t end[4];          // cumulative record counts
+    uint32_t total;
+};
+
+struct NavArgs {
+    DevIndex ix1, ix2;
+    uint32_t *thr;            // 2 bits per merged position
+    uint32_t *minima;         // 1 bit per merged position
+    uint32_t *da;             // 1 bit per merged position (mode -2)
+    unsigned long long *stripes;
+    unsigned long long *desc;
+    LaunchCtl *ctl;
+    uint64_t *out[4];
+    uint32_t epoch;
+    uint32_t n_tiles;
+    uint32_t K, k_right;
+    int write;                // 0: expand only (redundant top of the tree on shards != 0)
+};
+
+__device__ __forceinline__ const uint64_t *seg_record(const Segs &s, uint32_t g, int words) {
+    int k = 0;
+    uint32_t start = 0;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+        if (g >= s.end[i]) { k = i + 1; start = s.end[i]; }
+    return s.p[k] + (size_t)(g - start) * words;
+}
+
+__device__ __forceinline__ void stripe_add(unsigned long long *stripes, uint32_t tile, int which, unsigned long long v) {
+    if (v) atomicAdd(stripes + (size_t)(tile & (kStripes - 1)) * C_NCOUNTERS + which, v);
+}
+
+// set bits [lo, hi) of a u32 bit array, keeping only those selected by the 32-bit periodic pattern
+__device__ __forceinline__ void fill_bits(uint32_t *words, uint64_t lo, uint64_t hi, uint32_t pattern) {
+    if (hi <= lo || pattern == 0) return;
+    uint64_t w = lo >> 5;
+    const uint64_t wl = (hi - 1) >> 5;
+    for (; w <= wl; ++w) {
+        uint32_t m = pattern;
+        if (w == (lo >> 5)) m &= 0xffffffffu << (lo & 31);
+        if (w == wl && (hi & 31)) m &= 0xffffffffu >> (32 - (hi & 31));
+        if (m) atomicOr(words + w, m);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Phase 3 sweep: internal nodes.  GRP = 8 lanes per node (one BWT) or 16 per node pair (two BWTs).
+// Record = GRP u64 words: [0..5] boundaries in BWT 1, [6] depth, [8..13] boundaries in BWT 2.
+// ---------------------------------------------------------------------------------------------
+template <bool TWO>
+__global__ void __launch_bounds__(kNavThreads)
+expand_nodes_kernel(const NavArgs a, const Segs in) {
+    constexpr int GRP = TWO ? 16 : 8;
+    constexpr int IPW = 32 / GRP;                      // items per warp per iteration
+    constexpr int IPI = IPW * (kNavThreads / 32);      // items per CTA per iteration
+    constexpr int TILE = IPI * kNodeIter;
+    __shared__ uint32_t s_tile;
+    __shared__ uint32_t s_cnt[kNodeIter * 8];          // packed 4 x 8-bit child counts per (iter, warp)
+    __shared__ uint32_t s_excl[kNodeIter * 8];
+    __shared__ unsigned long long s_base[4];
+    __shared__ unsigned long long s_stat[C_NCOUNTERS];
+
+    if (threadIdx.x == 0) s_tile = atomicAdd(&a.ctl->ticket, 1u);
+    if (threadIdx.x < C_NCOUNTERS) s_stat[threadIdx.x] = 0;
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int l = lane % GRP, j = l & 7, half = l >> 3, item = lane / GRP, base = item * GRP;
+    const DevIndex &ix = (TWO && half) ? a.ix2 : a.ix1;
+
+    uint64_t r[kNodeIter][4];
+    uint64_t depth1[kNodeIter];
+    uint32_t valid[kNodeIter];
+    uint32_t st_lcp = 0, st_min = 0, st_rank = 0, st_upd = 0, st_da = 0;
+
+#pragma unroll
+    for (int it = 0; it < kNodeIter; ++it) {
+        const uint32_t g = tile * TILE + it * IPI + warp * IPW + item;
+        const bool active = g < in.total;
+        uint64_t w = 0;
+        if (active) w = seg_record(in, g, GRP)[l];
+        const bool isb = active && j < 6;
+        uint64_t rr[4] = {0, 0, 0, 0};
+        if (isb) rank4(ix, w, rr);
+        const uint64_t wprev = shfl_up_u64(w, 1, 8);
+        if (isb && (j == 0 || w != wprev)) st_rank++;   // distinct boundaries (dna_bwt.hpp:332-347)
+        // merged coordinates (merge_nodes, include.hpp:476-490)
+        const uint64_t mb = TWO ? w + __shfl_xor_sync(0xffffffffu, w, 8) : w;
+        const uint64_t mprev = shfl_up_u64(mb, 1, 8);
+        const uint64_t last = shfl_u64(mb, base + 5);
+        const uint64_t depth = shfl_u64(w, base + 6);
+        depth1[it] = depth + 1;
+        if (TWO) {
+            // find_leaves (ebwt2InDel.cpp:474-527): children of summed size exactly 1
+            const uint64_t wnext = shfl_down_u64(w, 1, 8);
+            const uint64_t sz = (j < 5) ? wnext - w : 0;
+            const uint64_t sz_other = __shfl_xor_sync(0xffffffffu, sz, 8);
+            if (active && a.write && half == 0 && j < 5 && sz + sz_other == 1) {
+                st_da++;
+                if (sz_other == 1) atomicOr(a.da + (mb >> 5), 1u << (mb & 31));
+            }
+        }
+        if (active && a.write && half == 0) {
+            // update_lcp_threshold (include.hpp:826-860): border j written iff child j-1 is non-empty and border != last
+            if (j >= 1 && j <= 4 && mb > mprev && mb != last) {
+                st_lcp++;
+                const uint32_t bits = (depth >= a.K ? 1u : 0u) | (depth >= a.k_right ? 2u : 0u);
+                if (bits) { atomicOr(a.thr + (mb >> 4), bits << ((mb & 15) * 2)); st_upd++; }
+            }
+            // update_lcp_minima (ebwt2InDel.cpp:357-391): children A, C, G of size >= 2
+            if (j >= 2 && j <= 4 && mb - mprev >= 2 && mb < last - 1) {
+                st_min++;
+                st_upd++;
+                atomicOr(a.minima + (mb >> 5), 1u << (mb & 31));
+            }
+        }
+        // child c is right-maximal iff >= 2 of its 5 gaps are non-empty (number_of_children, include.hpp:760-792)
+        uint32_t vm = 0;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const uint64_t nxt = shfl_down_u64(rr[c], 1, 8);
+            int nz = (j < 5) && (nxt != rr[c]);
+            if (TWO) nz |= __shfl_xor_sync(0xffffffffu, nz, 8);
+            const uint32_t bal = __ballot_sync(0xffffffffu, nz);
+            if (active && __popc((bal >> base) & 0x1fu) >= 2) vm |= 1u << c;
+            r[it][c] = rr[c];
+        }
+        valid[it] = vm;
+        uint32_t packed = 0;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const uint32_t vb = __ballot_sync(0xffffffffu, ((vm >> c) & 1u) && l == 0);
+            packed |= (uint32_t)__popc(vb) << (8 * c);
+        }
+        if (lane == 0) s_cnt[it * 8 + warp] = packed;
+    }
+    // block-level statistics
+    st_lcp = __reduce_add_sync(0xffffffffu, st_lcp);
+    st_min = __reduce_add_sync(0xffffffffu, st_min);
+    st_rank = __reduce_add_sync(0xffffffffu, st_rank);
+    st_upd = __reduce_add_sync(0xffffffffu, st_upd);
+    if (TWO) st_da = __reduce_add_sync(0xffffffffu, st_da);
+    if (lane == 0) {
+        if (st_lcp) atomicAdd(&s_stat[C_LCP], (unsigned long long)st_lcp);
+        if (st_min) atomicAdd(&s_stat[C_NMIN], (unsigned long long)st_min);
+        if (st_rank) atomicAdd(&s_stat[C_RANK], (unsigned long long)st_rank);
+        if (st_upd) atomicAdd(&s_stat[C_BITUPD], (unsigned long long)st_upd);
+        if (TWO && st_da) atomicAdd(&s_stat[C_DA], (unsigned long long)st_da);
+    }
+    __syncthreads();
+    if (warp == 0) {
+        // exclusive scan of the packed (iter, warp) counts, then the cross-tile look-back
+        const uint32_t mine = s_cnt[lane];
+        uint32_t incl = mine;
+#pragma unroll
+        for (int s = 1; s < 32; s <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, incl, s);
+            if (lane >= s) incl += y;
+        }
+        s_excl[lane] = incl - mine;
+        const uint32_t tot = __shfl_sync(0xffffffffu, incl, 31);
+        unsigned long long agg[4], excl[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) agg[c] = (tot >> (8 * c)) & 0xffu;
+        lookback_exclusive<4>(a.desc, a.epoch, tile, agg, excl);
+        if (lane < 4) {
+            unsigned long long e = 0, g2 = 0;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) if (lane == c) { e = excl[c]; g2 = agg[c]; }
+            s_base[lane] = e;
+            if (tile == a.n_tiles - 1) a.ctl->out_count[lane] = e + g2;
+        }
+        if (lane < C_NCOUNTERS && a.write) stripe_add(a.stripes, tile, lane, s_stat[lane]);
+    }
+    __syncthreads();
+    // ordered append of the surviving children
+#pragma unroll
+    for (int it = 0; it < kNodeIter; ++it) {
+        const uint32_t ex = s_excl[it * 8 + warp];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const bool v = (valid[it] >> c) & 1u;
+            const uint32_t vb = __ballot_sync(0xffffffffu, v && l == 0);
+            if (v) {
+                const unsigned long long slot = s_base[c] + ((ex >> (8 * c)) & 0xffu) + __popc(vb & ((1u << base) - 1u));
+                uint64_t word = 0;
+                if (j < 6) word = ix.F[c] + r[it][c];
+                else if (l == 6) word = depth1[it];
+                a.out[c][slot * GRP + l] = word;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Phase 2 sweep: leaves (intervals of W#).  One thread per leaf (pair).
+// Record = 4 u64 {first, second, depth, 0}; mode -2: 8 u64 {f1, s1, depth, 0, f2, s2, 0, 0}.
+// ---------------------------------------------------------------------------------------------
+template <bool TWO>
+__global__ void __launch_bounds__(kNavThreads)
+expand_leaves_kernel(const NavArgs a, const Segs in) {
+    constexpr int WORDS = TWO ? 8 : 4;
+    __shared__ uint32_t s_tile;
+    __shared__ uint32_t s_cnt[8];
+    __shared__ uint32_t s_excl[8];
+    __shared__ unsigned long long s_base[4];
+    __shared__ unsigned long long s_stat[C_NCOUNTERS];
+    if (threadIdx.x == 0) s_tile = atomicAdd(&a.ctl->ticket, 1u);
+    if (threadIdx.x < C_NCOUNTERS) s_stat[threadIdx.x] = 0;
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t g = tile * kNavThreads + threadIdx.x;
+    const bool active = g < in.total;
+    uint64_t f1 = 0, s1 = 0, f2 = 0, s2 = 0, depth = 0;
+    if (active) {
+        const ulonglong2 *rec = reinterpret_cast<const ulonglong2 *>(seg_record(in, g, WORDS));
+        const ulonglong2 x = rec[0], y = rec[1];
+        f1 = x.x; s1 = x.y; depth = y.x;
+        if (TWO) { const ulonglong2 z = rec[2]; f2 = z.x; s2 = z.y; }
+    }
+    unsigned long long st_lcp = 0, st_da = 0;
+    uint32_t st_rank = 0;
+    if (active && a.write) {
+        // update_LCP_leaf (:344-355) / update_DA (:394-425) at merged coordinates
+        const uint64_t start1 = f1 + f2, start2 = f2 + s1, end = s1 + s2;
+        if (end > start1) st_lcp = end - start1 - 1;
+        const uint32_t pat = (depth >= a.K ? 0x55555555u : 0u) | (depth >= a.k_right ? 0xaaaaaaaau : 0u);
+        if (end > start1 + 1) fill_bits(a.thr, 2 * (start1 + 1), 2 * end, pat);
+        if (TWO) {
+            st_da = end - start1;
+            fill_bits(a.da, start2, end, 0xffffffffu);
+        }
+    }
+    // next_leaves (dna_bwt.hpp:358-379; two BWTs: ebwt2InDel.cpp:452-472): LF(range) = 2 ranks per BWT
+    uint64_t lo1[4] = {0, 0, 0, 0}, hi1[4] = {0, 0, 0, 0}, lo2[4] = {0, 0, 0, 0}, hi2[4] = {0, 0, 0, 0};
+    if (active) {
+        rank4(a.ix1, f1, lo1);
+        st_rank++;
+        if (s1 > f1) { rank4(a.ix1, s1, hi1); st_rank++; }
+        else { hi1[0] = lo1[0]; hi1[1] = lo1[1]; hi1[2] = lo1[2]; hi1[3] = lo1[3]; }
+        if (TWO) {
+            rank4(a.ix2, f2, lo2);
+            st_rank++;
+            if (s2 > f2) { rank4(a.ix2, s2, hi2); st_rank++; }
+            else { hi2[0] = lo2[0]; hi2[1] = lo2[1]; hi2[2] = lo2[2]; hi2[3] = lo2[3]; }
+        }
+    }
+    uint32_t vm = 0, packed = 0, before[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const bool v = active && ((hi1[c] - lo1[c]) + (hi2[c] - lo2[c]) >= 2);
+        const uint32_t bal = __ballot_sync(0xffffffffu, v);
+        before[c] = __popc(bal & ((1u << lane) - 1u));
+        packed |= (uint32_t)__popc(bal) << (8 * c);
+        if (v) vm |= 1u << c;
+    }
+    // warp-level totals can reach 32 per symbol: 8-bit fields hold up to 255 per tile (256 leaves: use 9+ bits)
+    // -> keep per-warp counts in 8-bit fields but accumulate the tile scan in two u32 (16-bit fields).
+    if (lane == 0) s_cnt[warp] = packed;
+    st_lcp += __shfl_xor_sync(0xffffffffu, st_lcp, 16);
+    st_lcp += __shfl_xor_sync(0xffffffffu, st_lcp, 8);
+    st_lcp += __shfl_xor_sync(0xffffffffu, st_lcp, 4);
+    st_lcp += __shfl_xor_sync(0xffffffffu, st_lcp, 2);
+    st_lcp += __shfl_xor_sync(0xffffffffu, st_lcp, 1);
+    if (TWO) {
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) st_da += __shfl_xor_sync(0xffffffffu, st_da, s);
+    }
+    st_rank = __reduce_add_sync(0xffffffffu, st_rank);
+    if (lane == 0) {
+        if (st_lcp) atomicAdd(&s_stat[C_LCP], st_lcp);
+        if (st_rank) atomicAdd(&s_stat[C_RANK], (unsigned long long)st_rank);
+        if (TWO && st_da) atomicAdd(&s_stat[C_DA], st_da);
+    }
+    __syncthreads();
+    if (warp == 0) {
+        // 8 per-warp entries; widen to 16-bit fields (two words) before the scan
+        const uint32_t mine = lane < 8 ? s_cnt[lane] : 0u;
+        uint32_t lo = (mine & 0xffu) | (((mine >> 8) & 0xffu) << 16);          // A, C
+        uint32_t hi = ((mine >> 16) & 0xffu) | ((mine >> 24) << 16);           // G, T
+        const uint32_t mlo = lo, mhi = hi;
+#pragma unroll
+        for (int s = 1; s < 8; s <<= 1) {
+            const uint32_t ylo = __shfl_up_sync(0xffffffffu, lo, s), yhi = __shfl_up_sync(0xffffffffu, hi, s);
+            if (lane >= s) { lo += ylo; hi += yhi; }
+        }
+        if (lane < 8) {
+            s_excl[lane] = 0;  // unused
+            // store exclusive prefix as two words in s_cnt/s_excl
+            s_cnt[lane] = lo - mlo;
+            s_excl[lane] = hi - mhi;
+        }
+        const uint32_t tlo = __shfl_sync(0xffffffffu, lo, 7), thi = __shfl_sync(0xffffffffu, hi, 7);
+        unsigned long long agg[4] = {tlo & 0xffffu, tlo >> 16, thi & 0xffffu, thi >> 16}, excl[4];
+        lookback_exclusive<4>(a.desc, a.epoch, tile, agg, excl);
+        if (lane < 4) {
+            unsigned long long e = 0, g2 = 0;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) if (lane == c) { e = excl[c]; g2 = agg[c]; }
+            s_base[lane] = e;
+            if (tile == a.n_tiles - 1) a.ctl->out_count[lane] = e + g2;
+        }
+        if (lane < C_NCOUNTERS && a.write) stripe_add(a.stripes, tile, lane, s_stat[lane]);
+    }
+    __syncthreads();
+    const uint32_t exlo = s_cnt[warp], exhi = s_excl[warp];
+    const uint32_t exw[4] = {exlo & 0xffffu, exlo >> 16, exhi & 0xffffu, exhi >> 16};
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        if ((vm >> c) & 1u) {
+            const unsigned long long slot = s_base[c] + exw[c] + before[c];
+            ulonglong2 *o = reinterpret_cast<ulonglong2 *>(a.out[c] + slot * WORDS);
+            o[0] = make_ulonglong2(a.ix1.F[c] + lo1[c], a.ix1.F[c] + hi1[c]);
+            o[1] = make_ulonglong2(depth + 1, 0);
+            if (TWO) {
+                o[2] = make_ulonglong2(a.ix2.F[c] + lo2[c], a.ix2.F[c] + hi2[c]);
+                o[3] = make_ulonglong2(0, 0);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Host-side frontier driver
+// ---------------------------------------------------------------------------------------------
+struct Frame {
+    DevicePool *pool;
+    void *p;
+    ~Frame() { if (p) pool->free(p); }
+};
+
+struct Chunk {
+    uint64_t *p[4];
+    uint64_t cnt[4];
+    std::shared_ptr<Frame> frame;
+    uint64_t total() const { return cnt[0] + cnt[1] + cnt[2] + cnt[3]; }
+};
+
+struct SweepStats {
+    uint64_t items = 0, sweeps = 0, max_chunk = 0;
+};
+
+// Cut the first `take` records off a chunk (position-contiguous prefix).
+static Chunk split_head(Chunk &c, uint64_t take, int words) {
+    Chunk head = c;
+    uint64_t left = take;
+    for (int s = 0; s < 4; ++s) {
+        const uint64_t k = std::min<uint64_t>(left, c.cnt[s]);
+        head.cnt[s] = k;
+        c.p[s] += k * words;
+        c.cnt[s] -= k;
+        left -= k;
+    }
+    return head;
+}
+
+template <typename Launch>
+static int run_frontier(e2i_ctx *ctx, Chunk root, int words, int tile_items, uint64_t max_chunk, NavArgs &args,
+                        Launch launch, SweepStats &ss, uint64_t stop_at_items, std::vector<Chunk> *stopped) {
+    std::vector<Chunk> stack;
+    stack.push_back(std::move(root));
+    LaunchCtl *hctl = reinterpret_cast<LaunchCtl *>(ctx->ctl_host);
+    while (!stack.empty()) {
+        Chunk cur = std::move(stack.back());
+        stack.pop_back();
+        if (cur.total() == 0) continue;
+        if (stopped && cur.total() >= stop_at_items) {   // hand the frontier back to the caller (sharding)
+            stopped->push_back(std::move(cur));
+            continue;
+        }
+        Chunk work;
+        uint64_t take = std::min<uint64_t>(cur.total(), max_chunk);
+        void *mem = nullptr;
+        while (true) {   // shrink the chunk until its output frame fits the pool
+            const int rc = ctx->pool.alloc(&mem, take * 4 * words * sizeof(uint64_t));
+            if (rc == E2I_OK) break;
+            if (take <= 65536) { set_error("frontier memory exhausted (budget %llu bytes, %llu live): raise the frontier budget",
+                                           (unsigned long long)ctx->frontier_budget, (unsigned long long)ctx->pool.bytes_live()); return E2I_ERR_MEMORY; }
+            take /= 2;
+        }
+        if (take < cur.total()) {
+            work = split_head(cur, take, words);
+            stack.push_back(std::move(cur));
+        } else {
+            work = std::move(cur);
+        }
+        auto frame = std::make_shared<Frame>();
+        frame->pool = &ctx->pool;
+        frame->p = mem;
+        Segs segs;
+        uint32_t acc = 0;
+        for (int s = 0; s < 4; ++s) {
+            segs.p[s] = work.p[s];
+            acc += (uint32_t)work.cnt[s];
+            segs.end[s] = acc;
+        }
+        segs.total = acc;
+        const uint32_t n_tiles = (acc + tile_items - 1) / tile_items;
+        if ((size_t)n_tiles * 4 > ctx->desc_words) {
+            cudaFree(ctx->desc);
+            ctx->desc = nullptr;
+            ctx->desc_words = (size_t)n_tiles * 4 * 3 / 2 + 1024;
+            E2I_CUDA_TRY(cudaMalloc(&ctx->desc, ctx->desc_words * 8));
+            E2I_CUDA_TRY(cudaMemsetAsync(ctx->desc, 0, ctx->desc_words * 8, ctx->stream));
+            ctx->epoch = 0;
+        }
+        if (++ctx->epoch >= 0xffffu) {
+            E2I_CUDA_TRY(cudaMemsetAsync(ctx->desc, 0, ctx->desc_words * 8, ctx->stream));
+            ctx->epoch = 1;
+        }
+        for (int c = 0; c < 4; ++c) args.out[c] = reinterpret_cast<uint64_t *>(mem) + (size_t)c * take * words;
+        args.desc = ctx->desc;
+        args.epoch = ctx->epoch;
+        args.n_tiles = n_tiles;
+        args.ctl = reinterpret_cast<LaunchCtl *>(ctx->ctl);
+        E2I_CUDA_TRY(cudaMemsetAsync(ctx->ctl, 0, sizeof(LaunchCtl), ctx->stream));
+        launch(args, segs, n_tiles);
+        E2I_CUDA_TRY(cudaGetLastError());
+        E2I_CUDA_TRY(cudaMemcpyAsync(hctl, ctx->ctl, sizeof(LaunchCtl), cudaMemcpyDeviceToHost, ctx->stream));
+        E2I_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        ss.items += acc;
+        ss.sweeps++;
+        ss.max_chunk = std::max<uint64_t>(ss.max_chunk, acc);
+        Chunk next;
+        next.frame = frame;
+        for (int c = 0; c < 4; ++c) { next.p[c] = args.out[c]; next.cnt[c] = hctl->out_count[c]; }
+        work.frame.reset();
+        if (next.total()) stack.push_back(std::move(next));
+    }
+    return E2I_OK;
+}
+
+}  // namespace e2i
+
+using namespace e2i;
+
+static uint64_t padded_words32(uint64_t bits) { return ((bits + 31) / 32 + 63) / 64 * 64 + 64; }
+
+extern "C" int e2i_navigate_shard(e2i_ctx *ctx, const e2i_index *b1, const e2i_index *b2, const e2i_params *p,
+                                  int shard, int n_shards, e2i_lcpbits **out, e2i_bits **da_out, e2i_stats *st) {
+    if (!ctx || !b1 || !p || !out || !st) { set_error("e2i_navigate: null argument"); return E2I_ERR_ARG; }
+    if (b2 && !da_out) { set_error("e2i_navigate: da_out is required with two BWTs"); return E2I_ERR_ARG; }
+    if (n_shards < 1 || shard < 0 || shard >= n_shards) { set_error("e2i_navigate: bad shard %d/%d", shard, n_shards); return E2I_ERR_ARG; }
+    if (p->K < 1 || p->k_right < 1) { set_error("e2i_navigate: K and k_right must be >= 1"); return E2I_ERR_ARG; }
+    E2I_CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    const bool two = b2 != nullptr;
+    const uint64_t n = b1->n + (two ? b2->n : 0);
+
+    e2i_lcpbits *l = new e2i_lcpbits();
+    l->ctx = ctx;
+    l->n = n;
+    l->thr_words32 = padded_words32(2 * n);
+    l->min_words32 = padded_words32(n);
+    e2i_bits *da = nullptr;
+    unsigned long long *stripes = nullptr;
+    auto fail = [&](int rc) { e2i_lcpbits_free(l); e2i_bits_free(da); cudaFree(stripes); ctx->pool.release(); return rc; };
+#define TRYF(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { set_error("CUDA error %s at %s:%d: %s", cudaGetErrorName(_e), __FILE__, __LINE__, cudaGetErrorString(_e)); return fail(E2I_ERR_CUDA); } } while (0)
+    TRYF(cudaMalloc(&l->thr, l->thr_words32 * 4));
+    TRYF(cudaMalloc(&l->minima, l->min_words32 * 4));
+    TRYF(cudaMemsetAsync(l->thr, 0, l->thr_words32 * 4, s));
+    TRYF(cudaMemsetAsync(l->minima, 0, l->min_words32 * 4, s));
+    if (two) {
+        da = new e2i_bits();
+        da->ctx = ctx;
+        da->n = n;
+        da->n_words32 = padded_words32(n);
+        TRYF(cudaMalloc(&da->words, da->n_words32 * 4));
+        TRYF(cudaMemsetAsync(da->words, 0, da->n_words32 * 4, s));
+    }
+    const size_t stripe_bytes = (size_t)kStripes * C_NCOUNTERS * sizeof(unsigned long long);
+    TRYF(cudaMalloc(&stripes, stripe_bytes));
+
+    // frontier budget: what is free now, minus head-room, unless the caller set one
+    size_t free_b = 0, total_b = 0;
+    TRYF(cudaMemGetInfo(&free_b, &total_b));
+    uint64_t budget = ctx->frontier_budget ? ctx->frontier_budget : (uint64_t)(free_b * 0.85);
+    ctx->pool.set_limit(budget);
+
+    NavArgs args{};
+    args.ix1 = b1->dev();
+    args.ix2 = two ? b2->dev() : b1->dev();
+    args.thr = l->thr;
+    args.minima = l->minima;
+    args.da = da ? da->words : nullptr;
+    args.stripes = stripes;
+    args.K = (uint32_t)p->K;
+    args.k_right = (uint32_t)p->k_right;
+
+    std::vector<unsigned long long> hstripes((size_t)kStripes * C_NCOUNTERS);
+    auto sum_stripes = [&](unsigned long long tot[C_NCOUNTERS]) -> int {
+        E2I_CUDA_TRY(cudaMemcpyAsync(hstripes.data(), stripes, stripe_bytes, cudaMemcpyDeviceToHost, s));
+        E2I_CUDA_TRY(cudaStreamSynchronize(s));
+        for (int k = 0; k < C_NCOUNTERS; ++k) tot[k] = 0;
+        for (int i = 0; i < kStripes; ++i) for (int k = 0; k < C_NCOUNTERS; ++k) tot[k] += hstripes[(size_t)i * C_NCOUNTERS + k];
+        return E2I_OK;
+    };
+
+    // Sharding: the top of the tree is expanded on every shard (only shard 0 writes
+    // its bits); once a sweep holds >= kDealItems nodes it is dealt in position-contiguous slices of
+    // equal cumulated interval length, and every shard finishes its slice independently.
+    const uint64_t kDealItems = 4096ull * (uint64_t)n_shards;
+
+    auto run_pass = [&](bool leaves, SweepStats &ss) -> int {
+        const int words = leaves ? (two ? 8 : 4) : (two ? 16 : 8);
+        const int tile_items = leaves ? kNavThreads : (two ? 2 : 4) * (kNavThreads / 32) * kNodeIter;
+        const uint64_t max_chunk = std::max<uint64_t>(65536, budget / ((uint64_t)words * 8 * 4 * 4));
+        // root record
+        void *rootmem = nullptr;
+        if (ctx->pool.alloc(&rootmem, (size_t)words * 8) != E2I_OK) return E2I_ERR_MEMORY;
+        uint64_t rec[16] = {0};
+        if (leaves) {                                   // first_leaf (dna_bwt.hpp:313-317)
+            rec[0] = 0; rec[1] = b1->F[0]; rec[2] = 0;
+            if (two) { rec[4] = 0; rec[5] = b2->F[0]; }
+        } else {                                        // root (dna_bwt.hpp:296-308)
+            rec[0] = 0; rec[1] = b1->F[0]; rec[2] = b1->F[1]; rec[3] = b1->F[2]; rec[4] = b1->F[3]; rec[5] = b1->n; rec[6] = 0;
+            if (two) { rec[8] = 0; rec[9] = b2->F[0]; rec[10] = b2->F[1]; rec[11] = b2->F[2]; rec[12] = b2->F[3]; rec[13] = b2->n; }
+        }
+        E2I_CUDA_TRY(cudaMemcpyAsync(rootmem, rec, (size_t)words * 8, cudaMemcpyHostToDevice, s));
+        Chunk root{};
+        root.p[0] = reinterpret_cast<uint64_t *>(rootmem);
+        root.cnt[0] = 1;
+        root.frame = std::make_shared<Frame>();
+        root.frame->pool = &ctx->pool;
+        root.frame->p = rootmem;
+        auto launch = [&](NavArgs &a, const Segs &segs, uint32_t n_tiles) {
+            if (leaves) {
+                if (two) expand_leaves_kernel<true><<<n_tiles, kNavThreads, 0, s>>>(a, segs);
+                else expand_leaves_kernel<false><<<n_tiles, kNavThreads, 0, s>>>(a, segs);
+            } else {
+                if (two) expand_nodes_kernel<true><<<n_tiles, kNavThreads, 0, s>>>(a, segs);
+                else expand_nodes_kernel<false><<<n_tiles, kNavThreads, 0, s>>>(a, segs);
+            }
+        };
+        if (n_shards == 1) {
+            args.write = 1;
+            return run_frontier(ctx, std::move(root), words, tile_items, max_chunk, args, launch, ss, 0, nullptr);
+        }
+        // shared top of the tree
+        std::vector<Chunk> dealt;
+        args.write = shard == 0;
+        SweepStats top;
+        E2I_TRY(run_frontier(ctx, std::move(root), words, tile_items, max_chunk, args, launch, top, kDealItems, &dealt));
+        if (shard == 0) { ss.items += top.items; ss.sweeps += top.sweeps; ss.max_chunk = std::max(ss.max_chunk, top.max_chunk); }
+        args.write = 1;
+        for (Chunk &c : dealt) {
+            // deal by cumulated interval length: fetch (first, last) of every record
+            const uint64_t tot = c.total();
+            std::vector<uint64_t> host((size_t)tot * words);
+            uint64_t off = 0;
+            for (int q = 0; q < 4; ++q) {
+                if (!c.cnt[q]) continue;
+                E2I_CUDA_TRY(cudaMemcpyAsync(host.data() + off * words, c.p[q], c.cnt[q] * words * 8, cudaMemcpyDeviceToHost, s));
+                off += c.cnt[q];
+            }
+            E2I_CUDA_TRY(cudaStreamSynchronize(s));
+            auto weight = [&](uint64_t i) -> uint64_t {
+                const uint64_t *r = host.data() + i * words;
+                if (leaves) return (r[1] - r[0]) + (two ? r[5] - r[4] : 0) + 1;
+                return (r[5] - r[0]) + (two ? r[13] - r[8] : 0) + 1;
+            };
+            unsigned __int128 wsum = 0;
+            for (uint64_t i = 0; i < tot; ++i) wsum += weight(i);
+            unsigned __int128 acc = 0;
+            uint64_t lo = tot, hi = tot;
+            bool have_lo = false;
+            for (uint64_t i = 0; i < tot; ++i) {   // record i belongs to shard floor(acc * n_shards / wsum)
+                const int owner = (int)((acc * (unsigned)n_shards) / wsum);
+                if (owner == shard && !have_lo) { lo = i; have_lo = true; }
+                if (owner > shard) { hi = i; break; }
+                acc += weight(i);
+            }
+            if (!have_lo || lo >= hi) continue;
+            Chunk mine = c;
+            (void)split_head(mine, lo, words);          // drop [0, lo)
+            Chunk part = split_head(mine, hi - lo, words);
+            part.frame = c.frame;
+            E2I_TRY(run_frontier(ctx, std::move(part), words, tile_items, max_chunk, args, launch, ss, 0, nullptr));
+        }
+        return E2I_OK;
+    };
+
+    unsigned long long tot[C_NCOUNTERS];
+    // ---- Phase 2: leaves ----
+    TRYF(cudaMemsetAsync(stripes, 0, stripe_bytes, s));
+    TRYF(cudaEventRecord(ctx->ev[0], s));
+    SweepStats sl;
+    int rc = run_pass(true, sl);
+    if (rc != E2I_OK) return fail(rc);
+    TRYF(cudaEventRecord(ctx->ev[1], s));
+    rc = sum_stripes(tot);
+    if (rc != E2I_OK) return fail(rc);
+    const uint64_t first = shard == 0 ? 1 : 0;          // lcp_values starts at 1 (ebwt2InDel.cpp:575)
+    st->leaves += sl.items;
+    st->levels_leaves += sl.sweeps;
+    st->rank_leaves += tot[C_RANK];
+    st->lcp_values_leaves += first + tot[C_LCP];
+    st->lcp_values += first + tot[C_LCP];
+    st->da_values += tot[C_DA];
+    st->max_frontier = std::max<uint64_t>(st->max_frontier, sl.max_chunk);
+    // ---- Phase 3: internal nodes ----
+    TRYF(cudaMemsetAsync(stripes, 0, stripe_bytes, s));
+    TRYF(cudaEventRecord(ctx->ev[2], s));
+    SweepStats sn;
+    rc = run_pass(false, sn);
+    if (rc != E2I_OK) return fail(rc);
+    TRYF(cudaEventRecord(ctx->ev[3], s));
+    rc = sum_stripes(tot);
+    if (rc != E2I_OK) return fail(rc);
+    st->nodes += sn.items;
+    st->levels_nodes += sn.sweeps;
+    st->rank_nodes += tot[C_RANK];
+    st->lcp_values += tot[C_LCP];
+    st->n_min += tot[C_NMIN];
+    st->da_values += tot[C_DA];
+    st->bit_updates += tot[C_BITUPD];
+    st->max_frontier = std::max<uint64_t>(st->max_frontier, sn.max_chunk);
+    float ms = 0;
+    TRYF(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
+    st->ms_leaves += ms;
+    TRYF(cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]));
+    st->ms_nodes += ms;
+#undef TRYF
+    cudaFree(stripes);
+    ctx->pool.release();
+    *out = l;
+    if (da_out) *da_out = da;
+    return E2I_OK;
+}
+
+extern "C" int e2i_navigate(e2i_ctx *ctx, const e2i_index *b1, const e2i_index *b2, const e2i_params *p,
+                            e2i_lcpbits **out, e2i_bits **da_out, e2i_stats *st) {
+    return e2i_navigate_shard(ctx, b1, b2, p, 0, 1, out, da_out, st);
+}
+
+extern "C" int e2i_lcpbits_fetch(e2i_ctx *ctx, const e2i_lcpbits *l, uint64_t *host_thr_words, uint64_t *host_min_words) {
+    if (!ctx || !l) { set_error("e2i_lcpbits_fetch: null argument"); return E2I_ERR_ARG; }
+    if (host_thr_words) E2I_CUDA_TRY(cudaMemcpy(host_thr_words, l->thr, ((2 * l->n + 63) / 64) * 8, cudaMemcpyDeviceToHost));
+    if (host_min_words) E2I_CUDA_TRY(cudaMemcpy(host_min_words, l->minima, ((l->n + 63) / 64) * 8, cudaMemcpyDeviceToHost));
+    return E2I_OK;
+}
+
+extern "C" int e2i_lcpbits_device(const e2i_lcpbits *l, void **dev_thr, uint64_t *thr_words32, void **dev_min, uint64_t *min_words32) {
+    if (!l) { set_error("e2i_lcpbits_device: null argument"); return E2I_ERR_ARG; }
+    if (dev_thr) *dev_thr = l->thr;
+    if (thr_words32) *thr_words32 = l->thr_words32;
+    if (dev_min) *dev_min = l->minima;
+    if (min_words32) *min_words32 = l->min_words32;
+    return E2I_OK;
+}
+
+extern "C" void e2i_lcpbits_free(e2i_lcpbits *l) {
+    if (!l) return;
+    cudaFree(l->thr);
+    cudaFree(l->minima);
+    delete l;
+}

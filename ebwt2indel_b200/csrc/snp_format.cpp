@@ -1,0 +1,158 @@
+// snp_format.cpp -- a21-a23: event classification and KisSNP2-style .snp text (host side).
+//
+// Replaces has_run / dH / distance (/root/reference/ebwt2InDel.cpp:143-240), event_type
+// (:1102-1144) and the two to_file overloads (:1149-1252 for modes -2/-d, :1254-1330 for mode -1).
+// Input: the per-cluster records produced on the device by e2i_call, in suffix-array order.
+// Quirks kept on purpose (SURVEY.md §8a "parity hazards"): strict comparisons in distance(),
+// the good[1] operand of event_type in mode -1, cluster numbers that advance for clusters that
+// print nothing, the `right:` field printing the actual right-context length.
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+
+namespace {
+
+struct Dist { int mism; int gap; };   // gap > 0: insertion in a; gap < 0: insertion in b
+
+// right-aligned Hamming distance over the shorter length (:157-171)
+int hamming_right(const char *a, int la, const char *b, int lb) {
+    const int len = la < lb ? la : lb;
+    int d = 0;
+    for (int i = 0; i < len; ++i) d += a[la - 1 - i] != b[lb - 1 - i];
+    return d;
+}
+
+// :192-240.  Candidates: no indel, or drop 1..max_gap characters from the right end of a / of b.
+// "No indel" wins only if strictly better than both; "insert in a" only if strictly better than b.
+Dist distance(const char *a, const char *b, int len, int max_gap) {
+    const int plain = hamming_right(a, len, b, len);
+    if (max_gap <= 0) return {plain, 0};
+    int best_a = 0, gap_a = 0, best_b = 0, gap_b = 0;
+    for (int g = 1; g <= max_gap; ++g) {
+        const int keep = g <= len ? len - g : len;   // substr(0, len-g) wraps to the whole string when g > len
+        const int da = hamming_right(a, keep, b, len) + g;
+        const int db = hamming_right(a, len, b, keep) + g;
+        if (g == 1 || da < best_a) { best_a = da; gap_a = g; }
+        if (g == 1 || db < best_b) { best_b = db; gap_b = g; }
+    }
+    if (plain < best_a && plain < best_b) return {plain, 0};
+    if (best_a < best_b) return {best_a - gap_a, gap_a};
+    return {best_b - gap_b, -gap_b};
+}
+
+// true iff s starts with a run of >= k equal characters (:144-152)
+bool starts_with_run(const char *s, int len, int k) {
+    if (k < 0 || k > len) return false;
+    for (int i = 1; i < k; ++i)
+        if (s[i] != s[i - 1]) return false;
+    return true;
+}
+
+void append_event(std::string &o, const char *l0, const char *l1, int len, Dist d) {   // :1102-1144
+    o += "type:";
+    o += d.gap != 0 ? "_INDEL_event:" : "_SNP_event:";
+    if (d.gap == 0) { o += l0[len - 1]; o += '/'; o += l1[len - 1]; }
+    else if (d.gap > 0) { o.append(l0 + len - d.gap, (size_t)d.gap); o += '/'; }
+    else { o += '/'; o.append(l1 + len + d.gap, (size_t)(-d.gap)); }
+}
+
+void append_header(std::string &o, uint64_t cluster, uint64_t id, int right_len, int cov) {
+    o += ">cluster:"; o += std::to_string(cluster);
+    o += "_id:";      o += std::to_string(id);
+    o += "_right:";   o += std::to_string(right_len);
+    o += "_cov:";     o += std::to_string(cov);
+    o += '_';
+}
+
+}  // namespace
+
+extern "C" void e2i_distance(const char *a, const char *b, int32_t len, int32_t max_gap, int32_t out[2]) {
+    const Dist d = distance(a, b, len, max_gap);
+    out[0] = d.mism;
+    out[1] = d.gap;
+}
+
+extern "C" int e2i_snp_format(const e2i_call_rec *recs, const char *left, const char *right, uint64_t n_recs,
+                              const e2i_params *p, int two_samples, uint64_t first_cluster_nr,
+                              char **snp, size_t *snp_len, e2i_stats *st) {
+    if (!p || !snp || !snp_len || (n_recs && (!recs || !left || !right))) { e2i::set_error("e2i_snp_format: null argument"); return E2I_ERR_ARG; }
+    if (p->max_gap > p->k_left) { e2i::set_error("e2i_snp_format: max_gap (-g) must not exceed k_left (-L)"); return E2I_ERR_ARG; }
+    const int kl = p->k_left, kr = p->k_right;
+    uint64_t cluster_nr = first_cluster_nr ? first_cluster_nr : 1;
+    uint64_t events = 0;
+    std::string o;
+    for (uint64_t r = 0; r < n_recs; ++r) {
+        const e2i_call_rec &rec = recs[r];
+        const char *L = left + r * 8 * (size_t)kl;
+        const char *R = right + r * (size_t)kr;
+        const int rlen = rec.right_len;
+        if (!two_samples) {
+            // to_file(vector<variant_single_t>) :1254-1330
+            const int nv = rec.n0;
+            if (nv < 2) continue;
+            int max_dist = 0, good[4], ng = 0;
+            for (int i = 0; i + 1 < nv; ++i) {
+                const Dist d = distance(L + i * kl, L + (i + 1) * kl, kl, p->max_gap);
+                if (d.mism > max_dist) max_dist = d.mism;
+                if (rec.support[i] >= p->mcov_out) good[ng++] = i;
+            }
+            if (rec.support[nv - 1] >= p->mcov_out) good[ng++] = nv - 1;
+            if (max_dist <= p->max_snvs && ng >= 2) {
+                uint64_t id = 1;
+                for (int g = 0; g < ng; ++g) {
+                    if (starts_with_run(R, rlen, p->complexity)) continue;
+                    const char *me = L + good[g] * kl;
+                    append_header(o, cluster_nr, id++, rlen, rec.support[good[g]]);
+                    const char *x = g == 0 ? me : L + good[g - 1] * kl;   // :1299-1307
+                    const char *y = L + good[1] * kl;
+                    append_event(o, x, y, kl, distance(x, y, kl, p->max_gap));
+                    o += '\n';
+                    o.append(me, (size_t)kl);
+                    o.append(R, (size_t)rlen);
+                    o += '\n';
+                    events++;
+                }
+            }
+            cluster_nr++;                                                // :1328
+        } else {
+            // find_variants' cross product (:915-928, 1077-1090) + to_file(vector<variant_t>) :1149-1252
+            bool found = false;
+            uint64_t id = 1;
+            for (int i0 = 0; i0 < rec.n0; ++i0) for (int i1 = 0; i1 < rec.n1; ++i1) {
+                const char *l0 = L + i0 * kl, *l1 = L + (4 + i1) * kl;
+                if (l0[kl - 1] == l1[kl - 1]) continue;
+                const Dist d = distance(l0, l1, kl, p->max_gap);
+                const int s0 = rec.support[i0], s1 = rec.support[4 + i1];
+                if (starts_with_run(R, rlen, p->complexity) || d.mism > p->max_snvs || s0 < p->mcov_out || s1 < p->mcov_out) continue;
+                found = true;
+                for (int side = 0; side < 2; ++side) {
+                    append_header(o, cluster_nr, id, rlen, side ? s1 : s0);
+                    append_event(o, l0, l1, kl, d);
+                    o += '\n';
+                    int skip = 0;
+                    if (side == 0 && d.gap < 0) skip = -d.gap;           // :1199
+                    if (side == 1 && d.gap > 0) skip = d.gap;            // :1233
+                    o.append((side ? l1 : l0) + skip, (size_t)(kl - skip));
+                    o.append(R, (size_t)rlen);
+                    o += '\n';
+                }
+                id++;
+            }
+            cluster_nr += found ? 1 : 0;                                 // :1250
+        }
+    }
+    char *buf = static_cast<char *>(std::malloc(o.size() + 1));
+    if (!buf) { e2i::set_error("e2i_snp_format: out of host memory"); return E2I_ERR_MEMORY; }
+    std::memcpy(buf, o.data(), o.size());
+    buf[o.size()] = 0;
+    *snp = buf;
+    *snp_len = o.size();
+    if (st) {
+        st->events += events;
+        st->clusters_out += cluster_nr - (first_cluster_nr ? first_cluster_nr : 1);
+    }
+    return E2I_OK;
+}
+
+extern "C" void e2i_buffer_free(void *p) { std::free(p); }

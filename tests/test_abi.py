@@ -1,0 +1,109 @@
+"""CPU suite: the C-ABI library loads and exports every symbol include/e2i.h declares; host-only
+entry points (parameter resolution, distance, .snp formatting) behave like the reference; compute
+entry points fail loudly without a CUDA device (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+
+def header_functions():
+    src = open(os.path.join(ROOT, "include", "e2i.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(e2i_[a-z0-9_A-Z]+)\s*\(", src)))
+
+
+def test_exports_every_declared_symbol(e2i):
+    L = e2i.lib()
+    names = header_functions()
+    assert len(names) >= 35
+    for n in names:
+        assert hasattr(L, n), f"libe2i.so does not export {n}"
+    assert set(names) == set(e2i.SYMBOLS)
+
+
+def test_struct_layouts(e2i):
+    assert C.sizeof(e2i.Params) == 36
+    assert C.sizeof(e2i.CallRec) == 56
+    assert C.sizeof(e2i.Stats) == 8 * (10 + 201 + 8) + 8 * 6
+
+
+def test_params_default_and_resolve(e2i):
+    p = e2i.default_params()
+    assert (p.k_left, p.k_right, p.K, p.max_gap, p.max_snvs, p.mcov_out, p.complexity,
+            p.max_variants_per_position, p.term) == (31, 30, 16, 10, 2, 3, 20, 0, ord("#"))
+    # 0 means default, also for -g (ebwt2InDel.cpp:1740-1746); -c default does not follow -R (:64)
+    q = e2i.Params(k_left=0, k_right=50, K=0, max_gap=0, max_snvs=0, mcov_out=0, complexity=0,
+                   max_variants_per_position=0, term=36)
+    e2i.resolve_params(q)
+    assert (q.k_left, q.k_right, q.K, q.max_gap, q.max_snvs, q.mcov_out, q.complexity, q.term) == \
+        (31, 50, 16, 10, 2, 3, 20, 36)
+
+
+def test_distance_matches_reference_example_and_oracle(e2i, oracle):
+    assert e2i.distance("ACCTACTG", "TTACTTAC", 8) == (1, 2)      # ebwt2InDel.cpp:186-189
+    assert e2i.distance("TTACTTAC", "ACCTACTG", 8) == (1, -2)
+    rng = np.random.default_rng(1)
+    for _ in range(500):
+        n = int(rng.integers(5, 40))
+        a = "".join(rng.choice(list("ACGT"), n))
+        b = list(a)
+        for _ in range(int(rng.integers(0, 4))):
+            b[int(rng.integers(0, n))] = str(rng.choice(list("ACGT")))
+        sh = int(rng.integers(0, 6))
+        b = "".join(b)
+        b = ("".join(rng.choice(list("ACGT"), sh)) + b)[:n] if rng.random() < .5 else b
+        g = int(rng.integers(0, 12))
+        assert e2i.distance(a, b, g) == oracle.distance(a, b, g), (a, b, g)
+
+
+def test_snp_format_host_only(e2i):
+    """to_file(vector<variant_single_t>) quirks (ebwt2InDel.cpp:1254-1330) on hand-made records."""
+    p = e2i.default_params(k_left=8, k_right=6, max_gap=2, complexity=4)
+    recs = np.zeros(3, dtype=e2i.CALL_REC_DTYPE)
+    left = np.full(3 * 8 * 8, ord("A"), dtype=np.uint8)
+    right = np.zeros(3 * 6, dtype=np.uint8)
+
+    def put(r, slot, s):
+        left[(r * 8 + slot) * 8:(r * 8 + slot) * 8 + 8] = np.frombuffer(s.encode(), dtype=np.uint8)
+
+    # cluster 1: two alleles, SNP A/C
+    put(0, 0, "ACGTACGA"); put(0, 1, "ACGTACGC")
+    recs[0]["n0"] = 2; recs[0]["right_len"] = 6; recs[0]["support"][:2] = (5, 4)
+    right[0:6] = np.frombuffer(b"GATTAC", dtype=np.uint8)
+    # cluster 2: two alleles but one below coverage -> nothing printed, cluster number still advances (:1328)
+    put(1, 0, "ACGTACGA"); put(1, 1, "ACGTACGC")
+    recs[1]["n0"] = 2; recs[1]["right_len"] = 6; recs[1]["support"][:2] = (5, 1)
+    right[6:12] = np.frombuffer(b"GATTAC", dtype=np.uint8)
+    # cluster 3: low-complexity right context (run of 4) -> filtered by has_run, number advances
+    put(2, 0, "ACGTACGA"); put(2, 1, "ACGTACGT")
+    recs[2]["n0"] = 2; recs[2]["right_len"] = 6; recs[2]["support"][:2] = (3, 3)
+    right[12:18] = np.frombuffer(b"AAAATC", dtype=np.uint8)
+    snp, st = e2i.snp_format(recs, left, right, p, two_samples=False)
+    assert snp == (b">cluster:1_id:1_right:6_cov:5_type:_SNP_event:A/C\nACGTACGAGATTAC\n"
+                   b">cluster:1_id:2_right:6_cov:4_type:_SNP_event:A/C\nACGTACGCGATTAC\n")
+    assert st.events == 2 and st.clusters_out == 3
+
+
+def test_no_cuda_device_fails_loudly(e2i):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(e2i.E2iError) as ei:
+        e2i.Context(0)
+    assert ei.value.code == e2i.E2I_ERR_CUDA
+    assert "no CPU fallback" in str(ei.value)
+
+
+def test_cli_help_and_missing_file():
+    exe = os.path.join(ROOT, "bin", "ebwt2InDel")
+    assert os.access(exe, os.X_OK), "bin/ebwt2InDel is missing: run `make`"
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.startswith("ebwt2InDel [options]")          # argc < 3 -> help, exit 0
+    r = subprocess.run([exe, "-1", "/nonexistent.ebwt", "-o", "/tmp/x.snp"], capture_output=True, text=True)
+    assert r.returncode == 0 and "Error: could not find file /nonexistent.ebwt" in r.stdout

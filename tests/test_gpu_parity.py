@@ -1,0 +1,258 @@
+"""GPU suite (-m gpu): the CUDA path, called through the C ABI, against the CPU oracle and the
+golden vectors produced by the compiled reference.  Integer / byte / index work: bit-exact."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, golden_names, load_golden, resolved_fields
+
+pytestmark = pytest.mark.gpu
+
+COUNTERS = ("leaves", "nodes", "lcp_values", "lcp_values_leaves", "n_min", "da_values", "n_clusters",
+            "clust_size", "clusters_out")
+
+
+def mixed_bwt(n, seed, p_term=0.01):
+    rng = np.random.default_rng(seed)
+    p = [(1 - p_term) / 4] * 4 + [p_term]
+    return np.frombuffer(b"ACGT#", dtype=np.uint8)[rng.choice(5, size=n, p=p)]
+
+
+@pytest.mark.parametrize("n", [1, 2, 127, 128, 129, 16383, 16384, 16385, 100000, 1 << 20])
+def test_index_rank_access_fl(gpu_ctx, oracle, n):
+    bwt = mixed_bwt(n, seed=n)
+    ix = gpu_ctx.index(bwt)
+    ob = oracle.Bwt(bwt)
+    assert ix.n == n
+    assert np.array_equal(ix.F(), ob.F())
+    rng = np.random.default_rng(7)
+    pos = np.unique(np.concatenate([np.arange(0, min(n, 300) + 1), rng.integers(0, n + 1, 4000), [n]])).astype(np.uint64)
+    assert np.array_equal(ix.rank4(pos), ob.rank4(pos))
+    ipos = pos[pos < n]
+    assert np.array_equal(ix.access(ipos), bwt[ipos.astype(np.int64)])
+    # FL (dna_bwt.hpp:115-133) on positions whose F symbol is not the terminator
+    F = ob.F()
+    fpos = ipos[ipos >= F[0]][:1500]
+    if len(fpos):
+        lib = oracle.lib()
+        want = np.array([lib.orc_FL(ob.h, int(i)) for i in fpos], dtype=np.uint64)
+        assert np.array_equal(ix.FL(fpos), want)
+
+
+def test_forbidden_symbol(gpu_ctx):
+    bwt = mixed_bwt(50000, 1).copy()
+    bwt[31234] = ord("N")
+    bwt[40000] = ord("x")
+    with pytest.raises(ValueError, match="31234"):
+        gpu_ctx.index(bwt)
+
+
+def test_custom_terminator(gpu_ctx, oracle):
+    bwt = mixed_bwt(5000, 2).copy()
+    bwt[bwt == ord("#")] = ord("$")
+    ix = gpu_ctx.index(bwt, term=ord("$"))
+    assert np.array_equal(ix.F(), oracle.Bwt(bwt, term=ord("$")).F())
+    with pytest.raises(ValueError):
+        gpu_ctx.index(bwt)   # '$' is forbidden when the terminator is '#'
+
+
+def test_document_array_pack(gpu_ctx):
+    rng = np.random.default_rng(5)
+    for n in (1, 31, 32, 33, 1000, 100003):
+        raw = np.frombuffer(b"01x", dtype=np.uint8)[rng.choice(3, size=n, p=[.5, .45, .05])]
+        bits = gpu_ctx.document_array(raw).fetch()
+        want = np.packbits((raw == ord("1")).astype(np.uint8), bitorder="little")
+        want = np.concatenate([want, np.zeros(-len(want) % 8, dtype=np.uint8)]).view(np.uint64)
+        assert np.array_equal(bits, want)
+
+
+def _case_params(mod, g):
+    return mod.default_params(**resolved_fields(g["flags"]))
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_navigate_bitvectors_match_oracle(gpu_ctx, e2i, oracle, name):
+    g = load_golden(name)
+    term = resolved_fields(g["flags"]).get("term", ord("#"))
+    p, po = _case_params(e2i, g), _case_params(oracle, g)
+    b1 = gpu_ctx.index(g["bwt1"], term)
+    b2 = gpu_ctx.index(g["bwt2"], term) if g["bwt2"] is not None else None
+    lcp, da, st = gpu_ctx.navigate(b1, b2, p)
+    n = len(g["bwt1"]) + (len(g["bwt2"]) if b2 else 0)
+    thr, mn = lcp.fetch(n)
+    o1 = oracle.Bwt(g["bwt1"], term)
+    if b2:
+        o2 = oracle.Bwt(g["bwt2"], term)
+        othr, omn, oda, ost = oracle.navigate_two(o1, o2, po)
+        assert np.array_equal(da.fetch(), oda[:(n + 63) // 64])
+    else:
+        othr, omn, ost = oracle.navigate_one(o1, po)
+    assert np.array_equal(thr, othr[:len(thr)])
+    assert np.array_equal(mn, omn[:len(mn)])
+    for k in ("leaves", "nodes", "lcp_values", "lcp_values_leaves", "n_min", "da_values", "rank_leaves", "rank_nodes"):
+        assert getattr(st, k) == getattr(ost, k), k
+    for k, v in g["counters"].items():
+        if k != "n_clusters":
+            assert getattr(st, k) == v, f"{k} differs from the reference's printed counter"
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_whole_path_matches_reference_golden(gpu_ctx, e2i, oracle, name):
+    g = load_golden(name)
+    p = _case_params(e2i, g)
+    snp, st = gpu_ctx.run(g["bwt1"], g["bwt2"], g["da"], p)
+    assert snp == g["snp"], f"{name}: .snp differs from the compiled reference's"
+    for k, v in g["counters"].items():
+        assert getattr(st, k) == v, k
+    osnp, ost = oracle.run(g["bwt1"], g["bwt2"], g["da"], _case_params(oracle, g))
+    assert snp == osnp
+    for k in COUNTERS:
+        assert getattr(st, k) == getattr(ost, k), k
+    assert list(st.clust_sizes) == list(ost.clust_sizes)
+    if g["bwt2"] is None and g["da"] is None:
+        assert st.events == ost.events
+
+
+def test_whole_path_device_inputs(gpu_ctx, e2i):
+    import torch
+    g = load_golden("m3_default")
+    d1 = torch.from_numpy(g["bwt1"].copy()).cuda()
+    dd = torch.from_numpy(g["da"].copy()).cuda()
+    snp, _ = gpu_ctx.run(d1, None, dd, e2i.default_params())
+    assert snp == g["snp"]
+
+
+@pytest.mark.parametrize("seed,mode", [(101, 1), (102, 1), (103, 3), (104, 2)])
+def test_seeded_mid_size_vs_oracle(gpu_ctx, e2i, oracle, seed, mode):
+    """Fresh seeded inputs at a size the oracle finishes in seconds (n ~ 2-4 M)."""
+    from ebwt2indel_b200 import synth
+    if mode == 1:
+        reads = synth.diploid_reads(60000, 120, 30, 20, 100, seed=seed)
+        bwt, _ = synth.ebwt_bcr_numpy(reads)
+        args = (bwt, None, None)
+    else:
+        r0, r1 = synth.two_individuals_reads(20000, 40, 10, 20, 100, seed=seed)
+        if mode == 3:
+            args = synth.merged_ebwt_da(r0, r1, builder=synth.ebwt_bcr_numpy)
+            args = (args[0], None, args[1])
+        else:
+            args = (synth.ebwt_bcr_numpy(r0)[0], synth.ebwt_bcr_numpy(r1)[0], None)
+    snp, st = gpu_ctx.run(*args, e2i.default_params())
+    osnp, ost = oracle.run(*args, oracle.default_params())
+    assert snp == osnp
+    for k in COUNTERS:
+        assert getattr(st, k) == getattr(ost, k), k
+    assert len(snp) > 0
+
+
+def test_repetitive_and_degenerate_inputs(gpu_ctx, e2i, oracle):
+    """Edge cases: a single read, identical reads (deep unary paths, large leaves), homopolymers."""
+    from ebwt2indel_b200 import synth
+    cases = []
+    one = np.frombuffer(b"ACGTACGTTGCA", dtype=np.uint8)[None, :]
+    cases.append(one)
+    cases.append(np.repeat(one, 40, axis=0))
+    cases.append(np.full((25, 30), ord("A"), dtype=np.uint8))
+    rng = np.random.default_rng(9)
+    rep = synth.BASES[rng.integers(0, 4, 50)]
+    tandem = np.tile(rep, 20)
+    idx = np.arange(60)
+    cases.append(tandem[rng.integers(0, len(tandem) - 60, 300)[:, None] + idx[None, :]])
+    for reads in cases:
+        bwt, _ = synth.ebwt_naive(reads)
+        for kw in ({}, {"K": 4, "k_left": 8, "k_right": 6, "mcov_out": 2, "complexity": 5, "max_gap": 3}):
+            snp, st = gpu_ctx.run(bwt, None, None, e2i.default_params(**kw))
+            osnp, ost = oracle.run(bwt, None, None, oracle.default_params(**kw))
+            assert snp == osnp
+            for k in COUNTERS:
+                assert getattr(st, k) == getattr(ost, k), (k, reads.shape, kw)
+
+
+def test_sharded_navigation_ors_to_full(gpu_ctx, e2i):
+    """the bitvectors of the traversal shards OR-combine to the single-shard result,
+    every bit has one writer (so the integer sum of the words equals their OR)."""
+    g = load_golden("m1_default")
+    p = e2i.default_params()
+    b1 = gpu_ctx.index(g["bwt1"])
+    n = len(g["bwt1"])
+    full, _, fst = gpu_ctx.navigate(b1, None, p)
+    fthr, fmn = full.fetch(n)
+    for n_shards in (2, 3, 8):
+        sthr = np.zeros_like(fthr)
+        smn = np.zeros_like(fmn)
+        tot = {k: 0 for k in ("leaves", "nodes", "lcp_values", "n_min")}
+        for s in range(n_shards):
+            l, _, st = gpu_ctx.navigate(b1, None, p, shard=s, n_shards=n_shards)
+            t, m = l.fetch(n)
+            assert not np.any(sthr & t) and not np.any(smn & m)
+            sthr |= t
+            smn |= m
+            for k in tot:
+                tot[k] += getattr(st, k)
+        assert np.array_equal(sthr, fthr) and np.array_equal(smn, fmn)
+        for k in tot:
+            assert tot[k] == getattr(fst, k), (k, n_shards)
+
+
+def test_sharded_calls_concatenate(gpu_ctx, e2i):
+    g = load_golden("m3_default")
+    p = e2i.default_params()
+    b1 = gpu_ctx.index(g["bwt1"])
+    da = gpu_ctx.document_array(g["da"])
+    lcp, _, _ = gpu_ctx.navigate(b1, None, p)
+    n = len(g["bwt1"])
+    cuts = [0, n // 3 + 17, 2 * n // 3 + 5, n]
+    parts = [gpu_ctx.call(b1, None, da, lcp, p, cuts[i], cuts[i + 1]) for i in range(3)]
+    recs = np.concatenate([x[0] for x in parts])
+    left = np.concatenate([x[1] for x in parts])
+    right = np.concatenate([x[2] for x in parts])
+    snp, _ = e2i.snp_format(recs, left, right, p, two_samples=True)
+    assert snp == g["snp"]
+    assert sum(x[3].n_clusters for x in parts) == g["counters"]["n_clusters"]
+
+
+def test_small_frontier_budget_gives_same_result(e2i):
+    """Bounded-memory traversal: a tiny frontier budget forces chunked depth-first sweeps."""
+    g = load_golden("m1_default")
+    ctx = e2i.Context(0, frontier_bytes=24 << 20)
+    try:
+        snp, st = ctx.run(g["bwt1"], None, None, e2i.default_params())
+    finally:
+        ctx.close()
+    assert snp == g["snp"]
+    assert st.nodes == g["counters"]["nodes"]
+
+
+def test_cli_drop_in(tmp_path):
+    """bin/ebwt2InDel with the reference's argv: same .snp bytes, same counter lines."""
+    exe = os.path.join(ROOT, "bin", "ebwt2InDel")
+    for name in ("m1_flags", "m3_default", "m2_default", "m1_term36"):
+        g = load_golden(name)
+        f1 = tmp_path / "a.ebwt"
+        g["bwt1"].tofile(f1)
+        cmd = [exe, "-1", str(f1)]
+        if g["bwt2"] is not None:
+            f2 = tmp_path / "b.ebwt"
+            g["bwt2"].tofile(f2)
+            cmd += ["-2", str(f2)]
+        if g["da"] is not None:
+            f3 = tmp_path / "da.txt"
+            g["da"].tofile(f3)
+            cmd += ["-d", str(f3)]
+        out = tmp_path / "out.snp"
+        inv = {v: k for k, v in {"-L": "k_left", "-R": "k_right", "-k": "K", "-g": "max_gap", "-v": "max_snvs",
+                                 "-m": "mcov_out", "-c": "complexity", "-q": "max_variants_per_position",
+                                 "-t": "term"}.items()}
+        for k, v in g["flags"].items():
+            cmd += [inv[k], str(v)]
+        r = subprocess.run(cmd + ["-o", str(out)], capture_output=True, text=True)
+        assert r.returncode == 0, r.stdout + r.stderr
+        assert out.read_bytes() == g["snp"]
+        assert f"Processed {g['counters']['nodes']} suffix-tree nodes." in r.stdout
+        assert f"Analyzed {g['counters']['n_clusters']} clusters." in r.stdout
+    bad = tmp_path / "bad.ebwt"
+    bad.write_bytes(b"ACGTNACGT#")
+    r = subprocess.run([exe, "-1", str(bad), "-o", str(tmp_path / "x.snp")], capture_output=True, text=True)
+    assert r.returncode == 1 and "read forbidden character 'N' (ASCII code 78)" in r.stdout
