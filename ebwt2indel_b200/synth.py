@@ -159,3 +159,55 @@ def merged_ebwt_da(reads0: np.ndarray, reads1: np.ndarray, builder=ebwt_naive):
     bwt, owner = builder(np.concatenate([reads0, reads1], axis=0))
     da = np.where(owner >= len(reads0), np.uint8(ord("1")), np.uint8(ord("0"))).astype(np.uint8)
     return bwt, da
+
+
+def ebwt_bcr_torch(reads, device=None, term: int = ord("#"), want_owner: bool = False):
+    """eBWT by BCR-style column insertion with torch ops (runs on the GPU for bench-sized inputs).
+
+    Same algorithm and result as `ebwt_bcr_numpy`; `reads` is an (m, L) uint8 array/tensor.  Returns
+    a uint8 tensor on `device` (and, with `want_owner`, a bool tensor: suffix belongs to the second
+    half of the reads -- used to derive the document array of a merged collection).
+    Tooling for synthetic inputs only: not part of the product path.
+    """
+    import torch
+
+    if not torch.is_tensor(reads):
+        reads = torch.from_numpy(np.ascontiguousarray(reads))
+    dev = torch.device(device) if device is not None else reads.device
+    reads = reads.to(dev)
+    m, L = reads.shape
+    idt = torch.int32 if m * (L + 1) < 2 ** 31 - 1 else torch.int64
+    bwt = reads[:, L - 1].clone()
+    P = torch.arange(m, device=dev, dtype=idt)
+    owner = (torch.arange(m, device=dev) >= m // 2) if want_owner else None
+    second = owner.clone() if want_owner else None
+    syms = [ord(c) for c in "ACGT"]
+    for k in range(L):
+        c = reads[:, L - 1 - k]                     # == bwt[P]
+        newP = torch.empty(m, device=dev, dtype=idt)
+        base = m
+        for sym in syms:
+            is_c = bwt == sym
+            incl = torch.cumsum(is_c, 0, dtype=idt)
+            sel = c == sym
+            Ps = P[sel].long()
+            newP[sel] = (base + incl[Ps] - is_c[Ps].to(idt)).to(idt)
+            base += int(incl[-1])
+            del incl, is_c
+        new_sym = reads[:, L - k - 2] if k + 1 < L else torch.full((m,), term, dtype=torch.uint8, device=dev)
+        size = bwt.numel() + m
+        mark = torch.zeros(size, dtype=torch.bool, device=dev)
+        idx = newP.long()
+        mark[idx] = True
+        nb = torch.empty(size, dtype=torch.uint8, device=dev)
+        keep = ~mark
+        nb[keep] = bwt
+        nb[idx] = new_sym
+        if want_owner:
+            no = torch.empty(size, dtype=torch.bool, device=dev)
+            no[keep] = owner
+            no[idx] = second
+            owner = no
+        bwt, P = nb, newP
+        del mark, keep, idx
+    return (bwt, owner) if want_owner else bwt
