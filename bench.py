@@ -1,0 +1,424 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the ebwt2InDel hot path on B200 (contract: see DESIGN.md §measurement).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config C1|C2|C3|...] [--impl reference]
+
+One "step" = one pass of the whole hot path (index build, leaf + internal-node traversal, cluster
+scan, context extraction, .snp formatting) over one synthetic read collection of the named shape.
+`value`   = suffix-tree nodes processed per second, inputs (ASCII eBWT / DA) already resident in HBM.
+`e2e`     = the same through the C ABI with HOST buffers (pinned), H2D copies and the D2H of the call
+            records inside the timed region -- what `bin/ebwt2InDel` does after reading its files.
+`--impl reference` times the UNMODIFIED reference (oracle/_ref/ebwt2InDel, compiled from
+/root/reference by oracle/Makefile) on the box's host cores on a bounded sample of the same shape.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "suffix_tree_nodes_per_s"
+UNIT = "nodes/s"
+
+# SURVEY.md §8(d) / BASELINE.json configs.  `scale` < 1 shrinks genome length and variant counts
+# together (same coverage, read length and variant density) -- used for bounded CPU samples.
+CONFIGS = {
+    "C1": dict(mode=1, genome=1_000_000, snps=1000, indels=200, cov=20, read_len=100, revcomp=True, seed=1,
+               desc="mode -1: 1 Mbp random diploid (1k SNPs, 200 indels), 20x 100bp + revcomp, n=40.4M"),
+    "C2": dict(mode=3, genome=5_000_000, snps=5000, indels=1000, cov=50, read_len=100, revcomp=True, seed=2,
+               desc="mode -d: two 5 Mbp individuals, 50x 100bp + revcomp each, merged eBWT + DA, n=1.01G"),
+    "C3": dict(mode=2, genome=50_000_000, snps=50_000, indels=10_000, cov=30, read_len=150, revcomp=False, seed=3,
+               desc="mode -2: two eBWTs of 50 Mbp genomes, 30x 150bp, n=1.51G each"),
+    "C4": dict(mode=1, genome=250_000_000, snps=250_000, indels=50_000, cov=30, read_len=150, revcomp=True, seed=4,
+               desc="mode -1: 250 Mbp diploid, 30x 150bp + revcomp, n=15.1G"),
+    # intermediate mode -1 sizes (same shape as C4) used while the C4 pipeline is brought up
+    "C4s16": dict(mode=1, genome=15_625_000, snps=15_625, indels=3_125, cov=30, read_len=150, revcomp=True, seed=4,
+                  desc="mode -1: 1/16 of C4 (15.6 Mbp diploid, 30x 150bp + revcomp), n=0.94G"),
+    "C4s4": dict(mode=1, genome=62_500_000, snps=62_500, indels=12_500, cov=30, read_len=150, revcomp=True, seed=4,
+                 desc="mode -1: 1/4 of C4 (62.5 Mbp diploid, 30x 150bp + revcomp), n=3.8G"),
+}
+
+
+def scaled(cfg: dict, scale: float) -> dict:
+    c = dict(cfg)
+    c["genome"] = max(2000, int(cfg["genome"] * scale))
+    c["snps"] = max(1, int(cfg["snps"] * scale))
+    c["indels"] = max(1, int(cfg["indels"] * scale))
+    return c
+
+
+def make_workload(cfg: dict, device):
+    """Synthetic inputs of the named shape; returns dict(mode, bwt1, bwt2, da, n) of uint8 tensors on `device`."""
+    import torch
+    from ebwt2indel_b200 import synth
+    if cfg["mode"] == 1:
+        reads = synth.diploid_reads(cfg["genome"], cfg["snps"], cfg["indels"], cfg["cov"], cfg["read_len"],
+                                    cfg["seed"], cfg["revcomp"])
+        bwt = synth.ebwt_bcr_torch(reads, device)
+        return dict(mode=1, bwt1=bwt, bwt2=None, da=None, n=bwt.numel(), reads=len(reads))
+    r0, r1 = synth.two_individuals_reads(cfg["genome"], cfg["snps"], cfg["indels"], cfg["cov"], cfg["read_len"],
+                                         cfg["seed"], cfg["revcomp"])
+    if cfg["mode"] == 3:
+        bwt, owner = synth.ebwt_bcr_torch(np.concatenate([r0, r1], axis=0), device, want_owner=True)
+        da = torch.where(owner, torch.tensor(ord("1"), dtype=torch.uint8, device=device),
+                         torch.tensor(ord("0"), dtype=torch.uint8, device=device))
+        return dict(mode=3, bwt1=bwt, bwt2=None, da=da, n=bwt.numel(), reads=len(r0) + len(r1))
+    b0 = synth.ebwt_bcr_torch(r0, device)
+    b1 = synth.ebwt_bcr_torch(r1, device)
+    return dict(mode=2, bwt1=b0, bwt2=b1, da=None, n=b0.numel() + b1.numel(), reads=len(r0) + len(r1))
+
+
+# ---- clocks ------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx, self.lines, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.idx), "-lms", "200"], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---- the reference on host cores ---------------------------------------------------------------
+def ref_binary():
+    p = os.path.join(ROOT, "oracle", "_ref", "ebwt2InDel")
+    return p if os.access(p, os.X_OK) else None
+
+
+def run_reference_once(files, flags=()):
+    """One run of the compiled reference; returns (nodes, seconds, per-phase seconds)."""
+    from oracle import binding as ob
+    cmd = [ob.REF_BIN] + files + [str(f) for f in flags]
+    t0 = time.perf_counter()
+    marks, nodes = {}, 0
+    proc = subprocess.Popen(cmd, stdout=subprocess.PIPE, text=True)
+    for line in proc.stdout:
+        for key, pat in (("p2", "Phase 2/4"), ("p3", "Phase 3/4"), ("p4", "Phase 4/4"), ("done", "Done.")):
+            if key not in marks and line.startswith(pat):
+                marks[key] = time.perf_counter() - t0
+        if line.startswith("Processed") and "suffix-tree nodes" in line:
+            nodes = int(line.split()[1])
+    proc.wait()
+    total = time.perf_counter() - t0
+    if proc.returncode != 0:
+        raise RuntimeError("reference run failed")
+    return nodes, total, marks
+
+
+def write_inputs(d, wl, tag=""):
+    files = []
+    f1 = os.path.join(d, f"a{tag}.ebwt")
+    wl["bwt1"].cpu().numpy().tofile(f1)
+    files += ["-1", f1]
+    if wl["bwt2"] is not None:
+        f2 = os.path.join(d, f"b{tag}.ebwt")
+        wl["bwt2"].cpu().numpy().tofile(f2)
+        files += ["-2", f2]
+    if wl["da"] is not None:
+        f3 = os.path.join(d, f"da{tag}.txt")
+        wl["da"].cpu().numpy().tofile(f3)
+        files += ["-d", f3]
+    return files + ["-o", os.path.join(d, f"out{tag}.snp")]
+
+
+def cpu_sample_config(cfg: dict, target_n: float = 40e6) -> tuple[dict, float]:
+    """A bounded sample of the workload: same shape, genome scaled so that n ~ target_n (10-30 s of CPU)."""
+    per_bp = cfg["cov"] * (cfg["read_len"] + 1) / cfg["read_len"] * (2 if cfg["revcomp"] else 1)
+    per_bp *= 1 if cfg["mode"] == 1 else 2
+    n_full = cfg["genome"] * per_bp
+    scale = min(1.0, target_n / n_full)
+    return scaled(cfg, scale), scale
+
+
+def cpu_baseline_single(cfg: dict, device) -> dict:
+    """The unmodified reference, one thread (it has no threads), on a bounded sample of the workload."""
+    if ref_binary() is None:
+        return {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "oracle/_ref/ebwt2InDel absent"}
+    sc, scale = cpu_sample_config(cfg, 24e6 if cfg["mode"] == 1 else 6e6)
+    wl = make_workload(sc, device)
+    with tempfile.TemporaryDirectory() as d:
+        files = write_inputs(d, wl)
+        nodes, total, marks = run_reference_once(files)
+    p3 = marks.get("p4", total) - marks.get("p3", 0.0)
+    return {"value": nodes / total, "unit": UNIT, "cores": 1, "kind": "reference",
+            "sample": f"same shape at scale {scale:.4g} (n={wl['n']}), whole run incl. load: {total:.1f} s, {nodes} nodes",
+            "phase3_nodes_per_s": nodes / p3 if p3 > 0 else None, "seconds": total}
+
+
+def reference_arm(args, cfg):
+    """--impl reference: the reference's own CPU implementation with all the host threads it can use.
+    The reference is single-threaded; its multi-core mode is pebwt2InDel.sh (split the reads into
+    pieces, one process per piece, concatenate).  HARC/BCR are not available, so the split is by
+    read index and each piece's eBWT comes from this repo's builder."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    if ref_binary() is None:
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/ebwt2InDel not built (needs /root/reference at build time)"}))
+        return
+    import torch
+    from ebwt2indel_b200 import synth
+    device = torch.device("cuda:0" if torch.cuda.is_available() else "cpu")
+    cores = os.cpu_count() or 1
+    pieces = max(1, min(cores, 32))
+    # bounded sample: ~6 M symbols per piece => a few seconds per step per core
+    sc, scale = cpu_sample_config(cfg, 6e6 * pieces if cfg["mode"] == 1 else 1.5e6 * pieces)
+    with tempfile.TemporaryDirectory() as d:
+        cmds = []
+        if sc["mode"] == 1:
+            reads = synth.diploid_reads(sc["genome"], sc["snps"], sc["indels"], sc["cov"], sc["read_len"], sc["seed"], sc["revcomp"])
+            rng = np.random.default_rng(0)
+            perm = rng.permutation(len(reads))
+            n_tot = 0
+            for i in range(pieces):
+                part = reads[perm[i::pieces]]
+                bwt = synth.ebwt_bcr_torch(part, device)
+                n_tot += bwt.numel()
+                cmds.append(write_inputs(d, dict(bwt1=bwt, bwt2=None, da=None), tag=str(i)) + ["-m", "3"])
+        else:
+            r0, r1 = synth.two_individuals_reads(sc["genome"], sc["snps"], sc["indels"], sc["cov"], sc["read_len"], sc["seed"], sc["revcomp"])
+            rng = np.random.default_rng(0)
+            p0, p1 = rng.permutation(len(r0)), rng.permutation(len(r1))
+            n_tot = 0
+            for i in range(pieces):
+                wl = {"bwt2": None, "da": None}
+                a, b = r0[p0[i::pieces]], r1[p1[i::pieces]]
+                if sc["mode"] == 3:
+                    bwt, owner = synth.ebwt_bcr_torch(np.concatenate([a, b]), device, want_owner=True)
+                    wl["bwt1"] = bwt
+                    wl["da"] = torch.where(owner, torch.tensor(49, dtype=torch.uint8, device=device), torch.tensor(48, dtype=torch.uint8, device=device))
+                    n_tot += bwt.numel()
+                else:
+                    wl["bwt1"], wl["bwt2"] = synth.ebwt_bcr_torch(a, device), synth.ebwt_bcr_torch(b, device)
+                    n_tot += wl["bwt1"].numel() + wl["bwt2"].numel()
+                cmds.append(write_inputs(d, wl, tag=str(i)) + ["-m", "3"])
+
+        def step():
+            res = [None] * pieces
+
+            def work(i):
+                res[i] = run_reference_once(cmds[i])
+            th = [threading.Thread(target=work, args=(i,)) for i in range(pieces)]
+            t0 = time.perf_counter()
+            for t in th:
+                t.start()
+            for t in th:
+                t.join()
+            return sum(r[0] for r in res), time.perf_counter() - t0
+
+        for _ in range(args.warmup):
+            step()
+        nodes, secs = 0, 0.0
+        for _ in range(args.steps):
+            a, b = step()
+            nodes, secs = nodes + a, secs + b
+    value = nodes / secs
+    sample = (f"pebwt2InDel.sh-equivalent: same shape at scale {scale:.4g}, reads split into {pieces} pieces "
+              f"(n={n_tot} total), {pieces} concurrent single-threaded processes; nodes summed over pieces")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": args.config, "desc": cfg["desc"], "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": pieces, "kind": "reference", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# ---- own arm -----------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="own", choices=["own", "reference"])
+    ap.add_argument("--config", default=os.environ.get("E2I_BENCH_CONFIG", "C1"), choices=sorted(CONFIGS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--frontier-gb", type=float, default=0.0)
+    args = ap.parse_args()
+    cfg = CONFIGS[args.config]
+    if args.impl == "reference":
+        reference_arm(args, cfg)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from ebwt2indel_b200 import api, distributed as dd
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the hot path has no CPU fallback)")
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+
+    wl = make_workload(cfg, device)
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
+    ctx = api.Context(local, frontier_bytes=int(args.frontier_gb * 2 ** 30))
+    p = api.default_params()
+    ext = torch.cuda.ExternalStream(ctx.stream_ptr, device=device)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_device():
+        if world == 1:
+            snp, st = ctx.run(wl["bwt1"], wl["bwt2"], wl["da"], p)
+            return snp, st.as_dict()
+        snp, st, _ = dd.run_sharded(ctx, api, wl["bwt1"], wl["bwt2"], wl["da"], p, rank, world)
+        return snp, st
+
+    def timed(fn, k):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record(ext)
+        outs = [fn() for _ in range(k)]
+        e1.record(ext)
+        barrier()
+        wall = time.perf_counter() - t0
+        dev_s = e0.elapsed_time(e1) / 1e3
+        t = torch.tensor([max(dev_s, 0.0), wall], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return outs, float(t[0]), float(t[1])
+
+    for _ in range(args.warmup):
+        step_device()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    outs, dev_s, wall_s = timed(step_device, args.steps)
+    clk = clocks.stop() if rank == 0 else None
+    snp, st = outs[-1]
+    nodes = st["nodes"]
+    value = nodes * args.steps / dev_s
+
+    # ---- e2e: host buffers through the C ABI (N=1: e2i_run; N>1: H2D of the inputs + sharded path) ----
+    def pin(t):
+        return None if t is None else t.cpu().pin_memory()
+    h1, h2, hd = pin(wl["bwt1"]), pin(wl["bwt2"]), pin(wl["da"])
+
+    def step_host():
+        if world == 1:
+            s, stt = ctx.run(h1.numpy(), None if h2 is None else h2.numpy(), None if hd is None else hd.numpy(), p)
+            return s, stt.as_dict()
+        d1 = h1.to(device, non_blocking=True)
+        d2 = None if h2 is None else h2.to(device, non_blocking=True)
+        d3 = None if hd is None else hd.to(device, non_blocking=True)
+        torch.cuda.synchronize()
+        s, stt, _ = dd.run_sharded(ctx, api, d1, d2, d3, p, rank, world)
+        stt["h2d_bytes"] += (h1.numel() + (h2.numel() if h2 is not None else 0) + (hd.numel() if hd is not None else 0)) * world
+        return s, stt
+
+    step_host()
+    e_outs, e_dev_s, e_wall_s = timed(step_host, max(1, min(args.steps, 3)))
+    e_steps = len(e_outs)
+    e_snp, e_st = e_outs[-1]
+    e2e_value = e_st["nodes"] * e_steps / e_wall_s
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except OSError:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        alg_bytes = 64.0 * (st["rank_nodes"] + st["bit_updates"])          # 64 B per rank query / bit update
+        achieved = alg_bytes / (st["ms_nodes"] / 1e3) / 1e9 if st["ms_nodes"] > 0 else None
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.config)
+        except (OSError, ValueError):
+            pass
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * dev_s / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "u64", "data": "synthetic",
+            "config": {"workload": args.config, "desc": cfg["desc"], "n_symbols": wl["n"], "reads": wl["reads"],
+                       "nodes_per_step": nodes, "leaves_per_step": st["leaves"],
+                       "l2": "inputs larger than L2 (index + bitvectors > 126 MB)" if wl["n"] * 0.875 > 126e6 else
+                             "index fits L2; every step rebuilds it from the ASCII input",
+                       "parallelism": f"replicated index, {world} traversal shard(s), 1 OR all-reduce" if world > 1 else "single GPU"},
+            "phase_ms": {k: st[k] for k in ("ms_index", "ms_leaves", "ms_nodes", "ms_call")},
+            "wall_ms_per_step": 1e3 * wall_s / args.steps,
+            "rank_queries_per_s": (st["rank_leaves"] + st["rank_nodes"] + st["rank_call"]) * args.steps / dev_s,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": e_st["h2d_bytes"],
+                    "d2h_bytes_per_step": e_st["d2h_bytes"], "ms_per_step": 1e3 * e_wall_s / e_steps, "steps": e_steps},
+            "gpu_launches": st["kernel_launches"] * args.steps,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": (achieved / peak) if achieved else None, "traffic": traffic,
+                         "kernel": "expand_nodes_kernel (all launches of one step)",
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
+                         "algorithmic_bytes_per_step": alg_bytes, "kernel_ms_per_step": st["ms_nodes"]},
+            "clocks": clk,
+            "snp_bytes": len(snp) if snp is not None else None,
+            "e2e_matches_device": (e_snp == snp),
+        }
+        if not args.no_cpu_baseline and world == 1:
+            try:
+                line["cpu_baseline"] = cpu_baseline_single(cfg, device)
+            except Exception as ex:  # the baseline is reported, never fatal
+                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": f"failed: {ex}"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -38,14 +38,16 @@ _U64_FIELDS = ("leaves", "nodes", "lcp_values", "lcp_values_leaves", "n_min", "d
 _WORK_FIELDS = ("rank_leaves", "rank_nodes", "rank_call", "bit_updates", "candidates", "levels_leaves",
                 "levels_nodes", "max_frontier")
 _MS_FIELDS = ("ms_index", "ms_leaves", "ms_nodes", "ms_call", "ms_h2d", "ms_d2h")
+_IO_FIELDS = ("kernel_launches", "h2d_bytes", "d2h_bytes")
 
 
 class Stats(C.Structure):
     _fields_ = ([(k, C.c_uint64) for k in _U64_FIELDS] + [("clust_sizes", C.c_uint64 * 201)] +
-                [(k, C.c_uint64) for k in _WORK_FIELDS] + [(k, C.c_double) for k in _MS_FIELDS])
+                [(k, C.c_uint64) for k in _WORK_FIELDS] + [(k, C.c_double) for k in _MS_FIELDS] +
+                [(k, C.c_uint64) for k in _IO_FIELDS])
 
     def as_dict(self):
-        d = {k: int(getattr(self, k)) for k in _U64_FIELDS + _WORK_FIELDS}
+        d = {k: int(getattr(self, k)) for k in _U64_FIELDS + _WORK_FIELDS + _IO_FIELDS}
         d.update({k: float(getattr(self, k)) for k in _MS_FIELDS})
         d["clust_sizes"] = list(self.clust_sizes)
         return d
@@ -63,7 +65,7 @@ assert CALL_REC_DTYPE.itemsize == C.sizeof(CallRec) == 56
 # every symbol include/e2i.h declares (tests check that the library exports all of them)
 SYMBOLS = (
     "e2i_last_error", "e2i_version", "e2i_params_default", "e2i_params_resolve", "e2i_create", "e2i_destroy",
-    "e2i_set_frontier_budget", "e2i_host_alloc", "e2i_host_free", "e2i_index_build", "e2i_index_build_device",
+    "e2i_set_frontier_budget", "e2i_stream", "e2i_host_alloc", "e2i_host_free", "e2i_index_build", "e2i_index_build_device",
     "e2i_index_free", "e2i_index_size", "e2i_index_F", "e2i_index_bytes", "e2i_rank_batch", "e2i_access_batch",
     "e2i_fl_batch", "e2i_rank_batch_device", "e2i_da_load", "e2i_da_load_device", "e2i_bits_fetch",
     "e2i_bits_size", "e2i_bits_free", "e2i_navigate", "e2i_navigate_shard", "e2i_lcpbits_fetch",
@@ -93,6 +95,7 @@ def lib():
         "e2i_create": (C.c_int, [C.c_int, C.POINTER(vp)]),
         "e2i_destroy": (None, [vp]),
         "e2i_set_frontier_budget": (C.c_int, [vp, u64]),
+        "e2i_stream": (C.c_void_p, [vp]),
         "e2i_host_alloc": (C.c_int, [u64, C.POINTER(vp)]),
         "e2i_host_free": (None, [vp]),
         "e2i_index_build": (C.c_int, [vp, u8p, u64, C.c_uint8, C.POINTER(vp), C.POINTER(u64)]),
@@ -190,6 +193,11 @@ class Context:
         if getattr(self, "h", None):
             lib().e2i_destroy(self.h)
             self.h = None
+
+    @property
+    def stream_ptr(self) -> int:
+        """cudaStream_t of the context (wrap with torch.cuda.ExternalStream to record events on it)."""
+        return int(lib().e2i_stream(self.h))
 
     def __del__(self):
         self.close()

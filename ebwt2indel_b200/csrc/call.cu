@@ -379,6 +379,7 @@ static int build_da_rank(e2i_ctx *ctx, e2i_bits *da) {
     da_group_popc_kernel<<<(unsigned)((n_groups + 255) / 256), 256, 0, ctx->stream>>>(da->words, n_groups, da->rank512);
     scan_u64_kernel<<<1, 1024, 0, ctx->stream>>>(da->rank512, n_groups);
     E2I_CUDA_TRY(cudaGetLastError());
+    ctx->n_launch += 2;
     return E2I_OK;
 }
 
@@ -393,6 +394,7 @@ extern "C" int e2i_call(e2i_ctx *ctx, const e2i_index *b1, const e2i_index *b2, 
     const uint64_t n = b1->n + (b2 ? b2->n : 0);
     if (l->n != n || (da && da->n != n)) { set_error("e2i_call: bitvector length does not match the BWT length"); return E2I_ERR_ARG; }
     E2I_CUDA_TRY(cudaSetDevice(ctx->device));
+    Accounting acct(ctx, st);
     cudaStream_t s = ctx->stream;
     if (mode == 2) E2I_TRY(build_da_rank(ctx, const_cast<e2i_bits *>(da)));
     pos_end = std::min<uint64_t>(pos_end, n);
@@ -462,6 +464,8 @@ extern "C" int e2i_call(e2i_ctx *ctx, const e2i_index *b1, const e2i_index *b2, 
         const int grid = (int)std::min<uint64_t>(a.n_tiles, (uint64_t)ctx->sm_count * 8);
         scan_clusters_kernel<<<grid, kScanThreads, 0, s>>>(a);
         TRYF(cudaGetLastError());
+        ctx->n_launch++;
+        ctx->n_d2h += sizeof(CallCtl);
         TRYF(cudaMemcpyAsync(&hctl, dctl, sizeof(CallCtl), cudaMemcpyDeviceToHost, s));
         TRYF(cudaStreamSynchronize(s));
         st->n_clusters += hctl.n_clusters;
@@ -491,6 +495,8 @@ extern "C" int e2i_call(e2i_ctx *ctx, const e2i_index *b1, const e2i_index *b2, 
         TRYF(cudaMemcpyAsync(h_reached.data(), d_reached, nc * 8, cudaMemcpyDeviceToHost, s));
         TRYF(cudaMemcpyAsync(h_rlen.data(), d_rlen, nc, cudaMemcpyDeviceToHost, s));
         TRYF(cudaMemcpyAsync(h_has.data(), d_has, nc, cudaMemcpyDeviceToHost, s));
+        ctx->n_launch += 2;
+        ctx->n_d2h += nc * (sizeof(Candidate) + 8 * (size_t)p->k_left + (size_t)p->k_right + 8 * sizeof(int32_t) + 8 + 2);
         TRYF(cudaStreamSynchronize(s));
         cudaFree(d_left); cudaFree(d_right); cudaFree(d_support); cudaFree(d_reached); cudaFree(d_rlen); cudaFree(d_has);
         d_left = d_right = nullptr; d_support = nullptr; d_reached = d_rlen = d_has = nullptr;

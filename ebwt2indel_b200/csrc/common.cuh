@@ -90,7 +90,22 @@ struct e2i_ctx {
     uint32_t epoch = 0;
     void *ctl = nullptr;        // device control block (ticket + counters), see navigate.cu
     void *ctl_host = nullptr;   // pinned mirror
+    // accounting (kernels launched, bytes copied) since the context was created
+    uint64_t n_launch = 0, n_h2d = 0, n_d2h = 0;
 };
+
+namespace e2i {
+struct Accounting {            // adds what a call launched / copied to its e2i_stats on scope exit
+    e2i_ctx *ctx; e2i_stats *st; uint64_t l0, h0, d0;
+    Accounting(e2i_ctx *c, e2i_stats *s) : ctx(c), st(s), l0(c->n_launch), h0(c->n_h2d), d0(c->n_d2h) {}
+    ~Accounting() {
+        if (!st) return;
+        st->kernel_launches += ctx->n_launch - l0;
+        st->h2d_bytes += ctx->n_h2d - h0;
+        st->d2h_bytes += ctx->n_d2h - d0;
+    }
+};
+}  // namespace e2i
 
 struct e2i_index {
     e2i_ctx *ctx = nullptr;

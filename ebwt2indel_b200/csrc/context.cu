@@ -144,6 +144,8 @@ extern "C" void e2i_destroy(e2i_ctx *ctx) {
     delete ctx;
 }
 
+extern "C" void *e2i_stream(const e2i_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+
 extern "C" int e2i_set_frontier_budget(e2i_ctx *ctx, uint64_t bytes) {
     if (!ctx) { set_error("e2i_set_frontier_budget: null context"); return E2I_ERR_ARG; }
     ctx->frontier_budget = bytes;
@@ -165,9 +167,11 @@ static int run_on_device(e2i_ctx *ctx, const uint8_t *dev_bwt1, uint64_t n1, con
     cudaStream_t s = ctx->stream;
     cudaEventRecord(ctx->ev[6], s);
     uint64_t bad = 0;
+    Accounting *acct = new Accounting(ctx, st);
     int rc = e2i_index_build_device(ctx, dev_bwt1, n1, (uint8_t)p->term, &b1, &bad);
     if (rc == E2I_OK && dev_bwt2) rc = e2i_index_build_device(ctx, dev_bwt2, n2, (uint8_t)p->term, &b2, &bad);
     if (rc == E2I_OK && dev_da) rc = e2i_da_load_device(ctx, dev_da, n1, &da);
+    delete acct;   // index + DA build only; navigate and call account for themselves
     cudaEventRecord(ctx->ev[7], s);
     if (rc == E2I_OK) {
         cudaEventSynchronize(ctx->ev[7]);
@@ -229,6 +233,7 @@ extern "C" int e2i_run(e2i_ctx *ctx, const uint8_t *host_bwt1, uint64_t n1, cons
     float ms = 0;
     cudaEventElapsedTime(&ms, ctx->ev[6], ctx->ev[7]);
     st->ms_h2d += ms;
+    st->h2d_bytes += n1 + (host_bwt2 ? n2 : 0) + (host_da ? n1 : 0);
     const int rc = run_on_device(ctx, in.d1, n1, in.d2, n2, in.dd, p, snp, snp_len, st, free_inputs, &in);
     free_inputs(&in);
     return rc;

@@ -304,6 +304,9 @@ extern "C" int e2i_index_build_device(e2i_ctx *ctx, const uint8_t *dev_ascii, ui
     pack_tiles_kernel<<<grid, kBuildThreads, 0, s>>>(dev_ascii, n, term, n_tiles, tile_prefix, ix->blocks,
                                                      reinterpret_cast<unsigned long long *>(ix->super));
     TRYF(cudaGetLastError());
+    ctx->n_launch += 3;
+    ctx->n_h2d += sizeof init;
+    ctx->n_d2h += 5 * sizeof(unsigned long long);
     unsigned long long res[5];
     TRYF(cudaMemcpyAsync(res, scal, sizeof res, cudaMemcpyDeviceToHost, s));
     TRYF(cudaStreamSynchronize(s));
@@ -334,6 +337,7 @@ extern "C" int e2i_index_build(e2i_ctx *ctx, const uint8_t *host_ascii, uint64_t
     E2I_CUDA_TRY(cudaMalloc(&d, n + 16));
     cudaError_t e = cudaMemcpyAsync(d, host_ascii, n, cudaMemcpyHostToDevice, ctx->stream);
     if (e != cudaSuccess) { cudaFree(d); set_error("H2D copy failed: %s", cudaGetErrorString(e)); return E2I_ERR_CUDA; }
+    ctx->n_h2d += n;
     const int rc = e2i_index_build_device(ctx, d, n, term, out, bad_pos);
     cudaFree(d);
     return rc;
@@ -428,6 +432,7 @@ extern "C" int e2i_da_load_device(e2i_ctx *ctx, const uint8_t *dev_ascii01, uint
     if (e == cudaSuccess && nw) {
         da_pack_kernel<<<(unsigned)((nw + 255) / 256), 256, 0, ctx->stream>>>(dev_ascii01, n, b->words, nw);
         e = cudaGetLastError();
+        ctx->n_launch++;
     }
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) { set_error("e2i_da_load_device: %s", cudaGetErrorString(e)); e2i_bits_free(b); return E2I_ERR_CUDA; }
@@ -442,6 +447,7 @@ extern "C" int e2i_da_load(e2i_ctx *ctx, const uint8_t *host_ascii01, uint64_t n
     E2I_CUDA_TRY(cudaMalloc(&d, n + 16));
     cudaError_t e = cudaMemcpyAsync(d, host_ascii01, n, cudaMemcpyHostToDevice, ctx->stream);
     if (e != cudaSuccess) { cudaFree(d); set_error("H2D copy failed: %s", cudaGetErrorString(e)); return E2I_ERR_CUDA; }
+    ctx->n_h2d += n;
     const int rc = e2i_da_load_device(ctx, d, n, out);
     cudaFree(d);
     return rc;

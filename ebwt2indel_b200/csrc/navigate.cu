@@ -460,6 +460,8 @@ static int run_frontier(e2i_ctx *ctx, Chunk root, int words, int tile_items, uin
         E2I_CUDA_TRY(cudaMemsetAsync(ctx->ctl, 0, sizeof(LaunchCtl), ctx->stream));
         launch(args, segs, n_tiles);
         E2I_CUDA_TRY(cudaGetLastError());
+        ctx->n_launch++;
+        ctx->n_d2h += sizeof(LaunchCtl);
         E2I_CUDA_TRY(cudaMemcpyAsync(hctl, ctx->ctl, sizeof(LaunchCtl), cudaMemcpyDeviceToHost, ctx->stream));
         E2I_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
         ss.items += acc;
@@ -487,6 +489,7 @@ extern "C" int e2i_navigate_shard(e2i_ctx *ctx, const e2i_index *b1, const e2i_i
     if (n_shards < 1 || shard < 0 || shard >= n_shards) { set_error("e2i_navigate: bad shard %d/%d", shard, n_shards); return E2I_ERR_ARG; }
     if (p->K < 1 || p->k_right < 1) { set_error("e2i_navigate: K and k_right must be >= 1"); return E2I_ERR_ARG; }
     E2I_CUDA_TRY(cudaSetDevice(ctx->device));
+    Accounting acct(ctx, st);
     cudaStream_t s = ctx->stream;
     const bool two = b2 != nullptr;
     const uint64_t n = b1->n + (two ? b2->n : 0);
@@ -534,6 +537,7 @@ extern "C" int e2i_navigate_shard(e2i_ctx *ctx, const e2i_index *b1, const e2i_i
     std::vector<unsigned long long> hstripes((size_t)kStripes * C_NCOUNTERS);
     auto sum_stripes = [&](unsigned long long tot[C_NCOUNTERS]) -> int {
         E2I_CUDA_TRY(cudaMemcpyAsync(hstripes.data(), stripes, stripe_bytes, cudaMemcpyDeviceToHost, s));
+        ctx->n_d2h += stripe_bytes;
         E2I_CUDA_TRY(cudaStreamSynchronize(s));
         for (int k = 0; k < C_NCOUNTERS; ++k) tot[k] = 0;
         for (int i = 0; i < kStripes; ++i) for (int k = 0; k < C_NCOUNTERS; ++k) tot[k] += hstripes[(size_t)i * C_NCOUNTERS + k];

@@ -1,0 +1,113 @@
+"""Multi-GPU driver of the hot path: one process per GPU, torch.distributed for the plumbing.
+
+SURVEY.md §8(e): the index is replicated in every GPU's HBM; the traversal (phases 2-3) is sharded
+by position-contiguous slices of a shallow frontier (e2i_navigate_shard); the shards' bit writes
+land all over [0, n), so ONE exchange step is needed -- a bitwise OR of the 3n-bit LCP vectors
+(+ n-bit DA in mode -2).  Every bit has a single writer and the vectors start at zero, so an
+integer SUM all-reduce of the 32-bit words is exactly that OR (no carries).  Phase 4 is then
+sharded by contiguous suffix-array ranges; the per-cluster records are gathered on rank 0, which
+numbers clusters in SA order and writes the .snp text (cluster numbering is sequential by nature,
+/root/reference/ebwt2InDel.cpp:1250, 1328).
+
+The collective helpers take plain tensors so that the host logic is testable with the gloo
+backend on CPU (tests/test_distributed_gloo.py).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+class _DeviceWords:
+    """Zero-copy view of `words32` int32 words at a raw device pointer (CUDA array interface)."""
+
+    def __init__(self, ptr: int, words32: int):
+        self.__cuda_array_interface__ = {"shape": (int(words32),), "typestr": "<i4", "data": (int(ptr), False),
+                                         "version": 2, "strides": None}
+
+
+def wrap_device_words(ptr: int, words32: int, device) -> torch.Tensor:
+    return torch.as_tensor(_DeviceWords(ptr, words32), device=device)
+
+
+def position_cuts(n: int, world: int):
+    """Contiguous suffix-array ranges for phase 4: clusters are assigned by their START position."""
+    return [n * r // world for r in range(world + 1)]
+
+
+def or_reduce_words(tensors, group=None, chunk_words: int = 1 << 28):
+    """In-place OR-combine of single-writer bitvectors across ranks (SUM all-reduce of int32 words)."""
+    for t in tensors:
+        flat = t.view(-1)
+        for off in range(0, flat.numel(), chunk_words):
+            dist.all_reduce(flat[off:off + chunk_words], op=dist.ReduceOp.SUM, group=group)
+
+
+def gather_calls(recs: np.ndarray, left: np.ndarray, right: np.ndarray, rank: int, world: int, group=None):
+    """Gather the per-rank call records on rank 0 in rank (= suffix-array) order."""
+    out = [None] * world if rank == 0 else None
+    dist.gather_object((recs, left, right), out, dst=0, group=group)
+    if rank != 0:
+        return None
+    return (np.concatenate([o[0] for o in out]), np.concatenate([o[1] for o in out]),
+            np.concatenate([o[2] for o in out]))
+
+
+_SUM_FIELDS = ("leaves", "nodes", "lcp_values", "lcp_values_leaves", "n_min", "da_values", "n_clusters",
+               "clust_size", "rank_leaves", "rank_nodes", "rank_call", "bit_updates", "candidates",
+               "kernel_launches", "h2d_bytes", "d2h_bytes")
+_MAX_FIELDS = ("ms_index", "ms_leaves", "ms_nodes", "ms_call", "ms_h2d", "max_frontier", "levels_leaves", "levels_nodes")
+
+
+def reduce_stats(st: dict, device, group=None) -> dict:
+    """Counters are summed over ranks (every unit of work is done by exactly one rank), phase times
+    take the max over ranks."""
+    out = dict(st)
+    s = torch.tensor([int(st[k]) for k in _SUM_FIELDS] + list(st["clust_sizes"]), dtype=torch.int64, device=device)
+    dist.all_reduce(s, op=dist.ReduceOp.SUM, group=group)
+    m = torch.tensor([float(st[k]) for k in _MAX_FIELDS], dtype=torch.float64, device=device)
+    dist.all_reduce(m, op=dist.ReduceOp.MAX, group=group)
+    vals = s.tolist()
+    for i, k in enumerate(_SUM_FIELDS):
+        out[k] = vals[i]
+    out["clust_sizes"] = vals[len(_SUM_FIELDS):]
+    for i, k in enumerate(_MAX_FIELDS):
+        out[k] = type(st[k])(m[i].item())
+    return out
+
+
+def run_sharded(ctx, api, bwt1, bwt2, da, params, rank: int, world: int, group=None):
+    """Whole path on `world` GPUs.  Inputs are CUDA uint8 tensors (replicated on every rank).
+    Returns (.snp bytes on rank 0 else None, reduced stats dict, seconds spent in the exchange)."""
+    device = bwt1.device
+    term = params.term
+    b1 = ctx.index(bwt1, term)
+    b2 = ctx.index(bwt2, term) if bwt2 is not None else None
+    dabits = ctx.document_array(da) if da is not None else None
+    st = api.Stats()
+    lcp, da_nav, st = ctx.navigate(b1, b2, params, shard=rank, n_shards=world, stats=st)
+    (pt, wt), (pm, wm) = lcp.device_words()
+    words = [wrap_device_words(pt, wt, device), wrap_device_words(pm, wm, device)]
+    if da_nav is not None:
+        pd, wd = da_nav.device_words()
+        words.append(wrap_device_words(pd, wd, device))
+    t0 = torch.cuda.Event(enable_timing=True)
+    t1 = torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(device)
+    t0.record()
+    or_reduce_words(words, group)
+    t1.record()
+    torch.cuda.synchronize(device)
+    n = b1.n + (b2.n if b2 is not None else 0)
+    cuts = position_cuts(n, world)
+    recs, left, right, st = ctx.call(b1, b2, da_nav if b2 is not None else dabits, lcp, params,
+                                     cuts[rank], cuts[rank + 1], stats=st)
+    g = gather_calls(recs, left, right, rank, world, group)
+    stats = reduce_stats(st.as_dict(), device, group)
+    snp = None
+    if rank == 0:
+        fst = api.Stats()
+        snp, fst = api.snp_format(g[0], g[1], g[2], params, two_samples=(b2 is not None or da is not None), stats=fst)
+        stats["events"], stats["clusters_out"] = int(fst.events), int(fst.clusters_out)
+    return snp, stats, t0.elapsed_time(t1) / 1e3

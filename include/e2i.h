@@ -79,6 +79,10 @@ typedef struct {
     double ms_call;
     double ms_h2d;
     double ms_d2h;
+    /* launch / transfer accounting of the calls that filled this struct */
+    uint64_t kernel_launches;    /* kernels of this library launched */
+    uint64_t h2d_bytes;          /* host -> device bytes copied (inputs) */
+    uint64_t d2h_bytes;          /* device -> host bytes copied (call records, counters) */
 } e2i_stats;
 
 /* One analysed cluster that passed the allele filter and has a right context.
@@ -107,6 +111,8 @@ void e2i_destroy(e2i_ctx *ctx);
 int e2i_set_frontier_budget(e2i_ctx *ctx, uint64_t bytes);
 /* Page-locked host staging buffers for the ASCII inputs (what the CLI reads the files into;
  * replaces the byte-at-a-time ifstream loops of dna_string.hpp:82-101 and ebwt2InDel.cpp:1503-1508). */
+/* The context's CUDA stream (a cudaStream_t), so that callers can record their own events on it. */
+void *e2i_stream(const e2i_ctx *ctx);
 int e2i_host_alloc(uint64_t bytes, void **out);
 void e2i_host_free(void *p);
 
