@@ -65,7 +65,7 @@ assert CALL_REC_DTYPE.itemsize == C.sizeof(CallRec) == 56
 # every symbol include/e2i.h declares (tests check that the library exports all of them)
 SYMBOLS = (
     "e2i_last_error", "e2i_version", "e2i_params_default", "e2i_params_resolve", "e2i_create", "e2i_destroy",
-    "e2i_set_frontier_budget", "e2i_stream", "e2i_host_alloc", "e2i_host_free", "e2i_index_build", "e2i_index_build_device",
+    "e2i_set_frontier_budget", "e2i_trim", "e2i_stream", "e2i_host_alloc", "e2i_host_free", "e2i_index_build", "e2i_index_build_device",
     "e2i_index_free", "e2i_index_size", "e2i_index_F", "e2i_index_bytes", "e2i_rank_batch", "e2i_access_batch",
     "e2i_fl_batch", "e2i_rank_batch_device", "e2i_da_load", "e2i_da_load_device", "e2i_bits_fetch",
     "e2i_bits_size", "e2i_bits_free", "e2i_navigate", "e2i_navigate_shard", "e2i_lcpbits_fetch",
@@ -95,6 +95,7 @@ def lib():
         "e2i_create": (C.c_int, [C.c_int, C.POINTER(vp)]),
         "e2i_destroy": (None, [vp]),
         "e2i_set_frontier_budget": (C.c_int, [vp, u64]),
+        "e2i_trim": (C.c_int, [vp]),
         "e2i_stream": (C.c_void_p, [vp]),
         "e2i_host_alloc": (C.c_int, [u64, C.POINTER(vp)]),
         "e2i_host_free": (None, [vp]),
@@ -193,6 +194,10 @@ class Context:
         if getattr(self, "h", None):
             lib().e2i_destroy(self.h)
             self.h = None
+
+    def trim(self):
+        """Give the device memory cached by the library back to the driver."""
+        _check(lib().e2i_trim(self.h))
 
     @property
     def stream_ptr(self) -> int:

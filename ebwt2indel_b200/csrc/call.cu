@@ -375,7 +375,7 @@ using namespace e2i;
 static int build_da_rank(e2i_ctx *ctx, e2i_bits *da) {
     if (da->rank512) return E2I_OK;
     const uint64_t n_groups = da->n_words32 / 16;
-    E2I_CUDA_TRY(cudaMalloc(&da->rank512, (n_groups + 1) * 8));
+    E2I_CUDA_TRY(dmalloc(ctx, &da->rank512, (n_groups + 1) * 8));
     da_group_popc_kernel<<<(unsigned)((n_groups + 255) / 256), 256, 0, ctx->stream>>>(da->words, n_groups, da->rank512);
     scan_u64_kernel<<<1, 1024, 0, ctx->stream>>>(da->rank512, n_groups);
     E2I_CUDA_TRY(cudaGetLastError());
@@ -424,17 +424,17 @@ extern "C" int e2i_call(e2i_ctx *ctx, const e2i_index *b1, const e2i_index *b2, 
     char *d_left = nullptr, *d_right = nullptr;
     int32_t *d_support = nullptr;
     uint8_t *d_reached = nullptr, *d_rlen = nullptr, *d_has = nullptr;
-    auto cleanup = [&] { cudaFree(dctl); cudaFree(rank_q); cudaFree(cand); cudaFree(d_left); cudaFree(d_right); cudaFree(d_support); cudaFree(d_reached); cudaFree(d_rlen); cudaFree(d_has); };
+    auto cleanup = [&] { dfree(ctx, dctl); dfree(ctx, rank_q); dfree(ctx, cand); dfree(ctx, d_left); dfree(ctx, d_right); dfree(ctx, d_support); dfree(ctx, d_reached); dfree(ctx, d_rlen); dfree(ctx, d_has); };
     auto fail = [&](int rc) { cleanup(); delete calls; return rc; };
 #define TRYF(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { set_error("CUDA error %s at %s:%d: %s", cudaGetErrorName(_e), __FILE__, __LINE__, cudaGetErrorString(_e)); return fail(E2I_ERR_CUDA); } } while (0)
-    TRYF(cudaMalloc(&dctl, sizeof(CallCtl)));
-    TRYF(cudaMalloc(&rank_q, 64 * 8));
+    TRYF(dmalloc(ctx, &dctl, sizeof(CallCtl)));
+    TRYF(dmalloc(ctx, &rank_q, 64 * 8));
     TRYF(cudaMemsetAsync(rank_q, 0, 64 * 8, s));
     TRYF(cudaEventRecord(ctx->ev[4], s));
 
     const uint64_t slab = 1ull << 28;   // positions per slab: bounds the candidate list
     const uint64_t cand_cap = slab / (2ull * a.mcov + 1) + kMaxCand + 2;
-    TRYF(cudaMalloc(&cand, cand_cap * sizeof(Candidate)));
+    TRYF(dmalloc(ctx, &cand, cand_cap * sizeof(Candidate)));
     a.cand = cand;
     a.cand_cap = cand_cap;
     CallCtl hctl;
@@ -449,10 +449,10 @@ extern "C" int e2i_call(e2i_ctx *ctx, const e2i_index *b1, const e2i_index *b2, 
         a.first_tile = sb / kScanTile;
         a.n_tiles = (uint32_t)((se - sb + kScanTile - 1) / kScanTile);
         if ((size_t)a.n_tiles > ctx->desc_words) {
-            cudaFree(ctx->desc);
+            dfree(ctx, ctx->desc);
             ctx->desc = nullptr;
             ctx->desc_words = (size_t)a.n_tiles + 1024;
-            TRYF(cudaMalloc(&ctx->desc, ctx->desc_words * 8));
+            TRYF(dmalloc(ctx, &ctx->desc, ctx->desc_words * 8));
             TRYF(cudaMemsetAsync(ctx->desc, 0, ctx->desc_words * 8, s));
             ctx->epoch = 0;
         }
@@ -476,12 +476,12 @@ extern "C" int e2i_call(e2i_ctx *ctx, const e2i_index *b1, const e2i_index *b2, 
         if (nc > cand_cap) { set_error("e2i_call: candidate list overflow (%llu > %llu)", (unsigned long long)nc, (unsigned long long)cand_cap); return fail(E2I_ERR_MEMORY); }
         st->candidates += nc;
         if (nc == 0) continue;
-        TRYF(cudaMalloc(&d_left, nc * 8 * (size_t)p->k_left));
-        TRYF(cudaMalloc(&d_right, nc * (size_t)p->k_right));
-        TRYF(cudaMalloc(&d_support, nc * 8 * sizeof(int32_t)));
-        TRYF(cudaMalloc(&d_reached, nc * 8));
-        TRYF(cudaMalloc(&d_rlen, nc));
-        TRYF(cudaMalloc(&d_has, nc));
+        TRYF(dmalloc(ctx, &d_left, nc * 8 * (size_t)p->k_left));
+        TRYF(dmalloc(ctx, &d_right, nc * (size_t)p->k_right));
+        TRYF(dmalloc(ctx, &d_support, nc * 8 * sizeof(int32_t)));
+        TRYF(dmalloc(ctx, &d_reached, nc * 8));
+        TRYF(dmalloc(ctx, &d_rlen, nc));
+        TRYF(dmalloc(ctx, &d_has, nc));
         TRYF(cudaMemsetAsync(d_support, 0, nc * 8 * sizeof(int32_t), s));
         consensus_kernel<<<(unsigned)((nc * 8 + 127) / 128), 128, 0, s>>>(a, nc, d_left, d_support, d_reached, rank_q);
         right_context_kernel<<<(unsigned)((nc + 127) / 128), 128, 0, s>>>(a, nc, d_right, d_rlen, d_has, rank_q);
@@ -498,7 +498,7 @@ extern "C" int e2i_call(e2i_ctx *ctx, const e2i_index *b1, const e2i_index *b2, 
         ctx->n_launch += 2;
         ctx->n_d2h += nc * (sizeof(Candidate) + 8 * (size_t)p->k_left + (size_t)p->k_right + 8 * sizeof(int32_t) + 8 + 2);
         TRYF(cudaStreamSynchronize(s));
-        cudaFree(d_left); cudaFree(d_right); cudaFree(d_support); cudaFree(d_reached); cudaFree(d_rlen); cudaFree(d_has);
+        dfree(ctx, d_left); dfree(ctx, d_right); dfree(ctx, d_support); dfree(ctx, d_reached); dfree(ctx, d_rlen); dfree(ctx, d_has);
         d_left = d_right = nullptr; d_support = nullptr; d_reached = d_rlen = d_has = nullptr;
         // compact on the host: keep clusters with a right context; pack reached contexts per individual
         const size_t kl = (size_t)p->k_left, kr = (size_t)p->k_right;

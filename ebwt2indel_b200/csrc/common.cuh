@@ -56,22 +56,24 @@ void set_error(const char *fmt, ...);
         if (_rc != E2I_OK) return _rc; \
     } while (0)
 
-// Size-class caching allocator for frontier frames (sizes change every sweep; cudaMalloc per
-// sweep would serialise the device).  Classes are {1, 1.25, 1.5, 1.75} x 2^k bytes.
+// Frontier frames: sizes change every sweep, so all device memory of the library comes from the
+// device's stream-ordered memory pool (cudaMallocAsync on the context's stream, release threshold
+// raised so that freed blocks stay cached): no cudaMalloc / cudaFree on the hot path.
+// DevicePool only enforces the frontier budget.
 class DevicePool {
   public:
-    ~DevicePool() { release(); }
+    void bind(cudaStream_t s) { stream_ = s; }
     int alloc(void **p, size_t bytes);
     void free(void *p);
     void release();
     size_t bytes_live() const { return live_; }
-    size_t bytes_reserved() const { return reserved_; }
     void set_limit(size_t bytes) { limit_ = bytes; }
 
   private:
-    struct Blk { void *p; size_t cls; bool used; };
+    struct Blk { void *p; size_t bytes; };
     std::vector<Blk> blks_;
-    size_t live_ = 0, reserved_ = 0, limit_ = 0;
+    cudaStream_t stream_ = nullptr;
+    size_t live_ = 0, limit_ = 0;
 };
 
 }  // namespace e2i
@@ -95,6 +97,13 @@ struct e2i_ctx {
 };
 
 namespace e2i {
+template <typename T>
+inline cudaError_t dmalloc(e2i_ctx *ctx, T **p, size_t bytes) {
+    return cudaMallocAsync(reinterpret_cast<void **>(p), bytes ? bytes : 16, ctx->stream);
+}
+inline void dfree(e2i_ctx *ctx, void *p) {
+    if (p) cudaFreeAsync(p, ctx->stream);
+}
 struct Accounting {            // adds what a call launched / copied to its e2i_stats on scope exit
     e2i_ctx *ctx; e2i_stats *st; uint64_t l0, h0, d0;
     Accounting(e2i_ctx *c, e2i_stats *s) : ctx(c), st(s), l0(c->n_launch), h0(c->n_h2d), d0(c->n_d2h) {}

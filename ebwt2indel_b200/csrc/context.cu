@@ -22,57 +22,32 @@ void set_error(const char *fmt, ...) {
 }
 
 // ---- DevicePool ------------------------------------------------------------------------------
-static size_t size_class(size_t bytes) {
-    if (bytes < 4096) bytes = 4096;
-    size_t p = 4096;
-    while (p * 2 <= bytes) p *= 2;         // p <= bytes < 2p
-    if (bytes == p) return p;
-    for (int q = 5; q <= 8; ++q) {          // 1.25p, 1.5p, 1.75p, 2p
-        const size_t c = p / 4 * q;
-        if (bytes <= c) return c;
-    }
-    return 2 * p;
-}
-
 int DevicePool::alloc(void **out, size_t bytes) {
-    const size_t cls = size_class(bytes);
-    for (Blk &b : blks_)
-        if (!b.used && b.cls == cls) { b.used = true; live_ += cls; *out = b.p; return E2I_OK; }
-    if (limit_ && reserved_ + cls > limit_) {
-        // drop cached blocks of other classes before giving up
-        for (size_t i = 0; i < blks_.size();) {
-            if (!blks_[i].used) { cudaFree(blks_[i].p); reserved_ -= blks_[i].cls; blks_[i] = blks_.back(); blks_.pop_back(); }
-            else ++i;
-        }
-        if (reserved_ + cls > limit_) return E2I_ERR_MEMORY;
-    }
+    if (bytes < 256) bytes = 256;
+    if (limit_ && live_ + bytes > limit_) return E2I_ERR_MEMORY;
     void *p = nullptr;
-    cudaError_t e = cudaMalloc(&p, cls);
-    if (e != cudaSuccess) {
-        cudaGetLastError();
-        for (size_t i = 0; i < blks_.size();) {
-            if (!blks_[i].used) { cudaFree(blks_[i].p); reserved_ -= blks_[i].cls; blks_[i] = blks_.back(); blks_.pop_back(); }
-            else ++i;
-        }
-        e = cudaMalloc(&p, cls);
-        if (e != cudaSuccess) { cudaGetLastError(); return E2I_ERR_MEMORY; }
-    }
-    blks_.push_back({p, cls, true});
-    reserved_ += cls;
-    live_ += cls;
+    if (cudaMallocAsync(&p, bytes, stream_) != cudaSuccess) { cudaGetLastError(); return E2I_ERR_MEMORY; }
+    blks_.push_back({p, bytes});
+    live_ += bytes;
     *out = p;
     return E2I_OK;
 }
 
 void DevicePool::free(void *p) {
-    for (Blk &b : blks_)
-        if (b.p == p) { b.used = false; live_ -= b.cls; return; }
+    for (size_t i = 0; i < blks_.size(); ++i)
+        if (blks_[i].p == p) {
+            cudaFreeAsync(p, stream_);
+            live_ -= blks_[i].bytes;
+            blks_[i] = blks_.back();
+            blks_.pop_back();
+            return;
+        }
 }
 
 void DevicePool::release() {
-    for (Blk &b : blks_) cudaFree(b.p);
+    for (Blk &b : blks_) cudaFreeAsync(b.p, stream_);
     blks_.clear();
-    live_ = reserved_ = 0;
+    live_ = 0;
 }
 
 }  // namespace e2i
@@ -124,6 +99,13 @@ extern "C" int e2i_create(int device, e2i_ctx **out) {
     ctx->sm_count = prop.multiProcessorCount;
     E2I_CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     E2I_CUDA_TRY(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    ctx->pool.bind(ctx->stream);
+    {   // keep freed blocks cached in the device's stream-ordered pool (released by e2i_destroy / e2i_trim)
+        cudaMemPool_t mp;
+        E2I_CUDA_TRY(cudaDeviceGetDefaultMemPool(&mp, device));
+        uint64_t thr = UINT64_MAX;
+        E2I_CUDA_TRY(cudaMemPoolSetAttribute(mp, cudaMemPoolAttrReleaseThreshold, &thr));
+    }
     for (auto &ev : ctx->ev) E2I_CUDA_TRY(cudaEventCreate(&ev));
     E2I_CUDA_TRY(cudaMalloc(&ctx->ctl, 4096));
     E2I_CUDA_TRY(cudaMallocHost(&ctx->ctl_host, 4096));
@@ -135,13 +117,25 @@ extern "C" void e2i_destroy(e2i_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     ctx->pool.release();
-    cudaFree(ctx->desc);
+    dfree(ctx, ctx->desc);
+    cudaStreamSynchronize(ctx->stream);
+    e2i_trim(ctx);
     cudaFree(ctx->ctl);
     cudaFreeHost(ctx->ctl_host);
     for (auto &ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     delete ctx;
+}
+
+extern "C" int e2i_trim(e2i_ctx *ctx) {
+    if (!ctx) { set_error("e2i_trim: null context"); return E2I_ERR_ARG; }
+    E2I_CUDA_TRY(cudaSetDevice(ctx->device));
+    E2I_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    cudaMemPool_t mp;
+    E2I_CUDA_TRY(cudaDeviceGetDefaultMemPool(&mp, ctx->device));
+    E2I_CUDA_TRY(cudaMemPoolTrimTo(mp, 0));
+    return E2I_OK;
 }
 
 extern "C" void *e2i_stream(const e2i_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
@@ -201,9 +195,11 @@ namespace {
 struct HostInputs {
     uint8_t *d1 = nullptr, *d2 = nullptr, *dd = nullptr;
 };
+struct HostInputsRef { HostInputs *in; e2i_ctx *ctx; };
 void free_inputs(void *arg) {
-    HostInputs *h = static_cast<HostInputs *>(arg);
-    cudaFree(h->d1); cudaFree(h->d2); cudaFree(h->dd);
+    HostInputsRef *r = static_cast<HostInputsRef *>(arg);
+    HostInputs *h = r->in;
+    dfree(r->ctx, h->d1); dfree(r->ctx, h->d2); dfree(r->ctx, h->dd);
     h->d1 = h->d2 = h->dd = nullptr;
 }
 }  // namespace
@@ -215,16 +211,17 @@ extern "C" int e2i_run(e2i_ctx *ctx, const uint8_t *host_bwt1, uint64_t n1, cons
     E2I_CUDA_TRY(cudaSetDevice(ctx->device));
     cudaStream_t s = ctx->stream;
     HostInputs in;
-    auto fail = [&](cudaError_t e) { set_error("e2i_run: %s", cudaGetErrorString(e)); free_inputs(&in); return E2I_ERR_CUDA; };
+    HostInputsRef ref{&in, ctx};
+    auto fail = [&](cudaError_t e) { set_error("e2i_run: %s", cudaGetErrorString(e)); free_inputs(&ref); return E2I_ERR_CUDA; };
     cudaError_t e = cudaEventRecord(ctx->ev[6], s);
-    if (e == cudaSuccess) e = cudaMalloc(&in.d1, n1 + 16);
+    if (e == cudaSuccess) e = dmalloc(ctx, &in.d1, n1 + 16);
     if (e == cudaSuccess) e = cudaMemcpyAsync(in.d1, host_bwt1, n1, cudaMemcpyHostToDevice, s);
     if (e == cudaSuccess && host_bwt2) {
-        e = cudaMalloc(&in.d2, n2 + 16);
+        e = dmalloc(ctx, &in.d2, n2 + 16);
         if (e == cudaSuccess) e = cudaMemcpyAsync(in.d2, host_bwt2, n2, cudaMemcpyHostToDevice, s);
     }
     if (e == cudaSuccess && host_da) {
-        e = cudaMalloc(&in.dd, n1 + 16);
+        e = dmalloc(ctx, &in.dd, n1 + 16);
         if (e == cudaSuccess) e = cudaMemcpyAsync(in.dd, host_da, n1, cudaMemcpyHostToDevice, s);
     }
     if (e == cudaSuccess) e = cudaEventRecord(ctx->ev[7], s);
@@ -234,8 +231,8 @@ extern "C" int e2i_run(e2i_ctx *ctx, const uint8_t *host_bwt1, uint64_t n1, cons
     cudaEventElapsedTime(&ms, ctx->ev[6], ctx->ev[7]);
     st->ms_h2d += ms;
     st->h2d_bytes += n1 + (host_bwt2 ? n2 : 0) + (host_da ? n1 : 0);
-    const int rc = run_on_device(ctx, in.d1, n1, in.d2, n2, in.dd, p, snp, snp_len, st, free_inputs, &in);
-    free_inputs(&in);
+    const int rc = run_on_device(ctx, in.d1, n1, in.d2, n2, in.dd, p, snp, snp_len, st, free_inputs, &ref);
+    free_inputs(&ref);
     return rc;
 }
 

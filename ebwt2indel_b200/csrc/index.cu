@@ -289,13 +289,13 @@ extern "C" int e2i_index_build_device(e2i_ctx *ctx, const uint8_t *dev_ascii, ui
     uint4 *tile_cnt = nullptr;
     ulonglong4 *tile_prefix = nullptr;
     unsigned long long *scal = nullptr;  // [0..3] totals, [4] bad position
-    auto fail = [&](int rc) { cudaFree(tile_cnt); cudaFree(tile_prefix); cudaFree(scal); e2i_index_free(ix); return rc; };
+    auto fail = [&](int rc) { dfree(ctx, tile_cnt); dfree(ctx, tile_prefix); dfree(ctx, scal); e2i_index_free(ix); return rc; };
 #define TRYF(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { set_error("CUDA error %s at %s:%d: %s", cudaGetErrorName(_e), __FILE__, __LINE__, cudaGetErrorString(_e)); return fail(E2I_ERR_CUDA); } } while (0)
-    TRYF(cudaMalloc(&ix->blocks, blk_bytes));
-    TRYF(cudaMalloc(&ix->super, ix->n_super * 32));
-    TRYF(cudaMalloc(&tile_cnt, n_tiles * sizeof(uint4)));
-    TRYF(cudaMalloc(&tile_prefix, n_tiles * sizeof(ulonglong4)));
-    TRYF(cudaMalloc(&scal, 5 * sizeof(unsigned long long)));
+    TRYF(dmalloc(ctx, &ix->blocks, blk_bytes));
+    TRYF(dmalloc(ctx, &ix->super, ix->n_super * 32));
+    TRYF(dmalloc(ctx, &tile_cnt, n_tiles * sizeof(uint4)));
+    TRYF(dmalloc(ctx, &tile_prefix, n_tiles * sizeof(ulonglong4)));
+    TRYF(dmalloc(ctx, &scal, 5 * sizeof(unsigned long long)));
     unsigned long long init[5] = {0, 0, 0, 0, ~0ull};
     TRYF(cudaMemcpyAsync(scal, init, sizeof init, cudaMemcpyHostToDevice, s));
     const int grid = (int)std::min<uint64_t>(n_tiles, (uint64_t)ctx->sm_count * 16);
@@ -311,7 +311,7 @@ extern "C" int e2i_index_build_device(e2i_ctx *ctx, const uint8_t *dev_ascii, ui
     TRYF(cudaMemcpyAsync(res, scal, sizeof res, cudaMemcpyDeviceToHost, s));
     TRYF(cudaStreamSynchronize(s));
 #undef TRYF
-    cudaFree(tile_cnt); cudaFree(tile_prefix); cudaFree(scal);
+    dfree(ctx, tile_cnt); dfree(ctx, tile_prefix); dfree(ctx, scal);
     tile_cnt = nullptr; tile_prefix = nullptr; scal = nullptr;
     if (res[4] != ~0ull) {
         if (bad_pos) *bad_pos = res[4];
@@ -334,19 +334,19 @@ extern "C" int e2i_index_build(e2i_ctx *ctx, const uint8_t *host_ascii, uint64_t
     if (!ctx || !out || (n && !host_ascii)) { set_error("e2i_index_build: null argument"); return E2I_ERR_ARG; }
     E2I_CUDA_TRY(cudaSetDevice(ctx->device));
     uint8_t *d = nullptr;
-    E2I_CUDA_TRY(cudaMalloc(&d, n + 16));
+    E2I_CUDA_TRY(dmalloc(ctx, &d, n + 16));
     cudaError_t e = cudaMemcpyAsync(d, host_ascii, n, cudaMemcpyHostToDevice, ctx->stream);
-    if (e != cudaSuccess) { cudaFree(d); set_error("H2D copy failed: %s", cudaGetErrorString(e)); return E2I_ERR_CUDA; }
+    if (e != cudaSuccess) { dfree(ctx, d); set_error("H2D copy failed: %s", cudaGetErrorString(e)); return E2I_ERR_CUDA; }
     ctx->n_h2d += n;
     const int rc = e2i_index_build_device(ctx, d, n, term, out, bad_pos);
-    cudaFree(d);
+    dfree(ctx, d);
     return rc;
 }
 
 extern "C" void e2i_index_free(e2i_index *ix) {
     if (!ix) return;
-    cudaFree(ix->blocks);
-    cudaFree(ix->super);
+    dfree(ix->ctx, ix->blocks);
+    dfree(ix->ctx, ix->super);
     delete ix;
 }
 
@@ -366,14 +366,14 @@ int batch_hook(e2i_ctx *ctx, const uint64_t *host_pos, uint64_t m, TOut *host_ou
     E2I_CUDA_TRY(cudaSetDevice(ctx->device));
     uint64_t *dpos = nullptr;
     TOut *dout = nullptr;
-    E2I_CUDA_TRY(cudaMalloc(&dpos, m * sizeof(uint64_t)));
-    cudaError_t e = cudaMalloc(&dout, m * out_per * sizeof(TOut));
+    E2I_CUDA_TRY(dmalloc(ctx, &dpos, m * sizeof(uint64_t)));
+    cudaError_t e = dmalloc(ctx, &dout, m * out_per * sizeof(TOut));
     if (e == cudaSuccess) e = cudaMemcpyAsync(dpos, host_pos, m * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) { launch(dpos, dout); e = cudaGetLastError(); }
     if (e == cudaSuccess) e = cudaMemcpyAsync(host_out, dout, m * out_per * sizeof(TOut), cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    cudaFree(dpos);
-    cudaFree(dout);
+    dfree(ctx, dpos);
+    dfree(ctx, dout);
     if (e != cudaSuccess) { set_error("batch hook failed: %s", cudaGetErrorString(e)); return E2I_ERR_CUDA; }
     return E2I_OK;
 }
@@ -426,7 +426,7 @@ extern "C" int e2i_da_load_device(e2i_ctx *ctx, const uint8_t *dev_ascii01, uint
     b->ctx = ctx;
     b->n = n;
     b->n_words32 = padded_words32(n);
-    cudaError_t e = cudaMalloc(&b->words, b->n_words32 * 4);
+    cudaError_t e = dmalloc(ctx, &b->words, b->n_words32 * 4);
     if (e == cudaSuccess) e = cudaMemsetAsync(b->words, 0, b->n_words32 * 4, ctx->stream);
     const uint64_t nw = (n + 31) / 32;
     if (e == cudaSuccess && nw) {
@@ -444,12 +444,12 @@ extern "C" int e2i_da_load(e2i_ctx *ctx, const uint8_t *host_ascii01, uint64_t n
     if (!ctx || !out || (n && !host_ascii01)) { set_error("e2i_da_load: null argument"); return E2I_ERR_ARG; }
     E2I_CUDA_TRY(cudaSetDevice(ctx->device));
     uint8_t *d = nullptr;
-    E2I_CUDA_TRY(cudaMalloc(&d, n + 16));
+    E2I_CUDA_TRY(dmalloc(ctx, &d, n + 16));
     cudaError_t e = cudaMemcpyAsync(d, host_ascii01, n, cudaMemcpyHostToDevice, ctx->stream);
-    if (e != cudaSuccess) { cudaFree(d); set_error("H2D copy failed: %s", cudaGetErrorString(e)); return E2I_ERR_CUDA; }
+    if (e != cudaSuccess) { dfree(ctx, d); set_error("H2D copy failed: %s", cudaGetErrorString(e)); return E2I_ERR_CUDA; }
     ctx->n_h2d += n;
     const int rc = e2i_da_load_device(ctx, d, n, out);
-    cudaFree(d);
+    dfree(ctx, d);
     return rc;
 }
 
@@ -473,7 +473,7 @@ extern "C" int e2i_bits_device(const e2i_bits *b, void **dev_words, uint64_t *wo
 
 extern "C" void e2i_bits_free(e2i_bits *b) {
     if (!b) return;
-    cudaFree(b->words);
-    cudaFree(b->rank512);
+    dfree(b->ctx, b->words);
+    dfree(b->ctx, b->rank512);
     delete b;
 }

@@ -441,10 +441,10 @@ static int run_frontier(e2i_ctx *ctx, Chunk root, int words, int tile_items, uin
         segs.total = acc;
         const uint32_t n_tiles = (acc + tile_items - 1) / tile_items;
         if ((size_t)n_tiles * 4 > ctx->desc_words) {
-            cudaFree(ctx->desc);
+            dfree(ctx, ctx->desc);
             ctx->desc = nullptr;
             ctx->desc_words = (size_t)n_tiles * 4 * 3 / 2 + 1024;
-            E2I_CUDA_TRY(cudaMalloc(&ctx->desc, ctx->desc_words * 8));
+            E2I_CUDA_TRY(dmalloc(ctx, &ctx->desc, ctx->desc_words * 8));
             E2I_CUDA_TRY(cudaMemsetAsync(ctx->desc, 0, ctx->desc_words * 8, ctx->stream));
             ctx->epoch = 0;
         }
@@ -501,10 +501,10 @@ extern "C" int e2i_navigate_shard(e2i_ctx *ctx, const e2i_index *b1, const e2i_i
     l->min_words32 = padded_words32(n);
     e2i_bits *da = nullptr;
     unsigned long long *stripes = nullptr;
-    auto fail = [&](int rc) { e2i_lcpbits_free(l); e2i_bits_free(da); cudaFree(stripes); ctx->pool.release(); return rc; };
+    auto fail = [&](int rc) { e2i_lcpbits_free(l); e2i_bits_free(da); dfree(ctx, stripes); ctx->pool.release(); return rc; };
 #define TRYF(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { set_error("CUDA error %s at %s:%d: %s", cudaGetErrorName(_e), __FILE__, __LINE__, cudaGetErrorString(_e)); return fail(E2I_ERR_CUDA); } } while (0)
-    TRYF(cudaMalloc(&l->thr, l->thr_words32 * 4));
-    TRYF(cudaMalloc(&l->minima, l->min_words32 * 4));
+    TRYF(dmalloc(ctx, &l->thr, l->thr_words32 * 4));
+    TRYF(dmalloc(ctx, &l->minima, l->min_words32 * 4));
     TRYF(cudaMemsetAsync(l->thr, 0, l->thr_words32 * 4, s));
     TRYF(cudaMemsetAsync(l->minima, 0, l->min_words32 * 4, s));
     if (two) {
@@ -512,15 +512,23 @@ extern "C" int e2i_navigate_shard(e2i_ctx *ctx, const e2i_index *b1, const e2i_i
         da->ctx = ctx;
         da->n = n;
         da->n_words32 = padded_words32(n);
-        TRYF(cudaMalloc(&da->words, da->n_words32 * 4));
+        TRYF(dmalloc(ctx, &da->words, da->n_words32 * 4));
         TRYF(cudaMemsetAsync(da->words, 0, da->n_words32 * 4, s));
     }
     const size_t stripe_bytes = (size_t)kStripes * C_NCOUNTERS * sizeof(unsigned long long);
-    TRYF(cudaMalloc(&stripes, stripe_bytes));
+    TRYF(dmalloc(ctx, &stripes, stripe_bytes));
 
     // frontier budget: what is free now, minus head-room, unless the caller set one
     size_t free_b = 0, total_b = 0;
     TRYF(cudaMemGetInfo(&free_b, &total_b));
+    {   // blocks cached by the stream-ordered pool are available to us as well
+        cudaMemPool_t mp;
+        uint64_t reserved = 0, used = 0;
+        TRYF(cudaDeviceGetDefaultMemPool(&mp, ctx->device));
+        TRYF(cudaMemPoolGetAttribute(mp, cudaMemPoolAttrReservedMemCurrent, &reserved));
+        TRYF(cudaMemPoolGetAttribute(mp, cudaMemPoolAttrUsedMemCurrent, &used));
+        if (reserved > used) free_b += reserved - used;
+    }
     uint64_t budget = ctx->frontier_budget ? ctx->frontier_budget : (uint64_t)(free_b * 0.85);
     ctx->pool.set_limit(budget);
 
@@ -669,7 +677,7 @@ extern "C" int e2i_navigate_shard(e2i_ctx *ctx, const e2i_index *b1, const e2i_i
     TRYF(cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]));
     st->ms_nodes += ms;
 #undef TRYF
-    cudaFree(stripes);
+    dfree(ctx, stripes);
     ctx->pool.release();
     *out = l;
     if (da_out) *da_out = da;
@@ -699,7 +707,7 @@ extern "C" int e2i_lcpbits_device(const e2i_lcpbits *l, void **dev_thr, uint64_t
 
 extern "C" void e2i_lcpbits_free(e2i_lcpbits *l) {
     if (!l) return;
-    cudaFree(l->thr);
-    cudaFree(l->minima);
+    dfree(l->ctx, l->thr);
+    dfree(l->ctx, l->minima);
     delete l;
 }

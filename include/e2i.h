@@ -111,6 +111,8 @@ void e2i_destroy(e2i_ctx *ctx);
 int e2i_set_frontier_budget(e2i_ctx *ctx, uint64_t bytes);
 /* Page-locked host staging buffers for the ASCII inputs (what the CLI reads the files into;
  * replaces the byte-at-a-time ifstream loops of dna_string.hpp:82-101 and ebwt2InDel.cpp:1503-1508). */
+/* Return the device memory cached by the library's stream-ordered pool to the driver. */
+int e2i_trim(e2i_ctx *ctx);
 /* The context's CUDA stream (a cudaStream_t), so that callers can record their own events on it. */
 void *e2i_stream(const e2i_ctx *ctx);
 int e2i_host_alloc(uint64_t bytes, void **out);
