@@ -394,7 +394,7 @@ def main():
                        "l2": "inputs larger than L2 (index + bitvectors > 126 MB)" if wl["n"] * 0.875 > 126e6 else
                              "index fits L2; every step rebuilds it from the ASCII input",
                        "parallelism": f"replicated index, {world} traversal shard(s), 1 OR all-reduce" if world > 1 else "single GPU"},
-            "phase_ms": {k: st[k] for k in ("ms_index", "ms_leaves", "ms_nodes", "ms_call")},
+            "phase_ms": {k: st[k] for k in ("ms_index", "ms_leaves", "ms_nodes", "ms_call", "ms_format", "ms_wall")},
             "wall_ms_per_step": 1e3 * wall_s / args.steps,
             "rank_queries_per_s": (st["rank_leaves"] + st["rank_nodes"] + st["rank_call"]) * args.steps / dev_s,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": e_st["h2d_bytes"],

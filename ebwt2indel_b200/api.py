@@ -39,16 +39,17 @@ _WORK_FIELDS = ("rank_leaves", "rank_nodes", "rank_call", "bit_updates", "candid
                 "levels_nodes", "max_frontier")
 _MS_FIELDS = ("ms_index", "ms_leaves", "ms_nodes", "ms_call", "ms_h2d", "ms_d2h")
 _IO_FIELDS = ("kernel_launches", "h2d_bytes", "d2h_bytes")
+_WALL_FIELDS = ("ms_format", "ms_wall")
 
 
 class Stats(C.Structure):
     _fields_ = ([(k, C.c_uint64) for k in _U64_FIELDS] + [("clust_sizes", C.c_uint64 * 201)] +
                 [(k, C.c_uint64) for k in _WORK_FIELDS] + [(k, C.c_double) for k in _MS_FIELDS] +
-                [(k, C.c_uint64) for k in _IO_FIELDS])
+                [(k, C.c_uint64) for k in _IO_FIELDS] + [(k, C.c_double) for k in _WALL_FIELDS])
 
     def as_dict(self):
         d = {k: int(getattr(self, k)) for k in _U64_FIELDS + _WORK_FIELDS + _IO_FIELDS}
-        d.update({k: float(getattr(self, k)) for k in _MS_FIELDS})
+        d.update({k: float(getattr(self, k)) for k in _MS_FIELDS + _WALL_FIELDS})
         d["clust_sizes"] = list(self.clust_sizes)
         return d
 

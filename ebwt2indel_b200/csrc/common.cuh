@@ -163,11 +163,9 @@ __device__ __forceinline__ uint32_t prefix_mask32(int off, int word) {
     return k >= 32 ? 0xffffffffu : (k <= 0 ? 0u : ((1u << k) - 1u));
 }
 
-// a2: parallel_rank (dna_string.hpp:140-152): #A,#C,#G,#T in [0, i), 0 <= i <= n.
-__device__ __forceinline__ void rank4(const DevIndex &ix, uint64_t i, uint64_t out[4]) {
-    const uint4 *p = ix.blocks + (i >> kBlockShift) * 4;
-    const uint4 cnt = __ldg(p), a = __ldg(p + 1), b = __ldg(p + 2), t = __ldg(p + 3);
-    const uint64_t *sb = ix.super + (i >> kSuperShift) * 4;
+// rank inside one 64-byte block (counter quad + three planes) already in registers
+__device__ __forceinline__ void rank4_block(const DevIndex &ix, const uint4 cnt, const uint4 a, const uint4 b, const uint4 t,
+                                            uint64_t i, uint64_t out[4]) {
     const int off = (int)(i & (kBlockSyms - 1));
     const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w}, tw[4] = {t.x, t.y, t.z, t.w};
     uint32_t nN = 0, nC = 0, nG = 0, nT = 0;
@@ -181,10 +179,40 @@ __device__ __forceinline__ void rank4(const DevIndex &ix, uint64_t i, uint64_t o
     }
     nC -= nT;
     nG -= nT;
-    out[0] = sb[0] + cnt.x + (nN - nC - nG - nT);
-    out[1] = sb[1] + cnt.y + nC;
-    out[2] = sb[2] + cnt.z + nG;
-    out[3] = sb[3] + cnt.w + nT;
+    out[0] = (uint64_t)cnt.x + (nN - nC - nG - nT);
+    out[1] = (uint64_t)cnt.y + nC;
+    out[2] = (uint64_t)cnt.z + nG;
+    out[3] = (uint64_t)cnt.w + nT;
+    if (ix.n >> kSuperShift) {                       // more than one superblock: lift to absolute counts
+        const uint64_t *sb = ix.super + (i >> kSuperShift) * 4;
+        out[0] += sb[0]; out[1] += sb[1]; out[2] += sb[2]; out[3] += sb[3];
+    }
+}
+
+// Index blocks staged in shared memory: block r of the window lives at stage[4r .. 4r+3] with its
+// four 16-byte quarters XOR-swizzled by (r >> 1) & 3, so that lanes reading the same quarter of
+// eight consecutive blocks hit eight different bank groups.
+__device__ __forceinline__ int stage_slot(uint32_t r, int q) { return (int)(r * 4 + (q ^ ((r >> 1) & 3))); }
+
+__device__ __forceinline__ void rank4_staged(const DevIndex &ix, const uint4 *stage, uint64_t blk_lo, uint32_t n_staged,
+                                             uint64_t i, uint64_t out[4]) {
+    const uint64_t rel = (i >> kBlockShift) - blk_lo;   // wraps to a huge value below the window
+    uint4 cnt, a, b, t;
+    if (rel < n_staged) {
+        const uint32_t r = (uint32_t)rel;
+        cnt = stage[stage_slot(r, 0)]; a = stage[stage_slot(r, 1)]; b = stage[stage_slot(r, 2)]; t = stage[stage_slot(r, 3)];
+    } else {
+        const uint4 *p = ix.blocks + (i >> kBlockShift) * 4;
+        cnt = __ldg(p); a = __ldg(p + 1); b = __ldg(p + 2); t = __ldg(p + 3);
+    }
+    rank4_block(ix, cnt, a, b, t, i, out);
+}
+
+// a2: parallel_rank (dna_string.hpp:140-152): #A,#C,#G,#T in [0, i), 0 <= i <= n.
+__device__ __forceinline__ void rank4(const DevIndex &ix, uint64_t i, uint64_t out[4]) {
+    const uint4 *p = ix.blocks + (i >> kBlockShift) * 4;
+    const uint4 cnt = __ldg(p), a = __ldg(p + 1), b = __ldg(p + 2), t = __ldg(p + 3);
+    rank4_block(ix, cnt, a, b, t, i, out);
 }
 
 // single-symbol count before block `blk` (absolute)

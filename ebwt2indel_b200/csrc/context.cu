@@ -5,6 +5,7 @@
 // (/root/reference/ebwt2InDel.cpp:1584-1674, 1344-1465, 1471-1579): load + index the eBWT(s),
 // traverse (phases 2-3), scan clusters and extract contexts (phase 4), format the .snp text.
 #include <algorithm>
+#include <chrono>
 
 #include "common.cuh"
 
@@ -159,6 +160,7 @@ static int run_on_device(e2i_ctx *ctx, const uint8_t *dev_bwt1, uint64_t n1, con
         e2i_index_free(b1); e2i_index_free(b2);
     };
     cudaStream_t s = ctx->stream;
+    const auto w0 = std::chrono::steady_clock::now();
     cudaEventRecord(ctx->ev[6], s);
     uint64_t bad = 0;
     Accounting *acct = new Accounting(ctx, st);
@@ -176,10 +178,14 @@ static int run_on_device(e2i_ctx *ctx, const uint8_t *dev_bwt1, uint64_t n1, con
     if (release_inputs) release_inputs(release_arg);   // the ASCII copies are dead once the index exists
     if (rc == E2I_OK) rc = e2i_navigate(ctx, b1, b2, p, &lcp, b2 ? &da_nav : nullptr, st);
     if (rc == E2I_OK) rc = e2i_call(ctx, b1, b2, b2 ? da_nav : da, lcp, p, 0, UINT64_MAX, &calls, st);
+    const auto w1 = std::chrono::steady_clock::now();
     if (rc == E2I_OK)
         rc = e2i_snp_format(calls->recs.data(), calls->left.data(), calls->right.data(), calls->recs.size(), p,
                             (b2 || da) ? 1 : 0, 1, snp, snp_len, st);
+    const auto w2 = std::chrono::steady_clock::now();
     cleanup();
+    st->ms_format += std::chrono::duration<double, std::milli>(w2 - w1).count();
+    st->ms_wall += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - w0).count();
     return rc;
 }
 

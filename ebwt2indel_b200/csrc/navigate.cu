@@ -16,10 +16,11 @@
 // single-pass decoupled look-back (lookback.cuh).  When a sweep would not fit the frontier budget
 // it is cut into position-contiguous chunks that are finished depth-first (bounded memory).
 //
-// Work mapping.  Internal nodes: 8 lanes per node (16 per node pair in mode -2): lane j < 6 owns
-// boundary j (first_TERM .. last), fetches its 64-byte block and computes the four ranks; child c
-// is valid iff >= 2 of the 5 boundary gaps are non-empty for c (number_of_children >= 2), found
-// with one ballot per symbol.  Leaves: one thread per leaf (two ranks per BWT).
+// Work mapping.  One thread per internal node (per node pair in mode -2): it walks the node's <= 6
+// distinct boundaries (neighbouring boundaries of a small node share one 64-byte index block, so
+// all but the first fetch hit L1), turns the rank differences into the five sub-interval sizes of
+// each child cW, keeps the children with >= 2 non-empty sub-intervals (number_of_children >= 2) and
+// appends them, in order, as 32-byte compact records.  Leaves: one thread per leaf (two ranks per BWT).
 #include <algorithm>
 #include <memory>
 
@@ -29,7 +30,7 @@
 namespace e2i {
 
 constexpr int kNavThreads = 256;
-constexpr int kNodeIter = 4;            // node groups per lane-group per tile
+constexpr int kStageBlocks = 512;       // index blocks staged in shared memory per CTA (32 KB)
 constexpr int kStripes = 128;           // striped statistics counters (avoid single-address atomics)
 enum { C_LCP = 0, C_NMIN, C_RANK, C_BITUPD, C_DA, C_NCOUNTERS = 8 };
 
@@ -87,97 +88,228 @@ __device__ __forceinline__ void fill_bits(uint32_t *words, uint64_t lo, uint64_t
 }
 
 // ---------------------------------------------------------------------------------------------
-// Phase 3 sweep: internal nodes.  GRP = 8 lanes per node (one BWT) or 16 per node pair (two BWTs).
-// Record = GRP u64 words: [0..5] boundaries in BWT 1, [6] depth, [8..13] boundaries in BWT 2.
+// Phase 3 sweep: internal nodes.  One THREAD per node (per node pair with two BWTs).
+//
+// Compact node record, 32 bytes = 2 x uint4 (a pair is two records, BWT 1 then BWT 2):
+//   lo = { s0, s1, s2, s3 }                        low 32 bits of the sizes of the TERM,A,C,G children
+//   hi = { s4, base, hi8(s0..s3), hi8(s4) | hi8(base) << 8 | depth << 16 }
+// i.e. 40-bit first position, five 40-bit child sizes (first_A = base + s0, ... last = base + sum)
+// and a 16-bit saturating depth (only depth >= K and depth >= k_right are ever tested,
+// include.hpp:836-837).  Replaces the 56-byte sa_node (include.hpp:394-413).
 // ---------------------------------------------------------------------------------------------
+constexpr uint32_t kDepthMax = 0xffffu;
+
+__device__ __forceinline__ void unpack_node(const uint4 lo, const uint4 hi, uint64_t &base, uint64_t (&s)[5], uint32_t &depth) {
+    s[0] = lo.x | ((uint64_t)(hi.z & 0xffu) << 32);
+    s[1] = lo.y | ((uint64_t)((hi.z >> 8) & 0xffu) << 32);
+    s[2] = lo.z | ((uint64_t)((hi.z >> 16) & 0xffu) << 32);
+    s[3] = lo.w | ((uint64_t)(hi.z >> 24) << 32);
+    s[4] = hi.x | ((uint64_t)(hi.w & 0xffu) << 32);
+    base = hi.y | ((uint64_t)((hi.w >> 8) & 0xffu) << 32);
+    depth = hi.w >> 16;
+}
+
+// children of one BWT side, kept in registers between the rank phase and the ordered append
+struct ChildSide {
+    uint64_t base[4];       // F[c] + rank_c(first)
+    uint32_t lo[5][4];      // low 32 bits of the five sub-interval sizes of child c
+    uint32_t hz[4];         // high bytes of sizes 0..3 of child c
+    uint32_t h4;            // high byte of size 4, one byte per c
+};
+
+__device__ __forceinline__ void store_child(uint4 *dst, const ChildSide &k, int c, uint32_t depth1) {
+    dst[0] = make_uint4(k.lo[0][c], k.lo[1][c], k.lo[2][c], k.lo[3][c]);
+    dst[1] = make_uint4(k.lo[4][c], (uint32_t)k.base[c], k.hz[c],
+                        ((k.h4 >> (8 * c)) & 0xffu) | ((uint32_t)(k.base[c] >> 32) << 8) | (depth1 << 16));
+}
+
+// one atomicOr per touched word instead of one per bit
+struct WordAcc {
+    uint32_t *words;
+    uint64_t w;
+    uint32_t m;
+    __device__ __forceinline__ void add(uint64_t word, uint32_t mask) {
+        if (word != w) { flush(); w = word; m = mask; } else m |= mask;
+    }
+    __device__ __forceinline__ void flush() { if (m) atomicOr(words + w, m); m = 0; }
+};
+
 template <bool TWO>
 __global__ void __launch_bounds__(kNavThreads)
 expand_nodes_kernel(const NavArgs a, const Segs in) {
-    constexpr int GRP = TWO ? 16 : 8;
-    constexpr int IPW = 32 / GRP;                      // items per warp per iteration
-    constexpr int IPI = IPW * (kNavThreads / 32);      // items per CTA per iteration
-    constexpr int TILE = IPI * kNodeIter;
+    constexpr int WORDS = TWO ? 8 : 4;                 // u64 words per record
     __shared__ uint32_t s_tile;
-    __shared__ uint32_t s_cnt[kNodeIter * 8];          // packed 4 x 8-bit child counts per (iter, warp)
-    __shared__ uint32_t s_excl[kNodeIter * 8];
+    __shared__ uint32_t s_wpk[kNavThreads / 32];       // per-warp child counts, 4 x 8 bit
+    __shared__ uint32_t s_wlo[kNavThreads / 32], s_whi[kNavThreads / 32];   // exclusive prefix, 2 x 16 bit each
     __shared__ unsigned long long s_base[4];
     __shared__ unsigned long long s_stat[C_NCOUNTERS];
+    __shared__ unsigned long long s_rng[4];            // first / last index block touched by the tile, per BWT
+    constexpr int STAGE = TWO ? kStageBlocks / 2 : kStageBlocks;   // blocks staged per BWT
+    __shared__ uint4 s_stage[kStageBlocks * 4];
 
     if (threadIdx.x == 0) s_tile = atomicAdd(&a.ctl->ticket, 1u);
     if (threadIdx.x < C_NCOUNTERS) s_stat[threadIdx.x] = 0;
     __syncthreads();
     const uint32_t tile = s_tile;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int l = lane % GRP, j = l & 7, half = l >> 3, item = lane / GRP, base = item * GRP;
-    const DevIndex &ix = (TWO && half) ? a.ix2 : a.ix1;
+    const uint32_t g = tile * kNavThreads + threadIdx.x;
+    const bool active = g < in.total;
 
-    uint64_t r[kNodeIter][4];
-    uint64_t depth1[kNodeIter];
-    uint32_t valid[kNodeIter];
+    uint64_t base1 = 0, s1[5] = {0, 0, 0, 0, 0}, base2 = 0, s2[5] = {0, 0, 0, 0, 0};
+    uint32_t depth = 0;
+    if (active) {
+        const uint4 *rec = reinterpret_cast<const uint4 *>(seg_record(in, g, WORDS));
+        unpack_node(__ldg(rec), __ldg(rec + 1), base1, s1, depth);
+        if (TWO) { uint32_t d2; unpack_node(__ldg(rec + 2), __ldg(rec + 3), base2, s2, d2); }
+    }
     uint32_t st_lcp = 0, st_min = 0, st_rank = 0, st_upd = 0, st_da = 0;
 
-#pragma unroll
-    for (int it = 0; it < kNodeIter; ++it) {
-        const uint32_t g = tile * TILE + it * IPI + warp * IPW + item;
-        const bool active = g < in.total;
-        uint64_t w = 0;
-        if (active) w = seg_record(in, g, GRP)[l];
-        const bool isb = active && j < 6;
-        uint64_t rr[4] = {0, 0, 0, 0};
-        if (isb) rank4(ix, w, rr);
-        const uint64_t wprev = shfl_up_u64(w, 1, 8);
-        if (isb && (j == 0 || w != wprev)) st_rank++;   // distinct boundaries (dna_bwt.hpp:332-347)
-        // merged coordinates (merge_nodes, include.hpp:476-490)
-        const uint64_t mb = TWO ? w + __shfl_xor_sync(0xffffffffu, w, 8) : w;
-        const uint64_t mprev = shfl_up_u64(mb, 1, 8);
-        const uint64_t last = shfl_u64(mb, base + 5);
-        const uint64_t depth = shfl_u64(w, base + 6);
-        depth1[it] = depth + 1;
-        if (TWO) {
-            // find_leaves (ebwt2InDel.cpp:474-527): children of summed size exactly 1
-            const uint64_t wnext = shfl_down_u64(w, 1, 8);
-            const uint64_t sz = (j < 5) ? wnext - w : 0;
-            const uint64_t sz_other = __shfl_xor_sync(0xffffffffu, sz, 8);
-            if (active && a.write && half == 0 && j < 5 && sz + sz_other == 1) {
-                st_da++;
-                if (sz_other == 1) atomicOr(a.da + (mb >> 5), 1u << (mb & 31));
-            }
+    // ---- stage the index blocks of the tile in shared memory ----
+    // All nodes of a sweep have the same depth, so their intervals are disjoint and the frontier is
+    // sorted: the tile touches the block range [block(first node), block(end of last node)].  When
+    // that range is dense enough it is copied once, coalesced, and the up to 6 rank queries per node
+    // read shared memory; boundaries outside the window fall back to global loads.
+    {
+        const uint32_t last_active = min((uint32_t)kNavThreads, in.total - tile * kNavThreads) - 1;
+        if (threadIdx.x == 0) { s_rng[0] = base1 >> kBlockShift; if (TWO) s_rng[2] = base2 >> kBlockShift; }
+        if (threadIdx.x == last_active) {
+            s_rng[1] = (base1 + s1[0] + s1[1] + s1[2] + s1[3] + s1[4]) >> kBlockShift;
+            if (TWO) s_rng[3] = (base2 + s2[0] + s2[1] + s2[2] + s2[3] + s2[4]) >> kBlockShift;
         }
-        if (active && a.write && half == 0) {
-            // update_lcp_threshold (include.hpp:826-860): border j written iff child j-1 is non-empty and border != last
-            if (j >= 1 && j <= 4 && mb > mprev && mb != last) {
-                st_lcp++;
-                const uint32_t bits = (depth >= a.K ? 1u : 0u) | (depth >= a.k_right ? 2u : 0u);
-                if (bits) { atomicOr(a.thr + (mb >> 4), bits << ((mb & 15) * 2)); st_upd++; }
-            }
-            // update_lcp_minima (ebwt2InDel.cpp:357-391): children A, C, G of size >= 2
-            if (j >= 2 && j <= 4 && mb - mprev >= 2 && mb < last - 1) {
-                st_min++;
-                st_upd++;
-                atomicOr(a.minima + (mb >> 5), 1u << (mb & 31));
-            }
-        }
-        // child c is right-maximal iff >= 2 of its 5 gaps are non-empty (number_of_children, include.hpp:760-792)
-        uint32_t vm = 0;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            const uint64_t nxt = shfl_down_u64(rr[c], 1, 8);
-            int nz = (j < 5) && (nxt != rr[c]);
-            if (TWO) nz |= __shfl_xor_sync(0xffffffffu, nz, 8);
-            const uint32_t bal = __ballot_sync(0xffffffffu, nz);
-            if (active && __popc((bal >> base) & 0x1fu) >= 2) vm |= 1u << c;
-            r[it][c] = rr[c];
-        }
-        valid[it] = vm;
-        uint32_t packed = 0;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            const uint32_t vb = __ballot_sync(0xffffffffu, ((vm >> c) & 1u) && l == 0);
-            packed |= (uint32_t)__popc(vb) << (8 * c);
-        }
-        if (lane == 0) s_cnt[it * 8 + warp] = packed;
     }
-    // block-level statistics
+    __syncthreads();
+    const uint64_t lo1 = s_rng[0], lo2 = TWO ? s_rng[2] : 0;
+    uint32_t nst1 = 0, nst2 = 0;
+    {
+        const uint64_t span1 = s_rng[1] >= lo1 ? s_rng[1] - lo1 + 1 : 0;
+        if (span1 <= 2ull * STAGE) nst1 = (uint32_t)min((unsigned long long)span1, (unsigned long long)STAGE);
+        constexpr int ITER = STAGE * 4 / kNavThreads;      // all loads of a thread are issued before the first store
+        uint4 v[ITER];
+#pragma unroll
+        for (int it = 0; it < ITER; ++it) {
+            const uint32_t k = threadIdx.x + it * kNavThreads;
+            if (k < nst1 * 4) v[it] = __ldg(a.ix1.blocks + lo1 * 4 + k);
+        }
+#pragma unroll
+        for (int it = 0; it < ITER; ++it) {
+            const uint32_t k = threadIdx.x + it * kNavThreads;
+            if (k < nst1 * 4) s_stage[stage_slot(k >> 2, k & 3)] = v[it];
+        }
+        if (TWO) {
+            const uint64_t end2 = s_rng[3] + 1;
+            const uint64_t span2 = end2 > lo2 ? end2 - lo2 : 0;
+            if (span2 <= 2ull * STAGE) nst2 = (uint32_t)min((unsigned long long)span2, (unsigned long long)STAGE);
+#pragma unroll
+            for (int it = 0; it < ITER; ++it) {
+                const uint32_t k = threadIdx.x + it * kNavThreads;
+                if (k < nst2 * 4) v[it] = __ldg(a.ix2.blocks + lo2 * 4 + k);
+            }
+#pragma unroll
+            for (int it = 0; it < ITER; ++it) {
+                const uint32_t k = threadIdx.x + it * kNavThreads;
+                if (k < nst2 * 4) s_stage[STAGE * 4 + stage_slot(k >> 2, k & 3)] = v[it];
+            }
+        }
+    }
+    __syncthreads();
+    const uint4 *stage1 = s_stage, *stage2 = s_stage + STAGE * 4;
+
+    // ---- bit updates on the merged node (merge_nodes, include.hpp:476-490) ----
+    if (active && a.write) {
+        const uint64_t mbase = base1 + base2;
+        uint64_t ms[5], last = mbase;
+#pragma unroll
+        for (int j = 0; j < 5; ++j) { ms[j] = s1[j] + s2[j]; last += ms[j]; }
+        const uint32_t bits = (depth >= a.K ? 1u : 0u) | (depth >= a.k_right ? 2u : 0u);
+        WordAcc thr{a.thr, ~0ull, 0u}, mn{a.minima, ~0ull, 0u};
+        uint64_t mb = mbase;
+#pragma unroll
+        for (int j = 0; j < 5; ++j) {
+            if (TWO) {
+                // find_leaves (ebwt2InDel.cpp:474-527): children of summed size exactly 1
+                if (ms[j] == 1) {
+                    st_da++;
+                    if (s2[j] == 1) atomicOr(a.da + (mb >> 5), 1u << (mb & 31));
+                }
+            }
+            mb += ms[j];                           // border after child j = first position of child j+1
+            if (j < 4 && mb != last) {
+                // update_lcp_threshold (include.hpp:826-860): border written iff the child before it is non-empty
+                if (ms[j] > 0) {
+                    st_lcp++;
+                    if (bits) { thr.add(mb >> 4, bits << ((mb & 15) * 2)); st_upd++; }
+                }
+                // update_lcp_minima (ebwt2InDel.cpp:357-391): after children A, C, G of size >= 2
+                if (j >= 1 && ms[j] >= 2 && mb < last - 1) {
+                    st_min++;
+                    st_upd++;
+                    mn.add(mb >> 5, 1u << (mb & 31));
+                }
+            }
+        }
+        thr.flush();
+        mn.flush();
+    }
+
+    // ---- LF(sa_node) (dna_bwt.hpp:323-356): ranks at the distinct boundaries, as sub-interval counts ----
+    ChildSide k1, k2;
+    uint32_t nzp = 0;                                  // per symbol: number of non-empty gaps (union of both BWTs), 4 x 8 bit
+    k1.h4 = 0; k2.h4 = 0;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) { k1.hz[c] = 0; k2.hz[c] = 0; k1.base[c] = 0; k2.base[c] = 0; }
+    if (active) {
+        uint64_t prev1[4], cur1[4], prev2[4] = {0, 0, 0, 0}, cur2[4] = {0, 0, 0, 0};
+        rank4_staged(a.ix1, stage1, lo1, nst1, base1, prev1);
+        st_rank++;
+        if (TWO) { rank4_staged(a.ix2, stage2, lo2, nst2, base2, prev2); st_rank++; }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { k1.base[c] = a.ix1.F[c] + prev1[c]; if (TWO) k2.base[c] = a.ix2.F[c] + prev2[c]; }
+        uint64_t b1 = base1, b2 = base2;
+#pragma unroll
+        for (int j = 0; j < 5; ++j) {
+            b1 += s1[j];
+            if (s1[j]) { rank4_staged(a.ix1, stage1, lo1, nst1, b1, cur1); st_rank++; }
+            else { cur1[0] = prev1[0]; cur1[1] = prev1[1]; cur1[2] = prev1[2]; cur1[3] = prev1[3]; }
+            if (TWO) {
+                b2 += s2[j];
+                if (s2[j]) { rank4_staged(a.ix2, stage2, lo2, nst2, b2, cur2); st_rank++; }
+                else { cur2[0] = prev2[0]; cur2[1] = prev2[1]; cur2[2] = prev2[2]; cur2[3] = prev2[3]; }
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const uint64_t d1 = cur1[c] - prev1[c];
+                uint64_t any = d1;
+                k1.lo[j][c] = (uint32_t)d1;
+                if (j < 4) k1.hz[c] |= (uint32_t)(d1 >> 32) << (8 * j); else k1.h4 |= (uint32_t)(d1 >> 32) << (8 * c);
+                prev1[c] = cur1[c];
+                if (TWO) {
+                    const uint64_t d2 = cur2[c] - prev2[c];
+                    any |= d2;
+                    k2.lo[j][c] = (uint32_t)d2;
+                    if (j < 4) k2.hz[c] |= (uint32_t)(d2 >> 32) << (8 * j); else k2.h4 |= (uint32_t)(d2 >> 32) << (8 * c);
+                    prev2[c] = cur2[c];
+                }
+                nzp += (any != 0 ? 1u : 0u) << (8 * c);
+            }
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 5; ++j)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) { k1.lo[j][c] = 0; k2.lo[j][c] = 0; }
+    }
+
+    // ---- child c is right-maximal iff >= 2 of its 5 gaps are non-empty (number_of_children, include.hpp:760-792) ----
+    uint32_t vm = 0, packed = 0, before[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const bool v = ((nzp >> (8 * c)) & 0xffu) >= 2u;
+        const uint32_t bal = __ballot_sync(0xffffffffu, v);
+        before[c] = __popc(bal & ((1u << lane) - 1u));
+        packed |= (uint32_t)__popc(bal) << (8 * c);     // <= 32 per warp and symbol
+        if (v) vm |= 1u << c;
+    }
+    if (lane == 0) s_wpk[warp] = packed;
     st_lcp = __reduce_add_sync(0xffffffffu, st_lcp);
     st_min = __reduce_add_sync(0xffffffffu, st_min);
     st_rank = __reduce_add_sync(0xffffffffu, st_rank);
@@ -192,20 +324,21 @@ expand_nodes_kernel(const NavArgs a, const Segs in) {
     }
     __syncthreads();
     if (warp == 0) {
-        // exclusive scan of the packed (iter, warp) counts, then the cross-tile look-back
-        const uint32_t mine = s_cnt[lane];
-        uint32_t incl = mine;
+        // exclusive scan of the 8 per-warp counts (16-bit fields: up to 256 per symbol and tile), then the look-back
+        const uint32_t mine = lane < kNavThreads / 32 ? s_wpk[lane] : 0u;
+        uint32_t lo = (mine & 0xffu) | (((mine >> 8) & 0xffu) << 16);          // A, C
+        uint32_t hi = ((mine >> 16) & 0xffu) | ((mine >> 24) << 16);           // G, T
+        const uint32_t mlo = lo, mhi = hi;
 #pragma unroll
-        for (int s = 1; s < 32; s <<= 1) {
-            const uint32_t y = __shfl_up_sync(0xffffffffu, incl, s);
-            if (lane >= s) incl += y;
+        for (int s = 1; s < 8; s <<= 1) {
+            const uint32_t ylo = __shfl_up_sync(0xffffffffu, lo, s), yhi = __shfl_up_sync(0xffffffffu, hi, s);
+            if (lane >= s) { lo += ylo; hi += yhi; }
         }
-        s_excl[lane] = incl - mine;
-        const uint32_t tot = __shfl_sync(0xffffffffu, incl, 31);
-        unsigned long long agg[4], excl[4];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) agg[c] = (tot >> (8 * c)) & 0xffu;
-        lookback_exclusive<4>(a.desc, a.epoch, tile, agg, excl);
+        if (lane < kNavThreads / 32) { s_wlo[lane] = lo - mlo; s_whi[lane] = hi - mhi; }
+        const uint32_t tlo = __shfl_sync(0xffffffffu, lo, 7), thi = __shfl_sync(0xffffffffu, hi, 7);
+        const uint32_t agg[4] = {tlo & 0xffffu, tlo >> 16, thi & 0xffffu, thi >> 16};
+        unsigned long long excl[4];
+        lookback4(a.desc, a.epoch, tile, agg, excl);
         if (lane < 4) {
             unsigned long long e = 0, g2 = 0;
 #pragma unroll
@@ -216,20 +349,18 @@ expand_nodes_kernel(const NavArgs a, const Segs in) {
         if (lane < C_NCOUNTERS && a.write) stripe_add(a.stripes, tile, lane, s_stat[lane]);
     }
     __syncthreads();
-    // ordered append of the surviving children
-#pragma unroll
-    for (int it = 0; it < kNodeIter; ++it) {
-        const uint32_t ex = s_excl[it * 8 + warp];
+    // ---- ordered append of the surviving children ----
+    if (vm) {
+        const uint32_t exlo = s_wlo[warp], exhi = s_whi[warp];
+        const uint32_t exw[4] = {exlo & 0xffffu, exlo >> 16, exhi & 0xffffu, exhi >> 16};
+        const uint32_t depth1 = depth >= kDepthMax ? kDepthMax : depth + 1;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-            const bool v = (valid[it] >> c) & 1u;
-            const uint32_t vb = __ballot_sync(0xffffffffu, v && l == 0);
-            if (v) {
-                const unsigned long long slot = s_base[c] + ((ex >> (8 * c)) & 0xffu) + __popc(vb & ((1u << base) - 1u));
-                uint64_t word = 0;
-                if (j < 6) word = ix.F[c] + r[it][c];
-                else if (l == 6) word = depth1[it];
-                a.out[c][slot * GRP + l] = word;
+            if ((vm >> c) & 1u) {
+                const unsigned long long slot = s_base[c] + exw[c] + before[c];
+                uint4 *dst = reinterpret_cast<uint4 *>(a.out[c] + slot * WORDS);
+                store_child(dst, k1, c, depth1);
+                if (TWO) store_child(dst + 2, k2, c, depth1);
             }
         }
     }
@@ -367,6 +498,27 @@ expand_leaves_kernel(const NavArgs a, const Segs in) {
 // ---------------------------------------------------------------------------------------------
 // Host-side frontier driver
 // ---------------------------------------------------------------------------------------------
+// host-side view of the compact node record (see unpack_node)
+static void pack_node_host(uint64_t *rec, uint64_t base, const uint64_t F[4], uint64_t n, uint32_t depth) {
+    const uint64_t s[5] = {F[0] - base, F[1] - F[0], F[2] - F[1], F[3] - F[2], n - F[3]};
+    uint32_t w[8];
+    for (int j = 0; j < 4; ++j) w[j] = (uint32_t)s[j];
+    w[4] = (uint32_t)s[4];
+    w[5] = (uint32_t)base;
+    w[6] = (uint32_t)((s[0] >> 32) & 0xff) | (uint32_t)((s[1] >> 32) & 0xff) << 8 | (uint32_t)((s[2] >> 32) & 0xff) << 16 |
+           (uint32_t)((s[3] >> 32) & 0xff) << 24;
+    w[7] = (uint32_t)((s[4] >> 32) & 0xff) | (uint32_t)((base >> 32) & 0xff) << 8 | depth << 16;
+    std::memcpy(rec, w, sizeof w);
+}
+
+static uint64_t node_size_host(const uint64_t *rec) {
+    uint32_t w[8];
+    std::memcpy(w, rec, sizeof w);
+    uint64_t t = (uint64_t)w[0] + w[1] + w[2] + w[3] + w[4];
+    t += ((uint64_t)(w[6] & 0xff) + ((w[6] >> 8) & 0xff) + ((w[6] >> 16) & 0xff) + (w[6] >> 24) + (w[7] & 0xff)) << 32;
+    return t;
+}
+
 struct Frame {
     DevicePool *pool;
     void *p;
@@ -440,10 +592,10 @@ static int run_frontier(e2i_ctx *ctx, Chunk root, int words, int tile_items, uin
         }
         segs.total = acc;
         const uint32_t n_tiles = (acc + tile_items - 1) / tile_items;
-        if ((size_t)n_tiles * 4 > ctx->desc_words) {
+        if ((size_t)n_tiles * kLb4Words > ctx->desc_words) {
             dfree(ctx, ctx->desc);
             ctx->desc = nullptr;
-            ctx->desc_words = (size_t)n_tiles * 4 * 3 / 2 + 1024;
+            ctx->desc_words = (size_t)n_tiles * kLb4Words * 3 / 2 + 1024;
             E2I_CUDA_TRY(dmalloc(ctx, &ctx->desc, ctx->desc_words * 8));
             E2I_CUDA_TRY(cudaMemsetAsync(ctx->desc, 0, ctx->desc_words * 8, ctx->stream));
             ctx->epoch = 0;
@@ -487,7 +639,8 @@ extern "C" int e2i_navigate_shard(e2i_ctx *ctx, const e2i_index *b1, const e2i_i
     if (!ctx || !b1 || !p || !out || !st) { set_error("e2i_navigate: null argument"); return E2I_ERR_ARG; }
     if (b2 && !da_out) { set_error("e2i_navigate: da_out is required with two BWTs"); return E2I_ERR_ARG; }
     if (n_shards < 1 || shard < 0 || shard >= n_shards) { set_error("e2i_navigate: bad shard %d/%d", shard, n_shards); return E2I_ERR_ARG; }
-    if (p->K < 1 || p->k_right < 1) { set_error("e2i_navigate: K and k_right must be >= 1"); return E2I_ERR_ARG; }
+    if (p->K < 1 || p->k_right < 1 || p->K > 65535 || p->k_right > 65535) { set_error("e2i_navigate: K and k_right must be in [1, 65535]"); return E2I_ERR_ARG; }
+    if ((b1->n >> 40) || (b2 && (b2->n >> 40))) { set_error("e2i_navigate: BWT longer than 2^40 symbols"); return E2I_ERR_ARG; }
     E2I_CUDA_TRY(cudaSetDevice(ctx->device));
     Accounting acct(ctx, st);
     cudaStream_t s = ctx->stream;
@@ -558,8 +711,8 @@ extern "C" int e2i_navigate_shard(e2i_ctx *ctx, const e2i_index *b1, const e2i_i
     const uint64_t kDealItems = 4096ull * (uint64_t)n_shards;
 
     auto run_pass = [&](bool leaves, SweepStats &ss) -> int {
-        const int words = leaves ? (two ? 8 : 4) : (two ? 16 : 8);
-        const int tile_items = leaves ? kNavThreads : (two ? 2 : 4) * (kNavThreads / 32) * kNodeIter;
+        const int words = two ? 8 : 4;                  // u64 words per record (leaf: 32 B, compact node: 32 B)
+        const int tile_items = kNavThreads;
         const uint64_t max_chunk = std::max<uint64_t>(65536, budget / ((uint64_t)words * 8 * 4 * 4));
         // root record
         void *rootmem = nullptr;
@@ -568,9 +721,9 @@ extern "C" int e2i_navigate_shard(e2i_ctx *ctx, const e2i_index *b1, const e2i_i
         if (leaves) {                                   // first_leaf (dna_bwt.hpp:313-317)
             rec[0] = 0; rec[1] = b1->F[0]; rec[2] = 0;
             if (two) { rec[4] = 0; rec[5] = b2->F[0]; }
-        } else {                                        // root (dna_bwt.hpp:296-308)
-            rec[0] = 0; rec[1] = b1->F[0]; rec[2] = b1->F[1]; rec[3] = b1->F[2]; rec[4] = b1->F[3]; rec[5] = b1->n; rec[6] = 0;
-            if (two) { rec[8] = 0; rec[9] = b2->F[0]; rec[10] = b2->F[1]; rec[11] = b2->F[2]; rec[12] = b2->F[3]; rec[13] = b2->n; }
+        } else {                                        // root (dna_bwt.hpp:296-308) as a compact record
+            pack_node_host(rec, 0, b1->F, b1->n, 0);
+            if (two) pack_node_host(rec + 4, 0, b2->F, b2->n, 0);
         }
         E2I_CUDA_TRY(cudaMemcpyAsync(rootmem, rec, (size_t)words * 8, cudaMemcpyHostToDevice, s));
         Chunk root{};
@@ -613,7 +766,7 @@ extern "C" int e2i_navigate_shard(e2i_ctx *ctx, const e2i_index *b1, const e2i_i
             auto weight = [&](uint64_t i) -> uint64_t {
                 const uint64_t *r = host.data() + i * words;
                 if (leaves) return (r[1] - r[0]) + (two ? r[5] - r[4] : 0) + 1;
-                return (r[5] - r[0]) + (two ? r[13] - r[8] : 0) + 1;
+                return node_size_host(r) + (two ? node_size_host(r + 4) : 0) + 1;
             };
             unsigned __int128 wsum = 0;
             for (uint64_t i = 0; i < tot; ++i) wsum += weight(i);

@@ -74,6 +74,8 @@ def reduce_stats(st: dict, device, group=None) -> dict:
     out["clust_sizes"] = vals[len(_SUM_FIELDS):]
     for i, k in enumerate(_MAX_FIELDS):
         out[k] = type(st[k])(m[i].item())
+    for k in ("ms_format", "ms_wall"):
+        out.setdefault(k, 0.0)
     return out
 
 

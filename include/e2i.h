@@ -83,6 +83,9 @@ typedef struct {
     uint64_t kernel_launches;    /* kernels of this library launched */
     uint64_t h2d_bytes;          /* host -> device bytes copied (inputs) */
     uint64_t d2h_bytes;          /* device -> host bytes copied (call records, counters) */
+    /* host wall-clock milliseconds (e2i_run / e2i_run_device only) */
+    double ms_format;            /* e2i_snp_format */
+    double ms_wall;              /* the whole call */
 } e2i_stats;
 
 /* One analysed cluster that passed the allele filter and has a right context.
