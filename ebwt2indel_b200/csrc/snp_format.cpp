@@ -6,7 +6,11 @@
 // Quirks kept on purpose (SURVEY.md §8a "parity hazards"): strict comparisons in distance(),
 // the good[1] operand of event_type in mode -1, cluster numbers that advance for clusters that
 // print nothing, the `right:` field printing the actual right-context length.
+#include <algorithm>
+#include <functional>
 #include <string>
+#include <thread>
+#include <utility>
 #include <vector>
 
 #include "common.cuh"
@@ -57,32 +61,31 @@ void append_event(std::string &o, const char *l0, const char *l1, int len, Dist 
     else { o += '/'; o.append(l1 + len + d.gap, (size_t)(-d.gap)); }
 }
 
-void append_header(std::string &o, uint64_t cluster, uint64_t id, int right_len, int cov) {
-    o += ">cluster:"; o += std::to_string(cluster);
-    o += "_id:";      o += std::to_string(id);
-    o += "_right:";   o += std::to_string(right_len);
-    o += "_cov:";     o += std::to_string(cov);
-    o += '_';
+// Header with a placeholder for the cluster number: numbering is sequential over the whole run
+// (cluster_nr, ebwt2InDel.cpp:1250/1328), so record ranges are formatted in parallel with local
+// cluster indices and the numbers are filled in once the per-range totals are known.
+struct Piece {
+    std::string text;                                   // '\x01' marks where a cluster number goes
+    std::vector<std::pair<size_t, uint64_t>> marks;     // (offset of the placeholder, local cluster index)
+    uint64_t clusters = 0, events = 0;
+};
+
+void append_header(Piece &o, uint64_t local_cluster, uint64_t id, int right_len, int cov) {
+    o.text += ">cluster:";
+    o.marks.emplace_back(o.text.size(), local_cluster);
+    o.text += '\x01';
+    o.text += "_id:";      o.text += std::to_string(id);
+    o.text += "_right:";   o.text += std::to_string(right_len);
+    o.text += "_cov:";     o.text += std::to_string(cov);
+    o.text += '_';
 }
 
-}  // namespace
-
-extern "C" void e2i_distance(const char *a, const char *b, int32_t len, int32_t max_gap, int32_t out[2]) {
-    const Dist d = distance(a, b, len, max_gap);
-    out[0] = d.mism;
-    out[1] = d.gap;
-}
-
-extern "C" int e2i_snp_format(const e2i_call_rec *recs, const char *left, const char *right, uint64_t n_recs,
-                              const e2i_params *p, int two_samples, uint64_t first_cluster_nr,
-                              char **snp, size_t *snp_len, e2i_stats *st) {
-    if (!p || !snp || !snp_len || (n_recs && (!recs || !left || !right))) { e2i::set_error("e2i_snp_format: null argument"); return E2I_ERR_ARG; }
-    if (p->max_gap > p->k_left) { e2i::set_error("e2i_snp_format: max_gap (-g) must not exceed k_left (-L)"); return E2I_ERR_ARG; }
+void format_range(const e2i_call_rec *recs, const char *left, const char *right, uint64_t r0, uint64_t r1,
+                  const e2i_params *p, int two_samples, Piece &out) {
     const int kl = p->k_left, kr = p->k_right;
-    uint64_t cluster_nr = first_cluster_nr ? first_cluster_nr : 1;
-    uint64_t events = 0;
-    std::string o;
-    for (uint64_t r = 0; r < n_recs; ++r) {
+    std::string &o = out.text;
+    uint64_t cluster = 0;                               // local index; global number = first + cluster
+    for (uint64_t r = r0; r < r1; ++r) {
         const e2i_call_rec &rec = recs[r];
         const char *L = left + r * 8 * (size_t)kl;
         const char *R = right + r * (size_t)kr;
@@ -98,12 +101,11 @@ extern "C" int e2i_snp_format(const e2i_call_rec *recs, const char *left, const 
                 if (rec.support[i] >= p->mcov_out) good[ng++] = i;
             }
             if (rec.support[nv - 1] >= p->mcov_out) good[ng++] = nv - 1;
-            if (max_dist <= p->max_snvs && ng >= 2) {
+            if (max_dist <= p->max_snvs && ng >= 2 && !starts_with_run(R, rlen, p->complexity)) {
                 uint64_t id = 1;
                 for (int g = 0; g < ng; ++g) {
-                    if (starts_with_run(R, rlen, p->complexity)) continue;
                     const char *me = L + good[g] * kl;
-                    append_header(o, cluster_nr, id++, rlen, rec.support[good[g]]);
+                    append_header(out, cluster, id++, rlen, rec.support[good[g]]);
                     const char *x = g == 0 ? me : L + good[g - 1] * kl;   // :1299-1307
                     const char *y = L + good[1] * kl;
                     append_event(o, x, y, kl, distance(x, y, kl, p->max_gap));
@@ -111,23 +113,25 @@ extern "C" int e2i_snp_format(const e2i_call_rec *recs, const char *left, const 
                     o.append(me, (size_t)kl);
                     o.append(R, (size_t)rlen);
                     o += '\n';
-                    events++;
+                    out.events++;
                 }
             }
-            cluster_nr++;                                                // :1328
+            cluster++;                                                   // :1328
         } else {
             // find_variants' cross product (:915-928, 1077-1090) + to_file(vector<variant_t>) :1149-1252
             bool found = false;
             uint64_t id = 1;
+            if (starts_with_run(R, rlen, p->complexity)) continue;        // :1159 rejects every pair of the cluster
             for (int i0 = 0; i0 < rec.n0; ++i0) for (int i1 = 0; i1 < rec.n1; ++i1) {
                 const char *l0 = L + i0 * kl, *l1 = L + (4 + i1) * kl;
                 if (l0[kl - 1] == l1[kl - 1]) continue;
-                const Dist d = distance(l0, l1, kl, p->max_gap);
                 const int s0 = rec.support[i0], s1 = rec.support[4 + i1];
-                if (starts_with_run(R, rlen, p->complexity) || d.mism > p->max_snvs || s0 < p->mcov_out || s1 < p->mcov_out) continue;
+                if (s0 < p->mcov_out || s1 < p->mcov_out) continue;
+                const Dist d = distance(l0, l1, kl, p->max_gap);
+                if (d.mism > p->max_snvs) continue;
                 found = true;
                 for (int side = 0; side < 2; ++side) {
-                    append_header(o, cluster_nr, id, rlen, side ? s1 : s0);
+                    append_header(out, cluster, id, rlen, side ? s1 : s0);
                     append_event(o, l0, l1, kl, d);
                     o += '\n';
                     int skip = 0;
@@ -139,18 +143,79 @@ extern "C" int e2i_snp_format(const e2i_call_rec *recs, const char *left, const 
                 }
                 id++;
             }
-            cluster_nr += found ? 1 : 0;                                 // :1250
+            cluster += found ? 1 : 0;                                    // :1250
         }
     }
-    char *buf = static_cast<char *>(std::malloc(o.size() + 1));
+    out.clusters = cluster;
+}
+
+int digits10(uint64_t v) { int d = 1; while (v >= 10) { v /= 10; ++d; } return d; }
+
+}  // namespace
+
+extern "C" void e2i_distance(const char *a, const char *b, int32_t len, int32_t max_gap, int32_t out[2]) {
+    const Dist d = distance(a, b, len, max_gap);
+    out[0] = d.mism;
+    out[1] = d.gap;
+}
+
+extern "C" int e2i_snp_format(const e2i_call_rec *recs, const char *left, const char *right, uint64_t n_recs,
+                              const e2i_params *p, int two_samples, uint64_t first_cluster_nr,
+                              char **snp, size_t *snp_len, e2i_stats *st) {
+    if (!p || !snp || !snp_len || (n_recs && (!recs || !left || !right))) { e2i::set_error("e2i_snp_format: null argument"); return E2I_ERR_ARG; }
+    if (p->max_gap > p->k_left) { e2i::set_error("e2i_snp_format: max_gap (-g) must not exceed k_left (-L)"); return E2I_ERR_ARG; }
+    const uint64_t first = first_cluster_nr ? first_cluster_nr : 1;
+    unsigned hw = std::thread::hardware_concurrency();
+    if (hw == 0) hw = 1;
+    const uint64_t nt = std::max<uint64_t>(1, std::min<uint64_t>({(uint64_t)hw, 64, n_recs / 2048}));
+    std::vector<Piece> pieces(nt);
+    {
+        std::vector<std::thread> th;
+        for (uint64_t t = 1; t < nt; ++t)
+            th.emplace_back(format_range, recs, left, right, n_recs * t / nt, n_recs * (t + 1) / nt, p, two_samples, std::ref(pieces[t]));
+        format_range(recs, left, right, 0, n_recs / nt, p, two_samples, pieces[0]);
+        for (auto &x : th) x.join();
+    }
+    // global cluster numbers and output offsets
+    std::vector<uint64_t> start(nt + 1, first);
+    std::vector<size_t> off(nt + 1, 0);
+    uint64_t events = 0;
+    for (uint64_t t = 0; t < nt; ++t) {
+        start[t + 1] = start[t] + pieces[t].clusters;
+        size_t len = pieces[t].text.size() - pieces[t].marks.size();
+        for (const auto &m : pieces[t].marks) len += (size_t)digits10(start[t] + m.second);
+        off[t + 1] = off[t] + len;
+        events += pieces[t].events;
+    }
+    char *buf = static_cast<char *>(std::malloc(off[nt] + 1));
     if (!buf) { e2i::set_error("e2i_snp_format: out of host memory"); return E2I_ERR_MEMORY; }
-    std::memcpy(buf, o.data(), o.size());
-    buf[o.size()] = 0;
+    auto emit = [&](uint64_t t) {
+        const Piece &pc = pieces[t];
+        char *w = buf + off[t];
+        size_t pos = 0;
+        for (const auto &m : pc.marks) {
+            std::memcpy(w, pc.text.data() + pos, m.first - pos);
+            w += m.first - pos;
+            char num[24];
+            const int nd = std::snprintf(num, sizeof num, "%llu", (unsigned long long)(start[t] + m.second));
+            std::memcpy(w, num, (size_t)nd);
+            w += nd;
+            pos = m.first + 1;
+        }
+        std::memcpy(w, pc.text.data() + pos, pc.text.size() - pos);
+    };
+    {
+        std::vector<std::thread> th;
+        for (uint64_t t = 1; t < nt; ++t) th.emplace_back(emit, t);
+        emit(0);
+        for (auto &x : th) x.join();
+    }
+    buf[off[nt]] = 0;
     *snp = buf;
-    *snp_len = o.size();
+    *snp_len = off[nt];
     if (st) {
         st->events += events;
-        st->clusters_out += cluster_nr - (first_cluster_nr ? first_cluster_nr : 1);
+        st->clusters_out += start[nt] - first;
     }
     return E2I_OK;
 }

@@ -107,3 +107,34 @@ def test_cli_help_and_missing_file():
     assert r.returncode == 0 and r.stdout.startswith("ebwt2InDel [options]")          # argc < 3 -> help, exit 0
     r = subprocess.run([exe, "-1", "/nonexistent.ebwt", "-o", "/tmp/x.snp"], capture_output=True, text=True)
     assert r.returncode == 0 and "Error: could not find file /nonexistent.ebwt" in r.stdout
+
+
+def test_parallel_formatter_equals_sequential_chaining(e2i):
+    """e2i_snp_format formats record ranges on several host threads and fills in the sequential
+    cluster numbers (ebwt2InDel.cpp:1250/1328) afterwards: the text must equal small single-thread
+    slices chained through first_cluster_nr."""
+    rng = np.random.default_rng(0)
+    p = e2i.default_params(k_left=12, k_right=8, max_gap=3, complexity=5)
+    N = 30000
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    recs = np.zeros(N, dtype=e2i.CALL_REC_DTYPE)
+    left = acgt[rng.integers(0, 4, size=(N, 8, 12))].copy()
+    left[:, 1:, :] = left[:, :1, :]
+    left[:, :, -1] = acgt[rng.integers(0, 4, size=(N, 8))]
+    left = left.reshape(-1)
+    right = acgt[rng.integers(0, 4, size=N * 8)].copy()
+    recs["n0"] = rng.integers(0, 5, N)
+    recs["n1"] = rng.integers(0, 5, N)
+    recs["right_len"] = rng.integers(5, 9, N)
+    recs["support"] = rng.integers(1, 8, (N, 8))
+    for two in (False, True):
+        whole, st = e2i.snp_format(recs, left, right, p, two)
+        out, nr, ev = b"", 1, 0
+        for i in range(0, N, 1000):
+            s, st2 = e2i.snp_format(recs[i:i + 1000], left[i * 96:(i + 1000) * 96], right[i * 8:(i + 1000) * 8], p, two,
+                                    first_cluster_nr=nr)
+            out += s
+            nr += st2.clusters_out
+            ev += st2.events
+        assert whole == out
+        assert st.clusters_out == nr - 1 and st.events == ev and len(whole) > 100000
