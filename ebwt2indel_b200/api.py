@@ -17,7 +17,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libe2i.so")
+LIB_PATH = os.environ.get("E2I_LIB") or os.path.join(HERE, "libe2i.so")
 
 E2I_OK, E2I_ERR_CUDA, E2I_ERR_SYMBOL, E2I_ERR_ARG, E2I_ERR_MEMORY, E2I_ERR_IO = range(6)
 
@@ -192,9 +192,9 @@ class Context:
             _check(lib().e2i_set_frontier_budget(self.h, frontier_bytes))
 
     def close(self):
-        if getattr(self, "h", None):
-            lib().e2i_destroy(self.h)
-            self.h = None
+        if getattr(self, "h", None) and _lib is not None:
+            _lib.e2i_destroy(self.h)
+        self.h = None
 
     def trim(self):
         """Give the device memory cached by the library back to the driver."""

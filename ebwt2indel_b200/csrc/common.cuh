@@ -56,24 +56,25 @@ void set_error(const char *fmt, ...);
         if (_rc != E2I_OK) return _rc; \
     } while (0)
 
-// Frontier frames: sizes change every sweep, so all device memory of the library comes from the
-// device's stream-ordered memory pool (cudaMallocAsync on the context's stream, release threshold
-// raised so that freed blocks stay cached): no cudaMalloc / cudaFree on the hot path.
-// DevicePool only enforces the frontier budget.
-class DevicePool {
+// Frontier frames live in ONE device arena used as a double-ended stack: frames of even tree
+// depth grow up from the bottom, frames of odd depth grow down from the top.  A frame of depth d is
+// released either right after the sweep that produced depth d+1 (level-synchronous case) or after
+// the whole subtree below it is finished (chunked depth-first case); both are LIFO per end, so
+// allocation is a pointer bump: no driver call and no fragmentation on the hot path.
+class Arena {
   public:
-    void bind(cudaStream_t s) { stream_ = s; }
-    int alloc(void **p, size_t bytes);
-    void free(void *p);
-    void release();
-    size_t bytes_live() const { return live_; }
-    void set_limit(size_t bytes) { limit_ = bytes; }
+    void reset(char *base, size_t bytes) { base_ = base; size_ = bytes; lo_ = 0; hi_ = bytes; live_[0].clear(); live_[1].clear(); }
+    char *base() const { return base_; }
+    size_t size() const { return size_; }
+    size_t in_use() const { return lo_ + (size_ - hi_); }
+    void *alloc(int side, size_t bytes);            // nullptr when it does not fit
+    void free(int side, void *p);
 
   private:
-    struct Blk { void *p; size_t bytes; };
-    std::vector<Blk> blks_;
-    cudaStream_t stream_ = nullptr;
-    size_t live_ = 0, limit_ = 0;
+    struct Blk { size_t off, bytes; bool freed; };
+    char *base_ = nullptr;
+    size_t size_ = 0, lo_ = 0, hi_ = 0;
+    std::vector<Blk> live_[2];
 };
 
 }  // namespace e2i
@@ -85,7 +86,9 @@ struct e2i_ctx {
     cudaEvent_t ev[8] = {};
     int sm_count = 148;
     uint64_t frontier_budget = 0;
-    e2i::DevicePool pool;
+    e2i::Arena arena;           // frontier frames (device memory of `arena_mem`)
+    void *arena_mem = nullptr;
+    size_t arena_bytes = 0;
     // look-back descriptors shared by all ordered-compaction kernels
     unsigned long long *desc = nullptr;
     size_t desc_words = 0;
@@ -157,21 +160,26 @@ struct e2i_calls {
 #ifdef __CUDACC__
 namespace e2i {
 
-__device__ __forceinline__ uint32_t prefix_mask32(int off, int word) {
-    // bits of `word` (32 symbols) that lie before block offset `off`
-    int k = off - 32 * word;
-    return k >= 32 ? 0xffffffffu : (k <= 0 ? 0u : ((1u << k) - 1u));
+// lowest t bits set, t clamped to [0, 32]
+__device__ __forceinline__ uint32_t low_mask(int t) {
+    uint32_t m;
+    const int tt = t < 0 ? 0 : t;
+    asm("bmsk.clamp.b32 %0, 0, %1;" : "=r"(m) : "r"(tt));
+    return m;
 }
 
-// rank inside one 64-byte block (counter quad + three planes) already in registers
-__device__ __forceinline__ void rank4_block(const DevIndex &ix, const uint4 cnt, const uint4 a, const uint4 b, const uint4 t,
-                                            uint64_t i, uint64_t out[4]) {
-    const int off = (int)(i & (kBlockSyms - 1));
+__device__ __forceinline__ uint32_t prefix_mask32(int off, int word) {
+    // bits of `word` (32 symbols) that lie before block offset `off`
+    return low_mask(off - 32 * word);
+}
+
+// #A,#C,#G,#T among the first `off` symbols of a block given its three planes
+__device__ __forceinline__ void block_popc(const uint4 a, const uint4 b, const uint4 t, int off, uint32_t out[4]) {
     const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w}, tw[4] = {t.x, t.y, t.z, t.w};
     uint32_t nN = 0, nC = 0, nG = 0, nT = 0;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        const uint32_t nt = ~tw[k] & prefix_mask32(off, k);
+        const uint32_t nt = ~tw[k] & low_mask(off - 32 * k);
         nN += __popc(nt);
         nC += __popc(nt & aw[k]);
         nG += __popc(nt & bw[k]);
@@ -179,14 +187,10 @@ __device__ __forceinline__ void rank4_block(const DevIndex &ix, const uint4 cnt,
     }
     nC -= nT;
     nG -= nT;
-    out[0] = (uint64_t)cnt.x + (nN - nC - nG - nT);
-    out[1] = (uint64_t)cnt.y + nC;
-    out[2] = (uint64_t)cnt.z + nG;
-    out[3] = (uint64_t)cnt.w + nT;
-    if (ix.n >> kSuperShift) {                       // more than one superblock: lift to absolute counts
-        const uint64_t *sb = ix.super + (i >> kSuperShift) * 4;
-        out[0] += sb[0]; out[1] += sb[1]; out[2] += sb[2]; out[3] += sb[3];
-    }
+    out[0] = nN - nC - nG - nT;
+    out[1] = nC;
+    out[2] = nG;
+    out[3] = nT;
 }
 
 // Index blocks staged in shared memory: block r of the window lives at stage[4r .. 4r+3] with its
@@ -194,26 +198,44 @@ __device__ __forceinline__ void rank4_block(const DevIndex &ix, const uint4 cnt,
 // eight consecutive blocks hit eight different bank groups.
 __device__ __forceinline__ int stage_slot(uint32_t r, int q) { return (int)(r * 4 + (q ^ ((r >> 1) & 3))); }
 
-__device__ __forceinline__ void rank4_staged(const DevIndex &ix, const uint4 *stage, uint64_t blk_lo, uint32_t n_staged,
-                                             uint64_t i, uint64_t out[4]) {
-    const uint64_t rel = (i >> kBlockShift) - blk_lo;   // wraps to a huge value below the window
+// a2: parallel_rank (dna_string.hpp:140-152): #A,#C,#G,#T in [0, i), 0 <= i <= n, in W arithmetic:
+// W = uint64_t gives absolute counts; W = uint32_t gives them modulo 2^32, which is all that a
+// DIFFERENCE of two ranks less than 2^32 apart needs (half the integer work of the 64-bit form).
+// Blocks [blk_lo, blk_lo + n_staged) are read from the shared-memory window, the others from HBM.
+template <typename W>
+__device__ __forceinline__ void rank4w(const DevIndex &ix, const uint4 *stage, uint32_t blk_lo, uint32_t n_staged,
+                                       uint64_t i, W out[4]) {
+    const uint32_t blk = (uint32_t)(i >> kBlockShift);      // n < 2^39
+    const uint32_t rel = blk - blk_lo;                       // wraps to a huge value below the window
     uint4 cnt, a, b, t;
     if (rel < n_staged) {
-        const uint32_t r = (uint32_t)rel;
-        cnt = stage[stage_slot(r, 0)]; a = stage[stage_slot(r, 1)]; b = stage[stage_slot(r, 2)]; t = stage[stage_slot(r, 3)];
+        cnt = stage[stage_slot(rel, 0)]; a = stage[stage_slot(rel, 1)]; b = stage[stage_slot(rel, 2)]; t = stage[stage_slot(rel, 3)];
     } else {
-        const uint4 *p = ix.blocks + (i >> kBlockShift) * 4;
+        const uint4 *p = ix.blocks + (size_t)blk * 4;
         cnt = __ldg(p); a = __ldg(p + 1); b = __ldg(p + 2); t = __ldg(p + 3);
     }
-    rank4_block(ix, cnt, a, b, t, i, out);
+    uint32_t pc[4];
+    block_popc(a, b, t, (int)((uint32_t)i & (kBlockSyms - 1)), pc);
+    out[0] = (W)cnt.x + pc[0];
+    out[1] = (W)cnt.y + pc[1];
+    out[2] = (W)cnt.z + pc[2];
+    out[3] = (W)cnt.w + pc[3];
+    if (ix.n >> kSuperShift) {                               // more than one superblock: add its base counts
+        const uint64_t *sb = ix.super + (i >> kSuperShift) * 4;
+        out[0] += (W)sb[0]; out[1] += (W)sb[1]; out[2] += (W)sb[2]; out[3] += (W)sb[3];
+    }
 }
 
-// a2: parallel_rank (dna_string.hpp:140-152): #A,#C,#G,#T in [0, i), 0 <= i <= n.
 __device__ __forceinline__ void rank4(const DevIndex &ix, uint64_t i, uint64_t out[4]) {
-    const uint4 *p = ix.blocks + (i >> kBlockShift) * 4;
-    const uint4 cnt = __ldg(p), a = __ldg(p + 1), b = __ldg(p + 2), t = __ldg(p + 3);
-    rank4_block(ix, cnt, a, b, t, i, out);
+    rank4w<uint64_t>(ix, nullptr, 0u, 0u, i, out);
 }
+
+// 16-byte asynchronous global -> shared copy (LDGSTS), L2-only caching
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 // single-symbol count before block `blk` (absolute)
 __device__ __forceinline__ uint64_t block_count(const DevIndex &ix, uint64_t blk, int c) {

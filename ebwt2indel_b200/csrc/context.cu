@@ -22,33 +22,26 @@ void set_error(const char *fmt, ...) {
     g_last_error = buf;
 }
 
-// ---- DevicePool ------------------------------------------------------------------------------
-int DevicePool::alloc(void **out, size_t bytes) {
-    if (bytes < 256) bytes = 256;
-    if (limit_ && live_ + bytes > limit_) return E2I_ERR_MEMORY;
-    void *p = nullptr;
-    if (cudaMallocAsync(&p, bytes, stream_) != cudaSuccess) { cudaGetLastError(); return E2I_ERR_MEMORY; }
-    blks_.push_back({p, bytes});
-    live_ += bytes;
-    *out = p;
-    return E2I_OK;
+// ---- Arena -----------------------------------------------------------------------------------
+void *Arena::alloc(int side, size_t bytes) {
+    bytes = (bytes + 255) & ~(size_t)255;
+    if (bytes > hi_ - lo_) return nullptr;
+    size_t off;
+    if (side == 0) { off = lo_; lo_ += bytes; }
+    else { hi_ -= bytes; off = hi_; }
+    live_[side].push_back({off, bytes, false});
+    return base_ + off;
 }
 
-void DevicePool::free(void *p) {
-    for (size_t i = 0; i < blks_.size(); ++i)
-        if (blks_[i].p == p) {
-            cudaFreeAsync(p, stream_);
-            live_ -= blks_[i].bytes;
-            blks_[i] = blks_.back();
-            blks_.pop_back();
-            return;
-        }
-}
-
-void DevicePool::release() {
-    for (Blk &b : blks_) cudaFreeAsync(b.p, stream_);
-    blks_.clear();
-    live_ = 0;
+void Arena::free(int side, void *p) {
+    const size_t off = (size_t)(static_cast<char *>(p) - base_);
+    std::vector<Blk> &v = live_[side];
+    for (size_t i = v.size(); i-- > 0;)
+        if (v[i].off == off) { v[i].freed = true; break; }
+    while (!v.empty() && v.back().freed) {           // pop every released frame at the top of this end
+        if (side == 0) lo_ -= v.back().bytes; else hi_ += v.back().bytes;
+        v.pop_back();
+    }
 }
 
 }  // namespace e2i
@@ -100,7 +93,6 @@ extern "C" int e2i_create(int device, e2i_ctx **out) {
     ctx->sm_count = prop.multiProcessorCount;
     E2I_CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     E2I_CUDA_TRY(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
-    ctx->pool.bind(ctx->stream);
     {   // keep freed blocks cached in the device's stream-ordered pool (released by e2i_destroy / e2i_trim)
         cudaMemPool_t mp;
         E2I_CUDA_TRY(cudaDeviceGetDefaultMemPool(&mp, device));
@@ -117,7 +109,7 @@ extern "C" int e2i_create(int device, e2i_ctx **out) {
 extern "C" void e2i_destroy(e2i_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    ctx->pool.release();
+    dfree(ctx, ctx->arena_mem);
     dfree(ctx, ctx->desc);
     cudaStreamSynchronize(ctx->stream);
     e2i_trim(ctx);
@@ -132,6 +124,10 @@ extern "C" void e2i_destroy(e2i_ctx *ctx) {
 extern "C" int e2i_trim(e2i_ctx *ctx) {
     if (!ctx) { set_error("e2i_trim: null context"); return E2I_ERR_ARG; }
     E2I_CUDA_TRY(cudaSetDevice(ctx->device));
+    dfree(ctx, ctx->arena_mem);
+    ctx->arena_mem = nullptr;
+    ctx->arena_bytes = 0;
+    ctx->arena.reset(nullptr, 0);
     E2I_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     cudaMemPool_t mp;
     E2I_CUDA_TRY(cudaDeviceGetDefaultMemPool(&mp, ctx->device));

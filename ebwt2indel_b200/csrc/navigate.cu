@@ -22,6 +22,7 @@
 // each child cW, keeps the children with >= 2 non-empty sub-intervals (number_of_children >= 2) and
 // appends them, in order, as 32-byte compact records.  Leaves: one thread per leaf (two ranks per BWT).
 #include <algorithm>
+#include <chrono>
 #include <memory>
 
 #include "common.cuh"
@@ -134,8 +135,61 @@ struct WordAcc {
     __device__ __forceinline__ void flush() { if (m) atomicOr(words + w, m); m = 0; }
 };
 
+// LF(sa_node) (dna_bwt.hpp:323-356) for one node (pair): ranks at the distinct boundaries, turned
+// into the five sub-interval sizes of every child.  W = uint32_t when the whole node is shorter
+// than 2^32 (all but the top of the tree), uint64_t otherwise.
+template <bool TWO, typename W>
+__device__ __forceinline__ void expand_core(const NavArgs &a, const uint4 *stage1, uint32_t lo1, uint32_t nst1,
+                                            const uint4 *stage2, uint32_t lo2, uint32_t nst2,
+                                            uint64_t base1, const uint64_t (&s1)[5], uint64_t base2, const uint64_t (&s2)[5],
+                                            ChildSide &k1, ChildSide &k2, uint32_t &nzp, uint32_t &st_rank) {
+    constexpr bool WIDE = sizeof(W) == 8;
+    uint64_t abs1[4], abs2[4] = {0, 0, 0, 0};
+    rank4w<uint64_t>(a.ix1, stage1, lo1, nst1, base1, abs1);
+    st_rank++;
+    if (TWO) { rank4w<uint64_t>(a.ix2, stage2, lo2, nst2, base2, abs2); st_rank++; }
+    W prev1[4], cur1[4], prev2[4], cur2[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        k1.base[c] = a.ix1.F[c] + abs1[c];
+        prev1[c] = (W)abs1[c];
+        if (TWO) { k2.base[c] = a.ix2.F[c] + abs2[c]; prev2[c] = (W)abs2[c]; }
+    }
+    uint64_t b1 = base1, b2 = base2;
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+        b1 += s1[j];
+        if (s1[j]) { rank4w<W>(a.ix1, stage1, lo1, nst1, b1, cur1); st_rank++; }
+        else { cur1[0] = prev1[0]; cur1[1] = prev1[1]; cur1[2] = prev1[2]; cur1[3] = prev1[3]; }
+        if (TWO) {
+            b2 += s2[j];
+            if (s2[j]) { rank4w<W>(a.ix2, stage2, lo2, nst2, b2, cur2); st_rank++; }
+            else { cur2[0] = prev2[0]; cur2[1] = prev2[1]; cur2[2] = prev2[2]; cur2[3] = prev2[3]; }
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const W d1 = cur1[c] - prev1[c];
+            W any = d1;
+            k1.lo[j][c] = (uint32_t)d1;
+            if (WIDE) { if (j < 4) k1.hz[c] |= (uint32_t)((uint64_t)d1 >> 32) << (8 * j); else k1.h4 |= (uint32_t)((uint64_t)d1 >> 32) << (8 * c); }
+            prev1[c] = cur1[c];
+            if (TWO) {
+                const W d2 = cur2[c] - prev2[c];
+                any |= d2;
+                k2.lo[j][c] = (uint32_t)d2;
+                if (WIDE) { if (j < 4) k2.hz[c] |= (uint32_t)((uint64_t)d2 >> 32) << (8 * j); else k2.h4 |= (uint32_t)((uint64_t)d2 >> 32) << (8 * c); }
+                prev2[c] = cur2[c];
+            }
+            nzp += (any != 0 ? 1u : 0u) << (8 * c);
+        }
+    }
+}
+
 template <bool TWO>
-__global__ void __launch_bounds__(kNavThreads)
+#ifndef E2I_NODE_MINBLOCKS
+#define E2I_NODE_MINBLOCKS 4
+#endif
+__global__ void __launch_bounds__(kNavThreads, TWO ? 2 : E2I_NODE_MINBLOCKS)
 expand_nodes_kernel(const NavArgs a, const Segs in) {
     constexpr int WORDS = TWO ? 8 : 4;                 // u64 words per record
     __shared__ uint32_t s_tile;
@@ -143,7 +197,7 @@ expand_nodes_kernel(const NavArgs a, const Segs in) {
     __shared__ uint32_t s_wlo[kNavThreads / 32], s_whi[kNavThreads / 32];   // exclusive prefix, 2 x 16 bit each
     __shared__ unsigned long long s_base[4];
     __shared__ unsigned long long s_stat[C_NCOUNTERS];
-    __shared__ unsigned long long s_rng[4];            // first / last index block touched by the tile, per BWT
+    __shared__ uint32_t s_rng[4];                      // first / last index block touched by the tile, per BWT
     constexpr int STAGE = TWO ? kStageBlocks / 2 : kStageBlocks;   // blocks staged per BWT
     __shared__ uint4 s_stage[kStageBlocks * 4];
 
@@ -157,64 +211,63 @@ expand_nodes_kernel(const NavArgs a, const Segs in) {
 
     uint64_t base1 = 0, s1[5] = {0, 0, 0, 0, 0}, base2 = 0, s2[5] = {0, 0, 0, 0, 0};
     uint32_t depth = 0;
+    bool narrow = true;                                // every size of the node (pair) fits 32 bits, and so does their sum
     if (active) {
         const uint4 *rec = reinterpret_cast<const uint4 *>(seg_record(in, g, WORDS));
-        unpack_node(__ldg(rec), __ldg(rec + 1), base1, s1, depth);
-        if (TWO) { uint32_t d2; unpack_node(__ldg(rec + 2), __ldg(rec + 3), base2, s2, d2); }
+        const uint4 lo = __ldg(rec), hi = __ldg(rec + 1);
+        unpack_node(lo, hi, base1, s1, depth);
+        narrow = (hi.z | (hi.w & 0xffu)) == 0 && ((s1[0] + s1[1] + s1[2] + s1[3] + s1[4]) >> 32) == 0;
+        if (TWO) {
+            uint32_t d2;
+            const uint4 lo2 = __ldg(rec + 2), hi2 = __ldg(rec + 3);
+            unpack_node(lo2, hi2, base2, s2, d2);
+            narrow = narrow && (hi2.z | (hi2.w & 0xffu)) == 0 && ((s2[0] + s2[1] + s2[2] + s2[3] + s2[4]) >> 32) == 0;
+        }
     }
     uint32_t st_lcp = 0, st_min = 0, st_rank = 0, st_upd = 0, st_da = 0;
 
     // ---- stage the index blocks of the tile in shared memory ----
     // All nodes of a sweep have the same depth, so their intervals are disjoint and the frontier is
     // sorted: the tile touches the block range [block(first node), block(end of last node)].  When
-    // that range is dense enough it is copied once, coalesced, and the up to 6 rank queries per node
-    // read shared memory; boundaries outside the window fall back to global loads.
+    // that range is dense enough it is copied once with 16-byte asynchronous copies (LDGSTS) while
+    // the threads do their bit updates, and the up to 6 rank queries per node read shared memory;
+    // boundaries outside the window fall back to global loads.
     {
         const uint32_t last_active = min((uint32_t)kNavThreads, in.total - tile * kNavThreads) - 1;
-        if (threadIdx.x == 0) { s_rng[0] = base1 >> kBlockShift; if (TWO) s_rng[2] = base2 >> kBlockShift; }
+        if (threadIdx.x == 0) { s_rng[0] = (uint32_t)(base1 >> kBlockShift); if (TWO) s_rng[2] = (uint32_t)(base2 >> kBlockShift); }
         if (threadIdx.x == last_active) {
-            s_rng[1] = (base1 + s1[0] + s1[1] + s1[2] + s1[3] + s1[4]) >> kBlockShift;
-            if (TWO) s_rng[3] = (base2 + s2[0] + s2[1] + s2[2] + s2[3] + s2[4]) >> kBlockShift;
+            s_rng[1] = (uint32_t)((base1 + s1[0] + s1[1] + s1[2] + s1[3] + s1[4]) >> kBlockShift);
+            if (TWO) s_rng[3] = (uint32_t)((base2 + s2[0] + s2[1] + s2[2] + s2[3] + s2[4]) >> kBlockShift);
         }
     }
     __syncthreads();
-    const uint64_t lo1 = s_rng[0], lo2 = TWO ? s_rng[2] : 0;
+    const uint32_t lo1 = s_rng[0], lo2 = TWO ? s_rng[2] : 0u;
     uint32_t nst1 = 0, nst2 = 0;
     {
-        const uint64_t span1 = s_rng[1] >= lo1 ? s_rng[1] - lo1 + 1 : 0;
-        if (span1 <= 2ull * STAGE) nst1 = (uint32_t)min((unsigned long long)span1, (unsigned long long)STAGE);
-        constexpr int ITER = STAGE * 4 / kNavThreads;      // all loads of a thread are issued before the first store
-        uint4 v[ITER];
+        constexpr int ITER = STAGE * 4 / kNavThreads;
+        const uint32_t span1 = s_rng[1] >= lo1 ? s_rng[1] - lo1 + 1 : 0u;
+        if (span1 <= 2u * STAGE) nst1 = min(span1, (uint32_t)STAGE);
+        const uint4 *src1 = a.ix1.blocks + (size_t)lo1 * 4;
 #pragma unroll
         for (int it = 0; it < ITER; ++it) {
             const uint32_t k = threadIdx.x + it * kNavThreads;
-            if (k < nst1 * 4) v[it] = __ldg(a.ix1.blocks + lo1 * 4 + k);
-        }
-#pragma unroll
-        for (int it = 0; it < ITER; ++it) {
-            const uint32_t k = threadIdx.x + it * kNavThreads;
-            if (k < nst1 * 4) s_stage[stage_slot(k >> 2, k & 3)] = v[it];
+            if (k < nst1 * 4) cp_async16(&s_stage[stage_slot(k >> 2, k & 3)], src1 + k);
         }
         if (TWO) {
-            const uint64_t end2 = s_rng[3] + 1;
-            const uint64_t span2 = end2 > lo2 ? end2 - lo2 : 0;
-            if (span2 <= 2ull * STAGE) nst2 = (uint32_t)min((unsigned long long)span2, (unsigned long long)STAGE);
+            const uint32_t end2 = s_rng[3] + 1;
+            const uint32_t span2 = end2 > lo2 ? end2 - lo2 : 0u;
+            if (span2 <= 2u * STAGE) nst2 = min(span2, (uint32_t)STAGE);
+            const uint4 *src2 = a.ix2.blocks + (size_t)lo2 * 4;
 #pragma unroll
             for (int it = 0; it < ITER; ++it) {
                 const uint32_t k = threadIdx.x + it * kNavThreads;
-                if (k < nst2 * 4) v[it] = __ldg(a.ix2.blocks + lo2 * 4 + k);
-            }
-#pragma unroll
-            for (int it = 0; it < ITER; ++it) {
-                const uint32_t k = threadIdx.x + it * kNavThreads;
-                if (k < nst2 * 4) s_stage[STAGE * 4 + stage_slot(k >> 2, k & 3)] = v[it];
+                if (k < nst2 * 4) cp_async16(&s_stage[STAGE * 4 + stage_slot(k >> 2, k & 3)], src2 + k);
             }
         }
     }
-    __syncthreads();
     const uint4 *stage1 = s_stage, *stage2 = s_stage + STAGE * 4;
 
-    // ---- bit updates on the merged node (merge_nodes, include.hpp:476-490) ----
+    // ---- bit updates on the merged node (merge_nodes, include.hpp:476-490), while the copies are in flight ----
     if (active && a.write) {
         const uint64_t mbase = base1 + base2;
         uint64_t ms[5], last = mbase;
@@ -250,53 +303,18 @@ expand_nodes_kernel(const NavArgs a, const Segs in) {
         thr.flush();
         mn.flush();
     }
+    cp_async_wait_all();
+    __syncthreads();
 
-    // ---- LF(sa_node) (dna_bwt.hpp:323-356): ranks at the distinct boundaries, as sub-interval counts ----
+    // ---- ranks -> children ----
     ChildSide k1, k2;
     uint32_t nzp = 0;                                  // per symbol: number of non-empty gaps (union of both BWTs), 4 x 8 bit
     k1.h4 = 0; k2.h4 = 0;
 #pragma unroll
     for (int c = 0; c < 4; ++c) { k1.hz[c] = 0; k2.hz[c] = 0; k1.base[c] = 0; k2.base[c] = 0; }
     if (active) {
-        uint64_t prev1[4], cur1[4], prev2[4] = {0, 0, 0, 0}, cur2[4] = {0, 0, 0, 0};
-        rank4_staged(a.ix1, stage1, lo1, nst1, base1, prev1);
-        st_rank++;
-        if (TWO) { rank4_staged(a.ix2, stage2, lo2, nst2, base2, prev2); st_rank++; }
-#pragma unroll
-        for (int c = 0; c < 4; ++c) { k1.base[c] = a.ix1.F[c] + prev1[c]; if (TWO) k2.base[c] = a.ix2.F[c] + prev2[c]; }
-        uint64_t b1 = base1, b2 = base2;
-#pragma unroll
-        for (int j = 0; j < 5; ++j) {
-            b1 += s1[j];
-            if (s1[j]) { rank4_staged(a.ix1, stage1, lo1, nst1, b1, cur1); st_rank++; }
-            else { cur1[0] = prev1[0]; cur1[1] = prev1[1]; cur1[2] = prev1[2]; cur1[3] = prev1[3]; }
-            if (TWO) {
-                b2 += s2[j];
-                if (s2[j]) { rank4_staged(a.ix2, stage2, lo2, nst2, b2, cur2); st_rank++; }
-                else { cur2[0] = prev2[0]; cur2[1] = prev2[1]; cur2[2] = prev2[2]; cur2[3] = prev2[3]; }
-            }
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                const uint64_t d1 = cur1[c] - prev1[c];
-                uint64_t any = d1;
-                k1.lo[j][c] = (uint32_t)d1;
-                if (j < 4) k1.hz[c] |= (uint32_t)(d1 >> 32) << (8 * j); else k1.h4 |= (uint32_t)(d1 >> 32) << (8 * c);
-                prev1[c] = cur1[c];
-                if (TWO) {
-                    const uint64_t d2 = cur2[c] - prev2[c];
-                    any |= d2;
-                    k2.lo[j][c] = (uint32_t)d2;
-                    if (j < 4) k2.hz[c] |= (uint32_t)(d2 >> 32) << (8 * j); else k2.h4 |= (uint32_t)(d2 >> 32) << (8 * c);
-                    prev2[c] = cur2[c];
-                }
-                nzp += (any != 0 ? 1u : 0u) << (8 * c);
-            }
-        }
-    } else {
-#pragma unroll
-        for (int j = 0; j < 5; ++j)
-#pragma unroll
-            for (int c = 0; c < 4; ++c) { k1.lo[j][c] = 0; k2.lo[j][c] = 0; }
+        if (narrow) expand_core<TWO, uint32_t>(a, stage1, lo1, nst1, stage2, lo2, nst2, base1, s1, base2, s2, k1, k2, nzp, st_rank);
+        else expand_core<TWO, uint64_t>(a, stage1, lo1, nst1, stage2, lo2, nst2, base1, s1, base2, s2, k1, k2, nzp, st_rank);
     }
 
     // ---- child c is right-maximal iff >= 2 of its 5 gaps are non-empty (number_of_children, include.hpp:760-792) ----
@@ -520,21 +538,28 @@ static uint64_t node_size_host(const uint64_t *rec) {
 }
 
 struct Frame {
-    DevicePool *pool;
+    Arena *arena;
+    int side;
     void *p;
-    ~Frame() { if (p) pool->free(p); }
+    ~Frame() { if (p) arena->free(side, p); }
 };
 
 struct Chunk {
     uint64_t *p[4];
     uint64_t cnt[4];
+    int level = 0;                      // tree depth of the records (selects the arena end of the next frame)
     std::shared_ptr<Frame> frame;
     uint64_t total() const { return cnt[0] + cnt[1] + cnt[2] + cnt[3]; }
 };
 
 struct SweepStats {
     uint64_t items = 0, sweeps = 0, max_chunk = 0;
+    double ms_alloc = 0, ms_sync = 0, ms_max_alloc = 0, ms_max_sync = 0;   // host wall time (E2I_DEBUG)
 };
+
+static inline double now_ms() {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
 
 // Cut the first `take` records off a chunk (position-contiguous prefix).
 static Chunk split_head(Chunk &c, uint64_t take, int words) {
@@ -567,13 +592,15 @@ static int run_frontier(e2i_ctx *ctx, Chunk root, int words, int tile_items, uin
         Chunk work;
         uint64_t take = std::min<uint64_t>(cur.total(), max_chunk);
         void *mem = nullptr;
+        const double ta = now_ms();
         while (true) {   // shrink the chunk until its output frame fits the pool
-            const int rc = ctx->pool.alloc(&mem, take * 4 * words * sizeof(uint64_t));
-            if (rc == E2I_OK) break;
-            if (take <= 65536) { set_error("frontier memory exhausted (budget %llu bytes, %llu live): raise the frontier budget",
-                                           (unsigned long long)ctx->frontier_budget, (unsigned long long)ctx->pool.bytes_live()); return E2I_ERR_MEMORY; }
+            mem = ctx->arena.alloc((cur.level + 1) & 1, take * 4 * words * sizeof(uint64_t));
+            if (mem) break;
+            if (take <= 4096) { set_error("frontier memory exhausted (arena %llu bytes, %llu in use): raise the frontier budget",
+                                          (unsigned long long)ctx->arena.size(), (unsigned long long)ctx->arena.in_use()); return E2I_ERR_MEMORY; }
             take /= 2;
         }
+        { const double d = now_ms() - ta; ss.ms_alloc += d; ss.ms_max_alloc = std::max(ss.ms_max_alloc, d); }
         if (take < cur.total()) {
             work = split_head(cur, take, words);
             stack.push_back(std::move(cur));
@@ -581,7 +608,8 @@ static int run_frontier(e2i_ctx *ctx, Chunk root, int words, int tile_items, uin
             work = std::move(cur);
         }
         auto frame = std::make_shared<Frame>();
-        frame->pool = &ctx->pool;
+        frame->arena = &ctx->arena;
+        frame->side = (work.level + 1) & 1;
         frame->p = mem;
         Segs segs;
         uint32_t acc = 0;
@@ -615,12 +643,15 @@ static int run_frontier(e2i_ctx *ctx, Chunk root, int words, int tile_items, uin
         ctx->n_launch++;
         ctx->n_d2h += sizeof(LaunchCtl);
         E2I_CUDA_TRY(cudaMemcpyAsync(hctl, ctx->ctl, sizeof(LaunchCtl), cudaMemcpyDeviceToHost, ctx->stream));
+        const double tsy = now_ms();
         E2I_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        { const double d = now_ms() - tsy; ss.ms_sync += d; ss.ms_max_sync = std::max(ss.ms_max_sync, d); }
         ss.items += acc;
         ss.sweeps++;
         ss.max_chunk = std::max<uint64_t>(ss.max_chunk, acc);
         Chunk next;
         next.frame = frame;
+        next.level = work.level + 1;
         for (int c = 0; c < 4; ++c) { next.p[c] = args.out[c]; next.cnt[c] = hctl->out_count[c]; }
         work.frame.reset();
         if (next.total()) stack.push_back(std::move(next));
@@ -640,11 +671,17 @@ extern "C" int e2i_navigate_shard(e2i_ctx *ctx, const e2i_index *b1, const e2i_i
     if (b2 && !da_out) { set_error("e2i_navigate: da_out is required with two BWTs"); return E2I_ERR_ARG; }
     if (n_shards < 1 || shard < 0 || shard >= n_shards) { set_error("e2i_navigate: bad shard %d/%d", shard, n_shards); return E2I_ERR_ARG; }
     if (p->K < 1 || p->k_right < 1 || p->K > 65535 || p->k_right > 65535) { set_error("e2i_navigate: K and k_right must be in [1, 65535]"); return E2I_ERR_ARG; }
-    if ((b1->n >> 40) || (b2 && (b2->n >> 40))) { set_error("e2i_navigate: BWT longer than 2^40 symbols"); return E2I_ERR_ARG; }
+    if ((b1->n >> 39) || (b2 && (b2->n >> 39))) { set_error("e2i_navigate: BWT longer than 2^39 symbols"); return E2I_ERR_ARG; }
     E2I_CUDA_TRY(cudaSetDevice(ctx->device));
     Accounting acct(ctx, st);
     cudaStream_t s = ctx->stream;
     const bool two = b2 != nullptr;
+    // the node kernels stage 32 KB per CTA: ask for the large shared-memory carveout so that 4 CTAs fit an SM
+    if (const char *cv = std::getenv("E2I_CARVEOUT")) {
+        const int pct = atoi(cv);
+        E2I_CUDA_TRY(cudaFuncSetAttribute(expand_nodes_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+        E2I_CUDA_TRY(cudaFuncSetAttribute(expand_nodes_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+    }
     const uint64_t n = b1->n + (two ? b2->n : 0);
 
     e2i_lcpbits *l = new e2i_lcpbits();
@@ -654,7 +691,7 @@ extern "C" int e2i_navigate_shard(e2i_ctx *ctx, const e2i_index *b1, const e2i_i
     l->min_words32 = padded_words32(n);
     e2i_bits *da = nullptr;
     unsigned long long *stripes = nullptr;
-    auto fail = [&](int rc) { e2i_lcpbits_free(l); e2i_bits_free(da); dfree(ctx, stripes); ctx->pool.release(); return rc; };
+    auto fail = [&](int rc) { e2i_lcpbits_free(l); e2i_bits_free(da); dfree(ctx, stripes); return rc; };
 #define TRYF(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { set_error("CUDA error %s at %s:%d: %s", cudaGetErrorName(_e), __FILE__, __LINE__, cudaGetErrorString(_e)); return fail(E2I_ERR_CUDA); } } while (0)
     TRYF(dmalloc(ctx, &l->thr, l->thr_words32 * 4));
     TRYF(dmalloc(ctx, &l->minima, l->min_words32 * 4));
@@ -683,7 +720,19 @@ extern "C" int e2i_navigate_shard(e2i_ctx *ctx, const e2i_index *b1, const e2i_i
         if (reserved > used) free_b += reserved - used;
     }
     uint64_t budget = ctx->frontier_budget ? ctx->frontier_budget : (uint64_t)(free_b * 0.85);
-    ctx->pool.set_limit(budget);
+    {   // the frame arena: kept across calls, re-allocated only when this input needs a larger one
+        const uint64_t want = std::min<uint64_t>(budget, std::max<uint64_t>(1ull << 30, 4 * n));
+        if (ctx->arena_bytes < want && ctx->arena_bytes < budget) {
+            dfree(ctx, ctx->arena_mem);
+            ctx->arena_mem = nullptr;
+            ctx->arena_bytes = 0;
+            TRYF(dmalloc(ctx, &ctx->arena_mem, want));
+            ctx->arena_bytes = want;
+        }
+        const uint64_t use = ctx->frontier_budget ? std::min<uint64_t>(ctx->arena_bytes, ctx->frontier_budget) : ctx->arena_bytes;
+        ctx->arena.reset(static_cast<char *>(ctx->arena_mem), use);
+        budget = use;
+    }
 
     NavArgs args{};
     args.ix1 = b1->dev();
@@ -713,10 +762,12 @@ extern "C" int e2i_navigate_shard(e2i_ctx *ctx, const e2i_index *b1, const e2i_i
     auto run_pass = [&](bool leaves, SweepStats &ss) -> int {
         const int words = two ? 8 : 4;                  // u64 words per record (leaf: 32 B, compact node: 32 B)
         const int tile_items = kNavThreads;
-        const uint64_t max_chunk = std::max<uint64_t>(65536, budget / ((uint64_t)words * 8 * 4 * 4));
+        // two frames of the largest chunk (input's successor + its own output) plus slack must fit the arena
+        const uint64_t max_chunk = std::max<uint64_t>(65536, (uint64_t)((double)budget / ((double)words * 8 * 4 * 2.5)));
         // root record
         void *rootmem = nullptr;
-        if (ctx->pool.alloc(&rootmem, (size_t)words * 8) != E2I_OK) return E2I_ERR_MEMORY;
+        rootmem = ctx->arena.alloc(0, (size_t)words * 8);
+        if (!rootmem) { set_error("frontier arena too small"); return E2I_ERR_MEMORY; }
         uint64_t rec[16] = {0};
         if (leaves) {                                   // first_leaf (dna_bwt.hpp:313-317)
             rec[0] = 0; rec[1] = b1->F[0]; rec[2] = 0;
@@ -730,7 +781,8 @@ extern "C" int e2i_navigate_shard(e2i_ctx *ctx, const e2i_index *b1, const e2i_i
         root.p[0] = reinterpret_cast<uint64_t *>(rootmem);
         root.cnt[0] = 1;
         root.frame = std::make_shared<Frame>();
-        root.frame->pool = &ctx->pool;
+        root.frame->arena = &ctx->arena;
+        root.frame->side = 0;
         root.frame->p = rootmem;
         auto launch = [&](NavArgs &a, const Segs &segs, uint32_t n_tiles) {
             if (leaves) {
@@ -824,6 +876,10 @@ extern "C" int e2i_navigate_shard(e2i_ctx *ctx, const e2i_index *b1, const e2i_i
     st->da_values += tot[C_DA];
     st->bit_updates += tot[C_BITUPD];
     st->max_frontier = std::max<uint64_t>(st->max_frontier, sn.max_chunk);
+    if (std::getenv("E2I_DEBUG"))
+        std::fprintf(stderr, "[e2i] leaves: %llu sweeps, alloc %.2f ms (max %.2f), sync %.2f ms (max %.2f) | nodes: %llu sweeps, alloc %.2f ms (max %.2f), sync %.2f ms (max %.2f)\n",
+                     (unsigned long long)sl.sweeps, sl.ms_alloc, sl.ms_max_alloc, sl.ms_sync, sl.ms_max_sync,
+                     (unsigned long long)sn.sweeps, sn.ms_alloc, sn.ms_max_alloc, sn.ms_sync, sn.ms_max_sync);
     float ms = 0;
     TRYF(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
     st->ms_leaves += ms;
@@ -831,7 +887,6 @@ extern "C" int e2i_navigate_shard(e2i_ctx *ctx, const e2i_index *b1, const e2i_i
     st->ms_nodes += ms;
 #undef TRYF
     dfree(ctx, stripes);
-    ctx->pool.release();
     *out = l;
     if (da_out) *da_out = da;
     return E2I_OK;
