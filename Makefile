@@ -7,9 +7,14 @@ NVFLAGS := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC,-Wall,-Wno-unused-f
 CSRC := ebwt2indel_b200/csrc
 OBJ := build/context.o build/index.o build/navigate.o build/call.o build/snp_format.o
 LIB := ebwt2indel_b200/libe2i.so
+TOOLS := ebwt2indel_b200/libe2i_tools.so
 BIN := bin/ebwt2InDel
 
-all: $(LIB) $(BIN)
+all: $(LIB) $(BIN) $(TOOLS)
+
+# synthetic-input tooling (eBWT construction for bench / tests); not linked into the product
+$(TOOLS): $(CSRC)/tools.cu
+	$(NVCC) $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -shared $< -o $@
 
 build/%.o: $(CSRC)/%.cu $(CSRC)/common.cuh $(CSRC)/lookback.cuh include/e2i.h
 	@mkdir -p build
@@ -30,5 +35,5 @@ oracle:
 	$(MAKE) -C oracle
 
 clean:
-	rm -rf build $(LIB) $(BIN)
+	rm -rf build $(LIB) $(BIN) $(TOOLS)
 .PHONY: all oracle clean

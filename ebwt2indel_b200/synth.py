@@ -55,23 +55,47 @@ def mutate(genome: np.ndarray, n_snps: int, n_indels: int, rng: np.random.Genera
     return np.concatenate(pieces)
 
 
+class ReadPlan:
+    """Reads described by start offsets into the concatenated haplotypes (nothing materialised):
+    forward read i = hap[starts[i] : starts[i] + read_len]; with `revcomp`, read n_fwd + i is the
+    reverse complement of forward read i.  Lets the GPU builder make 10^8-read sets in place."""
+
+    def __init__(self, hap: np.ndarray, starts: np.ndarray, read_len: int, revcomp: bool):
+        self.hap, self.starts, self.read_len, self.revcomp = hap, starts, read_len, revcomp
+
+    @property
+    def n_fwd(self) -> int:
+        return len(self.starts)
+
+    @property
+    def n_reads(self) -> int:
+        return len(self.starts) * (2 if self.revcomp else 1)
+
+    def materialize(self) -> np.ndarray:
+        idx = np.arange(self.read_len)
+        fwd = self.hap[self.starts[:, None] + idx[None, :]]
+        if not self.revcomp:
+            return fwd
+        return np.concatenate([fwd, _COMP[fwd[:, ::-1]]], axis=0)
+
+
+def read_plan(haplotypes, n_reads: int, read_len: int, rng: np.random.Generator, revcomp: bool = True) -> ReadPlan:
+    """Error-free reads, uniform starts, split evenly over `haplotypes` (same draws as sample_reads)."""
+    per = n_reads // len(haplotypes)
+    starts, off = [], 0
+    for h in haplotypes:
+        starts.append(off + rng.integers(0, len(h) - read_len + 1, size=per))
+        off += len(h)
+    return ReadPlan(np.concatenate(haplotypes), np.concatenate(starts).astype(np.int64), read_len, revcomp)
+
+
 def sample_reads(haplotypes, n_reads: int, read_len: int, rng: np.random.Generator,
                  revcomp: bool = True) -> np.ndarray:
     """Error-free reads, uniform starts, split evenly over `haplotypes`; (m, read_len) ASCII matrix.
 
     With `revcomp`, the reverse complement of every read is appended after all forward reads.
     """
-    per = n_reads // len(haplotypes)
-    out = []
-    idx = np.arange(read_len)
-    for h in haplotypes:
-        starts = rng.integers(0, len(h) - read_len + 1, size=per)
-        out.append(h[starts[:, None] + idx[None, :]])
-    fwd = np.concatenate(out, axis=0)
-    if not revcomp:
-        return fwd
-    rc = _COMP[fwd[:, ::-1]]
-    return np.concatenate([fwd, rc], axis=0)
+    return read_plan(haplotypes, n_reads, read_len, rng, revcomp).materialize()
 
 
 def ebwt_naive(reads: np.ndarray, term: int = ord("#")):
@@ -132,26 +156,37 @@ def ebwt_bcr_numpy(reads: np.ndarray, term: int = ord("#")):
     return bwt, owner
 
 
-def diploid_reads(genome_len: int, n_snps: int, n_indels: int, coverage: float, read_len: int,
-                  seed: int, revcomp: bool = True) -> np.ndarray:
+def diploid_plan(genome_len: int, n_snps: int, n_indels: int, coverage: float, read_len: int,
+                 seed: int, revcomp: bool = True) -> ReadPlan:
     """Mode -1 shape: one diploid individual (two haplotypes), total `coverage` split over both."""
     rng = np.random.default_rng(seed)
     h1 = random_genome(genome_len, rng)
     h2 = mutate(h1, n_snps, n_indels, rng)
     n_reads = int(round(coverage * genome_len / read_len))
-    return sample_reads([h1, h2], n_reads, read_len, rng, revcomp)
+    return read_plan([h1, h2], n_reads, read_len, rng, revcomp)
 
 
-def two_individuals_reads(genome_len: int, n_snps: int, n_indels: int, coverage: float,
+def diploid_reads(genome_len: int, n_snps: int, n_indels: int, coverage: float, read_len: int,
+                  seed: int, revcomp: bool = True) -> np.ndarray:
+    return diploid_plan(genome_len, n_snps, n_indels, coverage, read_len, seed, revcomp).materialize()
+
+
+def two_individuals_plans(genome_len: int, n_snps: int, n_indels: int, coverage: float,
                           read_len: int, seed: int, revcomp: bool = True):
-    """Modes -2/-d shape: two haploid individuals, `coverage` each; returns (reads0, reads1)."""
+    """Modes -2/-d shape: two haploid individuals, `coverage` each; returns (plan0, plan1)."""
     rng = np.random.default_rng(seed)
     g1 = random_genome(genome_len, rng)
     g2 = mutate(g1, n_snps, n_indels, rng)
     n_reads = int(round(coverage * genome_len / read_len))
-    r0 = sample_reads([g1], n_reads, read_len, rng, revcomp)
-    r1 = sample_reads([g2], n_reads, read_len, rng, revcomp)
-    return r0, r1
+    p0 = read_plan([g1], n_reads, read_len, rng, revcomp)
+    p1 = read_plan([g2], n_reads, read_len, rng, revcomp)
+    return p0, p1
+
+
+def two_individuals_reads(genome_len: int, n_snps: int, n_indels: int, coverage: float,
+                          read_len: int, seed: int, revcomp: bool = True):
+    p0, p1 = two_individuals_plans(genome_len, n_snps, n_indels, coverage, read_len, seed, revcomp)
+    return p0.materialize(), p1.materialize()
 
 
 def merged_ebwt_da(reads0: np.ndarray, reads1: np.ndarray, builder=ebwt_naive):
@@ -210,4 +245,114 @@ def ebwt_bcr_torch(reads, device=None, term: int = ord("#"), want_owner: bool = 
             owner = no
         bwt, P = nb, newP
         del mark, keep, idx
+    return (bwt, owner) if want_owner else bwt
+
+
+# ---- GPU builder (bench-sized inputs) ------------------------------------------------------------
+_tools = None
+
+
+def tools_lib():
+    """libe2i_tools.so: merge kernels of the GPU eBWT builder (csrc/tools.cu); tooling, not product."""
+    global _tools
+    if _tools is None:
+        import ctypes as C
+        import os
+        L = C.CDLL(os.path.join(os.path.dirname(os.path.abspath(__file__)), "libe2i_tools.so"))
+        vp, u64 = C.c_void_p, C.c_uint64
+        L.e2i_tool_bcr_mark.argtypes = [vp, u64, vp, u64, vp]
+        L.e2i_tool_bcr_mark.restype = C.c_int
+        L.e2i_tool_bcr_merge.argtypes = [vp, vp, vp, vp, u64, u64, vp, vp, vp, vp]
+        L.e2i_tool_bcr_merge.restype = C.c_int
+        _tools = L
+    return _tools
+
+
+class DevicePlans:
+    """One or more ReadPlans (read sets, concatenated in order) resident on the GPU; column(j) is
+    reads[:, j] over all reads, computed by gathers from the haplotypes."""
+
+    def __init__(self, plans, device):
+        import torch
+        self.dev = torch.device(device)
+        self.L = plans[0].read_len
+        self.parts = []
+        comp = torch.zeros(256, dtype=torch.uint8)
+        for a, b in zip(b"ACGT", b"TGCA"):
+            comp[a] = b
+        self.comp = comp.to(self.dev)
+        for p in plans:
+            assert p.read_len == self.L
+            self.parts.append((torch.from_numpy(p.hap).to(self.dev), torch.from_numpy(p.starts).to(self.dev), p.revcomp))
+        self.m = sum(p.n_reads for p in plans)
+        self.first_of_second_set = plans[0].n_reads if len(plans) > 1 else None
+
+    def column(self, j: int):
+        import torch
+        out = []
+        for hap, starts, rc in self.parts:
+            out.append(hap[starts + j])
+            if rc:
+                out.append(self.comp[hap[starts + (self.L - 1 - j)].long()])
+        return torch.cat(out)
+
+
+def ebwt_bcr_gpu(ctx, plans, device, term: int = ord("#"), want_owner: bool = False):
+    """eBWT of the reads of `plans` by BCR-style column insertion on the GPU.
+
+    Same result as `ebwt_bcr_torch` on the materialised reads.  The LF step of every iteration runs
+    on the product's own kernels (index build + batched rank through `ctx`, an api.Context); the
+    merge runs on csrc/tools.cu.  The reads stay sorted by the position of their newest suffix
+    (a stable 4-way partition by symbol keeps that order), so targets come out sorted and both the
+    rank queries and the merge are monotone sweeps.  Returns a uint8 tensor (and, with
+    `want_owner`, a uint8 0/1 tensor: suffix belongs to the second read set).
+    """
+    import torch
+    T = tools_lib()
+    dp = DevicePlans(plans, device)
+    dev, m, L = dp.dev, dp.m, dp.L
+    lut = torch.full((256,), 0, dtype=torch.int64, device=dev)
+    for i, ch in enumerate(b"ACGT"):
+        lut[ch] = i
+    bwt = dp.column(L - 1).clone()
+    P = torch.arange(m, dtype=torch.int64, device=dev)
+    order = torch.arange(m, dtype=torch.int64, device=dev)
+    read_owner = owner = None
+    if want_owner:
+        read_owner = (order >= dp.first_of_second_set).to(torch.uint8)
+        owner = read_owner.clone()
+    ranks = torch.empty((m, 4), dtype=torch.int64, device=dev)
+    for k in range(L):
+        S = bwt.numel()
+        ix = ctx.index(bwt, term)
+        torch.cuda.synchronize(dev)
+        ix.rank4_device(P, ranks)
+        F = torch.from_numpy(ix.F().astype(np.int64)).to(dev)
+        ix.close()
+        code = lut[dp.column(L - 1 - k)[order].long()]
+        newP = m + F[code] + ranks.gather(1, code[:, None]).squeeze(1)
+        perm = torch.cat([torch.nonzero(code == c).squeeze(1) for c in range(4)])   # stable 4-way partition
+        order = order[perm]
+        newP = newP[perm].contiguous()
+        del perm, code
+        new_sym = dp.column(L - 2 - k)[order] if k + 1 < L else torch.full((m,), term, dtype=torch.uint8, device=dev)
+        n_out = S + m
+        n_words = ((n_out + 31) // 32 + 127) // 128 * 128
+        bits = torch.zeros(n_words, dtype=torch.int32, device=dev)
+        groups = torch.empty(n_words // 128, dtype=torch.int64, device=dev)
+        rc = T.e2i_tool_bcr_mark(newP.data_ptr(), m, bits.data_ptr(), n_words, groups.data_ptr())
+        assert rc == 0
+        gex = torch.cumsum(groups, 0) - groups
+        out = torch.empty(n_out, dtype=torch.uint8, device=dev)
+        new_own = out_own = None
+        if want_owner:
+            new_own = read_owner[order]
+            out_own = torch.empty(n_out, dtype=torch.uint8, device=dev)
+        rc = T.e2i_tool_bcr_merge(bwt.data_ptr(), bits.data_ptr(), gex.data_ptr(), new_sym.data_ptr(), n_out, n_words,
+                                  out.data_ptr(), owner.data_ptr() if want_owner else None,
+                                  new_own.data_ptr() if want_owner else None, out_own.data_ptr() if want_owner else None)
+        assert rc == 0
+        torch.cuda.synchronize(dev)
+        bwt, P, owner = out, newP, out_own
+        del bits, groups, gex, new_sym
     return (bwt, owner) if want_owner else bwt
