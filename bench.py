@@ -57,10 +57,25 @@ def scaled(cfg: dict, scale: float) -> dict:
     return c
 
 
-def make_workload(cfg: dict, device):
-    """Synthetic inputs of the named shape; returns dict(mode, bwt1, bwt2, da, n) of uint8 tensors on `device`."""
+def make_workload(cfg: dict, device, ctx=None):
+    """Synthetic inputs of the named shape; returns dict(mode, bwt1, bwt2, da, n) of uint8 tensors on `device`.
+    With a context (GPU) the eBWT is built by synth.ebwt_bcr_gpu (nothing is materialised on the host),
+    otherwise by the torch builder on `device`."""
     import torch
     from ebwt2indel_b200 import synth
+    if ctx is not None:
+        if cfg["mode"] == 1:
+            plan = synth.diploid_plan(cfg["genome"], cfg["snps"], cfg["indels"], cfg["cov"], cfg["read_len"], cfg["seed"], cfg["revcomp"])
+            bwt = synth.ebwt_bcr_gpu(ctx, [plan], device)
+            return dict(mode=1, bwt1=bwt, bwt2=None, da=None, n=bwt.numel(), reads=plan.n_reads)
+        p0, p1 = synth.two_individuals_plans(cfg["genome"], cfg["snps"], cfg["indels"], cfg["cov"], cfg["read_len"], cfg["seed"], cfg["revcomp"])
+        if cfg["mode"] == 3:
+            bwt, owner = synth.ebwt_bcr_gpu(ctx, [p0, p1], device, want_owner=True)
+            da = owner + 48                                            # ASCII '0' / '1'
+            return dict(mode=3, bwt1=bwt, bwt2=None, da=da, n=bwt.numel(), reads=p0.n_reads + p1.n_reads)
+        b0 = synth.ebwt_bcr_gpu(ctx, [p0], device)
+        b1 = synth.ebwt_bcr_gpu(ctx, [p1], device)
+        return dict(mode=2, bwt1=b0, bwt2=b1, da=None, n=b0.numel() + b1.numel(), reads=p0.n_reads + p1.n_reads)
     if cfg["mode"] == 1:
         reads = synth.diploid_reads(cfg["genome"], cfg["snps"], cfg["indels"], cfg["cov"], cfg["read_len"],
                                     cfg["seed"], cfg["revcomp"])
@@ -178,12 +193,12 @@ def cpu_sample_config(cfg: dict, target_n: float = 40e6) -> tuple[dict, float]:
     return scaled(cfg, scale), scale
 
 
-def cpu_baseline_single(cfg: dict, device) -> dict:
+def cpu_baseline_single(cfg: dict, device, ctx=None) -> dict:
     """The unmodified reference, one thread (it has no threads), on a bounded sample of the workload."""
     if ref_binary() is None:
         return {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "oracle/_ref/ebwt2InDel absent"}
     sc, scale = cpu_sample_config(cfg, 24e6 if cfg["mode"] == 1 else 6e6)
-    wl = make_workload(sc, device)
+    wl = make_workload(sc, device, ctx)
     with tempfile.TemporaryDirectory() as d:
         files = write_inputs(d, wl)
         nodes, total, marks = run_reference_once(files)
@@ -303,10 +318,13 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
 
-    wl = make_workload(cfg, device)
-    torch.cuda.synchronize()
-    torch.cuda.empty_cache()
     ctx = api.Context(local, frontier_bytes=int(args.frontier_gb * 2 ** 30))
+    t_build = time.perf_counter()
+    wl = make_workload(cfg, device, ctx)
+    torch.cuda.synchronize()
+    t_build = time.perf_counter() - t_build
+    ctx.trim()
+    torch.cuda.empty_cache()
     p = api.default_params()
     ext = torch.cuda.ExternalStream(ctx.stream_ptr, device=device)
 
@@ -407,11 +425,12 @@ def main():
                          "algorithmic_bytes_per_step": alg_bytes, "kernel_ms_per_step": st["ms_nodes"]},
             "clocks": clk,
             "snp_bytes": len(snp) if snp is not None else None,
+            "input_build_s": t_build,
             "e2e_matches_device": (e_snp == snp),
         }
         if not args.no_cpu_baseline and world == 1:
             try:
-                line["cpu_baseline"] = cpu_baseline_single(cfg, device)
+                line["cpu_baseline"] = cpu_baseline_single(cfg, device, ctx)
             except Exception as ex:  # the baseline is reported, never fatal
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": f"failed: {ex}"}
         print(json.dumps(line))

@@ -36,7 +36,7 @@ struct CallCtl {
     uint32_t ticket;
     uint32_t pad;
     unsigned long long n_cand;
-    unsigned long long n_clusters, clust_size, rank_q;
+    unsigned long long n_clusters, clust_size, rank_q, n_pass;
     unsigned long long hist[201];
 };
 
@@ -92,6 +92,30 @@ __device__ __forceinline__ uint64_t da_rank1(const CallArgs &a, uint64_t i) {
     return r;
 }
 
+// Per-individual symbol histogram of BWT[begin, end) guided by the document array (mode -d,
+// ebwt2InDel.cpp:1019), 32 positions per step: plane words and DA words are equally aligned.
+// TERM has both low plane bits clear, so it lands in the A bin like base_to_int's default
+// (include.hpp:275-289).
+__device__ __forceinline__ void hist_da_words(const DevIndex &ix, const uint32_t *da, uint64_t begin, uint64_t end,
+                                              uint64_t cnt0[4], uint64_t cnt1[4]) {
+    const uint32_t *blocks32 = reinterpret_cast<const uint32_t *>(ix.blocks);
+    const uint64_t w0 = begin >> 5, w1 = (end - 1) >> 5;
+    uint32_t c0[4] = {0, 0, 0, 0}, c1[4] = {0, 0, 0, 0};
+    for (uint64_t w = w0; w <= w1; ++w) {
+        uint32_t m = 0xffffffffu;
+        if (w == w0) m &= 0xffffffffu << (begin & 31);
+        if (w == w1 && (end & 31)) m &= 0xffffffffu >> (32 - (end & 31));
+        const uint32_t *blk = blocks32 + (w >> 2) * 16;      // [0..3] counters, [4..7] plane 0, [8..11] plane 1, [12..15] TERM plane
+        const int k = (int)(w & 3);
+        const uint32_t pa = __ldg(blk + 4 + k), pb = __ldg(blk + 8 + k), d = __ldg(da + w);
+        const uint32_t m1 = m & d, m0 = m & ~d;
+        c0[0] += __popc(m0 & ~pa & ~pb); c0[1] += __popc(m0 & pa & ~pb); c0[2] += __popc(m0 & ~pa & pb); c0[3] += __popc(m0 & pa & pb);
+        c1[0] += __popc(m1 & ~pa & ~pb); c1[1] += __popc(m1 & pa & ~pb); c1[2] += __popc(m1 & ~pa & pb); c1[3] += __popc(m1 & pa & pb);
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) { cnt0[c] = c0[c]; cnt1[c] = c1[c]; }
+}
+
 __device__ __forceinline__ uint32_t frequent_mask(const uint64_t cnt[4], uint32_t mcov) {
     uint32_t m = 0;
 #pragma unroll
@@ -106,11 +130,11 @@ scan_clusters_kernel(const CallArgs a) {
     __shared__ uint32_t s_wcnt[kScanThreads / 32];
     __shared__ unsigned long long s_base;
     __shared__ unsigned int s_hist[201];
-    __shared__ unsigned long long s_stat[3];
+    __shared__ unsigned long long s_stat[4];
     for (int i = threadIdx.x; i < 201; i += kScanThreads) s_hist[i] = 0;
-    if (threadIdx.x < 3) s_stat[threadIdx.x] = 0;
+    if (threadIdx.x < 4) s_stat[threadIdx.x] = 0;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    unsigned long long t_clusters = 0, t_size = 0, t_rank = 0;
+    unsigned long long t_clusters = 0, t_size = 0, t_rank = 0, t_cand = 0;
     while (true) {
         __syncthreads();
         if (threadIdx.x == 0) s_tile = atomicAdd(&a.ctl->ticket, 1u);
@@ -158,11 +182,7 @@ scan_clusters_kernel(const CallArgs a) {
                 for (int c = 0; c < 4; ++c) { cnt0[c] = re[c] - rb[c]; acgt += cnt0[c]; }
                 cnt0[0] += len - acgt;                     // TERM counted as 'A'
             } else if (a.mode == 3) {
-                for (uint64_t i = begin; i < end; ++i) {
-                    int c = access_code(a.ix1, i);
-                    if (c == 4) c = 0;
-                    if (bit_at(a.da, i)) cnt1[c]++; else cnt0[c]++;
-                }
+                hist_da_words(a.ix1, a.da, begin, end, cnt0, cnt1);
             } else {
                 const uint64_t ob = da_rank1(a, begin), oe = da_rank1(a, end);
                 b2 = ob; e2 = oe; b1 = begin - ob; e1 = end - oe;
@@ -183,6 +203,12 @@ scan_clusters_kernel(const CallArgs a) {
             bool pass;
             if (a.mode == 1) pass = n0 >= 2 && !(a.q > 0 && (uint32_t)n0 > a.q);                         // :961-966
             else pass = n0 > 0 && n1 > 0 && !(a.q > 0 && ((uint32_t)n0 > a.q || (uint32_t)n1 > a.q));    // :870-880
+            if (pass) t_cand++;
+            // Two samples: a pair is only ever emitted when the last characters of the two left contexts --
+            // the alleles themselves -- differ (:921, :1083).  A cluster where both individuals have the same
+            // single frequent allele (the overwhelming majority) can produce no output and changes no
+            // counter, so its consensus walks and right context are never computed.
+            if (pass && a.mode != 1 && n0 == 1 && m0 == m1) pass = false;
             if (pass && nc < kMaxCand) {
                 c_begin[nc] = begin; c_end[nc] = end;
                 c_r[nc][0] = b1; c_r[nc][1] = e1; c_r[nc][2] = b2; c_r[nc][3] = e2;
@@ -231,17 +257,20 @@ scan_clusters_kernel(const CallArgs a) {
         t_clusters += __shfl_xor_sync(0xffffffffu, t_clusters, s);
         t_size += __shfl_xor_sync(0xffffffffu, t_size, s);
         t_rank += __shfl_xor_sync(0xffffffffu, t_rank, s);
+        t_cand += __shfl_xor_sync(0xffffffffu, t_cand, s);
     }
     if (lane == 0) {
         atomicAdd(&s_stat[0], t_clusters);
         atomicAdd(&s_stat[1], t_size);
         atomicAdd(&s_stat[2], t_rank);
+        atomicAdd(&s_stat[3], t_cand);
     }
     __syncthreads();
     if (threadIdx.x == 0) {
         if (s_stat[0]) atomicAdd(&a.ctl->n_clusters, s_stat[0]);
         if (s_stat[1]) atomicAdd(&a.ctl->clust_size, s_stat[1]);
         if (s_stat[2]) atomicAdd(&a.ctl->rank_q, s_stat[2]);
+        if (s_stat[3]) atomicAdd(&a.ctl->n_pass, s_stat[3]);
     }
     for (int i = threadIdx.x; i < 201; i += kScanThreads)
         if (s_hist[i]) atomicAdd(&a.ctl->hist[i], (unsigned long long)s_hist[i] * (unsigned long long)i);
@@ -260,6 +289,7 @@ __global__ void consensus_kernel(const CallArgs a, uint64_t n_cand, char *__rest
     const uint32_t mask = ind ? cd.mask1 : cd.mask0;
     reached[gid] = 0;
     if (!((mask >> c) & 1u)) return;
+    if (a.mode != 1 && !((ind ? cd.mask0 : cd.mask1) & ~(1u << c))) return;   // no partner allele differs: never emitted
     const bool second = a.mode == 2 && ind == 1;
     const DevIndex &ix = second ? a.ix2 : a.ix1;
     uint64_t first = second ? cd.b2 : cd.b1, last = second ? cd.e2 : cd.e1;
@@ -474,7 +504,7 @@ extern "C" int e2i_call(e2i_ctx *ctx, const e2i_index *b1, const e2i_index *b2, 
         for (int i = 0; i <= 200; ++i) st->clust_sizes[i] += hctl.hist[i];
         const uint64_t nc = hctl.n_cand;
         if (nc > cand_cap) { set_error("e2i_call: candidate list overflow (%llu > %llu)", (unsigned long long)nc, (unsigned long long)cand_cap); return fail(E2I_ERR_MEMORY); }
-        st->candidates += nc;
+        st->candidates += hctl.n_pass;
         if (nc == 0) continue;
         TRYF(dmalloc(ctx, &d_left, nc * 8 * (size_t)p->k_left));
         TRYF(dmalloc(ctx, &d_right, nc * (size_t)p->k_right));

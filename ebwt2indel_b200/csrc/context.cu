@@ -109,10 +109,9 @@ extern "C" int e2i_create(int device, e2i_ctx **out) {
 extern "C" void e2i_destroy(e2i_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    dfree(ctx, ctx->arena_mem);
     dfree(ctx, ctx->desc);
-    cudaStreamSynchronize(ctx->stream);
-    e2i_trim(ctx);
+    ctx->desc = nullptr;
+    e2i_trim(ctx);               // frees the frame arena and returns the cached pool memory
     cudaFree(ctx->ctl);
     cudaFreeHost(ctx->ctl_host);
     for (auto &ev : ctx->ev) if (ev) cudaEventDestroy(ev);

@@ -68,7 +68,7 @@ typedef struct {
     uint64_t rank_nodes;         /* parallel_rank queries in phase 3 (distinct boundaries per node, dna_bwt.hpp:332-347) */
     uint64_t rank_call;          /* rank queries issued by phase 4 */
     uint64_t bit_updates;        /* LCP border + minima bit writes in phase 3 */
-    uint64_t candidates;         /* clusters that passed the frequent-allele filter */
+    uint64_t candidates;         /* clusters that passed the reference's frequent-allele filter (:870-880, :961-966) */
     uint64_t levels_leaves;      /* frontier sweeps of phase 2 */
     uint64_t levels_nodes;       /* frontier sweeps of phase 3 */
     uint64_t max_frontier;       /* largest frontier chunk (nodes) */

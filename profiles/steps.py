@@ -12,10 +12,13 @@ from ebwt2indel_b200 import api  # noqa: E402
 cfg = bench.CONFIGS[sys.argv[1] if len(sys.argv) > 1 else "C4s16"]
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 6
 dev = torch.device("cuda:0")
-wl = bench.make_workload(cfg, dev)
-torch.cuda.synchronize()
-torch.cuda.empty_cache()
 ctx = api.Context(0)
+t0 = time.perf_counter()
+wl = bench.make_workload(cfg, dev, ctx)
+torch.cuda.synchronize()
+print(f"built n={wl['n']} in {time.perf_counter() - t0:.1f} s", flush=True)
+ctx.trim()
+torch.cuda.empty_cache()
 p = api.default_params()
 for i in range(steps):
     t0 = time.perf_counter()

@@ -256,3 +256,20 @@ def test_cli_drop_in(tmp_path):
     bad.write_bytes(b"ACGTNACGT#")
     r = subprocess.run([exe, "-1", str(bad), "-o", str(tmp_path / "x.snp")], capture_output=True, text=True)
     assert r.returncode == 1 and "read forbidden character 'N' (ASCII code 78)" in r.stdout
+
+
+def test_gpu_ebwt_builder_matches_reference_builders(gpu_ctx):
+    """Tooling check: the GPU BCR builder (product index + rank kernels for the LF step, csrc/tools.cu
+    for the merge) gives the eBWT / DA of the naive suffix sort."""
+    import torch
+    from ebwt2indel_b200 import synth
+    plan = synth.diploid_plan(3000, 8, 3, 20, 50, seed=31)
+    want, _ = synth.ebwt_naive(plan.materialize())
+    got = synth.ebwt_bcr_gpu(gpu_ctx, [plan], "cuda:0")
+    assert np.array_equal(got.cpu().numpy(), want)
+    p0, p1 = synth.two_individuals_plans(2000, 6, 2, 16, 40, seed=32)
+    m, da = synth.merged_ebwt_da(p0.materialize(), p1.materialize())
+    bwt, owner = synth.ebwt_bcr_gpu(gpu_ctx, [p0, p1], "cuda:0", want_owner=True)
+    assert np.array_equal(bwt.cpu().numpy(), m)
+    assert np.array_equal((owner + 48).cpu().numpy(), da)
+    torch.cuda.synchronize()
