@@ -56,11 +56,11 @@ class Stats(C.Structure):
 
 class CallRec(C.Structure):
     _fields_ = [("begin", C.c_uint64), ("end", C.c_uint64), ("n0", C.c_uint8), ("n1", C.c_uint8),
-                ("right_len", C.c_uint8), ("reserved", C.c_uint8), ("support", C.c_int32 * 8)]
+                ("right_len", C.c_uint8), ("has_right", C.c_uint8), ("support", C.c_int32 * 8)]
 
 
 CALL_REC_DTYPE = np.dtype([("begin", "<u8"), ("end", "<u8"), ("n0", "u1"), ("n1", "u1"), ("right_len", "u1"),
-                           ("reserved", "u1"), ("support", "<i4", (8,))], align=True)
+                           ("has_right", "u1"), ("support", "<i4", (8,))], align=True)
 assert CALL_REC_DTYPE.itemsize == C.sizeof(CallRec) == 56
 
 # every symbol include/e2i.h declares (tests check that the library exports all of them)

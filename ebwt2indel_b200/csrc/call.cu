@@ -15,6 +15,7 @@
 //   3. right_context: first position of the cluster with LCP >= k_right, then k_right FL steps.
 // Classification and text formatting (a21-a23) run on the host in snp_format.cpp.
 #include <algorithm>
+#include <chrono>
 
 #include "common.cuh"
 #include "lookback.cuh"
@@ -358,6 +359,41 @@ __global__ void right_context_kernel(const CallArgs a, uint64_t n_cand, char *__
     atomicAdd(rank_q + (ci & 63), (unsigned long long)nq);
 }
 
+// Kernel 4: final record layout on the device.  Per candidate: the reached left contexts of each
+// individual move to the front of its group of four slots (A,C,G,T order kept; a destination slot
+// never lies after its source), supports alike, and the e2i_call_rec is filled in.
+__global__ void pack_calls_kernel(const CallArgs a, uint64_t n_cand, char *__restrict__ left, const int32_t *__restrict__ support,
+                                  const uint8_t *__restrict__ reached, const uint8_t *__restrict__ right_len,
+                                  const uint8_t *__restrict__ has_right, e2i_call_rec *__restrict__ recs) {
+    const uint64_t ci = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (ci >= n_cand) return;
+    const Candidate cd = a.cand[ci];
+    e2i_call_rec rec;
+    rec.begin = cd.begin;
+    rec.end = cd.end;
+    rec.right_len = right_len[ci];
+    rec.has_right = has_right[ci];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) rec.support[k] = 0;
+    char *L = left + ci * 8 * (uint64_t)a.k_left;
+    for (int ind = 0; ind < 2; ++ind) {
+        int k = 0;
+        for (int c = 0; c < 4; ++c) {
+            const uint64_t src = ci * 8 + ind * 4 + c;
+            if (!reached[src]) continue;
+            if (k != c) {
+                const char *from = L + (ind * 4 + c) * a.k_left;
+                char *to = L + (ind * 4 + k) * a.k_left;
+                for (int i = 0; i < a.k_left; ++i) to[i] = from[i];
+            }
+            rec.support[ind * 4 + k] = support[src];
+            k++;
+        }
+        if (ind == 0) rec.n0 = (uint8_t)k; else rec.n1 = (uint8_t)k;
+    }
+    recs[ci] = rec;
+}
+
 // popcount of every 512-bit group of the DA, then an in-place exclusive scan (one CTA)
 __global__ void da_group_popc_kernel(const uint32_t *__restrict__ words, uint64_t n_groups, uint64_t *__restrict__ out) {
     const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -448,32 +484,38 @@ extern "C" int e2i_call(e2i_ctx *ctx, const e2i_index *b1, const e2i_index *b2, 
     a.k_left = p->k_left;
     a.k_right = p->k_right;
 
-    CallCtl *dctl = nullptr;
-    unsigned long long *rank_q = nullptr;
-    Candidate *cand = nullptr;
-    char *d_left = nullptr, *d_right = nullptr;
-    int32_t *d_support = nullptr;
-    uint8_t *d_reached = nullptr, *d_rlen = nullptr, *d_has = nullptr;
-    auto cleanup = [&] { dfree(ctx, dctl); dfree(ctx, rank_q); dfree(ctx, cand); dfree(ctx, d_left); dfree(ctx, d_right); dfree(ctx, d_support); dfree(ctx, d_reached); dfree(ctx, d_rlen); dfree(ctx, d_has); };
-    auto fail = [&](int rc) { cleanup(); delete calls; return rc; };
+    // Phase 4 runs after the traversal, so the frame arena is idle: the control block, the candidate
+    // list and the per-candidate outputs are carved out of it (no allocation on this path).
+    if (ctx->arena_bytes < (64ull << 20)) {
+        dfree(ctx, ctx->arena_mem);
+        ctx->arena_mem = nullptr;
+        ctx->arena_bytes = 0;
+        E2I_CUDA_TRY(dmalloc(ctx, &ctx->arena_mem, 1ull << 30));
+        ctx->arena_bytes = 1ull << 30;
+    }
+    char *const abase = static_cast<char *>(ctx->arena_mem);
+    CallCtl *dctl = reinterpret_cast<CallCtl *>(abase);
+    unsigned long long *rank_q = reinterpret_cast<unsigned long long *>(abase + 4096);
+    Candidate *cand = reinterpret_cast<Candidate *>(abase + 8192);
+    const size_t kl = (size_t)p->k_left, kr = (size_t)p->k_right;
+    const size_t out_per = 8 * kl + kr + sizeof(e2i_call_rec) + 8 * sizeof(int32_t) + 8 + 2 + 64;   // output bytes per candidate (+ slack)
+    const uint64_t cand_cap = (ctx->arena_bytes / 4) / sizeof(Candidate);
+    char *const obase = abase + 8192 + ((cand_cap * sizeof(Candidate) + 255) & ~(size_t)255);
+    const uint64_t batch_cap = (uint64_t)((abase + ctx->arena_bytes - obase) / out_per);
+    auto fail = [&](int rc) { delete calls; return rc; };
 #define TRYF(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { set_error("CUDA error %s at %s:%d: %s", cudaGetErrorName(_e), __FILE__, __LINE__, cudaGetErrorString(_e)); return fail(E2I_ERR_CUDA); } } while (0)
-    TRYF(dmalloc(ctx, &dctl, sizeof(CallCtl)));
-    TRYF(dmalloc(ctx, &rank_q, 64 * 8));
     TRYF(cudaMemsetAsync(rank_q, 0, 64 * 8, s));
     TRYF(cudaEventRecord(ctx->ev[4], s));
-
-    const uint64_t slab = 1ull << 28;   // positions per slab: bounds the candidate list
-    const uint64_t cand_cap = slab / (2ull * a.mcov + 1) + kMaxCand + 2;
-    TRYF(dmalloc(ctx, &cand, cand_cap * sizeof(Candidate)));
     a.cand = cand;
     a.cand_cap = cand_cap;
     CallCtl hctl;
-    std::vector<uint8_t> h_reached, h_rlen, h_has;
-    std::vector<int32_t> h_support;
-    std::vector<char> h_left, h_right;
-    std::vector<Candidate> h_cand;
-    for (uint64_t sb = pos_begin / kScanTile * kScanTile; sb < pos_end; sb += slab) {
-        const uint64_t se = std::min<uint64_t>(sb + slab, (pos_end + kScanTile - 1) / kScanTile * kScanTile);
+    auto now_ms = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    double t_scan = 0, t_walk = 0, t_host = 0, t_mark = now_ms();
+    auto lap = [&](double &acc) { const double t = now_ms(); acc += t - t_mark; t_mark = t; };
+    uint64_t slab = 1ull << 30;          // positions per scan launch; halved if its candidates overflow the list
+    const uint64_t first = pos_begin / kScanTile * kScanTile, last = (pos_end + kScanTile - 1) / kScanTile * kScanTile;
+    for (uint64_t sb = first; sb < pos_end;) {
+        const uint64_t se = std::min<uint64_t>(sb + slab, last);
         a.pos_begin = std::max(sb, pos_begin);
         a.pos_end = std::min(se, pos_end);
         a.first_tile = sb / kScanTile;
@@ -498,65 +540,57 @@ extern "C" int e2i_call(e2i_ctx *ctx, const e2i_index *b1, const e2i_index *b2, 
         ctx->n_d2h += sizeof(CallCtl);
         TRYF(cudaMemcpyAsync(&hctl, dctl, sizeof(CallCtl), cudaMemcpyDeviceToHost, s));
         TRYF(cudaStreamSynchronize(s));
+        lap(t_scan);
+        const uint64_t nc = hctl.n_cand;
+        if (nc > cand_cap) {             // too many candidates for the list: redo this slab in two halves
+            if (slab <= (uint64_t)kScanTile) { set_error("e2i_call: candidate list overflow (%llu > %llu)", (unsigned long long)nc, (unsigned long long)cand_cap); return fail(E2I_ERR_MEMORY); }
+            slab = std::max<uint64_t>((uint64_t)kScanTile, (slab / 2) / kScanTile * kScanTile);
+            continue;
+        }
+        sb = se;
         st->n_clusters += hctl.n_clusters;
         st->clust_size += hctl.clust_size;
         st->rank_call += hctl.rank_q;
         for (int i = 0; i <= 200; ++i) st->clust_sizes[i] += hctl.hist[i];
-        const uint64_t nc = hctl.n_cand;
-        if (nc > cand_cap) { set_error("e2i_call: candidate list overflow (%llu > %llu)", (unsigned long long)nc, (unsigned long long)cand_cap); return fail(E2I_ERR_MEMORY); }
         st->candidates += hctl.n_pass;
-        if (nc == 0) continue;
-        TRYF(dmalloc(ctx, &d_left, nc * 8 * (size_t)p->k_left));
-        TRYF(dmalloc(ctx, &d_right, nc * (size_t)p->k_right));
-        TRYF(dmalloc(ctx, &d_support, nc * 8 * sizeof(int32_t)));
-        TRYF(dmalloc(ctx, &d_reached, nc * 8));
-        TRYF(dmalloc(ctx, &d_rlen, nc));
-        TRYF(dmalloc(ctx, &d_has, nc));
-        TRYF(cudaMemsetAsync(d_support, 0, nc * 8 * sizeof(int32_t), s));
-        consensus_kernel<<<(unsigned)((nc * 8 + 127) / 128), 128, 0, s>>>(a, nc, d_left, d_support, d_reached, rank_q);
-        right_context_kernel<<<(unsigned)((nc + 127) / 128), 128, 0, s>>>(a, nc, d_right, d_rlen, d_has, rank_q);
-        TRYF(cudaGetLastError());
-        h_cand.resize(nc); h_left.resize(nc * 8 * (size_t)p->k_left); h_right.resize(nc * (size_t)p->k_right);
-        h_support.resize(nc * 8); h_reached.resize(nc * 8); h_rlen.resize(nc); h_has.resize(nc);
-        TRYF(cudaMemcpyAsync(h_cand.data(), cand, nc * sizeof(Candidate), cudaMemcpyDeviceToHost, s));
-        TRYF(cudaMemcpyAsync(h_left.data(), d_left, h_left.size(), cudaMemcpyDeviceToHost, s));
-        TRYF(cudaMemcpyAsync(h_right.data(), d_right, h_right.size(), cudaMemcpyDeviceToHost, s));
-        TRYF(cudaMemcpyAsync(h_support.data(), d_support, nc * 8 * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
-        TRYF(cudaMemcpyAsync(h_reached.data(), d_reached, nc * 8, cudaMemcpyDeviceToHost, s));
-        TRYF(cudaMemcpyAsync(h_rlen.data(), d_rlen, nc, cudaMemcpyDeviceToHost, s));
-        TRYF(cudaMemcpyAsync(h_has.data(), d_has, nc, cudaMemcpyDeviceToHost, s));
-        ctx->n_launch += 2;
-        ctx->n_d2h += nc * (sizeof(Candidate) + 8 * (size_t)p->k_left + (size_t)p->k_right + 8 * sizeof(int32_t) + 8 + 2);
-        TRYF(cudaStreamSynchronize(s));
-        dfree(ctx, d_left); dfree(ctx, d_right); dfree(ctx, d_support); dfree(ctx, d_reached); dfree(ctx, d_rlen); dfree(ctx, d_has);
-        d_left = d_right = nullptr; d_support = nullptr; d_reached = d_rlen = d_has = nullptr;
-        // compact on the host: keep clusters with a right context; pack reached contexts per individual
-        const size_t kl = (size_t)p->k_left, kr = (size_t)p->k_right;
-        for (uint64_t ci = 0; ci < nc; ++ci) {
-            if (!h_has[ci]) continue;
-            e2i_call_rec rec{};
-            rec.begin = h_cand[ci].begin;
-            rec.end = h_cand[ci].end;
-            rec.right_len = h_rlen[ci];
-            const size_t base = calls->left.size();
-            calls->left.resize(base + 8 * kl, 0);
-            for (int ind = 0; ind < 2; ++ind) {
-                int k = 0;
-                for (int c = 0; c < 4; ++c) {
-                    const size_t src = ci * 8 + ind * 4 + c;
-                    if (!h_reached[src]) continue;
-                    std::memcpy(&calls->left[base + (ind * 4 + k) * kl], &h_left[src * kl], kl);
-                    rec.support[ind * 4 + k] = h_support[src];
-                    k++;
-                }
-                if (ind == 0) rec.n0 = (uint8_t)k; else rec.n1 = (uint8_t)k;
-            }
-            const size_t rb = calls->right.size();
-            calls->right.resize(rb + kr, 0);
-            std::memcpy(&calls->right[rb], &h_right[ci * kr], rec.right_len);
-            calls->recs.push_back(rec);
+        for (uint64_t c0 = 0; c0 < nc; c0 += batch_cap) {
+            const uint64_t nb = std::min<uint64_t>(batch_cap, nc - c0);
+            char *o = obase;
+            auto carve = [&](size_t bytes) { char *r = o; o += (bytes + 63) & ~(size_t)63; return r; };
+            char *d_left = carve(nb * 8 * kl);
+            char *d_right = carve(nb * kr);
+            e2i_call_rec *d_recs = reinterpret_cast<e2i_call_rec *>(carve(nb * sizeof(e2i_call_rec)));
+            int32_t *d_support = reinterpret_cast<int32_t *>(carve(nb * 8 * sizeof(int32_t)));
+            uint8_t *d_reached = reinterpret_cast<uint8_t *>(carve(nb * 8));
+            uint8_t *d_rlen = reinterpret_cast<uint8_t *>(carve(nb));
+            uint8_t *d_has = reinterpret_cast<uint8_t *>(carve(nb));
+            CallArgs ab = a;
+            ab.cand = cand + c0;
+            TRYF(cudaMemsetAsync(d_support, 0, nb * 8 * sizeof(int32_t), s));
+            TRYF(cudaMemsetAsync(d_left, 0, nb * 8 * kl, s));
+            TRYF(cudaMemsetAsync(d_right, 0, nb * kr, s));
+            consensus_kernel<<<(unsigned)((nb * 8 + 127) / 128), 128, 0, s>>>(ab, nb, d_left, d_support, d_reached, rank_q);
+            right_context_kernel<<<(unsigned)((nb + 127) / 128), 128, 0, s>>>(ab, nb, d_right, d_rlen, d_has, rank_q);
+            pack_calls_kernel<<<(unsigned)((nb + 127) / 128), 128, 0, s>>>(ab, nb, d_left, d_support, d_reached, d_rlen, d_has, d_recs);
+            TRYF(cudaGetLastError());
+            // the device layout is the final one: three copies straight into the result vectors
+            const size_t r0 = calls->recs.size();
+            calls->recs.resize(r0 + nb);
+            calls->left.resize((r0 + nb) * 8 * kl);
+            calls->right.resize((r0 + nb) * kr);
+            TRYF(cudaMemcpyAsync(calls->recs.data() + r0, d_recs, nb * sizeof(e2i_call_rec), cudaMemcpyDeviceToHost, s));
+            TRYF(cudaMemcpyAsync(calls->left.data() + r0 * 8 * kl, d_left, nb * 8 * kl, cudaMemcpyDeviceToHost, s));
+            TRYF(cudaMemcpyAsync(calls->right.data() + r0 * kr, d_right, nb * kr, cudaMemcpyDeviceToHost, s));
+            ctx->n_launch += 3;
+            ctx->n_d2h += nb * (sizeof(e2i_call_rec) + 8 * kl + kr);
+            TRYF(cudaStreamSynchronize(s));
+            lap(t_walk);
+            lap(t_host);
         }
     }
+    if (std::getenv("E2I_DEBUG"))
+        std::fprintf(stderr, "[e2i] call: scan+sync %.1f ms, walks+d2h %.1f ms, host %.1f ms, %llu records\n",
+                     t_scan, t_walk, t_host, (unsigned long long)calls->recs.size());
     unsigned long long hq[64];
     TRYF(cudaMemcpyAsync(hq, rank_q, sizeof hq, cudaMemcpyDeviceToHost, s));
     TRYF(cudaEventRecord(ctx->ev[5], s));
@@ -566,7 +600,6 @@ extern "C" int e2i_call(e2i_ctx *ctx, const e2i_index *b1, const e2i_index *b2, 
     TRYF(cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5]));
     st->ms_call += ms;
 #undef TRYF
-    cleanup();
     *out = calls;
     return E2I_OK;
 }

@@ -87,6 +87,7 @@ void format_range(const e2i_call_rec *recs, const char *left, const char *right,
     uint64_t cluster = 0;                               // local index; global number = first + cluster
     for (uint64_t r = r0; r < r1; ++r) {
         const e2i_call_rec &rec = recs[r];
+        if (!rec.has_right) continue;                       // empty variant vector: nothing printed, nothing counted
         const char *L = left + r * 8 * (size_t)kl;
         const char *R = right + r * (size_t)kr;
         const int rlen = rec.right_len;

@@ -88,15 +88,18 @@ typedef struct {
     double ms_wall;              /* the whole call */
 } e2i_stats;
 
-/* One analysed cluster that passed the allele filter and has a right context.
+/* One analysed cluster that passed the allele filter (and, with two samples, can emit a pair).
  * Left contexts live in a separate char array: 8 slots of k_left chars per record
- * (slots 0-3: individual 0 / the single sample; slots 4-7: individual 1). */
+ * (slots 0-3: individual 0 / the single sample; slots 4-7: individual 1), packed to the front
+ * of each group in A,C,G,T order.  Records without a right context (has_right == 0) are kept in
+ * the list but produce no output and advance no counter, like the reference's empty variant
+ * vector (ebwt2InDel.cpp:909, 985, 1071). */
 typedef struct {
     uint64_t begin;          /* merged SA position of the first flagged position */
     uint64_t end;            /* merged SA position one past the last */
     uint8_t n0, n1;          /* left contexts of individual 0 / 1 that reached k_left chars */
     uint8_t right_len;       /* chars in the right context (stops early at a terminator) */
-    uint8_t reserved;
+    uint8_t has_right;       /* a position with LCP >= k_right exists in the cluster */
     int32_t support[8];      /* |LF(range, c)| per left context (ebwt2InDel.cpp:310) */
 } e2i_call_rec;
 

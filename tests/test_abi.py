@@ -74,6 +74,7 @@ def test_snp_format_host_only(e2i):
 
     # cluster 1: two alleles, SNP A/C
     put(0, 0, "ACGTACGA"); put(0, 1, "ACGTACGC")
+    recs["has_right"] = 1
     recs[0]["n0"] = 2; recs[0]["right_len"] = 6; recs[0]["support"][:2] = (5, 4)
     right[0:6] = np.frombuffer(b"GATTAC", dtype=np.uint8)
     # cluster 2: two alleles but one below coverage -> nothing printed, cluster number still advances (:1328)
@@ -126,6 +127,7 @@ def test_parallel_formatter_equals_sequential_chaining(e2i):
     recs["n0"] = rng.integers(0, 5, N)
     recs["n1"] = rng.integers(0, 5, N)
     recs["right_len"] = rng.integers(5, 9, N)
+    recs["has_right"] = rng.integers(0, 8, N) > 0
     recs["support"] = rng.integers(1, 8, (N, 8))
     for two in (False, True):
         whole, st = e2i.snp_format(recs, left, right, p, two)

@@ -61,7 +61,7 @@ def _worker(rank, world, port, ret):
                 left[(i * 8 + 0) * 8:(i * 8 + 0) * 8 + 8] = np.frombuffer(a.encode(), dtype=np.uint8)
                 left[(i * 8 + 1) * 8:(i * 8 + 1) * 8 + 8] = np.frombuffer(b.encode(), dtype=np.uint8)
                 recs[i]["begin"], recs[i]["end"] = 100 * r + 10 * i, 100 * r + 10 * i + 7
-                recs[i]["n0"], recs[i]["right_len"] = 2, 6
+                recs[i]["n0"], recs[i]["right_len"], recs[i]["has_right"] = 2, 6, 1
                 recs[i]["support"][:2] = (4 + r, 3 + i)
             return recs, left, right
 
