@@ -506,13 +506,85 @@ extern "C" int e2i_call(e2i_ctx *ctx, const e2i_index *b1, const e2i_index *b2, 
 #define TRYF(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { set_error("CUDA error %s at %s:%d: %s", cudaGetErrorName(_e), __FILE__, __LINE__, cudaGetErrorString(_e)); return fail(E2I_ERR_CUDA); } } while (0)
     TRYF(cudaMemsetAsync(rank_q, 0, 64 * 8, s));
     TRYF(cudaEventRecord(ctx->ev[4], s));
-    a.cand = cand;
-    a.cand_cap = cand_cap;
     CallCtl hctl;
     auto now_ms = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
-    double t_scan = 0, t_walk = 0, t_host = 0, t_mark = now_ms();
+    double t_scan = 0, t_walk = 0, t_mark = now_ms();
     auto lap = [&](double &acc) { const double t = now_ms(); acc += t - t_mark; t_mark = t; };
-    uint64_t slab = 1ull << 30;          // positions per scan launch; halved if its candidates overflow the list
+
+    // page-locked result arrays [recs | left | right] with room for `cap` records; grown by moving
+    const uint64_t gen = ++ctx->pinned_gen;
+    uint64_t cap = 0, n_out = 0;
+    const size_t rec_bytes = sizeof(e2i_call_rec) + 8 * kl + kr;
+    auto layout = [&](void *basep, uint64_t c, e2i_call_rec *&r, char *&lf, char *&rt) {
+        char *bp = static_cast<char *>(basep);
+        r = reinterpret_cast<e2i_call_rec *>(bp);
+        lf = bp + c * sizeof(e2i_call_rec);
+        rt = lf + c * 8 * kl;
+    };
+    auto ensure = [&](uint64_t want) -> int {
+        if (want <= cap) return E2I_OK;
+        const uint64_t ncap = std::max<uint64_t>(want, std::max<uint64_t>(1024, 2 * cap));
+        if (ncap * rec_bytes <= ctx->pinned_bytes && n_out == 0) {       // the cached buffer is large enough
+            cap = ctx->pinned_bytes / rec_bytes;
+            layout(ctx->pinned, cap, calls->recs, calls->left, calls->right);
+            return E2I_OK;
+        }
+        void *np = nullptr;
+        if (cudaMallocHost(&np, ncap * rec_bytes) != cudaSuccess) { cudaGetLastError(); set_error("e2i_call: cannot page-lock %llu bytes", (unsigned long long)(ncap * rec_bytes)); return E2I_ERR_MEMORY; }
+        e2i_call_rec *r; char *lf, *rt;
+        layout(np, ncap, r, lf, rt);
+        if (n_out) {
+            std::memcpy(r, calls->recs, n_out * sizeof(e2i_call_rec));
+            std::memcpy(lf, calls->left, n_out * 8 * kl);
+            std::memcpy(rt, calls->right, n_out * kr);
+        }
+        if (ctx->pinned) cudaFreeHost(ctx->pinned);
+        ctx->pinned = np;
+        ctx->pinned_bytes = ncap * rec_bytes;
+        cap = ncap;
+        calls->recs = r; calls->left = lf; calls->right = rt;
+        return E2I_OK;
+    };
+
+    // consensus walks + right contexts + record packing for the candidates gathered so far
+    uint64_t n_acc = 0;
+    auto flush = [&]() -> int {
+        E2I_TRY(ensure(n_out + n_acc));
+        for (uint64_t c0 = 0; c0 < n_acc; c0 += batch_cap) {
+            const uint64_t nb = std::min<uint64_t>(batch_cap, n_acc - c0);
+            char *o = obase;
+            auto carve = [&](size_t bytes) { char *r = o; o += (bytes + 63) & ~(size_t)63; return r; };
+            char *d_left = carve(nb * 8 * kl);
+            char *d_right = carve(nb * kr);
+            e2i_call_rec *d_recs = reinterpret_cast<e2i_call_rec *>(carve(nb * sizeof(e2i_call_rec)));
+            int32_t *d_support = reinterpret_cast<int32_t *>(carve(nb * 8 * sizeof(int32_t)));
+            uint8_t *d_reached = reinterpret_cast<uint8_t *>(carve(nb * 8));
+            uint8_t *d_rlen = reinterpret_cast<uint8_t *>(carve(nb));
+            uint8_t *d_has = reinterpret_cast<uint8_t *>(carve(nb));
+            CallArgs ab = a;
+            ab.cand = cand + c0;
+            E2I_CUDA_TRY(cudaMemsetAsync(d_support, 0, nb * 8 * sizeof(int32_t), s));
+            E2I_CUDA_TRY(cudaMemsetAsync(d_left, 0, nb * 8 * kl, s));
+            E2I_CUDA_TRY(cudaMemsetAsync(d_right, 0, nb * kr, s));
+            consensus_kernel<<<(unsigned)((nb * 8 + 127) / 128), 128, 0, s>>>(ab, nb, d_left, d_support, d_reached, rank_q);
+            right_context_kernel<<<(unsigned)((nb + 127) / 128), 128, 0, s>>>(ab, nb, d_right, d_rlen, d_has, rank_q);
+            pack_calls_kernel<<<(unsigned)((nb + 127) / 128), 128, 0, s>>>(ab, nb, d_left, d_support, d_reached, d_rlen, d_has, d_recs);
+            E2I_CUDA_TRY(cudaGetLastError());
+            // the device layout is the final one: three copies straight into the page-locked result arrays
+            E2I_CUDA_TRY(cudaMemcpyAsync(calls->recs + n_out, d_recs, nb * sizeof(e2i_call_rec), cudaMemcpyDeviceToHost, s));
+            E2I_CUDA_TRY(cudaMemcpyAsync(calls->left + n_out * 8 * kl, d_left, nb * 8 * kl, cudaMemcpyDeviceToHost, s));
+            E2I_CUDA_TRY(cudaMemcpyAsync(calls->right + n_out * kr, d_right, nb * kr, cudaMemcpyDeviceToHost, s));
+            ctx->n_launch += 3;
+            ctx->n_d2h += nb * rec_bytes;
+            E2I_CUDA_TRY(cudaStreamSynchronize(s));
+            n_out += nb;
+        }
+        n_acc = 0;
+        return E2I_OK;
+    };
+
+    // scan [pos_begin, pos_end) slab by slab; the candidates of all slabs accumulate in one list
+    uint64_t slab = 1ull << 30;
     const uint64_t first = pos_begin / kScanTile * kScanTile, last = (pos_end + kScanTile - 1) / kScanTile * kScanTile;
     for (uint64_t sb = first; sb < pos_end;) {
         const uint64_t se = std::min<uint64_t>(sb + slab, last);
@@ -520,6 +592,8 @@ extern "C" int e2i_call(e2i_ctx *ctx, const e2i_index *b1, const e2i_index *b2, 
         a.pos_end = std::min(se, pos_end);
         a.first_tile = sb / kScanTile;
         a.n_tiles = (uint32_t)((se - sb + kScanTile - 1) / kScanTile);
+        a.cand = cand + n_acc;
+        a.cand_cap = cand_cap - n_acc;
         if ((size_t)a.n_tiles > ctx->desc_words) {
             dfree(ctx, ctx->desc);
             ctx->desc = nullptr;
@@ -542,55 +616,25 @@ extern "C" int e2i_call(e2i_ctx *ctx, const e2i_index *b1, const e2i_index *b2, 
         TRYF(cudaStreamSynchronize(s));
         lap(t_scan);
         const uint64_t nc = hctl.n_cand;
-        if (nc > cand_cap) {             // too many candidates for the list: redo this slab in two halves
+        if (nc > a.cand_cap) {           // the list is full: empty it, or (if it was empty) redo the slab in halves
+            if (n_acc) { const int rc = flush(); if (rc != E2I_OK) return fail(rc); lap(t_walk); continue; }
             if (slab <= (uint64_t)kScanTile) { set_error("e2i_call: candidate list overflow (%llu > %llu)", (unsigned long long)nc, (unsigned long long)cand_cap); return fail(E2I_ERR_MEMORY); }
             slab = std::max<uint64_t>((uint64_t)kScanTile, (slab / 2) / kScanTile * kScanTile);
             continue;
         }
         sb = se;
+        n_acc += nc;
         st->n_clusters += hctl.n_clusters;
         st->clust_size += hctl.clust_size;
         st->rank_call += hctl.rank_q;
         for (int i = 0; i <= 200; ++i) st->clust_sizes[i] += hctl.hist[i];
         st->candidates += hctl.n_pass;
-        for (uint64_t c0 = 0; c0 < nc; c0 += batch_cap) {
-            const uint64_t nb = std::min<uint64_t>(batch_cap, nc - c0);
-            char *o = obase;
-            auto carve = [&](size_t bytes) { char *r = o; o += (bytes + 63) & ~(size_t)63; return r; };
-            char *d_left = carve(nb * 8 * kl);
-            char *d_right = carve(nb * kr);
-            e2i_call_rec *d_recs = reinterpret_cast<e2i_call_rec *>(carve(nb * sizeof(e2i_call_rec)));
-            int32_t *d_support = reinterpret_cast<int32_t *>(carve(nb * 8 * sizeof(int32_t)));
-            uint8_t *d_reached = reinterpret_cast<uint8_t *>(carve(nb * 8));
-            uint8_t *d_rlen = reinterpret_cast<uint8_t *>(carve(nb));
-            uint8_t *d_has = reinterpret_cast<uint8_t *>(carve(nb));
-            CallArgs ab = a;
-            ab.cand = cand + c0;
-            TRYF(cudaMemsetAsync(d_support, 0, nb * 8 * sizeof(int32_t), s));
-            TRYF(cudaMemsetAsync(d_left, 0, nb * 8 * kl, s));
-            TRYF(cudaMemsetAsync(d_right, 0, nb * kr, s));
-            consensus_kernel<<<(unsigned)((nb * 8 + 127) / 128), 128, 0, s>>>(ab, nb, d_left, d_support, d_reached, rank_q);
-            right_context_kernel<<<(unsigned)((nb + 127) / 128), 128, 0, s>>>(ab, nb, d_right, d_rlen, d_has, rank_q);
-            pack_calls_kernel<<<(unsigned)((nb + 127) / 128), 128, 0, s>>>(ab, nb, d_left, d_support, d_reached, d_rlen, d_has, d_recs);
-            TRYF(cudaGetLastError());
-            // the device layout is the final one: three copies straight into the result vectors
-            const size_t r0 = calls->recs.size();
-            calls->recs.resize(r0 + nb);
-            calls->left.resize((r0 + nb) * 8 * kl);
-            calls->right.resize((r0 + nb) * kr);
-            TRYF(cudaMemcpyAsync(calls->recs.data() + r0, d_recs, nb * sizeof(e2i_call_rec), cudaMemcpyDeviceToHost, s));
-            TRYF(cudaMemcpyAsync(calls->left.data() + r0 * 8 * kl, d_left, nb * 8 * kl, cudaMemcpyDeviceToHost, s));
-            TRYF(cudaMemcpyAsync(calls->right.data() + r0 * kr, d_right, nb * kr, cudaMemcpyDeviceToHost, s));
-            ctx->n_launch += 3;
-            ctx->n_d2h += nb * (sizeof(e2i_call_rec) + 8 * kl + kr);
-            TRYF(cudaStreamSynchronize(s));
-            lap(t_walk);
-            lap(t_host);
-        }
     }
+    { const int rc = flush(); if (rc != E2I_OK) return fail(rc); lap(t_walk); }
+    calls->n = n_out;
+    calls->gen = gen;
     if (std::getenv("E2I_DEBUG"))
-        std::fprintf(stderr, "[e2i] call: scan+sync %.1f ms, walks+d2h %.1f ms, host %.1f ms, %llu records\n",
-                     t_scan, t_walk, t_host, (unsigned long long)calls->recs.size());
+        std::fprintf(stderr, "[e2i] call: scan+sync %.1f ms, walks+d2h %.1f ms, %llu records\n", t_scan, t_walk, (unsigned long long)n_out);
     unsigned long long hq[64];
     TRYF(cudaMemcpyAsync(hq, rank_q, sizeof hq, cudaMemcpyDeviceToHost, s));
     TRYF(cudaEventRecord(ctx->ev[5], s));
@@ -604,17 +648,18 @@ extern "C" int e2i_call(e2i_ctx *ctx, const e2i_index *b1, const e2i_index *b2, 
     return E2I_OK;
 }
 
-extern "C" uint64_t e2i_calls_count(const e2i_calls *c) { return c ? c->recs.size() : 0; }
+extern "C" uint64_t e2i_calls_count(const e2i_calls *c) { return c ? c->n : 0; }
 
 extern "C" int e2i_calls_fetch(const e2i_calls *c, e2i_call_rec *host_recs, char *host_left, char *host_right,
                                uint64_t cap, uint64_t *n) {
     if (!c || !n) { set_error("e2i_calls_fetch: null argument"); return E2I_ERR_ARG; }
-    const uint64_t k = std::min<uint64_t>(cap, c->recs.size());
+    if (c->gen != c->ctx->pinned_gen) { set_error("e2i_calls_fetch: stale handle (a later e2i_call on this context reused the staging buffer)"); return E2I_ERR_ARG; }
+    const uint64_t k = std::min<uint64_t>(cap, c->n);
     if (k && (!host_recs || !host_left || !host_right)) { set_error("e2i_calls_fetch: null buffer"); return E2I_ERR_ARG; }
     if (k) {
-        std::memcpy(host_recs, c->recs.data(), k * sizeof(e2i_call_rec));
-        std::memcpy(host_left, c->left.data(), k * 8 * (size_t)c->k_left);
-        std::memcpy(host_right, c->right.data(), k * (size_t)c->k_right);
+        std::memcpy(host_recs, c->recs, k * sizeof(e2i_call_rec));
+        std::memcpy(host_left, c->left, k * 8 * (size_t)c->k_left);
+        std::memcpy(host_right, c->right, k * (size_t)c->k_right);
     }
     *n = k;
     return E2I_OK;

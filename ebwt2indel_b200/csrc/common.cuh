@@ -95,6 +95,9 @@ struct e2i_ctx {
     uint32_t epoch = 0;
     void *ctl = nullptr;        // device control block (ticket + counters), see navigate.cu
     void *ctl_host = nullptr;   // pinned mirror
+    void *pinned = nullptr;     // page-locked staging of the call records
+    size_t pinned_bytes = 0;
+    uint64_t pinned_gen = 0;
     // accounting (kernels launched, bytes copied) since the context was created
     uint64_t n_launch = 0, n_h2d = 0, n_d2h = 0;
 };
@@ -150,10 +153,13 @@ struct e2i_lcpbits {
     uint64_t n = 0, thr_words32 = 0, min_words32 = 0;
 };
 
+// Call records live in the context's page-locked staging buffer (one D2H per array, no pageable
+// bounce): a handle is valid until the next e2i_call on the same context (checked by `gen`).
 struct e2i_calls {
     e2i_ctx *ctx = nullptr;
-    std::vector<e2i_call_rec> recs;
-    std::vector<char> left, right;
+    e2i_call_rec *recs = nullptr;
+    char *left = nullptr, *right = nullptr;
+    uint64_t n = 0, gen = 0;
     int k_left = 0, k_right = 0;
 };
 

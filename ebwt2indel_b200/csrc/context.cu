@@ -114,6 +114,7 @@ extern "C" void e2i_destroy(e2i_ctx *ctx) {
     e2i_trim(ctx);               // frees the frame arena and returns the cached pool memory
     cudaFree(ctx->ctl);
     cudaFreeHost(ctx->ctl_host);
+    if (ctx->pinned) cudaFreeHost(ctx->pinned);
     for (auto &ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
@@ -175,7 +176,7 @@ static int run_on_device(e2i_ctx *ctx, const uint8_t *dev_bwt1, uint64_t n1, con
     if (rc == E2I_OK) rc = e2i_call(ctx, b1, b2, b2 ? da_nav : da, lcp, p, 0, UINT64_MAX, &calls, st);
     const auto w1 = std::chrono::steady_clock::now();
     if (rc == E2I_OK)
-        rc = e2i_snp_format(calls->recs.data(), calls->left.data(), calls->right.data(), calls->recs.size(), p,
+        rc = e2i_snp_format(calls->recs, calls->left, calls->right, calls->n, p,
                             (b2 || da) ? 1 : 0, 1, snp, snp_len, st);
     const auto w2 = std::chrono::steady_clock::now();
     cleanup();
