@@ -197,7 +197,7 @@ def cpu_baseline_single(cfg: dict, device, ctx=None) -> dict:
     """The unmodified reference, one thread (it has no threads), on a bounded sample of the workload."""
     if ref_binary() is None:
         return {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "oracle/_ref/ebwt2InDel absent"}
-    sc, scale = cpu_sample_config(cfg, 24e6 if cfg["mode"] == 1 else 6e6)
+    sc, scale = cpu_sample_config(cfg, 60e6 if cfg["mode"] == 1 else 8e6)
     wl = make_workload(sc, device, ctx)
     with tempfile.TemporaryDirectory() as d:
         files = write_inputs(d, wl)
@@ -295,7 +295,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
-    ap.add_argument("--config", default=os.environ.get("E2I_BENCH_CONFIG", "C1"), choices=sorted(CONFIGS))
+    ap.add_argument("--config", default=os.environ.get("E2I_BENCH_CONFIG", "C4"), choices=sorted(CONFIGS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--frontier-gb", type=float, default=0.0)
     args = ap.parse_args()
