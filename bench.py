@@ -335,7 +335,7 @@ def main():
 
     def step_device():
         if world == 1:
-            snp, st = ctx.run(wl["bwt1"], wl["bwt2"], wl["da"], p)
+            snp, st = ctx.run(wl["bwt1"], wl["bwt2"], wl["da"], p, copy=False)
             return snp, st.as_dict()
         snp, st, _ = dd.run_sharded(ctx, api, wl["bwt1"], wl["bwt2"], wl["da"], p, rank, world)
         return snp, st
@@ -363,6 +363,7 @@ def main():
     outs, dev_s, wall_s = timed(step_device, args.steps)
     clk = clocks.stop() if rank == 0 else None
     snp, st = outs[-1]
+    del outs
     nodes = st["nodes"]
     value = nodes * args.steps / dev_s
 
@@ -373,7 +374,7 @@ def main():
 
     def step_host():
         if world == 1:
-            s, stt = ctx.run(h1.numpy(), None if h2 is None else h2.numpy(), None if hd is None else hd.numpy(), p)
+            s, stt = ctx.run(h1.numpy(), None if h2 is None else h2.numpy(), None if hd is None else hd.numpy(), p, copy=False)
             return s, stt.as_dict()
         d1 = h1.to(device, non_blocking=True)
         d2 = None if h2 is None else h2.to(device, non_blocking=True)
@@ -387,8 +388,14 @@ def main():
     e_outs, e_dev_s, e_wall_s = timed(step_host, max(1, min(args.steps, 3)))
     e_steps = len(e_outs)
     e_snp, e_st = e_outs[-1]
+    del e_outs
     e2e_value = e_st["nodes"] * e_steps / e_wall_s
 
+    single_ok = None
+    if world > 1 and rank == 0:      # parity evidence: the sharded text equals an (untimed) single-GPU run
+        s1, _ = ctx.run(wl["bwt1"], wl["bwt2"], wl["da"], p, copy=False)
+        single_ok = bool(s1 == snp)
+        del s1
     if rank == 0:
         peaks = {}
         try:
@@ -427,6 +434,7 @@ def main():
             "snp_bytes": len(snp) if snp is not None else None,
             "input_build_s": t_build,
             "e2e_matches_device": (e_snp == snp),
+            "matches_single_gpu": single_ok,
         }
         if not args.no_cpu_baseline and world == 1:
             try:

@@ -180,6 +180,35 @@ def _ptr(x):
     return x.ctypes.data
 
 
+class SnpText:
+    """The .snp text returned by the library (malloc'ed by libe2i, freed with the object).
+    `bytes(x)` / `x.tobytes()` copies it out; `len(x)` and `x.view()` do not."""
+
+    def __init__(self, ptr, length: int):
+        self._ptr, self._len = ptr, int(length)
+
+    def __len__(self):
+        return self._len
+
+    def view(self) -> memoryview:
+        return memoryview((C.c_char * self._len).from_address(self._ptr.value)) if self._len else memoryview(b"")
+
+    def tobytes(self) -> bytes:
+        return C.string_at(self._ptr, self._len) if self._len else b""
+
+    __bytes__ = tobytes
+
+    def __eq__(self, other):
+        if isinstance(other, SnpText):
+            other = other.view()
+        return self.view() == other
+
+    def __del__(self):
+        if getattr(self, "_ptr", None) is not None and _lib is not None:
+            _lib.e2i_buffer_free(self._ptr)
+            self._ptr = None
+
+
 class Context:
     """One device context (e2i_ctx): a stream, scratch and the frame allocator.  One per GPU / thread."""
 
@@ -262,9 +291,11 @@ class Context:
         return recs, left, right, st
 
     # ---- whole path ----
-    def run(self, bwt1, bwt2=None, da=None, params: Params | None = None, stats: Stats | None = None):
+    def run(self, bwt1, bwt2=None, da=None, params: Params | None = None, stats: Stats | None = None,
+            copy: bool = True):
         """Whole path.  Inputs all on the host (numpy / bytes / pinned torch CPU tensors) -> e2i_run,
-        or all torch CUDA uint8 tensors -> e2i_run_device.  Returns (.snp bytes, Stats)."""
+        or all torch CUDA uint8 tensors -> e2i_run_device.  Returns (.snp bytes, Stats); with
+        copy=False the text comes back as a SnpText that wraps the library's buffer."""
         p = params or default_params()
         st = stats if stats is not None else Stats()
         on_dev = hasattr(bwt1, "is_cuda") and bwt1.is_cuda
@@ -288,9 +319,8 @@ class Context:
         if rc == E2I_ERR_SYMBOL:
             raise ValueError(lib().e2i_last_error().decode())
         _check(rc)
-        snp = C.string_at(out, ln.value)
-        lib().e2i_buffer_free(out)
-        return snp, st
+        text = SnpText(out, ln.value)
+        return (text.tobytes() if copy else text), st
 
 
 def snp_format(recs: np.ndarray, left: np.ndarray, right: np.ndarray, params: Params, two_samples: bool,

@@ -44,6 +44,26 @@ def or_reduce_words(tensors, group=None, chunk_words: int = 1 << 28):
             dist.all_reduce(flat[off:off + chunk_words], op=dist.ReduceOp.SUM, group=group)
 
 
+def format_sharded(api, recs, left, right, params, two_samples: bool, rank: int, world: int, device, group=None):
+    """Every rank formats the records of its own suffix-array slice; cluster numbers are sequential
+    over the whole run (ebwt2InDel.cpp:1250/1328), so each rank first counts the clusters its slice
+    numbers, the counts are exchanged, and ranks > 0 format again from their true first number.
+    The text pieces are concatenated on rank 0 in rank (= suffix-array) order.
+    Returns (.snp bytes on rank 0 else None, events, clusters_out) summed over ranks."""
+    txt, fst = api.snp_format(recs, left, right, params, two_samples, first_cluster_nr=1)
+    mine = torch.tensor([int(fst.clusters_out), int(fst.events)], dtype=torch.int64, device=device)
+    allc = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(allc, mine, group=group)
+    counts = [int(t[0]) for t in allc]
+    first = 1 + sum(counts[:rank])
+    if first != 1 and len(recs):
+        txt, _ = api.snp_format(recs, left, right, params, two_samples, first_cluster_nr=first)
+    out = [None] * world if rank == 0 else None
+    dist.gather_object(txt, out, dst=0, group=group)
+    events, clusters = sum(int(t[1]) for t in allc), sum(counts)
+    return (b"".join(out) if rank == 0 else None), events, clusters
+
+
 def gather_calls(recs: np.ndarray, left: np.ndarray, right: np.ndarray, rank: int, world: int, group=None):
     """Gather the per-rank call records on rank 0 in rank (= suffix-array) order."""
     out = [None] * world if rank == 0 else None
@@ -105,11 +125,8 @@ def run_sharded(ctx, api, bwt1, bwt2, da, params, rank: int, world: int, group=N
     cuts = position_cuts(n, world)
     recs, left, right, st = ctx.call(b1, b2, da_nav if b2 is not None else dabits, lcp, params,
                                      cuts[rank], cuts[rank + 1], stats=st)
-    g = gather_calls(recs, left, right, rank, world, group)
     stats = reduce_stats(st.as_dict(), device, group)
-    snp = None
-    if rank == 0:
-        fst = api.Stats()
-        snp, fst = api.snp_format(g[0], g[1], g[2], params, two_samples=(b2 is not None or da is not None), stats=fst)
-        stats["events"], stats["clusters_out"] = int(fst.events), int(fst.clusters_out)
+    snp, events, clusters = format_sharded(api, recs, left, right, params, (b2 is not None or da is not None),
+                                           rank, world, device, group)
+    stats["events"], stats["clusters_out"] = events, clusters
     return snp, stats, t0.elapsed_time(t1) / 1e3

@@ -77,6 +77,13 @@ def _worker(rank, world, port, ret):
         else:
             ok_gather = got is None
 
+        # 3b. every rank formats its own slice; numbering continues across ranks
+        txt, ev, cl = dd.format_sharded(api, *mine, p, False, rank, world, torch.device("cpu"))
+        if rank == 0:
+            ok_gather = ok_gather and txt == want and cl == 4 and ev == 8
+        else:
+            ok_gather = ok_gather and txt is None and cl == 4
+
         # 4. counters: sums and maxima
         st = api.Stats().as_dict()
         st["nodes"], st["ms_nodes"], st["clust_sizes"][3] = 10 + rank, 5.0 + rank, 7
