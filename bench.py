@@ -208,7 +208,7 @@ def cpu_baseline_single(cfg: dict, device, ctx=None) -> dict:
             "phase3_nodes_per_s": nodes / p3 if p3 > 0 else None, "seconds": total}
 
 
-def reference_arm(args, cfg):
+def reference_arm(args, cfg, out=sys.stdout):
     """--impl reference: the reference's own CPU implementation with all the host threads it can use.
     The reference is single-threaded; its multi-core mode is pebwt2InDel.sh (split the reads into
     pieces, one process per piece, concatenate).  HARC/BCR are not available, so the split is by
@@ -217,7 +217,7 @@ def reference_arm(args, cfg):
     if rank != 0:
         return
     if ref_binary() is None:
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/ebwt2InDel not built (needs /root/reference at build time)"}))
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/ebwt2InDel not built (needs /root/reference at build time)"}), file=out)
         return
     import torch
     from ebwt2indel_b200 import synth
@@ -285,7 +285,7 @@ def reference_arm(args, cfg):
         "config": {"workload": args.config, "desc": cfg["desc"], "sample": sample},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": pieces, "kind": "reference", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+    }), file=out)
 
 
 # ---- own arm -----------------------------------------------------------------------------------
@@ -300,8 +300,12 @@ def main():
     ap.add_argument("--frontier-gb", type=float, default=0.0)
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
+    # libraries (NCCL with NCCL_DEBUG=VERSION, ...) may print to stdout: keep fd 1 for the ONE JSON line
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
-        reference_arm(args, cfg)
+        reference_arm(args, cfg, real_stdout)
+        real_stdout.flush()
         return
 
     import torch
@@ -432,6 +436,7 @@ def main():
                          "algorithmic_bytes_per_step": alg_bytes, "kernel_ms_per_step": st["ms_nodes"]},
             "clocks": clk,
             "snp_bytes": len(snp) if snp is not None else None,
+            "sharded_host_ms": st.get("host_ms"),
             "input_build_s": t_build,
             "e2e_matches_device": (e_snp == snp),
             "matches_single_gpu": single_ok,
@@ -441,7 +446,8 @@ def main():
                 line["cpu_baseline"] = cpu_baseline_single(cfg, device, ctx)
             except Exception as ex:  # the baseline is reported, never fatal
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": f"failed: {ex}"}
-        print(json.dumps(line))
+        print(json.dumps(line), file=real_stdout)
+        real_stdout.flush()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -191,7 +191,7 @@ class SnpText:
         return self._len
 
     def view(self) -> memoryview:
-        return memoryview((C.c_char * self._len).from_address(self._ptr.value)) if self._len else memoryview(b"")
+        return memoryview((C.c_ubyte * self._len).from_address(self._ptr.value)).cast("B") if self._len else memoryview(b"")
 
     def tobytes(self) -> bytes:
         return C.string_at(self._ptr, self._len) if self._len else b""

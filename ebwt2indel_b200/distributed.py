@@ -102,13 +102,25 @@ def reduce_stats(st: dict, device, group=None) -> dict:
 def run_sharded(ctx, api, bwt1, bwt2, da, params, rank: int, world: int, group=None):
     """Whole path on `world` GPUs.  Inputs are CUDA uint8 tensors (replicated on every rank).
     Returns (.snp bytes on rank 0 else None, reduced stats dict, seconds spent in the exchange)."""
+    import time
     device = bwt1.device
     term = params.term
+    tm = {}
+    tp = time.perf_counter()
+
+    def lap(name):
+        nonlocal tp
+        torch.cuda.synchronize(device)
+        t = time.perf_counter()
+        tm[name] = tm.get(name, 0.0) + (t - tp) * 1e3
+        tp = t
     b1 = ctx.index(bwt1, term)
     b2 = ctx.index(bwt2, term) if bwt2 is not None else None
     dabits = ctx.document_array(da) if da is not None else None
     st = api.Stats()
+    lap("index")
     lcp, da_nav, st = ctx.navigate(b1, b2, params, shard=rank, n_shards=world, stats=st)
+    lap("navigate")
     (pt, wt), (pm, wm) = lcp.device_words()
     words = [wrap_device_words(pt, wt, device), wrap_device_words(pm, wm, device)]
     if da_nav is not None:
@@ -121,12 +133,17 @@ def run_sharded(ctx, api, bwt1, bwt2, da, params, rank: int, world: int, group=N
     or_reduce_words(words, group)
     t1.record()
     torch.cuda.synchronize(device)
+    lap("or_reduce")
     n = b1.n + (b2.n if b2 is not None else 0)
     cuts = position_cuts(n, world)
     recs, left, right, st = ctx.call(b1, b2, da_nav if b2 is not None else dabits, lcp, params,
                                      cuts[rank], cuts[rank + 1], stats=st)
+    lap("call")
     stats = reduce_stats(st.as_dict(), device, group)
+    lap("reduce_stats")
     snp, events, clusters = format_sharded(api, recs, left, right, params, (b2 is not None or da is not None),
                                            rank, world, device, group)
+    lap("format+gather")
     stats["events"], stats["clusters_out"] = events, clusters
+    stats["host_ms"] = tm
     return snp, stats, t0.elapsed_time(t1) / 1e3
