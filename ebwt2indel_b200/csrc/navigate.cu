@@ -385,6 +385,270 @@ expand_nodes_kernel(const NavArgs a, const Segs in) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// Phase 3 sweep, persistent warp-specialised form (the default).
+//
+// The ordered append makes a tile wait until every earlier tile has published its child counts;
+// with ~600 tiles in flight that wait was 40 % of the warp time of the one-tile-per-CTA kernel
+// above (profiles/r01_ncu_nodes_c4s16_v4_raw.csv).  Here a CTA is 8 compute warps + 1 scan warp
+// and loops over tiles taken by ticket:
+//   compute warps  tile t+1: records -> staged index window -> bit updates -> ranks -> children in
+//                  registers; THEN flush the children of tile t from shared memory to their final,
+//                  now resolved, global slots (coalesced 16-byte stores); park the children of t+1
+//                  in shared memory and post their counts to the scan warp;
+//   scan warp      publishes the counts of a posted tile at once, resolves its exclusive prefix by
+//                  look-back while the compute warps already work on the next tile, and hands the
+//                  four base slots back.
+// Publication is never delayed, so the look-back window stays short; nothing waits unless the
+// prefix of tile t is still unresolved after the whole compute phase of tile t+1.
+// ---------------------------------------------------------------------------------------------
+constexpr int kCompThreads = 256;                     // 8 compute warps
+constexpr int kPersistThreads = kCompThreads + 32;    // + the scan warp
+constexpr uint32_t kExitSeq = 0xffffffffu;
+
+__device__ __forceinline__ void bar_compute() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+template <bool TWO>
+struct PersistSmem {
+    static constexpr int RU = TWO ? 4 : 2;            // uint4 per record
+    uint4 stage[kStageBlocks * 4];                    // staged index window(s)
+    uint4 child[4][kCompThreads * RU];                // parked children of the pending tile, per symbol
+    unsigned long long base[4];                       // resolved exclusive prefix of the pending tile
+    unsigned long long stat[C_NCOUNTERS];
+    uint32_t agg[4];                                  // child counts of the pending tile
+    uint32_t pend_tile;
+    uint32_t seq_posted, seq_done;                    // handshake compute warps <-> scan warp
+    uint32_t tile;
+    uint32_t rng[4];
+    uint32_t wpk[kCompThreads / 32];
+};
+
+template <bool TWO>
+__global__ void __launch_bounds__(kPersistThreads, TWO ? 2 : 3)
+expand_nodes_persistent(const NavArgs a, const Segs in) {
+    constexpr int WORDS = TWO ? 8 : 4;
+    constexpr int RU = TWO ? 4 : 2;
+    constexpr int STAGE = TWO ? kStageBlocks / 2 : kStageBlocks;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    PersistSmem<TWO> &sm = *reinterpret_cast<PersistSmem<TWO> *>(smem_raw);
+    volatile uint32_t *v_posted = &sm.seq_posted, *v_done = &sm.seq_done;
+    volatile unsigned long long *v_base = sm.base;
+
+    if (threadIdx.x == 0) { sm.seq_posted = 0; sm.seq_done = 0; }
+    __syncthreads();
+
+    if (threadIdx.x >= kCompThreads) {
+        // ------------------------------- scan warp -------------------------------
+        const int lane = threadIdx.x & 31;
+        uint32_t seen = 0;
+        while (true) {
+            uint32_t p = *v_posted;
+            while (p == seen) { __nanosleep(40); p = *v_posted; }
+            if (p == kExitSeq) break;
+            seen = p;
+            __threadfence_block();
+            const uint32_t tile = *(volatile uint32_t *)&sm.pend_tile;
+            uint32_t agg[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) agg[c] = ((volatile uint32_t *)sm.agg)[c];
+            unsigned long long excl[4];
+            lookback4(a.desc, a.epoch, tile, agg, excl);
+            if (lane < 4) {
+                unsigned long long e = 0, g2 = 0;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) if (lane == c) { e = excl[c]; g2 = agg[c]; }
+                v_base[lane] = e;
+                if (tile == a.n_tiles - 1) a.ctl->out_count[lane] = e + g2;
+            }
+            __threadfence_block();
+            __syncwarp();
+            if (lane == 0) *v_done = seen;
+        }
+        return;
+    }
+
+    // --------------------------------- compute warps ---------------------------------
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t my_seq = 0;                    // tiles this CTA has posted so far
+    const uint4 *stage1 = sm.stage, *stage2 = sm.stage + STAGE * 4;
+
+    auto flush_pending = [&]() {
+        // children of the pending tile: shared memory -> their resolved global slots
+        while (*v_done != my_seq) { }
+        __threadfence_block();
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const uint32_t n16 = ((volatile uint32_t *)sm.agg)[c] * RU;
+            uint4 *dst = reinterpret_cast<uint4 *>(a.out[c]) + v_base[c] * RU;
+            for (uint32_t i = threadIdx.x; i < n16; i += kCompThreads) dst[i] = sm.child[c][i];
+        }
+    };
+
+    while (true) {
+        if (threadIdx.x == 0) sm.tile = atomicAdd(&a.ctl->ticket, 1u);
+        if (threadIdx.x < C_NCOUNTERS) sm.stat[threadIdx.x] = 0;
+        bar_compute();
+        const uint32_t tile = sm.tile;
+        if (tile >= a.n_tiles) break;
+        const uint32_t g = tile * kCompThreads + threadIdx.x;
+        const bool active = g < in.total;
+
+        uint64_t base1 = 0, s1[5] = {0, 0, 0, 0, 0}, base2 = 0, s2[5] = {0, 0, 0, 0, 0};
+        uint32_t depth = 0;
+        bool narrow = true;
+        if (active) {
+            const uint4 *rec = reinterpret_cast<const uint4 *>(seg_record(in, g, WORDS));
+            const uint4 lo = __ldg(rec), hi = __ldg(rec + 1);
+            unpack_node(lo, hi, base1, s1, depth);
+            narrow = (hi.z | (hi.w & 0xffu)) == 0 && ((s1[0] + s1[1] + s1[2] + s1[3] + s1[4]) >> 32) == 0;
+            if (TWO) {
+                uint32_t d2;
+                const uint4 lo2 = __ldg(rec + 2), hi2 = __ldg(rec + 3);
+                unpack_node(lo2, hi2, base2, s2, d2);
+                narrow = narrow && (hi2.z | (hi2.w & 0xffu)) == 0 && ((s2[0] + s2[1] + s2[2] + s2[3] + s2[4]) >> 32) == 0;
+            }
+        }
+        uint32_t st_lcp = 0, st_min = 0, st_rank = 0, st_upd = 0, st_da = 0;
+        {
+            const uint32_t last_active = min((uint32_t)kCompThreads, in.total - tile * kCompThreads) - 1;
+            if (threadIdx.x == 0) { sm.rng[0] = (uint32_t)(base1 >> kBlockShift); if (TWO) sm.rng[2] = (uint32_t)(base2 >> kBlockShift); }
+            if (threadIdx.x == last_active) {
+                sm.rng[1] = (uint32_t)((base1 + s1[0] + s1[1] + s1[2] + s1[3] + s1[4]) >> kBlockShift);
+                if (TWO) sm.rng[3] = (uint32_t)((base2 + s2[0] + s2[1] + s2[2] + s2[3] + s2[4]) >> kBlockShift);
+            }
+        }
+        bar_compute();
+        const uint32_t lo1 = sm.rng[0], lo2 = TWO ? sm.rng[2] : 0u;
+        uint32_t nst1 = 0, nst2 = 0;
+        {
+            constexpr int ITER = STAGE * 4 / kCompThreads;
+            const uint32_t span1 = sm.rng[1] >= lo1 ? sm.rng[1] - lo1 + 1 : 0u;
+            if (span1 <= 2u * STAGE) nst1 = min(span1, (uint32_t)STAGE);
+            const uint4 *src1 = a.ix1.blocks + (size_t)lo1 * 4;
+#pragma unroll
+            for (int it = 0; it < ITER; ++it) {
+                const uint32_t k = threadIdx.x + it * kCompThreads;
+                if (k < nst1 * 4) cp_async16(&sm.stage[stage_slot(k >> 2, k & 3)], src1 + k);
+            }
+            if (TWO) {
+                const uint32_t end2 = sm.rng[3] + 1;
+                const uint32_t span2 = end2 > lo2 ? end2 - lo2 : 0u;
+                if (span2 <= 2u * STAGE) nst2 = min(span2, (uint32_t)STAGE);
+                const uint4 *src2 = a.ix2.blocks + (size_t)lo2 * 4;
+#pragma unroll
+                for (int it = 0; it < ITER; ++it) {
+                    const uint32_t k = threadIdx.x + it * kCompThreads;
+                    if (k < nst2 * 4) cp_async16(&sm.stage[STAGE * 4 + stage_slot(k >> 2, k & 3)], src2 + k);
+                }
+            }
+        }
+        // bit updates on the merged node while the copies are in flight (same rules as expand_nodes_kernel)
+        if (active && a.write) {
+            const uint64_t mbase = base1 + base2;
+            uint64_t ms[5], last = mbase;
+#pragma unroll
+            for (int j = 0; j < 5; ++j) { ms[j] = s1[j] + s2[j]; last += ms[j]; }
+            const uint32_t bits = (depth >= a.K ? 1u : 0u) | (depth >= a.k_right ? 2u : 0u);
+            WordAcc thr{a.thr, ~0ull, 0u}, mn{a.minima, ~0ull, 0u};
+            uint64_t mb = mbase;
+#pragma unroll
+            for (int j = 0; j < 5; ++j) {
+                if (TWO) {
+                    if (ms[j] == 1) {                        // find_leaves (ebwt2InDel.cpp:474-527)
+                        st_da++;
+                        if (s2[j] == 1) atomicOr(a.da + (mb >> 5), 1u << (mb & 31));
+                    }
+                }
+                mb += ms[j];
+                if (j < 4 && mb != last) {
+                    if (ms[j] > 0) {                         // update_lcp_threshold (include.hpp:826-860)
+                        st_lcp++;
+                        if (bits) { thr.add(mb >> 4, bits << ((mb & 15) * 2)); st_upd++; }
+                    }
+                    if (j >= 1 && ms[j] >= 2 && mb < last - 1) {   // update_lcp_minima (ebwt2InDel.cpp:357-391)
+                        st_min++;
+                        st_upd++;
+                        mn.add(mb >> 5, 1u << (mb & 31));
+                    }
+                }
+            }
+            thr.flush();
+            mn.flush();
+        }
+        cp_async_wait_all();
+        bar_compute();
+
+        ChildSide k1, k2;
+        uint32_t nzp = 0;
+        k1.h4 = 0; k2.h4 = 0;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { k1.hz[c] = 0; k2.hz[c] = 0; k1.base[c] = 0; k2.base[c] = 0; }
+        if (active) {
+            if (narrow) expand_core<TWO, uint32_t>(a, stage1, lo1, nst1, stage2, lo2, nst2, base1, s1, base2, s2, k1, k2, nzp, st_rank);
+            else expand_core<TWO, uint64_t>(a, stage1, lo1, nst1, stage2, lo2, nst2, base1, s1, base2, s2, k1, k2, nzp, st_rank);
+        }
+        uint32_t vm = 0, packed = 0, before[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const bool v = ((nzp >> (8 * c)) & 0xffu) >= 2u;
+            const uint32_t bal = __ballot_sync(0xffffffffu, v);
+            before[c] = __popc(bal & ((1u << lane) - 1u));
+            packed |= (uint32_t)__popc(bal) << (8 * c);
+            if (v) vm |= 1u << c;
+        }
+        if (lane == 0) sm.wpk[warp] = packed;
+        st_lcp = __reduce_add_sync(0xffffffffu, st_lcp);
+        st_min = __reduce_add_sync(0xffffffffu, st_min);
+        st_rank = __reduce_add_sync(0xffffffffu, st_rank);
+        st_upd = __reduce_add_sync(0xffffffffu, st_upd);
+        if (TWO) st_da = __reduce_add_sync(0xffffffffu, st_da);
+        if (lane == 0) {
+            if (st_lcp) atomicAdd(&sm.stat[C_LCP], (unsigned long long)st_lcp);
+            if (st_min) atomicAdd(&sm.stat[C_NMIN], (unsigned long long)st_min);
+            if (st_rank) atomicAdd(&sm.stat[C_RANK], (unsigned long long)st_rank);
+            if (st_upd) atomicAdd(&sm.stat[C_BITUPD], (unsigned long long)st_upd);
+            if (TWO && st_da) atomicAdd(&sm.stat[C_DA], (unsigned long long)st_da);
+        }
+        // the staged window and the per-warp counts are complete; the previous tile's children can leave
+        if (my_seq) flush_pending();
+        bar_compute();                                   // wpk visible; child buffer and agg free again
+        uint32_t exw[4] = {0, 0, 0, 0}, tot[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int w = 0; w < kCompThreads / 32; ++w) {
+            const uint32_t pk = sm.wpk[w];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const uint32_t n = (pk >> (8 * c)) & 0xffu;
+                if (w < warp) exw[c] += n;
+                tot[c] += n;
+            }
+        }
+        if (vm) {
+            const uint32_t depth1 = depth >= kDepthMax ? kDepthMax : depth + 1;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                if ((vm >> c) & 1u) {
+                    uint4 *dst = &sm.child[c][(exw[c] + before[c]) * RU];
+                    store_child(dst, k1, c, depth1);
+                    if (TWO) store_child(dst + 2, k2, c, depth1);
+                }
+            }
+        }
+        if (threadIdx.x == 0) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) sm.agg[c] = tot[c];
+            sm.pend_tile = tile;
+        }
+        if (threadIdx.x < C_NCOUNTERS && a.write) stripe_add(a.stripes, tile, threadIdx.x, sm.stat[threadIdx.x]);
+        bar_compute();                                   // children, counts and tile id are in shared memory
+        ++my_seq;
+        if (threadIdx.x == 0) { __threadfence_block(); *v_posted = my_seq; }
+    }
+    if (my_seq) flush_pending();
+    bar_compute();
+    if (threadIdx.x == 0) *v_posted = kExitSeq;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Phase 2 sweep: leaves (intervals of W#).  One thread per leaf (pair).
 // Record = 4 u64 {first, second, depth, 0}; mode -2: 8 u64 {f1, s1, depth, 0, f2, s2, 0, 0}.
 // ---------------------------------------------------------------------------------------------
@@ -677,6 +941,11 @@ extern "C" int e2i_navigate_shard(e2i_ctx *ctx, const e2i_index *b1, const e2i_i
     cudaStream_t s = ctx->stream;
     const bool two = b2 != nullptr;
     // the node kernels stage 32 KB per CTA: ask for the large shared-memory carveout so that 4 CTAs fit an SM
+    // E2I_NODE_KERNEL=tile selects the one-tile-per-CTA kernel (kept for A/B measurements)
+    const char *nk = std::getenv("E2I_NODE_KERNEL");
+    const bool persistent = !(nk && std::strcmp(nk, "tile") == 0);
+    E2I_CUDA_TRY(cudaFuncSetAttribute(expand_nodes_persistent<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PersistSmem<false>)));
+    E2I_CUDA_TRY(cudaFuncSetAttribute(expand_nodes_persistent<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PersistSmem<true>)));
     if (const char *cv = std::getenv("E2I_CARVEOUT")) {
         const int pct = atoi(cv);
         E2I_CUDA_TRY(cudaFuncSetAttribute(expand_nodes_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
@@ -788,6 +1057,10 @@ extern "C" int e2i_navigate_shard(e2i_ctx *ctx, const e2i_index *b1, const e2i_i
             if (leaves) {
                 if (two) expand_leaves_kernel<true><<<n_tiles, kNavThreads, 0, s>>>(a, segs);
                 else expand_leaves_kernel<false><<<n_tiles, kNavThreads, 0, s>>>(a, segs);
+            } else if (persistent) {
+                const uint32_t grid = std::min<uint32_t>(n_tiles, (uint32_t)ctx->sm_count * (two ? 2u : 3u));
+                if (two) expand_nodes_persistent<true><<<grid, kPersistThreads, sizeof(PersistSmem<true>), s>>>(a, segs);
+                else expand_nodes_persistent<false><<<grid, kPersistThreads, sizeof(PersistSmem<false>), s>>>(a, segs);
             } else {
                 if (two) expand_nodes_kernel<true><<<n_tiles, kNavThreads, 0, s>>>(a, segs);
                 else expand_nodes_kernel<false><<<n_tiles, kNavThreads, 0, s>>>(a, segs);

@@ -58,10 +58,27 @@ def format_sharded(api, recs, left, right, params, two_samples: bool, rank: int,
     first = 1 + sum(counts[:rank])
     if first != 1 and len(recs):
         txt, _ = api.snp_format(recs, left, right, params, two_samples, first_cluster_nr=first)
-    out = [None] * world if rank == 0 else None
-    dist.gather_object(txt, out, dst=0, group=group)
     events, clusters = sum(int(t[1]) for t in allc), sum(counts)
-    return (b"".join(out) if rank == 0 else None), events, clusters
+    return gather_bytes(txt, rank, world, device, group), events, clusters
+
+
+def gather_bytes(data: bytes, rank: int, world: int, device, group=None):
+    """Concatenation of every rank's byte string on rank 0 (rank order), moved as uint8 tensors:
+    sizes are exchanged first, then one padded gather (NCCL over NVLink on GPUs, gloo on CPU)."""
+    size = torch.tensor([len(data)], dtype=torch.int64, device=device)
+    sizes = [torch.zeros_like(size) for _ in range(world)]
+    dist.all_gather(sizes, size, group=group)
+    sizes = [int(s) for s in sizes]
+    pad = max(max(sizes), 1)
+    buf = torch.zeros(pad, dtype=torch.uint8, device=device)
+    if len(data):
+        src = torch.frombuffer(bytearray(data), dtype=torch.uint8)
+        buf[:len(data)].copy_(src)
+    out = [torch.empty(pad, dtype=torch.uint8, device=device) for _ in range(world)] if rank == 0 else None
+    dist.gather(buf, out, dst=0, group=group)
+    if rank != 0:
+        return None
+    return b"".join(out[r][:sizes[r]].cpu().numpy().tobytes() for r in range(world))
 
 
 def gather_calls(recs: np.ndarray, left: np.ndarray, right: np.ndarray, rank: int, world: int, group=None):
