@@ -174,6 +174,12 @@ static int run_on_device(e2i_ctx *ctx, const uint8_t *dev_bwt1, uint64_t n1, con
     if (release_inputs) release_inputs(release_arg);   // the ASCII copies are dead once the index exists
     if (rc == E2I_OK) rc = e2i_navigate(ctx, b1, b2, p, &lcp, b2 ? &da_nav : nullptr, st);
     if (rc == E2I_OK) rc = e2i_call(ctx, b1, b2, b2 ? da_nav : da, lcp, p, 0, UINT64_MAX, &calls, st);
+    if (std::getenv("E2I_DEBUG")) {
+        cudaStreamSynchronize(s);
+        std::fprintf(stderr, "[e2i] run: %.1f ms of host wall time before formatting (phases: index %.1f leaves %.1f nodes %.1f call %.1f)\n",
+                     std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - w0).count(),
+                     st->ms_index, st->ms_leaves, st->ms_nodes, st->ms_call);
+    }
     const auto w1 = std::chrono::steady_clock::now();
     if (rc == E2I_OK)
         rc = e2i_snp_format(calls->recs, calls->left, calls->right, calls->n, p,
