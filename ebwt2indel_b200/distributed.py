@@ -19,6 +19,9 @@ import torch
 import torch.distributed as dist
 
 
+_pinned = None
+
+
 class _DeviceWords:
     """Zero-copy view of `words32` int32 words at a raw device pointer (CUDA array interface)."""
 
@@ -62,23 +65,40 @@ def format_sharded(api, recs, left, right, params, two_samples: bool, rank: int,
     return gather_bytes(txt, rank, world, device, group), events, clusters
 
 
-def gather_bytes(data: bytes, rank: int, world: int, device, group=None):
-    """Concatenation of every rank's byte string on rank 0 (rank order), moved as uint8 tensors:
-    sizes are exchanged first, then one padded gather (NCCL over NVLink on GPUs, gloo on CPU)."""
-    size = torch.tensor([len(data)], dtype=torch.int64, device=device)
+def gather_bytes(data, rank: int, world: int, device, group=None):
+    """Concatenation of every rank's byte string on rank 0 (rank order).  Sizes are exchanged first;
+    every rank > 0 then sends exactly its bytes and rank 0 receives them into consecutive slices
+    of ONE buffer (NCCL point-to-point over NVLink on GPUs, gloo on CPU), so the text is copied
+    once on each side."""
+    view = memoryview(data).cast("B") if len(data) else memoryview(b"")
+    size = torch.tensor([len(view)], dtype=torch.int64, device=device)
     sizes = [torch.zeros_like(size) for _ in range(world)]
     dist.all_gather(sizes, size, group=group)
     sizes = [int(s) for s in sizes]
-    pad = max(max(sizes), 1)
-    buf = torch.zeros(pad, dtype=torch.uint8, device=device)
-    if len(data):
-        src = torch.frombuffer(bytearray(data), dtype=torch.uint8)
-        buf[:len(data)].copy_(src)
-    out = [torch.empty(pad, dtype=torch.uint8, device=device) for _ in range(world)] if rank == 0 else None
-    dist.gather(buf, out, dst=0, group=group)
+    cuda = torch.device(device).type == "cuda"
     if rank != 0:
+        if sizes[rank]:
+            src = torch.frombuffer(bytearray(view), dtype=torch.uint8)
+            dist.send(src.to(device, non_blocking=True) if cuda else src, dst=0, group=group)
         return None
-    return b"".join(out[r][:sizes[r]].cpu().numpy().tobytes() for r in range(world))
+    total = sum(sizes)
+    buf = torch.empty(max(total, 1), dtype=torch.uint8, device=device)
+    if sizes[0]:
+        mine = torch.frombuffer(bytearray(view), dtype=torch.uint8)
+        buf[:sizes[0]].copy_(mine)
+    off = sizes[0]
+    for r in range(1, world):
+        if sizes[r]:
+            dist.recv(buf[off:off + sizes[r]], src=r, group=group)
+        off += sizes[r]
+    if cuda:
+        global _pinned
+        if _pinned is None or _pinned.numel() < total:
+            _pinned = torch.empty(max(total, 1) * 5 // 4, dtype=torch.uint8, pin_memory=True)   # page-locked once, reused
+        host = _pinned[:max(total, 1)]
+        host.copy_(buf, non_blocking=False)
+        buf = host
+    return buf[:total].numpy().tobytes()
 
 
 def gather_calls(recs: np.ndarray, left: np.ndarray, right: np.ndarray, rank: int, world: int, group=None):
