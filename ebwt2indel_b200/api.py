@@ -67,7 +67,8 @@ assert CALL_REC_DTYPE.itemsize == C.sizeof(CallRec) == 56
 SYMBOLS = (
     "e2i_last_error", "e2i_version", "e2i_params_default", "e2i_params_resolve", "e2i_create", "e2i_destroy",
     "e2i_set_frontier_budget", "e2i_trim", "e2i_stream", "e2i_host_alloc", "e2i_host_free", "e2i_index_build", "e2i_index_build_device",
-    "e2i_index_free", "e2i_index_size", "e2i_index_F", "e2i_index_bytes", "e2i_rank_batch", "e2i_access_batch",
+    "e2i_index_slice_align", "e2i_index_alloc", "e2i_index_slice_count", "e2i_index_slice_super",
+    "e2i_index_slice_pack", "e2i_index_finish", "e2i_index_device", "e2i_index_free", "e2i_index_size", "e2i_index_F", "e2i_index_bytes", "e2i_rank_batch", "e2i_access_batch",
     "e2i_fl_batch", "e2i_rank_batch_device", "e2i_da_load", "e2i_da_load_device", "e2i_bits_fetch",
     "e2i_bits_size", "e2i_bits_free", "e2i_navigate", "e2i_navigate_shard", "e2i_lcpbits_fetch",
     "e2i_lcpbits_device", "e2i_bits_device", "e2i_lcpbits_free", "e2i_call", "e2i_calls_count",
@@ -102,6 +103,13 @@ def lib():
         "e2i_host_free": (None, [vp]),
         "e2i_index_build": (C.c_int, [vp, u8p, u64, C.c_uint8, C.POINTER(vp), C.POINTER(u64)]),
         "e2i_index_build_device": (C.c_int, [vp, u8p, u64, C.c_uint8, C.POINTER(vp), C.POINTER(u64)]),
+        "e2i_index_slice_align": (u64, []),
+        "e2i_index_alloc": (C.c_int, [vp, u64, C.c_uint8, u64, C.POINTER(vp)]),
+        "e2i_index_slice_count": (C.c_int, [vp, vp, u8p, u64, u64, u64p, C.POINTER(u64)]),
+        "e2i_index_slice_super": (C.c_int, [vp, vp, u64p, u64p]),
+        "e2i_index_slice_pack": (C.c_int, [vp, vp, u8p, u64p, u64p]),
+        "e2i_index_finish": (C.c_int, [vp, u64p]),
+        "e2i_index_device": (C.c_int, [vp, C.POINTER(vp), C.POINTER(u64)]),
         "e2i_index_free": (None, [vp]),
         "e2i_index_size": (u64, [vp]),
         "e2i_index_F": (C.c_int, [vp, u64p]),
@@ -251,6 +259,12 @@ class Context:
         _check(rc)
         return Index(self, h)
 
+    def index_alloc(self, n: int, term: int = ord("#"), tile_multiple: int = 1) -> "Index":
+        """Empty index for slice-wise construction (Index.slice_count / slice_super / slice_pack / finish)."""
+        h = C.c_void_p()
+        _check(lib().e2i_index_alloc(self.h, n, term, tile_multiple, C.byref(h)))
+        return Index(self, h)
+
     def document_array(self, da) -> "Bits":
         h = C.c_void_p()
         if hasattr(da, "data_ptr") and da.is_cuda:
@@ -361,6 +375,39 @@ class Index:
         out = np.zeros(4, dtype=np.uint64)
         _check(lib().e2i_index_F(self.h, out.ctypes.data))
         return out
+
+    # ---- slice-wise construction (multi-GPU) ----
+    def slice_count(self, dev_slice, begin: int) -> np.ndarray:
+        counts = np.zeros(4, dtype=np.uint64)
+        bad = C.c_uint64(0)
+        rc = lib().e2i_index_slice_count(self.ctx.h, self.h, dev_slice.data_ptr() if dev_slice.numel() else None, begin,
+                                         dev_slice.numel(), counts.ctypes.data, C.byref(bad))
+        if rc == E2I_ERR_SYMBOL:
+            raise ValueError(f"forbidden symbol at position {bad.value}")
+        _check(rc)
+        return counts
+
+    def slice_super(self, before: np.ndarray, n_super: int) -> np.ndarray:
+        before = np.ascontiguousarray(before, dtype=np.uint64)
+        out = np.zeros(n_super * 4, dtype=np.uint64)
+        _check(lib().e2i_index_slice_super(self.ctx.h, self.h, before.ctypes.data, out.ctypes.data))
+        return out
+
+    def slice_pack(self, dev_slice, before: np.ndarray, super_table: np.ndarray):
+        before = np.ascontiguousarray(before, dtype=np.uint64)
+        super_table = np.ascontiguousarray(super_table, dtype=np.uint64)
+        _check(lib().e2i_index_slice_pack(self.ctx.h, self.h, dev_slice.data_ptr() if dev_slice.numel() else None,
+                                          before.ctypes.data, super_table.ctypes.data))
+
+    def finish(self, totals: np.ndarray):
+        totals = np.ascontiguousarray(totals, dtype=np.uint64)
+        _check(lib().e2i_index_finish(self.h, totals.ctypes.data))
+
+    def device_blocks(self):
+        """(device pointer, bytes) of the block array, for the all-gather of the slices."""
+        p, b = C.c_void_p(), C.c_uint64()
+        _check(lib().e2i_index_device(self.h, C.byref(p), C.byref(b)))
+        return int(p.value), int(b.value)
 
     def rank4(self, pos) -> np.ndarray:
         pos = np.ascontiguousarray(pos, dtype=np.uint64)

@@ -129,6 +129,9 @@ struct e2i_index {
     uint64_t n = 0, n_blocks = 0, n_super = 0, bytes = 0;
     uint64_t F[4] = {0, 0, 0, 0};
     uint8_t term = '#';
+    // slice-wise construction state (e2i_index_slice_*)
+    void *slice_cnt = nullptr, *slice_prefix = nullptr;
+    uint64_t slice_begin = 0, slice_len = 0, slice_tiles = 0;
     e2i::DevIndex dev() const {
         e2i::DevIndex d;
         d.blocks = blocks;

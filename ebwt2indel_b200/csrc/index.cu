@@ -62,10 +62,13 @@ constexpr int kPiecesPerThread = kPiecesPerTile / kBuildThreads;     // 4
 
 // Kernel 1: per-tile symbol totals.  Grid-stride over tiles; coalesced 16-byte loads.
 __global__ void __launch_bounds__(kBuildThreads)
-count_tiles_kernel(const uint8_t *__restrict__ ascii, uint64_t n, uint32_t term, uint64_t n_tiles,
+count_tiles_kernel(const uint8_t *__restrict__ ascii, uint64_t n, uint32_t term, uint64_t tile0, uint64_t n_tiles,
                    uint4 *__restrict__ tile_cnt, unsigned long long *bad_pos) {
+    // `ascii` points at global position tile0 << kTileShift; tiles tile0 .. tile0 + n_tiles - 1 are counted
+    ascii -= tile0 << kTileShift;
     __shared__ unsigned long long s_part[kBuildThreads / 32];
-    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    for (uint64_t lt = blockIdx.x; lt < n_tiles; lt += gridDim.x) {
+        const uint64_t tile = tile0 + lt;
         unsigned long long acc = 0;  // 4 x 16-bit fields
 #pragma unroll
         for (int it = 0; it < kPiecesPerThread; ++it) {
@@ -84,7 +87,7 @@ count_tiles_kernel(const uint8_t *__restrict__ ascii, uint64_t n, uint32_t term,
         if (threadIdx.x == 0) {
             unsigned long long t = 0;
             for (int w = 0; w < kBuildThreads / 32; ++w) t += s_part[w];
-            tile_cnt[tile] = make_uint4((uint32_t)(t & 0xffff), (uint32_t)((t >> 16) & 0xffff),
+            tile_cnt[lt] = make_uint4((uint32_t)(t & 0xffff), (uint32_t)((t >> 16) & 0xffff),
                                         (uint32_t)((t >> 32) & 0xffff), (uint32_t)(t >> 48));
         }
         __syncthreads();
@@ -144,14 +147,21 @@ scan_tiles_kernel(const uint4 *__restrict__ tile_cnt, uint64_t n_tiles, ulonglon
 
 // Kernel 3: pack one tile (128 blocks) per CTA iteration.
 __global__ void __launch_bounds__(kBuildThreads)
-pack_tiles_kernel(const uint8_t *__restrict__ ascii, uint64_t n, uint32_t term, uint64_t n_tiles,
-                  const ulonglong4 *__restrict__ tile_prefix, uint4 *__restrict__ blocks,
+pack_tiles_kernel(const uint8_t *__restrict__ ascii, uint64_t n, uint32_t term, uint64_t tile0, uint64_t n_tiles,
+                  const ulonglong4 *__restrict__ tile_prefix, const ulonglong4 base,
+                  const unsigned long long *__restrict__ super_in, uint4 *__restrict__ blocks,
                   unsigned long long *__restrict__ super) {
+    // Packs global tiles tile0 .. tile0 + n_tiles - 1 (`ascii` points at position tile0 << kTileShift);
+    // tile_prefix is local to the slice and `base` holds the counts before it.  Whole-string build:
+    // tile0 = 0, base = 0, super_in = nullptr (superblock entries are written here).  Slice build:
+    // super_in = the complete table of absolute counts at the superblock starts.
+    ascii -= tile0 << kTileShift;
     __shared__ uint16_t s_plane[3][kPiecesPerTile];
     __shared__ uint32_t s_cnt[kPiecesPerTile];
     __shared__ unsigned long long s_blk[kTileSyms / kBlockSyms];      // exclusive per-block prefix, 4 x 16 bit
     __shared__ unsigned long long s_wsum[4];
-    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    for (uint64_t lt = blockIdx.x; lt < n_tiles; lt += gridDim.x) {
+        const uint64_t tile = tile0 + lt;
 #pragma unroll
         for (int it = 0; it < kPiecesPerThread; ++it) {
             const int piece = it * kBuildThreads + threadIdx.x;
@@ -189,11 +199,17 @@ pack_tiles_kernel(const uint8_t *__restrict__ ascii, uint64_t n, uint32_t term, 
             s_blk[threadIdx.x] = off + incl - mine;
         }
         __syncthreads();
-        const ulonglong4 tp = tile_prefix[tile];
-        const ulonglong4 sp = tile_prefix[(tile >> kSuperTileShift) << kSuperTileShift];
-        if (threadIdx.x == 0 && (tile & ((1ull << kSuperTileShift) - 1)) == 0) {
-            unsigned long long *s = super + (tile >> kSuperTileShift) * 4;
-            s[0] = tp.x; s[1] = tp.y; s[2] = tp.z; s[3] = tp.w;
+        ulonglong4 tp = tile_prefix[lt], sp;
+        tp.x += base.x; tp.y += base.y; tp.z += base.z; tp.w += base.w;       // absolute counts before the tile
+        if (super_in) {
+            const unsigned long long *q = super_in + (tile >> kSuperTileShift) * 4;
+            sp = make_ulonglong4(q[0], q[1], q[2], q[3]);
+        } else {
+            sp = tile_prefix[((tile >> kSuperTileShift) << kSuperTileShift) - tile0];
+            if (threadIdx.x == 0 && (tile & ((1ull << kSuperTileShift) - 1)) == 0) {
+                unsigned long long *s = super + (tile >> kSuperTileShift) * 4;
+                s[0] = tp.x; s[1] = tp.y; s[2] = tp.z; s[3] = tp.w;
+            }
         }
         // 128 blocks x 4 uint4 = 512 uint4 per tile, written coalesced
         uint4 *out = blocks + (tile << (kTileShift - kBlockShift)) * 4;
@@ -299,10 +315,10 @@ extern "C" int e2i_index_build_device(e2i_ctx *ctx, const uint8_t *dev_ascii, ui
     unsigned long long init[5] = {0, 0, 0, 0, ~0ull};
     TRYF(cudaMemcpyAsync(scal, init, sizeof init, cudaMemcpyHostToDevice, s));
     const int grid = (int)std::min<uint64_t>(n_tiles, (uint64_t)ctx->sm_count * 16);
-    count_tiles_kernel<<<grid, kBuildThreads, 0, s>>>(dev_ascii, n, term, n_tiles, tile_cnt, scal + 4);
+    count_tiles_kernel<<<grid, kBuildThreads, 0, s>>>(dev_ascii, n, term, 0, n_tiles, tile_cnt, scal + 4);
     scan_tiles_kernel<<<1, kScanThreads, 0, s>>>(tile_cnt, n_tiles, tile_prefix, scal);
-    pack_tiles_kernel<<<grid, kBuildThreads, 0, s>>>(dev_ascii, n, term, n_tiles, tile_prefix, ix->blocks,
-                                                     reinterpret_cast<unsigned long long *>(ix->super));
+    pack_tiles_kernel<<<grid, kBuildThreads, 0, s>>>(dev_ascii, n, term, 0, n_tiles, tile_prefix, make_ulonglong4(0, 0, 0, 0), nullptr,
+                                                     ix->blocks, reinterpret_cast<unsigned long long *>(ix->super));
     TRYF(cudaGetLastError());
     ctx->n_launch += 3;
     ctx->n_h2d += sizeof init;
@@ -329,6 +345,128 @@ extern "C" int e2i_index_build_device(e2i_ctx *ctx, const uint8_t *dev_ascii, ui
     return E2I_OK;
 }
 
+// ---- slice-wise construction (multi-GPU): every rank packs the blocks of one tile-aligned slice ----
+extern "C" uint64_t e2i_index_slice_align(void) { return (uint64_t)kTileSyms; }
+
+extern "C" int e2i_index_alloc(e2i_ctx *ctx, uint64_t n, uint8_t term, uint64_t tile_multiple, e2i_index **out) {
+    if (!ctx || !out || tile_multiple == 0) { set_error("e2i_index_alloc: bad argument"); return E2I_ERR_ARG; }
+    E2I_CUDA_TRY(cudaSetDevice(ctx->device));
+    e2i_index *ix = new e2i_index();
+    ix->ctx = ctx;
+    ix->n = n;
+    ix->term = term;
+    ix->n_blocks = n / kBlockSyms + 1;
+    uint64_t n_tiles = (ix->n_blocks + 127) / 128;
+    n_tiles = (n_tiles + tile_multiple - 1) / tile_multiple * tile_multiple;   // equal slices for the all-gather
+    ix->n_super = (n >> kSuperShift) + 1;
+    const size_t blk_bytes = n_tiles * 128 * 64;
+    ix->bytes = blk_bytes + ix->n_super * 32;
+    if (dmalloc(ctx, &ix->blocks, blk_bytes) != cudaSuccess || dmalloc(ctx, &ix->super, ix->n_super * 32) != cudaSuccess) {
+        cudaGetLastError();
+        set_error("e2i_index_alloc: out of device memory");
+        e2i_index_free(ix);
+        return E2I_ERR_MEMORY;
+    }
+    *out = ix;
+    return E2I_OK;
+}
+
+extern "C" int e2i_index_slice_count(e2i_ctx *ctx, e2i_index *ix, const uint8_t *dev_slice, uint64_t begin, uint64_t len,
+                                     uint64_t counts[4], uint64_t *bad_pos) {
+    if (!ctx || !ix || !counts || (len && !dev_slice)) { set_error("e2i_index_slice_count: null argument"); return E2I_ERR_ARG; }
+    if ((begin & (kTileSyms - 1)) || begin + len > ix->n || (reinterpret_cast<uintptr_t>(dev_slice) & 15)) { set_error("e2i_index_slice_count: slice must start on a multiple of %d symbols, lie inside the string and be 16-byte aligned", kTileSyms); return E2I_ERR_ARG; }
+    E2I_CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    dfree(ctx, ix->slice_cnt); dfree(ctx, ix->slice_prefix);
+    ix->slice_cnt = nullptr; ix->slice_prefix = nullptr;
+    ix->slice_begin = begin;
+    ix->slice_len = len;
+    // the slice that reaches n also owns the block that makes rank(n) addressable
+    const uint64_t end = begin + len;
+    ix->slice_tiles = end == ix->n ? (ix->n_blocks + 127) / 128 - (begin >> kTileShift) : (len + kTileSyms - 1) >> kTileShift;
+    const uint64_t nt = ix->slice_tiles;
+    for (int k = 0; k < 4; ++k) counts[k] = 0;
+    if (nt == 0) return E2I_OK;
+    unsigned long long *scal = nullptr;
+    E2I_CUDA_TRY(dmalloc(ctx, &ix->slice_cnt, nt * sizeof(uint4)));
+    E2I_CUDA_TRY(dmalloc(ctx, &ix->slice_prefix, nt * sizeof(ulonglong4)));
+    E2I_CUDA_TRY(dmalloc(ctx, &scal, 5 * sizeof(unsigned long long)));
+    unsigned long long init[5] = {0, 0, 0, 0, ~0ull}, res[5];
+    E2I_CUDA_TRY(cudaMemcpyAsync(scal, init, sizeof init, cudaMemcpyHostToDevice, s));
+    const int grid = (int)std::min<uint64_t>(nt, (uint64_t)ctx->sm_count * 16);
+    count_tiles_kernel<<<grid, kBuildThreads, 0, s>>>(dev_slice, end, ix->term, begin >> kTileShift, nt,
+                                                      static_cast<uint4 *>(ix->slice_cnt), scal + 4);
+    scan_tiles_kernel<<<1, kScanThreads, 0, s>>>(static_cast<uint4 *>(ix->slice_cnt), nt, static_cast<ulonglong4 *>(ix->slice_prefix), scal);
+    E2I_CUDA_TRY(cudaGetLastError());
+    ctx->n_launch += 2;
+    E2I_CUDA_TRY(cudaMemcpyAsync(res, scal, sizeof res, cudaMemcpyDeviceToHost, s));
+    E2I_CUDA_TRY(cudaStreamSynchronize(s));
+    dfree(ctx, scal);
+    if (res[4] != ~0ull) {
+        if (bad_pos) *bad_pos = res[4];
+        set_error("forbidden character at position %llu: only A,C,G,T and the terminator (ASCII %d) are admitted in the input BWT", res[4], (int)ix->term);
+        return E2I_ERR_SYMBOL;
+    }
+    for (int k = 0; k < 4; ++k) counts[k] = res[k];
+    return E2I_OK;
+}
+
+extern "C" int e2i_index_slice_super(e2i_ctx *ctx, e2i_index *ix, const uint64_t before[4], uint64_t *host_super) {
+    if (!ctx || !ix || !before || !host_super) { set_error("e2i_index_slice_super: null argument"); return E2I_ERR_ARG; }
+    E2I_CUDA_TRY(cudaSetDevice(ctx->device));
+    const uint64_t tile0 = ix->slice_begin >> kTileShift;
+    for (uint64_t sb = 0; sb < ix->n_super; ++sb) {
+        uint64_t *o = host_super + sb * 4;
+        o[0] = o[1] = o[2] = o[3] = 0;
+        const uint64_t tile = sb << kSuperTileShift;              // first tile of the superblock
+        if (tile < tile0 || tile >= tile0 + ix->slice_tiles) continue;
+        unsigned long long tp[4];
+        E2I_CUDA_TRY(cudaMemcpy(tp, static_cast<ulonglong4 *>(ix->slice_prefix) + (tile - tile0), sizeof tp, cudaMemcpyDeviceToHost));
+        for (int k = 0; k < 4; ++k) o[k] = before[k] + tp[k];
+    }
+    return E2I_OK;
+}
+
+extern "C" int e2i_index_slice_pack(e2i_ctx *ctx, e2i_index *ix, const uint8_t *dev_slice, const uint64_t before[4],
+                                    const uint64_t *host_super) {
+    if (!ctx || !ix || !before || !host_super) { set_error("e2i_index_slice_pack: null argument"); return E2I_ERR_ARG; }
+    E2I_CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    E2I_CUDA_TRY(cudaMemcpyAsync(ix->super, host_super, ix->n_super * 32, cudaMemcpyHostToDevice, s));
+    const uint64_t nt = ix->slice_tiles;
+    if (nt) {
+        const int grid = (int)std::min<uint64_t>(nt, (uint64_t)ctx->sm_count * 16);
+        pack_tiles_kernel<<<grid, kBuildThreads, 0, s>>>(dev_slice, ix->slice_begin + ix->slice_len, ix->term, ix->slice_begin >> kTileShift, nt,
+                                                         static_cast<ulonglong4 *>(ix->slice_prefix),
+                                                         make_ulonglong4(before[0], before[1], before[2], before[3]),
+                                                         reinterpret_cast<const unsigned long long *>(ix->super), ix->blocks, nullptr);
+        E2I_CUDA_TRY(cudaGetLastError());
+        ctx->n_launch++;
+    }
+    E2I_CUDA_TRY(cudaStreamSynchronize(s));
+    dfree(ctx, ix->slice_cnt); dfree(ctx, ix->slice_prefix);
+    ix->slice_cnt = nullptr; ix->slice_prefix = nullptr;
+    return E2I_OK;
+}
+
+extern "C" int e2i_index_finish(e2i_index *ix, const uint64_t totals[4]) {
+    if (!ix || !totals) { set_error("e2i_index_finish: null argument"); return E2I_ERR_ARG; }
+    const uint64_t acgt = totals[0] + totals[1] + totals[2] + totals[3];
+    if (acgt > ix->n) { set_error("e2i_index_finish: symbol totals exceed the string length"); return E2I_ERR_ARG; }
+    ix->F[0] = ix->n - acgt;
+    ix->F[1] = ix->F[0] + totals[0];
+    ix->F[2] = ix->F[1] + totals[1];
+    ix->F[3] = ix->F[2] + totals[2];
+    return E2I_OK;
+}
+
+extern "C" int e2i_index_device(const e2i_index *ix, void **dev_blocks, uint64_t *block_bytes) {
+    if (!ix) { set_error("e2i_index_device: null argument"); return E2I_ERR_ARG; }
+    if (dev_blocks) *dev_blocks = ix->blocks;
+    if (block_bytes) *block_bytes = ix->bytes - ix->n_super * 32;
+    return E2I_OK;
+}
+
 extern "C" int e2i_index_build(e2i_ctx *ctx, const uint8_t *host_ascii, uint64_t n, uint8_t term,
                                e2i_index **out, uint64_t *bad_pos) {
     if (!ctx || !out || (n && !host_ascii)) { set_error("e2i_index_build: null argument"); return E2I_ERR_ARG; }
@@ -347,6 +485,8 @@ extern "C" void e2i_index_free(e2i_index *ix) {
     if (!ix) return;
     dfree(ix->ctx, ix->blocks);
     dfree(ix->ctx, ix->super);
+    dfree(ix->ctx, ix->slice_cnt);
+    dfree(ix->ctx, ix->slice_prefix);
     delete ix;
 }
 

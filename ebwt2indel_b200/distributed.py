@@ -34,6 +34,47 @@ def wrap_device_words(ptr: int, words32: int, device) -> torch.Tensor:
     return torch.as_tensor(_DeviceWords(ptr, words32), device=device)
 
 
+TILE = 16384            # e2i_index_slice_align(): slices of the index start on tile boundaries
+
+
+def index_slices(n: int, world: int):
+    """Tile-aligned, equally sized slices of [0, n) for the slice-wise index build: (begin, end) per rank."""
+    tiles = (n // 128 + 1 + 127) // 128
+    per = (tiles + world - 1) // world
+    return [(min(n, r * per * TILE), min(n, (r + 1) * per * TILE)) for r in range(world)], per
+
+
+def build_index_sharded(ctx, bwt_slice, n: int, term: int, rank: int, world: int, group=None):
+    """Index of the whole string from one ASCII slice per rank.
+
+    Every rank counts and packs its own tile-aligned slice (bwt_slice = CUDA uint8 tensor holding
+    positions index_slices(n, world)[rank]); symbol totals and the superblock table are exchanged
+    (a few integers), then the block ranges are all-gathered over NVLink.  Bit-identical to
+    ctx.index(whole string)."""
+    device = bwt_slice.device
+    slices, per = index_slices(n, world)
+    begin, end = slices[rank]
+    assert bwt_slice.numel() == end - begin
+    ix = ctx.index_alloc(n, term, tile_multiple=world)
+    counts = ix.slice_count(bwt_slice, begin)
+    mine = torch.from_numpy(counts.astype(np.int64)).to(device)
+    allc = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(allc, mine, group=group)
+    allc = torch.stack(allc).cpu().numpy().astype(np.uint64)
+    before = allc[:rank].sum(axis=0) if rank else np.zeros(4, dtype=np.uint64)
+    n_super = (n >> 32) + 1
+    sup = torch.from_numpy(ix.slice_super(before, n_super).astype(np.int64)).to(device)
+    dist.all_reduce(sup, op=dist.ReduceOp.SUM, group=group)
+    ix.slice_pack(bwt_slice, before, sup.cpu().numpy().astype(np.uint64))
+    ptr, nbytes = ix.device_blocks()
+    full = wrap_device_words(ptr, nbytes // 4, device)
+    per_words = per * 128 * 64 // 4
+    assert per_words * world == full.numel()
+    dist.all_gather_into_tensor(full, full[rank * per_words:(rank + 1) * per_words], group=group)
+    ix.finish(allc.sum(axis=0))
+    return ix
+
+
 def position_cuts(n: int, world: int):
     """Contiguous suffix-array ranges for phase 4: clusters are assigned by their START position."""
     return [n * r // world for r in range(world + 1)]
@@ -151,8 +192,15 @@ def run_sharded(ctx, api, bwt1, bwt2, da, params, rank: int, world: int, group=N
         t = time.perf_counter()
         tm[name] = tm.get(name, 0.0) + (t - tp) * 1e3
         tp = t
-    b1 = ctx.index(bwt1, term)
-    b2 = ctx.index(bwt2, term) if bwt2 is not None else None
+    def make_index(t):
+        n_t = t.numel()
+        if world == 1 or n_t < world * 4 * TILE:
+            return ctx.index(t, term)
+        lo, hi = index_slices(n_t, world)[0][rank]
+        return build_index_sharded(ctx, t[lo:hi], n_t, term, rank, world, group)
+
+    b1 = make_index(bwt1)
+    b2 = make_index(bwt2) if bwt2 is not None else None
     dabits = ctx.document_array(da) if da is not None else None
     st = api.Stats()
     lap("index")

@@ -136,6 +136,25 @@ uint64_t e2i_index_size(const e2i_index *ix);                   /* dna_bwt::size
 int e2i_index_F(const e2i_index *ix, uint64_t F[4]);            /* F_A,F_C,F_G,F_T          :412-415 */
 uint64_t e2i_index_bytes(const e2i_index *ix);                  /* HBM footprint */
 
+/* ---- slice-wise index construction for multi-GPU runs: the string is cut into
+ *      slices that start on multiples of e2i_index_slice_align() symbols; every rank counts and
+ *      packs ONE slice into a pre-allocated index, the block ranges are exchanged between the GPUs
+ *      (all-gather over NVLink, ebwt2indel_b200/distributed.py) and e2i_index_finish sets F.
+ *      Same result as e2i_index_build_device on the whole string.
+ *      tile_multiple: the block array is padded to a multiple of that many slices' worth of tiles.
+ *      slice_count: counts[4] = #A,#C,#G,#T of the slice.  slice_super: host_super[n_super*4]
+ *      receives the superblock entries this slice owns (zeros elsewhere) given the counts before
+ *      the slice; the SUM over ranks is the complete table that slice_pack takes. --------------- */
+uint64_t e2i_index_slice_align(void);
+int e2i_index_alloc(e2i_ctx *ctx, uint64_t n, uint8_t term, uint64_t tile_multiple, e2i_index **out);
+int e2i_index_slice_count(e2i_ctx *ctx, e2i_index *ix, const uint8_t *dev_slice, uint64_t begin, uint64_t len,
+                          uint64_t counts[4], uint64_t *bad_pos);
+int e2i_index_slice_super(e2i_ctx *ctx, e2i_index *ix, const uint64_t before[4], uint64_t *host_super);
+int e2i_index_slice_pack(e2i_ctx *ctx, e2i_index *ix, const uint8_t *dev_slice, const uint64_t before[4],
+                         const uint64_t *host_super);
+int e2i_index_finish(e2i_index *ix, const uint64_t totals[4]);
+int e2i_index_device(const e2i_index *ix, void **dev_blocks, uint64_t *block_bytes);
+
 /* ---- a2/a3/a4 test hooks.  parallel_rank (dna_string.hpp:140-152), operator[] (:113-135),
  *      FL = select (dna_bwt.hpp:115-133, dna_string.hpp:254-272), batched. ------------------ */
 int e2i_rank_batch(e2i_ctx *ctx, const e2i_index *ix, const uint64_t *host_pos, uint64_t m, uint64_t *host_out4);

@@ -273,3 +273,39 @@ def test_gpu_ebwt_builder_matches_reference_builders(gpu_ctx):
     assert np.array_equal(bwt.cpu().numpy(), m)
     assert np.array_equal((owner + 48).cpu().numpy(), da)
     torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize("n,world", [(200000, 2), (1 << 20, 3), (1000003, 8)])
+def test_slicewise_index_build_equals_whole_build(gpu_ctx, oracle, n, world):
+    """Multi-GPU index construction, emulated on one GPU: every 'rank' counts and packs its own
+    tile-aligned slice, the block ranges are put together, and the result answers rank queries
+    exactly like the index built from the whole string (and like the oracle)."""
+    import torch
+    from ebwt2indel_b200 import distributed as dd
+    bwt = mixed_bwt(n, seed=n + world)
+    dev = torch.from_numpy(bwt.copy()).cuda()
+    slices, per = dd.index_slices(n, world)
+    parts = [gpu_ctx.index_alloc(n, ord("#"), tile_multiple=world) for _ in range(world)]
+    counts = np.stack([parts[r].slice_count(dev[slices[r][0]:slices[r][1]], slices[r][0]) for r in range(world)])
+    n_super = (n >> 32) + 1
+    sup = np.zeros(n_super * 4, dtype=np.uint64)
+    for r in range(world):
+        sup += parts[r].slice_super(counts[:r].sum(axis=0), n_super)
+    views = []
+    for r in range(world):
+        parts[r].slice_pack(dev[slices[r][0]:slices[r][1]], counts[:r].sum(axis=0), sup)
+        ptr, nbytes = parts[r].device_blocks()
+        views.append(dd.wrap_device_words(ptr, nbytes // 4, dev.device))
+    w = per * 128 * 64 // 4
+    for r in range(1, world):
+        views[0][r * w:(r + 1) * w].copy_(views[r][r * w:(r + 1) * w])   # the all-gather, by hand
+    torch.cuda.synchronize()
+    parts[0].finish(counts.sum(axis=0))
+    whole = gpu_ctx.index(bwt)
+    assert np.array_equal(parts[0].F(), whole.F())
+    rng = np.random.default_rng(1)
+    cuts = [s[0] for s in slices] + [s[1] for s in slices]
+    pos = np.unique(np.concatenate([rng.integers(0, n + 1, 5000), [0, n], np.clip(np.array(cuts), 0, n),
+                                    np.clip(np.array(cuts) + 1, 0, n), np.clip(np.array(cuts) - 1, 0, n)])).astype(np.uint64)
+    assert np.array_equal(parts[0].rank4(pos), whole.rank4(pos))
+    assert np.array_equal(parts[0].rank4(pos), oracle.Bwt(bwt).rank4(pos))
