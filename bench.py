@@ -288,6 +288,17 @@ def reference_arm(args, cfg, out=sys.stdout):
     }), file=out)
 
 
+def same_text(a, b) -> bool:
+    """Byte equality of two .snp texts held as SnpText / numpy uint8 array / bytes."""
+    def mv(x):
+        if hasattr(x, "view") and not isinstance(x, np.ndarray):
+            return x.view()
+        if isinstance(x, np.ndarray):
+            return memoryview(np.ascontiguousarray(x)).cast("B")
+        return memoryview(x)
+    return a is not None and b is not None and mv(a) == mv(b)
+
+
 # ---- own arm -----------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -398,7 +409,7 @@ def main():
     single_ok = None
     if world > 1 and rank == 0:      # parity evidence: the sharded text equals an (untimed) single-GPU run
         s1, _ = ctx.run(wl["bwt1"], wl["bwt2"], wl["da"], p, copy=False)
-        single_ok = bool(s1 == snp)
+        single_ok = same_text(s1, snp)   # SnpText vs the uint8 array gathered on rank 0
         del s1
     if rank == 0:
         peaks = {}
@@ -438,7 +449,7 @@ def main():
             "snp_bytes": len(snp) if snp is not None else None,
             "sharded_host_ms": st.get("host_ms"),
             "input_build_s": t_build,
-            "e2e_matches_device": (e_snp == snp),
+            "e2e_matches_device": same_text(e_snp, snp),
             "matches_single_gpu": single_ok,
         }
         if not args.no_cpu_baseline and world == 1:

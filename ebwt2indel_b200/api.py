@@ -72,7 +72,7 @@ SYMBOLS = (
     "e2i_fl_batch", "e2i_rank_batch_device", "e2i_da_load", "e2i_da_load_device", "e2i_bits_fetch",
     "e2i_bits_size", "e2i_bits_free", "e2i_navigate", "e2i_navigate_shard", "e2i_lcpbits_fetch",
     "e2i_lcpbits_device", "e2i_bits_device", "e2i_lcpbits_free", "e2i_call", "e2i_calls_count",
-    "e2i_calls_fetch", "e2i_calls_free", "e2i_snp_format", "e2i_distance", "e2i_buffer_free", "e2i_run",
+    "e2i_calls_fetch", "e2i_calls_free", "e2i_snp_format", "e2i_snp_count", "e2i_distance", "e2i_buffer_free", "e2i_run",
     "e2i_run_device",
 )
 
@@ -134,6 +134,7 @@ def lib():
         "e2i_calls_fetch": (C.c_int, [vp, vp, vp, vp, u64, C.POINTER(u64)]),
         "e2i_calls_free": (None, [vp]),
         "e2i_snp_format": (C.c_int, [vp, vp, vp, u64, PP, C.c_int, u64, C.POINTER(vp), C.POINTER(C.c_size_t), PS]),
+        "e2i_snp_count": (C.c_int, [vp, vp, vp, u64, PP, C.c_int, C.POINTER(u64)]),
         "e2i_distance": (None, [C.c_char_p, C.c_char_p, C.c_int32, C.c_int32, C.POINTER(C.c_int32)]),
         "e2i_buffer_free": (None, [vp]),
         "e2i_run": (C.c_int, [vp, u8p, u64, u8p, u64, u8p, PP, C.POINTER(vp), C.POINTER(C.c_size_t), PS]),
@@ -209,6 +210,8 @@ class SnpText:
     def __eq__(self, other):
         if isinstance(other, SnpText):
             other = other.view()
+        elif isinstance(other, np.ndarray):
+            other = memoryview(np.ascontiguousarray(other)).cast("B")
         return self.view() == other
 
     def __del__(self):
@@ -337,8 +340,19 @@ class Context:
         return (text.tobytes() if copy else text), st
 
 
+def snp_count(recs: np.ndarray, left: np.ndarray, right: np.ndarray, params: Params, two_samples: bool) -> int:
+    """Cluster numbers the records consume (clusters_out of snp_format) without building the text."""
+    recs = np.ascontiguousarray(recs, dtype=CALL_REC_DTYPE)
+    left = np.ascontiguousarray(left, dtype=np.uint8)
+    right = np.ascontiguousarray(right, dtype=np.uint8)
+    out = C.c_uint64(0)
+    _check(lib().e2i_snp_count(recs.ctypes.data, left.ctypes.data, right.ctypes.data, len(recs), C.byref(params),
+                               1 if two_samples else 0, C.byref(out)))
+    return int(out.value)
+
+
 def snp_format(recs: np.ndarray, left: np.ndarray, right: np.ndarray, params: Params, two_samples: bool,
-               first_cluster_nr: int = 1, stats: Stats | None = None):
+               first_cluster_nr: int = 1, stats: Stats | None = None, copy: bool = True):
     st = stats if stats is not None else Stats()
     recs = np.ascontiguousarray(recs, dtype=CALL_REC_DTYPE)
     left = np.ascontiguousarray(left, dtype=np.uint8)
@@ -346,9 +360,8 @@ def snp_format(recs: np.ndarray, left: np.ndarray, right: np.ndarray, params: Pa
     out, ln = C.c_void_p(), C.c_size_t()
     _check(lib().e2i_snp_format(recs.ctypes.data, left.ctypes.data, right.ctypes.data, len(recs), C.byref(params),
                                 1 if two_samples else 0, first_cluster_nr, C.byref(out), C.byref(ln), C.byref(st)))
-    snp = C.string_at(out, ln.value)
-    lib().e2i_buffer_free(out)
-    return snp, st
+    text = SnpText(out, ln.value)
+    return (text.tobytes() if copy else text), st
 
 
 class Index:

@@ -174,6 +174,31 @@ void format_range(const e2i_call_rec *recs, const char *left, const char *right,
     out.clusters = cluster;
 }
 
+// Number of cluster numbers a range of records consumes (what format_range adds to cluster_nr),
+// without building any text.  Mode -1: every record with >= 2 variants; two samples: records with
+// at least one emitted pair.
+uint64_t count_range(const e2i_call_rec *recs, const char *left, const char *right, uint64_t r0, uint64_t r1,
+                     const e2i_params *p, int two_samples) {
+    const int kl = p->k_left, kr = p->k_right;
+    uint64_t cluster = 0;
+    for (uint64_t r = r0; r < r1; ++r) {
+        const e2i_call_rec &rec = recs[r];
+        if (!rec.has_right) continue;
+        if (!two_samples) { cluster += rec.n0 >= 2; continue; }
+        const char *L = left + r * 8 * (size_t)kl;
+        if (starts_with_run(right + r * (size_t)kr, rec.right_len, p->complexity)) continue;
+        bool found = false;
+        for (int i0 = 0; i0 < rec.n0 && !found; ++i0) for (int i1 = 0; i1 < rec.n1 && !found; ++i1) {
+            const char *l0 = L + i0 * kl, *l1 = L + (4 + i1) * kl;
+            if (l0[kl - 1] == l1[kl - 1]) continue;
+            if (rec.support[i0] < p->mcov_out || rec.support[4 + i1] < p->mcov_out) continue;
+            found = distance(l0, l1, kl, p->max_gap).mism <= p->max_snvs;
+        }
+        cluster += found;
+    }
+    return cluster;
+}
+
 int digits10(uint64_t v) { int d = 1; while (v >= 10) { v /= 10; ++d; } return d; }
 
 }  // namespace
@@ -182,6 +207,24 @@ extern "C" void e2i_distance(const char *a, const char *b, int32_t len, int32_t 
     const Dist d = distance(a, b, len, max_gap);
     out[0] = d.mism;
     out[1] = d.gap;
+}
+
+extern "C" int e2i_snp_count(const e2i_call_rec *recs, const char *left, const char *right, uint64_t n_recs,
+                             const e2i_params *p, int two_samples, uint64_t *clusters) {
+    if (!p || !clusters || (n_recs && (!recs || !left || !right))) { e2i::set_error("e2i_snp_count: null argument"); return E2I_ERR_ARG; }
+    unsigned hw = std::thread::hardware_concurrency();
+    if (hw == 0) hw = 1;
+    const uint64_t nt = std::max<uint64_t>(1, std::min<uint64_t>({(uint64_t)hw, 64, n_recs / 4096}));
+    std::vector<uint64_t> part(nt, 0);
+    std::vector<std::thread> th;
+    auto work = [&](uint64_t t) { part[t] = count_range(recs, left, right, n_recs * t / nt, n_recs * (t + 1) / nt, p, two_samples); };
+    for (uint64_t t = 1; t < nt; ++t) th.emplace_back(work, t);
+    work(0);
+    for (auto &x : th) x.join();
+    uint64_t tot = 0;
+    for (uint64_t v : part) tot += v;
+    *clusters = tot;
+    return E2I_OK;
 }
 
 extern "C" int e2i_snp_format(const e2i_call_rec *recs, const char *left, const char *right, uint64_t n_recs,

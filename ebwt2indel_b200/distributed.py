@@ -89,57 +89,55 @@ def or_reduce_words(tensors, group=None, chunk_words: int = 1 << 28):
 
 
 def format_sharded(api, recs, left, right, params, two_samples: bool, rank: int, world: int, device, group=None):
-    """Every rank formats the records of its own suffix-array slice; cluster numbers are sequential
-    over the whole run (ebwt2InDel.cpp:1250/1328), so each rank first counts the clusters its slice
-    numbers, the counts are exchanged, and ranks > 0 format again from their true first number.
-    The text pieces are concatenated on rank 0 in rank (= suffix-array) order.
-    Returns (.snp bytes on rank 0 else None, events, clusters_out) summed over ranks."""
-    txt, fst = api.snp_format(recs, left, right, params, two_samples, first_cluster_nr=1)
-    mine = torch.tensor([int(fst.clusters_out), int(fst.events)], dtype=torch.int64, device=device)
+    """Every rank formats the records of its own suffix-array slice.  Cluster numbers are sequential
+    over the whole run (ebwt2InDel.cpp:1250/1328): each rank first counts the numbers its slice
+    consumes (e2i_snp_count, no text), the counts are exchanged, and every rank formats once from
+    its true first number.  The text pieces are put together on rank 0 in rank (= SA) order.
+    Returns (text on rank 0 as a uint8 numpy array else None, events, clusters_out) over all ranks."""
+    mine = torch.tensor([api.snp_count(recs, left, right, params, two_samples)], dtype=torch.int64, device=device)
     allc = [torch.zeros_like(mine) for _ in range(world)]
     dist.all_gather(allc, mine, group=group)
     counts = [int(t[0]) for t in allc]
-    first = 1 + sum(counts[:rank])
-    if first != 1 and len(recs):
-        txt, _ = api.snp_format(recs, left, right, params, two_samples, first_cluster_nr=first)
-    events, clusters = sum(int(t[1]) for t in allc), sum(counts)
-    return gather_bytes(txt, rank, world, device, group), events, clusters
+    txt, fst = api.snp_format(recs, left, right, params, two_samples, first_cluster_nr=1 + sum(counts[:rank]), copy=False)
+    assert int(fst.clusters_out) == counts[rank]
+    ev = torch.tensor([int(fst.events)], dtype=torch.int64, device=device)
+    dist.all_reduce(ev, op=dist.ReduceOp.SUM, group=group)
+    return gather_bytes(txt.view(), rank, world, device, group), int(ev[0]), sum(counts)
 
 
-def gather_bytes(data, rank: int, world: int, device, group=None):
-    """Concatenation of every rank's byte string on rank 0 (rank order).  Sizes are exchanged first;
-    every rank > 0 then sends exactly its bytes and rank 0 receives them into consecutive slices
-    of ONE buffer (NCCL point-to-point over NVLink on GPUs, gloo on CPU), so the text is copied
-    once on each side."""
-    view = memoryview(data).cast("B") if len(data) else memoryview(b"")
+def gather_bytes(view, rank: int, world: int, device, group=None):
+    """Concatenation of every rank's bytes on rank 0 (rank order) as a uint8 numpy array.
+    Sizes are exchanged first; every rank > 0 sends exactly its bytes and rank 0 receives them
+    (NCCL point-to-point over NVLink on GPUs, gloo on CPU) into consecutive slices of ONE
+    page-locked host buffer that is kept across calls, so each side copies the text once."""
+    global _pinned
+    view = memoryview(view).cast("B") if len(view) else memoryview(b"")
     size = torch.tensor([len(view)], dtype=torch.int64, device=device)
     sizes = [torch.zeros_like(size) for _ in range(world)]
     dist.all_gather(sizes, size, group=group)
     sizes = [int(s) for s in sizes]
     cuda = torch.device(device).type == "cuda"
+    src = torch.from_numpy(np.frombuffer(view, dtype=np.uint8)) if len(view) else torch.empty(0, dtype=torch.uint8)
     if rank != 0:
         if sizes[rank]:
-            src = torch.frombuffer(bytearray(view), dtype=torch.uint8)
-            dist.send(src.to(device, non_blocking=True) if cuda else src, dst=0, group=group)
+            dist.send(src.to(device) if cuda else src.clone(), dst=0, group=group)
         return None
     total = sum(sizes)
-    buf = torch.empty(max(total, 1), dtype=torch.uint8, device=device)
-    if sizes[0]:
-        mine = torch.frombuffer(bytearray(view), dtype=torch.uint8)
-        buf[:sizes[0]].copy_(mine)
+    if _pinned is None or _pinned.numel() < total:
+        _pinned = torch.empty(max(total, 1) * 5 // 4, dtype=torch.uint8, pin_memory=cuda)
+    out = _pinned[:max(total, 1)]
+    out[:sizes[0]].copy_(src)
     off = sizes[0]
     for r in range(1, world):
         if sizes[r]:
-            dist.recv(buf[off:off + sizes[r]], src=r, group=group)
+            if cuda:
+                stage = torch.empty(sizes[r], dtype=torch.uint8, device=device)
+                dist.recv(stage, src=r, group=group)
+                out[off:off + sizes[r]].copy_(stage)
+            else:
+                dist.recv(out[off:off + sizes[r]], src=r, group=group)
         off += sizes[r]
-    if cuda:
-        global _pinned
-        if _pinned is None or _pinned.numel() < total:
-            _pinned = torch.empty(max(total, 1) * 5 // 4, dtype=torch.uint8, pin_memory=True)   # page-locked once, reused
-        host = _pinned[:max(total, 1)]
-        host.copy_(buf, non_blocking=False)
-        buf = host
-    return buf[:total].numpy().tobytes()
+    return out[:total].numpy()
 
 
 def gather_calls(recs: np.ndarray, left: np.ndarray, right: np.ndarray, rank: int, world: int, group=None):

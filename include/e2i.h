@@ -208,6 +208,10 @@ void e2i_calls_free(e2i_calls *c);
 int e2i_snp_format(const e2i_call_rec *recs, const char *left, const char *right, uint64_t n_recs,
                    const e2i_params *p, int two_samples, uint64_t first_cluster_nr,
                    char **snp, size_t *snp_len, e2i_stats *st);
+/* How many cluster numbers the records consume (= what e2i_snp_format adds to clusters_out),
+ * without building text: lets every GPU rank learn its first cluster number (distributed.py). */
+int e2i_snp_count(const e2i_call_rec *recs, const char *left, const char *right, uint64_t n_recs,
+                  const e2i_params *p, int two_samples, uint64_t *clusters);
 void e2i_distance(const char *a, const char *b, int32_t len, int32_t max_gap, int32_t out[2]);
 void e2i_buffer_free(void *p);
 

@@ -140,3 +140,4 @@ def test_parallel_formatter_equals_sequential_chaining(e2i):
             ev += st2.events
         assert whole == out
         assert st.clusters_out == nr - 1 and st.events == ev and len(whole) > 100000
+        assert e2i.snp_count(recs, left, right, p, two) == st.clusters_out

@@ -80,7 +80,7 @@ def _worker(rank, world, port, ret):
         # 3b. every rank formats its own slice; numbering continues across ranks
         txt, ev, cl = dd.format_sharded(api, *mine, p, False, rank, world, torch.device("cpu"))
         if rank == 0:
-            ok_gather = ok_gather and txt == want and cl == 4 and ev == 8
+            ok_gather = ok_gather and txt.tobytes() == want and cl == 4 and ev == 8
         else:
             ok_gather = ok_gather and txt is None and cl == 4
 
