@@ -391,12 +391,23 @@ def main():
         if world == 1:
             s, stt = ctx.run(h1.numpy(), None if h2 is None else h2.numpy(), None if hd is None else hd.numpy(), p, copy=False)
             return s, stt.as_dict()
-        d1 = h1.to(device, non_blocking=True)
-        d2 = None if h2 is None else h2.to(device, non_blocking=True)
+        # every rank uploads only the slice of the eBWT it indexes (the document array goes whole)
+        def up(h):
+            if h is None:
+                return None, None, 0
+            n_t = h.numel()
+            if n_t < world * 4 * dd.TILE:
+                return h.to(device, non_blocking=True), None, n_t
+            lo, hi = dd.index_slices(n_t, world)[0][rank]
+            return h[lo:hi].to(device, non_blocking=True), n_t, hi - lo
+        d1, t1, c1 = up(h1)
+        d2, t2, c2 = up(h2)
         d3 = None if hd is None else hd.to(device, non_blocking=True)
         torch.cuda.synchronize()
-        s, stt, _ = dd.run_sharded(ctx, api, d1, d2, d3, p, rank, world)
-        stt["h2d_bytes"] += (h1.numel() + (h2.numel() if h2 is not None else 0) + (hd.numel() if hd is not None else 0)) * world
+        s, stt, _ = dd.run_sharded(ctx, api, d1, d2, d3, p, rank, world, n1=t1, n2=t2)
+        sent = torch.tensor([c1 + c2 + (hd.numel() if hd is not None else 0)], dtype=torch.int64, device=device)
+        dist.all_reduce(sent)
+        stt["h2d_bytes"] += int(sent[0])
         return s, stt
 
     step_host()

@@ -72,7 +72,7 @@ SYMBOLS = (
     "e2i_fl_batch", "e2i_rank_batch_device", "e2i_da_load", "e2i_da_load_device", "e2i_bits_fetch",
     "e2i_bits_size", "e2i_bits_free", "e2i_navigate", "e2i_navigate_shard", "e2i_lcpbits_fetch",
     "e2i_lcpbits_device", "e2i_bits_device", "e2i_lcpbits_free", "e2i_call", "e2i_calls_count",
-    "e2i_calls_fetch", "e2i_calls_free", "e2i_snp_format", "e2i_snp_count", "e2i_distance", "e2i_buffer_free", "e2i_run",
+    "e2i_calls_fetch", "e2i_calls_view", "e2i_calls_free", "e2i_snp_format", "e2i_snp_count", "e2i_distance", "e2i_buffer_free", "e2i_run",
     "e2i_run_device",
 )
 
@@ -132,6 +132,7 @@ def lib():
         "e2i_call": (C.c_int, [vp, vp, vp, vp, vp, PP, u64, u64, C.POINTER(vp), PS]),
         "e2i_calls_count": (u64, [vp]),
         "e2i_calls_fetch": (C.c_int, [vp, vp, vp, vp, u64, C.POINTER(u64)]),
+        "e2i_calls_view": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(u64)]),
         "e2i_calls_free": (None, [vp]),
         "e2i_snp_format": (C.c_int, [vp, vp, vp, u64, PP, C.c_int, u64, C.POINTER(vp), C.POINTER(C.c_size_t), PS]),
         "e2i_snp_count": (C.c_int, [vp, vp, vp, u64, PP, C.c_int, C.POINTER(u64)]),
@@ -289,12 +290,29 @@ class Context:
 
     # ---- phase 4 ----
     def call(self, b1, b2, da, lcp, params: Params | None = None, pos_begin: int = 0,
-             pos_end: int = 2 ** 64 - 1, stats: Stats | None = None):
+             pos_end: int = 2 ** 64 - 1, stats: Stats | None = None, copy: bool = True):
+        """Phase 4 on [pos_begin, pos_end).  Returns (recs, left, right, Stats) as numpy arrays; with
+        copy=False they are zero-copy views of the context's page-locked result buffer, valid until
+        the next call() on this context."""
         p = params or default_params()
         st = stats if stats is not None else Stats()
         ch = C.c_void_p()
         _check(lib().e2i_call(self.h, b1.h, b2.h if b2 else None, da.h if da else None, lcp.h, C.byref(p),
                               pos_begin, pos_end, C.byref(ch), C.byref(st)))
+        if not copy:
+            try:
+                pr, pl, pt, n = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_uint64()
+                _check(lib().e2i_calls_view(ch, C.byref(pr), C.byref(pl), C.byref(pt), C.byref(n)))
+                n = int(n.value)
+
+                def view(ptr, nbytes, dtype):
+                    if not nbytes:
+                        return np.zeros(0, dtype=dtype)
+                    return np.frombuffer((C.c_ubyte * nbytes).from_address(ptr.value), dtype=dtype)
+                return (view(pr, n * CALL_REC_DTYPE.itemsize, CALL_REC_DTYPE), view(pl, n * 8 * p.k_left, np.uint8),
+                        view(pt, n * p.k_right, np.uint8), st)
+            finally:
+                lib().e2i_calls_free(ch)
         try:
             n = int(lib().e2i_calls_count(ch))
             recs = np.zeros(n, dtype=CALL_REC_DTYPE)

@@ -665,4 +665,11 @@ extern "C" int e2i_calls_fetch(const e2i_calls *c, e2i_call_rec *host_recs, char
     return E2I_OK;
 }
 
+extern "C" int e2i_calls_view(const e2i_calls *c, const e2i_call_rec **recs, const char **left, const char **right, uint64_t *n) {
+    if (!c || !recs || !left || !right || !n) { set_error("e2i_calls_view: null argument"); return E2I_ERR_ARG; }
+    if (c->gen != c->ctx->pinned_gen) { set_error("e2i_calls_view: stale handle (a later e2i_call on this context reused the staging buffer)"); return E2I_ERR_ARG; }
+    *recs = c->recs; *left = c->left; *right = c->right; *n = c->n;
+    return E2I_OK;
+}
+
 extern "C" void e2i_calls_free(e2i_calls *c) { delete c; }

@@ -175,9 +175,12 @@ def reduce_stats(st: dict, device, group=None) -> dict:
     return out
 
 
-def run_sharded(ctx, api, bwt1, bwt2, da, params, rank: int, world: int, group=None):
-    """Whole path on `world` GPUs.  Inputs are CUDA uint8 tensors (replicated on every rank).
-    Returns (.snp bytes on rank 0 else None, reduced stats dict, seconds spent in the exchange)."""
+def run_sharded(ctx, api, bwt1, bwt2, da, params, rank: int, world: int, group=None, n1=None, n2=None):
+    """Whole path on `world` GPUs.  bwt1 / bwt2 are CUDA uint8 tensors: either the whole eBWT
+    (replicated on every rank) or, when n1 / n2 give the total lengths, only this rank's slice
+    index_slices(n, world)[rank] -- all a rank needs, since the index is built slice-wise.  The
+    document array (mode -d) is passed whole.
+    Returns (.snp text on rank 0 else None, reduced stats dict, seconds spent in the exchange)."""
     import time
     device = bwt1.device
     term = params.term
@@ -190,15 +193,17 @@ def run_sharded(ctx, api, bwt1, bwt2, da, params, rank: int, world: int, group=N
         t = time.perf_counter()
         tm[name] = tm.get(name, 0.0) + (t - tp) * 1e3
         tp = t
-    def make_index(t):
+    def make_index(t, n_total):
+        if n_total is not None and n_total != t.numel():
+            return build_index_sharded(ctx, t, n_total, term, rank, world, group)      # t is this rank's slice
         n_t = t.numel()
         if world == 1 or n_t < world * 4 * TILE:
             return ctx.index(t, term)
         lo, hi = index_slices(n_t, world)[0][rank]
         return build_index_sharded(ctx, t[lo:hi], n_t, term, rank, world, group)
 
-    b1 = make_index(bwt1)
-    b2 = make_index(bwt2) if bwt2 is not None else None
+    b1 = make_index(bwt1, n1)
+    b2 = make_index(bwt2, n2) if bwt2 is not None else None
     dabits = ctx.document_array(da) if da is not None else None
     st = api.Stats()
     lap("index")
@@ -220,7 +225,7 @@ def run_sharded(ctx, api, bwt1, bwt2, da, params, rank: int, world: int, group=N
     n = b1.n + (b2.n if b2 is not None else 0)
     cuts = position_cuts(n, world)
     recs, left, right, st = ctx.call(b1, b2, da_nav if b2 is not None else dabits, lcp, params,
-                                     cuts[rank], cuts[rank + 1], stats=st)
+                                     cuts[rank], cuts[rank + 1], stats=st, copy=False)
     lap("call")
     stats = reduce_stats(st.as_dict(), device, group)
     lap("reduce_stats")

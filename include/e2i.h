@@ -199,6 +199,8 @@ uint64_t e2i_calls_count(const e2i_calls *c);
 /* host_left: cap * 8 * k_left chars; host_right: cap * k_right chars */
 int e2i_calls_fetch(const e2i_calls *c, e2i_call_rec *host_recs, char *host_left, char *host_right,
                     uint64_t cap, uint64_t *n);
+/* zero-copy view of the page-locked result arrays (valid until the next e2i_call on the context) */
+int e2i_calls_view(const e2i_calls *c, const e2i_call_rec **recs, const char **left, const char **right, uint64_t *n);
 void e2i_calls_free(e2i_calls *c);
 
 /* ---- a21-a23: classification + .snp text.  Replaces distance/event_type/to_file x2
