@@ -309,3 +309,80 @@ def test_slicewise_index_build_equals_whole_build(gpu_ctx, oracle, n, world):
                                     np.clip(np.array(cuts) + 1, 0, n), np.clip(np.array(cuts) - 1, 0, n)])).astype(np.uint64)
     assert np.array_equal(parts[0].rank4(pos), whole.rank4(pos))
     assert np.array_equal(parts[0].rank4(pos), oracle.Bwt(bwt).rank4(pos))
+
+
+def _bench_workload(gpu_ctx, name, scale=1.0):
+    import torch
+    import bench
+    cfg = bench.CONFIGS[name]
+    if scale != 1.0:
+        cfg = bench.scaled(cfg, scale)
+    wl = bench.make_workload(cfg, torch.device("cuda:0"), gpu_ctx)
+    torch.cuda.synchronize()
+    return wl
+
+
+def test_full_size_c1_matches_oracle(gpu_ctx, e2i, oracle):
+    """BASELINE.json configs[0] at full size (n = 40.4 M): .snp bytes and every counter against the oracle."""
+    wl = _bench_workload(gpu_ctx, "C1")
+    assert wl["n"] == 40_400_000
+    snp, st = gpu_ctx.run(wl["bwt1"], None, None, e2i.default_params())
+    osnp, ost = oracle.run(wl["bwt1"].cpu().numpy(), None, None, oracle.default_params())
+    assert snp == osnp and len(snp) > 100_000
+    for k in COUNTERS + ("events", "rank_leaves", "rank_nodes"):
+        assert getattr(st, k) == getattr(ost, k), k
+    assert st.lcp_values == wl["n"]
+
+
+@pytest.mark.parametrize("name,scale", [("C4", 1 / 16), ("C2", 1 / 4), ("C3", 1 / 8)])
+def test_large_inputs_size_independent_properties(gpu_ctx, e2i, name, scale):
+    """Sizes the oracle cannot finish in seconds (0.25 - 0.95 G symbols, shapes of configs 2-4):
+    properties that do not need it.  (1) every LCP position is computed exactly once -- the
+    reference's own 'Computed n/n LCP values' invariant; (2) every DA value too in mode -2;
+    (3) traversal shards write disjoint bits whose sum is the unsharded bitvector, word for word;
+    (4) the text does not depend on the frontier budget (chunked depth-first traversal), on where
+    the inputs live (host / device) or on the run (idempotence); (5) clusters are reported in
+    increasing cluster number."""
+    import re
+    import torch
+    from ebwt2indel_b200 import distributed as dd
+    wl = _bench_workload(gpu_ctx, name, scale)
+    p = e2i.default_params()
+    n = wl["n"]
+    snp, st = gpu_ctx.run(wl["bwt1"], wl["bwt2"], wl["da"], p)
+    assert st.lcp_values == n                                              # (1)
+    if wl["bwt2"] is not None:
+        assert st.da_values == n                                           # (2)
+    assert st.nodes > n // 2 and st.n_clusters > 0 and len(snp) > 0
+    # (3)
+    b1 = gpu_ctx.index(wl["bwt1"])
+    b2 = gpu_ctx.index(wl["bwt2"]) if wl["bwt2"] is not None else None
+    full, fda, fst = gpu_ctx.navigate(b1, b2, p)
+    (pt, wt), (pm, wm) = full.device_words()
+    fthr = dd.wrap_device_words(pt, wt, "cuda:0").clone()
+    fmin = dd.wrap_device_words(pm, wm, "cuda:0").clone()
+    del full, fda
+    sthr, smin, nodes = torch.zeros_like(fthr), torch.zeros_like(fmin), 0
+    for s in range(3):
+        part, pda, pst = gpu_ctx.navigate(b1, b2, p, shard=s, n_shards=3)
+        (pt, wt), (pm, wm) = part.device_words()
+        t, m = dd.wrap_device_words(pt, wt, "cuda:0"), dd.wrap_device_words(pm, wm, "cuda:0")
+        assert not bool((sthr & t).any()) and not bool((smin & m).any())
+        sthr += t
+        smin += m
+        nodes += pst.nodes
+        del part, pda
+    assert torch.equal(sthr, fthr) and torch.equal(smin, fmin) and nodes == fst.nodes
+    del b1, b2, sthr, smin, fthr, fmin
+    # (4)
+    host = [None if t is None else t.cpu().numpy() for t in (wl["bwt1"], wl["bwt2"], wl["da"])]
+    assert gpu_ctx.run(*host, p)[0] == snp
+    small = e2i.Context(0, frontier_bytes=1 << 30)
+    try:
+        s2, st2 = small.run(wl["bwt1"], wl["bwt2"], wl["da"], p)
+    finally:
+        small.close()
+    assert s2 == snp and st2.levels_nodes > st.levels_nodes               # the small budget really chunked the sweeps
+    # (5)
+    nums = [int(x) for x in re.findall(rb">cluster:(\d+)_", snp)]
+    assert nums == sorted(nums) and nums[0] == 1 and nums[-1] == st.clusters_out
