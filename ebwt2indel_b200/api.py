@@ -387,9 +387,9 @@ class Index:
         self.ctx, self.h = ctx, h
 
     def close(self):
-        if getattr(self, "h", None):
-            lib().e2i_index_free(self.h)
-            self.h = None
+        if getattr(self, "h", None) and _lib is not None:
+            _lib.e2i_index_free(self.h)
+        self.h = None
 
     def __del__(self):
         self.close()
@@ -471,9 +471,9 @@ class Bits:
         self.ctx, self.h = ctx, h
 
     def close(self):
-        if getattr(self, "h", None):
-            lib().e2i_bits_free(self.h)
-            self.h = None
+        if getattr(self, "h", None) and _lib is not None:
+            _lib.e2i_bits_free(self.h)
+        self.h = None
 
     def __del__(self):
         self.close()
@@ -500,9 +500,9 @@ class LcpBits:
         self.ctx, self.h = ctx, h
 
     def close(self):
-        if getattr(self, "h", None):
-            lib().e2i_lcpbits_free(self.h)
-            self.h = None
+        if getattr(self, "h", None) and _lib is not None:
+            _lib.e2i_lcpbits_free(self.h)
+        self.h = None
 
     def __del__(self):
         self.close()

@@ -361,6 +361,7 @@ def test_large_inputs_size_independent_properties(gpu_ctx, e2i, name, scale):
     (pt, wt), (pm, wm) = full.device_words()
     fthr = dd.wrap_device_words(pt, wt, "cuda:0").clone()
     fmin = dd.wrap_device_words(pm, wm, "cuda:0").clone()
+    torch.cuda.synchronize()
     del full, fda
     sthr, smin, nodes = torch.zeros_like(fthr), torch.zeros_like(fmin), 0
     for s in range(3):
@@ -371,6 +372,7 @@ def test_large_inputs_size_independent_properties(gpu_ctx, e2i, name, scale):
         sthr += t
         smin += m
         nodes += pst.nodes
+        torch.cuda.synchronize()          # torch reads the library's buffers on its own stream: finish before they are freed
         del part, pda
     assert torch.equal(sthr, fthr) and torch.equal(smin, fmin) and nodes == fst.nodes
     del b1, b2, sthr, smin, fthr, fmin
