@@ -840,8 +840,11 @@ static Chunk split_head(Chunk &c, uint64_t take, int words) {
 }
 
 template <typename Launch>
-static int run_frontier(e2i_ctx *ctx, Chunk root, int words, int tile_items, uint64_t max_chunk, NavArgs &args,
-                        Launch launch, SweepStats &ss, uint64_t stop_at_items, std::vector<Chunk> *stopped) {
+// max_chunk: largest chunk swept whole (two of its frames fit the arena: level-synchronous case).
+// split_chunk: chunk size once a level has to be cut (depth-first case): a path of such chunks down
+// to the deepest level must fit the arena next to the frame that is being cut.
+static int run_frontier(e2i_ctx *ctx, Chunk root, int words, int tile_items, uint64_t max_chunk, uint64_t split_chunk,
+                        NavArgs &args, Launch launch, SweepStats &ss, uint64_t stop_at_items, std::vector<Chunk> *stopped) {
     std::vector<Chunk> stack;
     stack.push_back(std::move(root));
     LaunchCtl *hctl = reinterpret_cast<LaunchCtl *>(ctx->ctl_host);
@@ -854,13 +857,13 @@ static int run_frontier(e2i_ctx *ctx, Chunk root, int words, int tile_items, uin
             continue;
         }
         Chunk work;
-        uint64_t take = std::min<uint64_t>(cur.total(), max_chunk);
+        uint64_t take = cur.total() <= max_chunk ? cur.total() : std::min<uint64_t>(cur.total(), split_chunk);
         void *mem = nullptr;
         const double ta = now_ms();
         while (true) {   // shrink the chunk until its output frame fits the pool
             mem = ctx->arena.alloc((cur.level + 1) & 1, take * 4 * words * sizeof(uint64_t));
             if (mem) break;
-            if (take <= 4096) { set_error("frontier memory exhausted (arena %llu bytes, %llu in use): raise the frontier budget",
+            if (take <= 256) { set_error("frontier memory exhausted (arena %llu bytes, %llu in use): raise the frontier budget",
                                           (unsigned long long)ctx->arena.size(), (unsigned long long)ctx->arena.in_use()); return E2I_ERR_MEMORY; }
             take /= 2;
         }
@@ -1033,6 +1036,9 @@ extern "C" int e2i_navigate_shard(e2i_ctx *ctx, const e2i_index *b1, const e2i_i
         const int tile_items = kNavThreads;
         // two frames of the largest chunk (input's successor + its own output) plus slack must fit the arena
         const uint64_t max_chunk = std::max<uint64_t>(65536, (uint64_t)((double)budget / ((double)words * 8 * 4 * 2.5)));
+        // depth of the traversal: the internal-node pass is never deeper than the leaf pass that ran before it
+        const uint64_t depth_hint = leaves ? 1024 : st->levels_leaves + 16;
+        const uint64_t split_chunk = std::max<uint64_t>(256, std::min<uint64_t>(max_chunk, (uint64_t)((double)budget * 0.45 / ((double)words * 8 * 4 * (double)depth_hint))));
         // root record
         void *rootmem = nullptr;
         rootmem = ctx->arena.alloc(0, (size_t)words * 8);
@@ -1068,13 +1074,13 @@ extern "C" int e2i_navigate_shard(e2i_ctx *ctx, const e2i_index *b1, const e2i_i
         };
         if (n_shards == 1) {
             args.write = 1;
-            return run_frontier(ctx, std::move(root), words, tile_items, max_chunk, args, launch, ss, 0, nullptr);
+            return run_frontier(ctx, std::move(root), words, tile_items, max_chunk, split_chunk, args, launch, ss, 0, nullptr);
         }
         // shared top of the tree
         std::vector<Chunk> dealt;
         args.write = shard == 0;
         SweepStats top;
-        E2I_TRY(run_frontier(ctx, std::move(root), words, tile_items, max_chunk, args, launch, top, kDealItems, &dealt));
+        E2I_TRY(run_frontier(ctx, std::move(root), words, tile_items, max_chunk, split_chunk, args, launch, top, kDealItems, &dealt));
         if (shard == 0) { ss.items += top.items; ss.sweeps += top.sweeps; ss.max_chunk = std::max(ss.max_chunk, top.max_chunk); }
         args.write = 1;
         for (Chunk &c : dealt) {
@@ -1109,7 +1115,7 @@ extern "C" int e2i_navigate_shard(e2i_ctx *ctx, const e2i_index *b1, const e2i_i
             (void)split_head(mine, lo, words);          // drop [0, lo)
             Chunk part = split_head(mine, hi - lo, words);
             part.frame = c.frame;
-            E2I_TRY(run_frontier(ctx, std::move(part), words, tile_items, max_chunk, args, launch, ss, 0, nullptr));
+            E2I_TRY(run_frontier(ctx, std::move(part), words, tile_items, max_chunk, split_chunk, args, launch, ss, 0, nullptr));
         }
         return E2I_OK;
     };
