@@ -63,7 +63,10 @@ void set_error(const char *fmt, ...);
 // allocation is a pointer bump: no driver call and no fragmentation on the hot path.
 class Arena {
   public:
-    void reset(char *base, size_t bytes) { base_ = base; size_ = bytes; lo_ = 0; hi_ = bytes; live_[0].clear(); live_[1].clear(); }
+    void reset(char *base, size_t bytes) {
+        bytes &= ~(size_t)255;                          // both ends hand out 256-byte aligned frames
+        base_ = base; size_ = bytes; lo_ = 0; hi_ = bytes; live_[0].clear(); live_[1].clear();
+    }
     char *base() const { return base_; }
     size_t size() const { return size_; }
     size_t in_use() const { return lo_ + (size_ - hi_); }
