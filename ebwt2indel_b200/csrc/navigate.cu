@@ -185,10 +185,76 @@ __device__ __forceinline__ void expand_core(const NavArgs &a, const uint4 *stage
     }
 }
 
+// The common case, stripped of everything it does not need: the tile's whole block range is staged,
+// lies inside one 2^32-symbol superblock, and the node is shorter than 2^32.  Positions are 32-bit
+// offsets into the staged window and ranks are block counter + popcount (the superblock base
+// cancels in every difference and is added once, to the child's first position).
+__device__ __forceinline__ void rank4_window(const uint4 *stage, uint32_t rpos, uint32_t out[4]) {
+    const uint32_t r = rpos >> kBlockShift;
+    const uint32_t sw = (r >> 1) & 3u;
+    const uint4 *p = stage + r * 4;
+    const uint4 cnt = p[sw], a = p[1u ^ sw], b = p[2u ^ sw], t = p[3u ^ sw];
+    uint32_t pc[4];
+    block_popc(a, b, t, (int)(rpos & (kBlockSyms - 1)), pc);
+    out[0] = cnt.x + pc[0];
+    out[1] = cnt.y + pc[1];
+    out[2] = cnt.z + pc[2];
+    out[3] = cnt.w + pc[3];
+}
+
 template <bool TWO>
+__device__ __forceinline__ void expand_core_window(const NavArgs &a, const uint4 *stage1, uint32_t r1, const uint64_t (&s1)[5],
+                                                   const uint4 *stage2, uint32_t r2, const uint64_t (&s2)[5],
+                                                   uint64_t sup_blk1, uint64_t sup_blk2,
+                                                   ChildSide &k1, ChildSide &k2, uint32_t &nzp, uint32_t &st_rank) {
+    uint32_t prev1[4], cur1[4], prev2[4] = {0, 0, 0, 0}, cur2[4] = {0, 0, 0, 0};
+    rank4_window(stage1, r1, prev1);
+    st_rank++;
+    if (TWO) { rank4_window(stage2, r2, prev2); st_rank++; }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        uint64_t b1 = a.ix1.F[c] + prev1[c];
+        if (a.ix1.n >> kSuperShift) b1 += a.ix1.super[sup_blk1 * 4 + c];
+        k1.base[c] = b1;
+        if (TWO) {
+            uint64_t b2 = a.ix2.F[c] + prev2[c];
+            if (a.ix2.n >> kSuperShift) b2 += a.ix2.super[sup_blk2 * 4 + c];
+            k2.base[c] = b2;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+        const uint32_t z1 = (uint32_t)s1[j];
+        r1 += z1;
+        if (z1) { rank4_window(stage1, r1, cur1); st_rank++; }
+        else { cur1[0] = prev1[0]; cur1[1] = prev1[1]; cur1[2] = prev1[2]; cur1[3] = prev1[3]; }
+        if (TWO) {
+            const uint32_t z2 = (uint32_t)s2[j];
+            r2 += z2;
+            if (z2) { rank4_window(stage2, r2, cur2); st_rank++; }
+            else { cur2[0] = prev2[0]; cur2[1] = prev2[1]; cur2[2] = prev2[2]; cur2[3] = prev2[3]; }
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const uint32_t d1 = cur1[c] - prev1[c];
+            uint32_t any = d1;
+            k1.lo[j][c] = d1;
+            prev1[c] = cur1[c];
+            if (TWO) {
+                const uint32_t d2 = cur2[c] - prev2[c];
+                any |= d2;
+                k2.lo[j][c] = d2;
+                prev2[c] = cur2[c];
+            }
+            nzp += (any != 0 ? 1u : 0u) << (8 * c);
+        }
+    }
+}
+
 #ifndef E2I_NODE_MINBLOCKS
 #define E2I_NODE_MINBLOCKS 4
 #endif
+template <bool TWO>
 __global__ void __launch_bounds__(kNavThreads, TWO ? 2 : E2I_NODE_MINBLOCKS)
 expand_nodes_kernel(const NavArgs a, const Segs in) {
     constexpr int WORDS = TWO ? 8 : 4;                 // u64 words per record
@@ -518,10 +584,11 @@ expand_nodes_persistent(const NavArgs a, const Segs in) {
         }
         bar_compute();
         const uint32_t lo1 = sm.rng[0], lo2 = TWO ? sm.rng[2] : 0u;
-        uint32_t nst1 = 0, nst2 = 0;
+        uint32_t nst1 = 0, nst2 = 0, span1_all = 0, span2_all = 0;
         {
             constexpr int ITER = STAGE * 4 / kCompThreads;
             const uint32_t span1 = sm.rng[1] >= lo1 ? sm.rng[1] - lo1 + 1 : 0u;
+            span1_all = span1;
             if (span1 <= 2u * STAGE) nst1 = min(span1, (uint32_t)STAGE);
             const uint4 *src1 = a.ix1.blocks + (size_t)lo1 * 4;
 #pragma unroll
@@ -532,6 +599,7 @@ expand_nodes_persistent(const NavArgs a, const Segs in) {
             if (TWO) {
                 const uint32_t end2 = sm.rng[3] + 1;
                 const uint32_t span2 = end2 > lo2 ? end2 - lo2 : 0u;
+                span2_all = span2;
                 if (span2 <= 2u * STAGE) nst2 = min(span2, (uint32_t)STAGE);
                 const uint4 *src2 = a.ix2.blocks + (size_t)lo2 * 4;
 #pragma unroll
@@ -582,8 +650,16 @@ expand_nodes_persistent(const NavArgs a, const Segs in) {
         k1.h4 = 0; k2.h4 = 0;
 #pragma unroll
         for (int c = 0; c < 4; ++c) { k1.hz[c] = 0; k2.hz[c] = 0; k1.base[c] = 0; k2.base[c] = 0; }
+        // whole range staged and inside one superblock (CTA-uniform), for both BWTs
+        bool window = nst1 == span1_all && nst1 > 0 && (lo1 >> (kSuperShift - kBlockShift)) == ((lo1 + nst1 - 1) >> (kSuperShift - kBlockShift));
+        if (TWO) window = window && nst2 == span2_all && nst2 > 0 &&
+                          (lo2 >> (kSuperShift - kBlockShift)) == ((lo2 + nst2 - 1) >> (kSuperShift - kBlockShift));
         if (active) {
-            if (narrow) expand_core<TWO, uint32_t>(a, stage1, lo1, nst1, stage2, lo2, nst2, base1, s1, base2, s2, k1, k2, nzp, st_rank);
+            if (window && narrow)
+                expand_core_window<TWO>(a, stage1, (uint32_t)(base1 - ((uint64_t)lo1 << kBlockShift)), s1,
+                                        stage2, (uint32_t)(base2 - ((uint64_t)lo2 << kBlockShift)), s2,
+                                        lo1 >> (kSuperShift - kBlockShift), lo2 >> (kSuperShift - kBlockShift), k1, k2, nzp, st_rank);
+            else if (narrow) expand_core<TWO, uint32_t>(a, stage1, lo1, nst1, stage2, lo2, nst2, base1, s1, base2, s2, k1, k2, nzp, st_rank);
             else expand_core<TWO, uint64_t>(a, stage1, lo1, nst1, stage2, lo2, nst2, base1, s1, base2, s2, k1, k2, nzp, st_rank);
         }
         uint32_t vm = 0, packed = 0, before[4];
