@@ -478,6 +478,7 @@ struct PersistSmem {
     static constexpr int RU = TWO ? 4 : 2;            // uint4 per record
     uint4 stage[kStageBlocks * 4];                    // staged index window(s)
     uint4 child[4][kCompThreads * RU];                // parked children of the pending tile, per symbol
+    uint4 recbuf[kCompThreads * RU];                  // records of the NEXT tile, prefetched by LDGSTS (slot = thread)
     unsigned long long base[4];                       // resolved exclusive prefix of the pending tile
     unsigned long long stat[C_NCOUNTERS];
     uint32_t agg[4];                                  // child counts of the pending tile
@@ -549,26 +550,38 @@ expand_nodes_persistent(const NavArgs a, const Segs in) {
         }
     };
 
-    while (true) {
-        if (threadIdx.x == 0) sm.tile = atomicAdd(&a.ctl->ticket, 1u);
+    // software pipeline: the ticket and the records of tile t+1 are fetched while tile t is processed
+    auto prefetch_records = [&](uint32_t tl) {
+        const uint32_t g = tl * kCompThreads + threadIdx.x;
+        if (tl < a.n_tiles && g < in.total) {
+            const uint4 *rec = reinterpret_cast<const uint4 *>(seg_record(in, g, WORDS));
+#pragma unroll
+            for (int k = 0; k < RU; ++k) cp_async16(&sm.recbuf[threadIdx.x * RU + k], rec + k);
+        }
+    };
+    if (threadIdx.x == 0) sm.tile = atomicAdd(&a.ctl->ticket, 1u);
+    bar_compute();
+    uint32_t tile = sm.tile;
+    prefetch_records(tile);
+    while (tile < a.n_tiles) {
+        uint32_t nxt = 0;
+        if (threadIdx.x == 0) nxt = atomicAdd(&a.ctl->ticket, 1u);          // its latency hides behind this tile
         if (threadIdx.x < C_NCOUNTERS) sm.stat[threadIdx.x] = 0;
-        bar_compute();
-        const uint32_t tile = sm.tile;
-        if (tile >= a.n_tiles) break;
         const uint32_t g = tile * kCompThreads + threadIdx.x;
         const bool active = g < in.total;
 
         uint64_t base1 = 0, s1[5] = {0, 0, 0, 0, 0}, base2 = 0, s2[5] = {0, 0, 0, 0, 0};
         uint32_t depth = 0;
         bool narrow = true;
+        cp_async_wait_all();                                                // this thread's own record has landed
         if (active) {
-            const uint4 *rec = reinterpret_cast<const uint4 *>(seg_record(in, g, WORDS));
-            const uint4 lo = __ldg(rec), hi = __ldg(rec + 1);
+            const uint4 *rec = &sm.recbuf[threadIdx.x * RU];
+            const uint4 lo = rec[0], hi = rec[1];
             unpack_node(lo, hi, base1, s1, depth);
             narrow = (hi.z | (hi.w & 0xffu)) == 0 && ((s1[0] + s1[1] + s1[2] + s1[3] + s1[4]) >> 32) == 0;
             if (TWO) {
                 uint32_t d2;
-                const uint4 lo2 = __ldg(rec + 2), hi2 = __ldg(rec + 3);
+                const uint4 lo2 = rec[2], hi2 = rec[3];
                 unpack_node(lo2, hi2, base2, s2, d2);
                 narrow = narrow && (hi2.z | (hi2.w & 0xffu)) == 0 && ((s2[0] + s2[1] + s2[2] + s2[3] + s2[4]) >> 32) == 0;
             }
@@ -642,8 +655,11 @@ expand_nodes_persistent(const NavArgs a, const Segs in) {
             thr.flush();
             mn.flush();
         }
+        if (threadIdx.x == 0) sm.tile = nxt;
         cp_async_wait_all();
         bar_compute();
+        const uint32_t next_tile = sm.tile;
+        prefetch_records(next_tile);                                         // overlaps with the rank phase below
 
         ChildSide k1, k2;
         uint32_t nzp = 0;
@@ -718,6 +734,7 @@ expand_nodes_persistent(const NavArgs a, const Segs in) {
         bar_compute();                                   // children, counts and tile id are in shared memory
         ++my_seq;
         if (threadIdx.x == 0) { __threadfence_block(); *v_posted = my_seq; }
+        tile = next_tile;
     }
     if (my_seq) flush_pending();
     bar_compute();
