@@ -41,6 +41,10 @@ CONFIGS = {
                desc="mode -2: two eBWTs of 50 Mbp genomes, 30x 150bp, n=1.51G each"),
     "C4": dict(mode=1, genome=250_000_000, snps=250_000, indels=50_000, cov=30, read_len=150, revcomp=True, seed=4,
                desc="mode -1: 250 Mbp diploid, 30x 150bp + revcomp, n=15.1G"),
+    "C5": dict(mode=1, meta=True, species=10, strains=10, genome=10_000_000, snp_rate=0.001, cov=10, read_len=100, revcomp=True,
+               seed=5, snps=0, indels=0,
+               desc="mode -1: metagenome, 10 species x 10 strains x 10 Mbp (0.1% SNPs between strains, log-normal abundances), "
+                    "10x mean 100bp + revcomp, n=20.2G"),
     # intermediate mode -1 sizes (same shape as C4) used while the C4 pipeline is brought up
     "C4s16": dict(mode=1, genome=15_625_000, snps=15_625, indels=3_125, cov=30, read_len=150, revcomp=True, seed=4,
                   desc="mode -1: 1/16 of C4 (15.6 Mbp diploid, 30x 150bp + revcomp), n=0.94G"),
@@ -63,6 +67,11 @@ def make_workload(cfg: dict, device, ctx=None):
     otherwise by the torch builder on `device`."""
     import torch
     from ebwt2indel_b200 import synth
+    if cfg.get("meta"):
+        plan = synth.metagenome_plan(cfg["species"], cfg["strains"], cfg["genome"], cfg["snp_rate"], cfg["cov"], cfg["read_len"],
+                                     cfg["seed"], cfg["revcomp"])
+        bwt = synth.ebwt_bcr_gpu(ctx, [plan], device) if ctx is not None else synth.ebwt_bcr_torch(plan.materialize(), device)
+        return dict(mode=1, bwt1=bwt, bwt2=None, da=None, n=bwt.numel(), reads=plan.n_reads)
     if ctx is not None:
         if cfg["mode"] == 1:
             plan = synth.diploid_plan(cfg["genome"], cfg["snps"], cfg["indels"], cfg["cov"], cfg["read_len"], cfg["seed"], cfg["revcomp"])
@@ -188,7 +197,7 @@ def cpu_sample_config(cfg: dict, target_n: float = 40e6) -> tuple[dict, float]:
     """A bounded sample of the workload: same shape, genome scaled so that n ~ target_n (10-30 s of CPU)."""
     per_bp = cfg["cov"] * (cfg["read_len"] + 1) / cfg["read_len"] * (2 if cfg["revcomp"] else 1)
     per_bp *= 1 if cfg["mode"] == 1 else 2
-    n_full = cfg["genome"] * per_bp
+    n_full = cfg["genome"] * per_bp * (cfg["species"] * cfg["strains"] if cfg.get("meta") else 1)
     scale = min(1.0, target_n / n_full)
     return scaled(cfg, scale), scale
 

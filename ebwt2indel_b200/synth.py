@@ -189,6 +189,28 @@ def two_individuals_reads(genome_len: int, n_snps: int, n_indels: int, coverage:
     return p0.materialize(), p1.materialize()
 
 
+def metagenome_plan(n_species: int, strains_per_species: int, genome_len: int, snp_rate: float, coverage: float,
+                    read_len: int, seed: int, revcomp: bool = True, sigma: float = 1.0) -> ReadPlan:
+    """Mode -1 metagenome shape (BASELINE.json configs[4]): `n_species` random base genomes, each with
+    `strains_per_species` strains that differ from it by `snp_rate` SNPs; strain abundances are
+    log-normal(0, sigma), so most variants are low-frequency; `coverage` is the mean over the total length."""
+    rng = np.random.default_rng(seed)
+    strains = []
+    for _ in range(n_species):
+        base = random_genome(genome_len, rng)
+        for _ in range(strains_per_species):
+            strains.append(mutate(base, int(round(snp_rate * genome_len)), 0, rng))
+    w = rng.lognormal(0.0, sigma, size=len(strains))
+    w /= w.sum()
+    n_reads = int(round(coverage * genome_len * len(strains) / read_len))
+    per = np.maximum(1, np.round(w * n_reads).astype(np.int64))
+    starts, off = [], 0
+    for h, k in zip(strains, per):
+        starts.append(off + rng.integers(0, len(h) - read_len + 1, size=int(k)))
+        off += len(h)
+    return ReadPlan(np.concatenate(strains), np.concatenate(starts).astype(np.int64), read_len, revcomp)
+
+
 def merged_ebwt_da(reads0: np.ndarray, reads1: np.ndarray, builder=ebwt_naive):
     """Merged eBWT of (reads0 then reads1) plus the ASCII '0'/'1' document array (mode -d input)."""
     bwt, owner = builder(np.concatenate([reads0, reads1], axis=0))

@@ -51,6 +51,9 @@ def main():
     short = synth.diploid_reads(1500, 6, 2, 30, 40, seed=12)
     sb, _ = synth.ebwt_naive(short)
     save("m1_short_reads", sb, flags=("-L", 12, "-R", 10, "-k", 8, "-c", 6, "-g", 3))
+    meta = synth.metagenome_plan(3, 4, 3000, 0.004, 12, 60, seed=9).materialize()
+    mb, _ = synth.ebwt_naive(meta)
+    save("m1_metagenome", mb, flags=("-m", 2))
     r0, r1 = synth.two_individuals_reads(4000, 10, 4, 24, 100, seed=13)
     merged, da = synth.merged_ebwt_da(r0, r1)
     save("m3_default", merged, da=da)
