@@ -25,24 +25,31 @@ struct Piece {               // 16 symbols
     int bad;                 // index (0..15) of the first forbidden symbol, or -1
 };
 
+// bit k of the result = least significant bit of byte k of x (x holds 0/1 per byte)
+__device__ __forceinline__ uint32_t gather4(uint32_t x) { return ((x & 0x01010101u) * 0x01020408u) >> 24; }
+
+// 16 symbols at once: four bytes per SIMD-in-register compare (__vcmpeq4 gives 0xff per equal byte)
 __device__ __forceinline__ Piece encode_piece(uint4 v, uint64_t pos0, uint64_t n, uint32_t term) {
     Piece pc{0, 0, 0, 0, -1};
     const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    const uint32_t t4 = term * 0x01010101u;
+    const int valid = pos0 + 16 <= n ? 16 : (int)(n - pos0);          // symbols of this piece inside the string
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-        const uint32_t ch = (w[j >> 2] >> (8 * (j & 3))) & 0xffu;
-        if (pos0 + j < n) {
-            const int c = classify(ch, term);
-            if (c == 5) {
-                if (pc.bad < 0) pc.bad = j;
-            } else if (c == 4) {
-                pc.pt |= 1u << j;
-            } else {
-                pc.p0 |= (uint32_t)(c & 1) << j;
-                pc.p1 |= (uint32_t)(c >> 1) << j;
-                pc.cnt += 1u << (8 * c);
-            }
-        }
+    for (int q = 0; q < 4; ++q) {
+        uint32_t live = 0xffffffffu;                                   // byte mask of the in-range symbols of this word
+        const int k = valid - 4 * q;
+        if (k < 4) live = k <= 0 ? 0u : (0xffffffffu >> (8 * (4 - k)));
+        const uint32_t isX = __vcmpeq4(w[q], t4) & live;                // the terminator test comes first, as in the reference
+        const uint32_t base = live & ~isX;
+        const uint32_t isA = __vcmpeq4(w[q], 0x41414141u) & base, isC = __vcmpeq4(w[q], 0x43434343u) & base,
+                       isG = __vcmpeq4(w[q], 0x47474747u) & base, isT = __vcmpeq4(w[q], 0x54545454u) & base;
+        const uint32_t ok = isA | isC | isG | isT | isX;
+        if (ok != live && pc.bad < 0) pc.bad = 4 * q + ((__ffs((int)(~ok & live)) - 1) >> 3);
+        pc.p0 |= gather4(isC | isT) << (4 * q);
+        pc.p1 |= gather4(isG | isT) << (4 * q);
+        pc.pt |= gather4(isX) << (4 * q);
+        pc.cnt += (uint32_t)__popc(isA & 0x01010101u) | ((uint32_t)__popc(isC & 0x01010101u) << 8) |
+                  ((uint32_t)__popc(isG & 0x01010101u) << 16) | ((uint32_t)__popc(isT & 0x01010101u) << 24);
     }
     return pc;
 }
