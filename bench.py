@@ -458,7 +458,8 @@ def main():
             "wall_ms_per_step": 1e3 * wall_s / args.steps,
             "rank_queries_per_s": (st["rank_leaves"] + st["rank_nodes"] + st["rank_call"]) * args.steps / dev_s,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": e_st["h2d_bytes"],
-                    "d2h_bytes_per_step": e_st["d2h_bytes"], "ms_per_step": 1e3 * e_wall_s / e_steps, "steps": e_steps},
+                    "d2h_bytes_per_step": e_st["d2h_bytes"], "ms_per_step": 1e3 * e_wall_s / e_steps, "steps": e_steps,
+                    "h2d_ms": e_st.get("ms_h2d")},
             "gpu_launches": st["kernel_launches"] * args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": (achieved / peak) if achieved else None, "traffic": traffic,
