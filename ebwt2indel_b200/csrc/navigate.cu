@@ -841,8 +841,9 @@ expand_leaves_kernel(const NavArgs a, const Segs in) {
             s_excl[lane] = hi - mhi;
         }
         const uint32_t tlo = __shfl_sync(0xffffffffu, lo, 7), thi = __shfl_sync(0xffffffffu, hi, 7);
-        unsigned long long agg[4] = {tlo & 0xffffu, tlo >> 16, thi & 0xffffu, thi >> 16}, excl[4];
-        lookback_exclusive<4>(a.desc, a.epoch, tile, agg, excl);
+        const uint32_t agg[4] = {tlo & 0xffffu, tlo >> 16, thi & 0xffffu, thi >> 16};
+        unsigned long long excl[4];
+        lookback4(a.desc, a.epoch, tile, agg, excl);      // all four queues in one look-back round
         if (lane < 4) {
             unsigned long long e = 0, g2 = 0;
 #pragma unroll
