@@ -350,6 +350,17 @@ def main():
     ctx.trim()
     torch.cuda.empty_cache()
     p = api.default_params()
+    random_gbs = None
+    if rank == 0:
+        try:     # random-sector gather roofline of this GPU, measured before the timed region (reported, not the denominator)
+            from ebwt2indel_b200 import synth as _synth
+            random_gbs = _synth.random_sector_bandwidth(device)
+            torch.cuda.empty_cache()
+        except Exception:  # noqa: BLE001
+            random_gbs = None
+    barrier_needed = world > 1
+    if barrier_needed:
+        dist.barrier()
     ext = torch.cuda.ExternalStream(ctx.stream_ptr, device=device)
 
     def barrier():
@@ -465,6 +476,8 @@ def main():
                          "frac": (achieved / peak) if achieved else None, "traffic": traffic,
                          "kernel": "expand_nodes_kernel (all launches of one step)",
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
+                         "random_sector_gbs": random_gbs,
+                         "frac_of_random_64B": (achieved / random_gbs["64"]) if (achieved and random_gbs) else None,
                          "algorithmic_bytes_per_step": alg_bytes, "kernel_ms_per_step": st["ms_nodes"]},
             "clocks": clk,
             "snp_bytes": len(snp) if snp is not None else None,

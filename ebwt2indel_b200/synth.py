@@ -286,8 +286,30 @@ def tools_lib():
         L.e2i_tool_bcr_mark.restype = C.c_int
         L.e2i_tool_bcr_merge.argtypes = [vp, vp, vp, vp, u64, u64, vp, vp, vp, vp]
         L.e2i_tool_bcr_merge.restype = C.c_int
+        L.e2i_tool_gather_bench.argtypes = [vp, u64, C.c_int, u64, vp, C.POINTER(C.c_float)]
+        L.e2i_tool_gather_bench.restype = C.c_int
         _tools = L
     return _tools
+
+
+def random_sector_bandwidth(device, buf_bytes: int = 8 << 30, n_access: int = 1 << 28):
+    """Measured GB/s of independent random 32 / 64 / 128-byte gathers over `buf_bytes` of HBM: the
+    random-sector roofline of an unsorted rank-query stream (BASELINE.json north_star)."""
+    import ctypes as C
+    import torch
+    T = tools_lib()
+    buf = torch.empty(buf_bytes, dtype=torch.uint8, device=device)
+    buf.random_(0, 255)
+    sink = torch.zeros(4, dtype=torch.int32, device=device)
+    out = {}
+    torch.cuda.synchronize(device)
+    for sector in (32, 64, 128):
+        ms = C.c_float(0)
+        rc = T.e2i_tool_gather_bench(buf.data_ptr(), buf_bytes, sector, n_access, sink.data_ptr(), C.byref(ms))
+        assert rc == 0
+        out[str(sector)] = n_access * sector / (ms.value / 1e3) / 1e9
+    del buf
+    return out
 
 
 class DevicePlans:
