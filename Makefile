@@ -9,8 +9,14 @@ OBJ := build/context.o build/index.o build/navigate.o build/call.o build/snp_for
 LIB := ebwt2indel_b200/libe2i.so
 TOOLS := ebwt2indel_b200/libe2i_tools.so
 BIN := bin/ebwt2InDel
+FILTER := bin/filter_snp
 
-all: $(LIB) $(BIN) $(TOOLS)
+all: $(LIB) $(BIN) $(FILTER) $(TOOLS)
+
+$(FILTER): $(CSRC)/filter_snp.cpp include/e2i.h $(LIB)
+	@mkdir -p bin
+	$(CXX) -O2 -std=c++17 -Wall -Iinclude $(CSRC)/filter_snp.cpp -o $@ -Lebwt2indel_b200 -le2i -Wl,-rpath,'$$ORIGIN/../ebwt2indel_b200'
+
 
 # synthetic-input tooling (eBWT construction for bench / tests); not linked into the product
 $(TOOLS): $(CSRC)/tools.cu
@@ -35,5 +41,5 @@ oracle:
 	$(MAKE) -C oracle
 
 clean:
-	rm -rf build $(LIB) $(BIN) $(TOOLS)
+	rm -rf build $(LIB) $(BIN) $(FILTER) $(TOOLS)
 .PHONY: all oracle clean

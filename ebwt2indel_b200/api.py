@@ -72,7 +72,7 @@ SYMBOLS = (
     "e2i_fl_batch", "e2i_rank_batch_device", "e2i_da_load", "e2i_da_load_device", "e2i_bits_fetch",
     "e2i_bits_size", "e2i_bits_free", "e2i_navigate", "e2i_navigate_shard", "e2i_lcpbits_fetch",
     "e2i_lcpbits_device", "e2i_bits_device", "e2i_lcpbits_free", "e2i_call", "e2i_calls_count",
-    "e2i_calls_fetch", "e2i_calls_view", "e2i_calls_free", "e2i_snp_format", "e2i_snp_count", "e2i_distance", "e2i_buffer_free", "e2i_run",
+    "e2i_calls_fetch", "e2i_calls_view", "e2i_calls_free", "e2i_snp_format", "e2i_snp_count", "e2i_filter_snp", "e2i_distance", "e2i_buffer_free", "e2i_run",
     "e2i_run_device",
 )
 
@@ -136,6 +136,7 @@ def lib():
         "e2i_calls_free": (None, [vp]),
         "e2i_snp_format": (C.c_int, [vp, vp, vp, u64, PP, C.c_int, u64, C.POINTER(vp), C.POINTER(C.c_size_t), PS]),
         "e2i_snp_count": (C.c_int, [vp, vp, vp, u64, PP, C.c_int, C.POINTER(u64)]),
+        "e2i_filter_snp": (C.c_int, [C.c_char_p, C.c_size_t, C.c_int32, C.c_int32, C.POINTER(vp), C.POINTER(C.c_size_t)]),
         "e2i_distance": (None, [C.c_char_p, C.c_char_p, C.c_int32, C.c_int32, C.POINTER(C.c_int32)]),
         "e2i_buffer_free": (None, [vp]),
         "e2i_run": (C.c_int, [vp, u8p, u64, u8p, u64, u8p, PP, C.POINTER(vp), C.POINTER(C.c_size_t), PS]),
@@ -356,6 +357,13 @@ class Context:
         _check(rc)
         text = SnpText(out, ln.value)
         return (text.tobytes() if copy else text), st
+
+
+def filter_snp(snp: bytes, m: int, M: int = 0) -> bytes:
+    """Coverage filter of the reference's filter_snp tool on an in-memory .snp text."""
+    out, ln = C.c_void_p(), C.c_size_t()
+    _check(lib().e2i_filter_snp(snp, len(snp), m, M, C.byref(out), C.byref(ln)))
+    return SnpText(out, ln.value).tobytes()
 
 
 def snp_count(recs: np.ndarray, left: np.ndarray, right: np.ndarray, params: Params, two_samples: bool) -> int:

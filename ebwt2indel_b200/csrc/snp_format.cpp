@@ -288,4 +288,48 @@ extern "C" int e2i_snp_format(const e2i_call_rec *recs, const char *left, const 
     return E2I_OK;
 }
 
+// Coverage filter of filter_snp.cpp:38-77.  Lines are taken in pairs (header, sequence); the
+// coverage is the integer after the first ':' of the 4th '_'-separated token of the header
+// (atoi semantics: 0 when absent); a pair is kept iff cov >= m and (M == 0 or cov <= M).  A
+// trailing header without its sequence line prints nothing, like the reference.
+extern "C" int e2i_filter_snp(const char *snp, size_t len, int32_t m, int32_t M, char **out, size_t *out_len) {
+    if (!out || !out_len || (len && !snp)) { e2i::set_error("e2i_filter_snp: null argument"); return E2I_ERR_ARG; }
+    char *buf = static_cast<char *>(std::malloc(len + 2));
+    if (!buf) { e2i::set_error("e2i_filter_snp: out of host memory"); return E2I_ERR_MEMORY; }
+    size_t w = 0, pos = 0, header_b = 0, header_e = 0;
+    bool have_header = false;
+    int cov = 0;
+    while (pos < len) {
+        size_t e = pos;
+        while (e < len && snp[e] != '\n') ++e;                   // getline: [pos, e)
+        if (!have_header) {
+            header_b = pos; header_e = e; have_header = true;
+            size_t t = pos;                                        // 4th '_' token
+            for (int k = 0; k < 3 && t < e; ++k) { while (t < e && snp[t] != '_') ++t; if (t < e) ++t; }
+            size_t te = t;
+            while (te < e && snp[te] != '_') ++te;
+            size_t c = t;
+            while (c < te && snp[c] != ':') ++c;
+            cov = 0;
+            if (c < te) {                                          // atoi of the text after the first ':' up to the next ':'
+                size_t v = c + 1, ve = v;
+                while (ve < te && snp[ve] != ':') ++ve;
+                cov = atoi(std::string(snp + v, ve - v).c_str());
+            }
+        } else {
+            if (cov >= m && (M == 0 || cov <= M)) {
+                std::memcpy(buf + w, snp + header_b, header_e - header_b); w += header_e - header_b; buf[w++] = '\n';
+                std::memcpy(buf + w, snp + pos, e - pos); w += e - pos; buf[w++] = '\n';
+            }
+            have_header = false;
+            cov = 0;
+        }
+        pos = e + 1;
+    }
+    buf[w] = 0;
+    *out = buf;
+    *out_len = w;
+    return E2I_OK;
+}
+
 extern "C" void e2i_buffer_free(void *p) { std::free(p); }

@@ -215,6 +215,9 @@ int e2i_snp_format(const e2i_call_rec *recs, const char *left, const char *right
 int e2i_snp_count(const e2i_call_rec *recs, const char *left, const char *right, uint64_t n_recs,
                   const e2i_params *p, int two_samples, uint64_t *clusters);
 void e2i_distance(const char *a, const char *b, int32_t len, int32_t max_gap, int32_t out[2]);
+/* ---- output-side coverage filter.  Replaces filter_snp (filter_snp.cpp:17-81): keeps the records
+ *      whose `cov:` field is >= m and (M == 0 or <= M); *out is malloc'ed (e2i_buffer_free). ------- */
+int e2i_filter_snp(const char *snp, size_t len, int32_t m, int32_t M, char **out, size_t *out_len);
 void e2i_buffer_free(void *p);
 
 /* ---- the whole path with host buffers: what bin/ebwt2InDel calls (run_one_dataset :1584,

@@ -50,13 +50,21 @@ def resolved_fields(fields):
 @pytest.fixture(scope="session")
 def oracle():
     from oracle import binding
+    if not os.path.exists(binding.LIB_PATH):
+        binding.build()
     binding.lib()
     return binding
 
 
 @pytest.fixture(scope="session")
 def e2i():
+    """The ctypes binding of libe2i.so.  The library and the CLI binaries are build products (not in
+    git): build them when they are missing (nvcc cross-compiles sm_100a without a GPU)."""
+    import subprocess
     from ebwt2indel_b200 import api
+    needed = [api.LIB_PATH, os.path.join(ROOT, "bin", "ebwt2InDel"), os.path.join(ROOT, "bin", "filter_snp")]
+    if not all(os.path.exists(p) for p in needed):
+        subprocess.run(["make", "-s", "-j8", "-C", ROOT, "all"], check=True)
     api.lib()
     return api
 

@@ -141,3 +141,44 @@ def test_parallel_formatter_equals_sequential_chaining(e2i):
         assert whole == out
         assert st.clusters_out == nr - 1 and st.events == ev and len(whole) > 100000
         assert e2i.snp_count(recs, left, right, p, two) == st.clusters_out
+
+
+def test_filter_snp_matches_reference_tool(e2i, oracle):
+    """e2i_filter_snp / bin/filter_snp against the reference's filter_snp (filter_snp.cpp:17-81):
+    committed expectations for the golden .snp files, and the compiled reference where it exists."""
+    from conftest import load_golden
+    ref_tool = os.path.join(ROOT, "oracle", "_ref", "filter_snp")
+    my_tool = os.path.join(ROOT, "bin", "filter_snp")
+    for name in ("m1_default", "m1_flags", "m3_default", "m2_flags", "m1_metagenome"):
+        snp = load_golden(name)["snp"]
+        for m, M in ((0, 0), (3, 0), (5, 0), (10, 20), (8, 8), (1000, 0), (4, 2)):
+            got = e2i.filter_snp(snp, m, M)
+            # independent restatement in Python of the reference's loop
+            lines = snp.split(b"\n")
+            if lines and lines[-1] == b"":
+                lines.pop()
+            want = b""
+            for i in range(0, len(lines) - 1, 2):
+                tok = lines[i].split(b"_")
+                cov = 0
+                if len(tok) >= 4:
+                    f = tok[3].split(b":")
+                    if len(f) >= 2:
+                        d = f[1].decode()
+                        k = 0
+                        while k < len(d) and (d[k].isdigit() or (k == 0 and d[k] in "+-")):
+                            k += 1
+                        cov = int(d[:k]) if d[:k] not in ("", "+", "-") else 0
+                if cov >= m and (M == 0 or cov <= M):
+                    want += lines[i] + b"\n" + lines[i + 1] + b"\n"
+            assert got == want, (name, m, M)
+            if os.access(ref_tool, os.X_OK):
+                import tempfile
+                with tempfile.NamedTemporaryFile(suffix=".snp") as f:
+                    f.write(snp)
+                    f.flush()
+                    args = [str(m)] + ([str(M)] if M else [])
+                    ref = subprocess.run([ref_tool, f.name] + args, capture_output=True).stdout
+                    mine = subprocess.run([my_tool, f.name] + args, capture_output=True).stdout
+                assert ref == got == mine, (name, m, M)
+    assert len(e2i.filter_snp(load_golden("m1_default")["snp"], 5)) > 0
