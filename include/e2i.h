@@ -192,6 +192,8 @@ void e2i_lcpbits_free(e2i_lcpbits *l);
  *      mode -1: b2 = NULL, da = NULL;  mode -2: b2, da = navigate's DA;  mode -d: b2 = NULL, da.
  *      [pos_begin, pos_end): only clusters that START in this merged SA range are analysed
  *      (0, UINT64_MAX = all); used to shard phase 4. ---------------------------------------- */
+/* The records of an e2i_calls handle live in the context's page-locked staging buffer: a handle is
+ * valid until the next e2i_call on the same context (e2i_calls_fetch / _view check this). */
 int e2i_call(e2i_ctx *ctx, const e2i_index *b1, const e2i_index *b2, const e2i_bits *da,
              const e2i_lcpbits *l, const e2i_params *p, uint64_t pos_begin, uint64_t pos_end,
              e2i_calls **out, e2i_stats *st);
