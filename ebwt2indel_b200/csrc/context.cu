@@ -221,20 +221,40 @@ extern "C" int e2i_run(e2i_ctx *ctx, const uint8_t *host_bwt1, uint64_t n1, cons
     HostInputs in;
     HostInputsRef ref{&in, ctx};
     auto fail = [&](cudaError_t e) { set_error("e2i_run: %s", cudaGetErrorString(e)); free_inputs(&ref); return E2I_ERR_CUDA; };
+    // One stream by default (a single copy engine saturates the link on an idle host).  With
+    // E2I_H2D_STREAMS=2 large inputs go up as 256 MB pieces alternating between the context's two
+    // streams; measurements on a shared host were too noisy to prefer either (profiles/e2e_time.py).
+    const char *hs = std::getenv("E2I_H2D_STREAMS");
+    const int n_streams = hs ? std::max(1, std::min(2, atoi(hs))) : 1;
+    cudaEvent_t ev_copy = nullptr;
+    auto upload = [&](uint8_t *dst, const uint8_t *src, uint64_t n) -> cudaError_t {
+        const uint64_t piece = 256ull << 20;
+        if (n_streams == 1 || n <= piece) return cudaMemcpyAsync(dst, src, n, cudaMemcpyHostToDevice, s);
+        int k = 0;
+        for (uint64_t off = 0; off < n; off += piece, ++k) {
+            const cudaError_t ce = cudaMemcpyAsync(dst + off, src + off, std::min(piece, n - off), cudaMemcpyHostToDevice,
+                                                   (k & 1) ? ctx->copy_stream : s);
+            if (ce != cudaSuccess) return ce;
+        }
+        return cudaSuccess;
+    };
     cudaError_t e = cudaEventRecord(ctx->ev[6], s);
     if (e == cudaSuccess) e = dmalloc(ctx, &in.d1, n1 + 16);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(in.d1, host_bwt1, n1, cudaMemcpyHostToDevice, s);
-    if (e == cudaSuccess && host_bwt2) {
-        e = dmalloc(ctx, &in.d2, n2 + 16);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(in.d2, host_bwt2, n2, cudaMemcpyHostToDevice, s);
-    }
-    if (e == cudaSuccess && host_da) {
-        e = dmalloc(ctx, &in.dd, n1 + 16);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(in.dd, host_da, n1, cudaMemcpyHostToDevice, s);
-    }
+    if (e == cudaSuccess && host_bwt2) e = dmalloc(ctx, &in.d2, n2 + 16);
+    if (e == cudaSuccess && host_da) e = dmalloc(ctx, &in.dd, n1 + 16);
+    // the second stream must not start before the allocations (stream-ordered) are done on the first
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev_copy, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventRecord(ev_copy, s);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->copy_stream, ev_copy, 0);
+    if (e == cudaSuccess) e = upload(in.d1, host_bwt1, n1);
+    if (e == cudaSuccess && host_bwt2) e = upload(in.d2, host_bwt2, n2);
+    if (e == cudaSuccess && host_da) e = upload(in.dd, host_da, n1);
+    if (e == cudaSuccess) e = cudaEventRecord(ev_copy, ctx->copy_stream);       // join the second stream
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(s, ev_copy, 0);
     if (e == cudaSuccess) e = cudaEventRecord(ctx->ev[7], s);
     if (e == cudaSuccess) e = cudaEventSynchronize(ctx->ev[7]);
     if (e != cudaSuccess) return fail(e);
+    if (ev_copy) cudaEventDestroy(ev_copy);
     float ms = 0;
     cudaEventElapsedTime(&ms, ctx->ev[6], ctx->ev[7]);
     st->ms_h2d += ms;
