@@ -474,7 +474,7 @@ def main():
             "gpu_launches": st["kernel_launches"] * args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": (achieved / peak) if achieved else None, "traffic": traffic,
-                         "kernel": "expand_nodes_kernel (all launches of one step)",
+                         "kernel": "expand_nodes_persistent (all launches of one step)",
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
                          "random_sector_gbs": random_gbs,
                          "frac_of_random_64B": (achieved / random_gbs["64"]) if (achieved and random_gbs) else None,
