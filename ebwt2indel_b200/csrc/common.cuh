@@ -96,8 +96,10 @@ struct e2i_ctx {
     unsigned long long *desc = nullptr;
     size_t desc_words = 0;
     uint32_t epoch = 0;
-    void *ctl = nullptr;        // device control block (ticket + counters), see navigate.cu
-    void *ctl_host = nullptr;   // pinned mirror
+    void *ctl = nullptr;        // device ring of per-sweep ticket counters, see navigate.cu
+    void *ctl_host = nullptr;   // page-locked, device-mapped block the sweeps report their counts to
+    uint32_t ticket_next = 0;
+    unsigned long long sweep_seq = 0;
     void *pinned = nullptr;     // page-locked staging of the call records
     size_t pinned_bytes = 0;
     uint64_t pinned_gen = 0;

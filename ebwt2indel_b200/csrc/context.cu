@@ -100,8 +100,9 @@ extern "C" int e2i_create(int device, e2i_ctx **out) {
         E2I_CUDA_TRY(cudaMemPoolSetAttribute(mp, cudaMemPoolAttrReleaseThreshold, &thr));
     }
     for (auto &ev : ctx->ev) E2I_CUDA_TRY(cudaEventCreate(&ev));
-    E2I_CUDA_TRY(cudaMalloc(&ctx->ctl, 4096));
-    E2I_CUDA_TRY(cudaMallocHost(&ctx->ctl_host, 4096));
+    E2I_CUDA_TRY(cudaMalloc(&ctx->ctl, 16384 * sizeof(uint32_t)));
+    E2I_CUDA_TRY(cudaHostAlloc(&ctx->ctl_host, 4096, cudaHostAllocMapped | cudaHostAllocPortable));
+    std::memset(ctx->ctl_host, 0, 4096);
     *out = ctx;
     return E2I_OK;
 }

@@ -22,6 +22,7 @@
 // each child cW, keeps the children with >= 2 non-empty sub-intervals (number_of_children >= 2) and
 // appends them, in order, as 32-byte compact records.  Leaves: one thread per leaf (two ranks per BWT).
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <memory>
 
@@ -35,10 +36,15 @@ constexpr int kStageBlocks = 512;       // index blocks staged in shared memory 
 constexpr int kStripes = 128;           // striped statistics counters (avoid single-address atomics)
 enum { C_LCP = 0, C_NMIN, C_RANK, C_BITUPD, C_DA, C_NCOUNTERS = 8 };
 
-struct LaunchCtl {
-    uint32_t ticket;
-    uint32_t pad;
+// Per-sweep control.  Device side: one zeroed ticket counter per sweep (a ring, so no per-sweep
+// memset).  Host side: a page-locked, device-mapped block that the last tile of the sweep writes
+// the four child counts into, followed by the sweep's sequence number; the host polls that word
+// instead of a copy + stream synchronisation and sizes the next sweep as soon as the counts exist
+// (the next launch is stream-ordered behind the running one anyway).
+constexpr uint32_t kTicketSlots = 16384;
+struct HostCtl {
     unsigned long long out_count[4];
+    unsigned long long seq;
 };
 
 struct Segs {                 // a position-sorted run of records given as <= 4 segments
@@ -54,7 +60,9 @@ struct NavArgs {
     uint32_t *da;             // 1 bit per merged position (mode -2)
     unsigned long long *stripes;
     unsigned long long *desc;
-    LaunchCtl *ctl;
+    uint32_t *ticket;          // this sweep's ticket counter
+    HostCtl *host;             // mapped page-locked result block
+    unsigned long long seq;    // sequence number of this sweep
     uint64_t *out[4];
     uint32_t epoch;
     uint32_t n_tiles;
@@ -267,7 +275,7 @@ expand_nodes_kernel(const NavArgs a, const Segs in) {
     constexpr int STAGE = TWO ? kStageBlocks / 2 : kStageBlocks;   // blocks staged per BWT
     __shared__ uint4 s_stage[kStageBlocks * 4];
 
-    if (threadIdx.x == 0) s_tile = atomicAdd(&a.ctl->ticket, 1u);
+    if (threadIdx.x == 0) s_tile = atomicAdd(a.ticket, 1u);
     if (threadIdx.x < C_NCOUNTERS) s_stat[threadIdx.x] = 0;
     __syncthreads();
     const uint32_t tile = s_tile;
@@ -428,7 +436,12 @@ expand_nodes_kernel(const NavArgs a, const Segs in) {
 #pragma unroll
             for (int c = 0; c < 4; ++c) if (lane == c) { e = excl[c]; g2 = agg[c]; }
             s_base[lane] = e;
-            if (tile == a.n_tiles - 1) a.ctl->out_count[lane] = e + g2;
+            if (tile == a.n_tiles - 1) ((volatile unsigned long long *)a.host->out_count)[lane] = e + g2;
+        }
+        if (tile == a.n_tiles - 1) {                       // tell the host that the counts of this sweep are final
+            __threadfence_system();
+            __syncwarp();
+            if (lane == 0) *(volatile unsigned long long *)&a.host->seq = a.seq;
         }
         if (lane < C_NCOUNTERS && a.write) stripe_add(a.stripes, tile, lane, s_stat[lane]);
     }
@@ -524,7 +537,12 @@ expand_nodes_persistent(const NavArgs a, const Segs in) {
 #pragma unroll
                 for (int c = 0; c < 4; ++c) if (lane == c) { e = excl[c]; g2 = agg[c]; }
                 v_base[lane] = e;
-                if (tile == a.n_tiles - 1) a.ctl->out_count[lane] = e + g2;
+                if (tile == a.n_tiles - 1) ((volatile unsigned long long *)a.host->out_count)[lane] = e + g2;
+            }
+            if (tile == a.n_tiles - 1) {                   // tell the host that the counts of this sweep are final
+                __threadfence_system();
+                __syncwarp();
+                if (lane == 0) *(volatile unsigned long long *)&a.host->seq = a.seq;
             }
             __threadfence_block();
             __syncwarp();
@@ -559,13 +577,13 @@ expand_nodes_persistent(const NavArgs a, const Segs in) {
             for (int k = 0; k < RU; ++k) cp_async16(&sm.recbuf[threadIdx.x * RU + k], rec + k);
         }
     };
-    if (threadIdx.x == 0) sm.tile = atomicAdd(&a.ctl->ticket, 1u);
+    if (threadIdx.x == 0) sm.tile = atomicAdd(a.ticket, 1u);
     bar_compute();
     uint32_t tile = sm.tile;
     prefetch_records(tile);
     while (tile < a.n_tiles) {
         uint32_t nxt = 0;
-        if (threadIdx.x == 0) nxt = atomicAdd(&a.ctl->ticket, 1u);          // its latency hides behind this tile
+        if (threadIdx.x == 0) nxt = atomicAdd(a.ticket, 1u);          // its latency hides behind this tile
         if (threadIdx.x < C_NCOUNTERS) sm.stat[threadIdx.x] = 0;
         const uint32_t g = tile * kCompThreads + threadIdx.x;
         const bool active = g < in.total;
@@ -754,7 +772,7 @@ expand_leaves_kernel(const NavArgs a, const Segs in) {
     __shared__ uint32_t s_excl[8];
     __shared__ unsigned long long s_base[4];
     __shared__ unsigned long long s_stat[C_NCOUNTERS];
-    if (threadIdx.x == 0) s_tile = atomicAdd(&a.ctl->ticket, 1u);
+    if (threadIdx.x == 0) s_tile = atomicAdd(a.ticket, 1u);
     if (threadIdx.x < C_NCOUNTERS) s_stat[threadIdx.x] = 0;
     __syncthreads();
     const uint32_t tile = s_tile;
@@ -849,7 +867,12 @@ expand_leaves_kernel(const NavArgs a, const Segs in) {
 #pragma unroll
             for (int c = 0; c < 4; ++c) if (lane == c) { e = excl[c]; g2 = agg[c]; }
             s_base[lane] = e;
-            if (tile == a.n_tiles - 1) a.ctl->out_count[lane] = e + g2;
+            if (tile == a.n_tiles - 1) ((volatile unsigned long long *)a.host->out_count)[lane] = e + g2;
+        }
+        if (tile == a.n_tiles - 1) {                       // tell the host that the counts of this sweep are final
+            __threadfence_system();
+            __syncwarp();
+            if (lane == 0) *(volatile unsigned long long *)&a.host->seq = a.seq;
         }
         if (lane < C_NCOUNTERS && a.write) stripe_add(a.stripes, tile, lane, s_stat[lane]);
     }
@@ -941,7 +964,7 @@ static int run_frontier(e2i_ctx *ctx, Chunk root, int words, int tile_items, uin
                         NavArgs &args, Launch launch, SweepStats &ss, uint64_t stop_at_items, std::vector<Chunk> *stopped) {
     std::vector<Chunk> stack;
     stack.push_back(std::move(root));
-    LaunchCtl *hctl = reinterpret_cast<LaunchCtl *>(ctx->ctl_host);
+    HostCtl *hctl = reinterpret_cast<HostCtl *>(ctx->ctl_host);
     while (!stack.empty()) {
         Chunk cur = std::move(stack.back());
         stack.pop_back();
@@ -997,15 +1020,35 @@ static int run_frontier(e2i_ctx *ctx, Chunk root, int words, int tile_items, uin
         args.desc = ctx->desc;
         args.epoch = ctx->epoch;
         args.n_tiles = n_tiles;
-        args.ctl = reinterpret_cast<LaunchCtl *>(ctx->ctl);
-        E2I_CUDA_TRY(cudaMemsetAsync(ctx->ctl, 0, sizeof(LaunchCtl), ctx->stream));
+        if (ctx->ticket_next == kTicketSlots) {          // ring of ticket counters used up: zero it again
+            E2I_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+            E2I_CUDA_TRY(cudaMemsetAsync(ctx->ctl, 0, kTicketSlots * sizeof(uint32_t), ctx->stream));
+            ctx->ticket_next = 0;
+        }
+        args.ticket = reinterpret_cast<uint32_t *>(ctx->ctl) + ctx->ticket_next++;
+        args.host = hctl;
+        args.seq = ++ctx->sweep_seq;
         launch(args, segs, n_tiles);
         E2I_CUDA_TRY(cudaGetLastError());
         ctx->n_launch++;
-        ctx->n_d2h += sizeof(LaunchCtl);
-        E2I_CUDA_TRY(cudaMemcpyAsync(hctl, ctx->ctl, sizeof(LaunchCtl), cudaMemcpyDeviceToHost, ctx->stream));
+        ctx->n_d2h += sizeof(HostCtl);
         const double tsy = now_ms();
-        E2I_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        {   // wait for the counts (not for the kernel): poll the mapped sequence word
+            volatile unsigned long long *seqp = &hctl->seq;
+            unsigned spins = 0;
+            while (*seqp != args.seq) {
+                if ((++spins & 0xfffu) == 0) {
+                    const cudaError_t q = cudaStreamQuery(ctx->stream);
+                    if (q == cudaSuccess) {
+                        if (*seqp == args.seq) break;
+                        set_error("traversal sweep finished without publishing its counts");
+                        return E2I_ERR_CUDA;
+                    }
+                    if (q != cudaErrorNotReady) { set_error("CUDA error in a traversal sweep: %s", cudaGetErrorString(q)); return E2I_ERR_CUDA; }
+                }
+            }
+            std::atomic_thread_fence(std::memory_order_acquire);
+        }
         { const double d = now_ms() - tsy; ss.ms_sync += d; ss.ms_max_sync = std::max(ss.ms_max_sync, d); }
         ss.items += acc;
         ss.sweeps++;
@@ -1013,7 +1056,7 @@ static int run_frontier(e2i_ctx *ctx, Chunk root, int words, int tile_items, uin
         Chunk next;
         next.frame = frame;
         next.level = work.level + 1;
-        for (int c = 0; c < 4; ++c) { next.p[c] = args.out[c]; next.cnt[c] = hctl->out_count[c]; }
+        for (int c = 0; c < 4; ++c) { next.p[c] = args.out[c]; next.cnt[c] = ((volatile unsigned long long *)hctl->out_count)[c]; }
         work.frame.reset();
         if (next.total()) stack.push_back(std::move(next));
     }
@@ -1073,6 +1116,8 @@ extern "C" int e2i_navigate_shard(e2i_ctx *ctx, const e2i_index *b1, const e2i_i
     }
     const size_t stripe_bytes = (size_t)kStripes * C_NCOUNTERS * sizeof(unsigned long long);
     TRYF(dmalloc(ctx, &stripes, stripe_bytes));
+    TRYF(cudaMemsetAsync(ctx->ctl, 0, kTicketSlots * sizeof(uint32_t), s));
+    ctx->ticket_next = 0;
 
     // frontier budget: what is free now, minus head-room, unless the caller set one
     size_t free_b = 0, total_b = 0;
