@@ -7,7 +7,9 @@
 // the good[1] operand of event_type in mode -1, cluster numbers that advance for clusters that
 // print nothing, the `right:` field printing the actual right-context length.
 #include <algorithm>
+#include <chrono>
 #include <functional>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <utility>
@@ -40,7 +42,59 @@ int hamming_right(const char *a, int la, const char *b, int lb) {
 
 // :192-240.  Candidates: no indel, or drop 1..max_gap characters from the right end of a / of b.
 // "No indel" wins only if strictly better than both; "insert in a" only if strictly better than b.
+// Contexts of <= 32 bases as 2-bit codes, character k at bits [2k, 2k+2): false if a character is not A,C,G,T.
+inline bool pack2(const char *s, int len, uint64_t &out) {
+    uint64_t v = 0;
+    int k = 0;
+    for (; k + 4 <= len; k += 4) {                      // four characters per step
+        uint32_t w;
+        std::memcpy(&w, s + k, 4);
+        const uint32_t y = (w >> 1) & 0x03030303u, code = y ^ ((y >> 1) & 0x01010101u);
+        // valid iff every byte equals "ACGT"[code]: A 0x41, C 0x43, G 0x47, T 0x54
+        const uint32_t lo = code & 0x01010101u, hi = (code >> 1) & 0x01010101u;
+        const uint32_t expect = 0x41414141u + lo * 2u + hi * 6u + (lo & hi) * 11u;   // +2 C, +6 G, +19 T
+        if (w != expect) return false;
+        v |= (uint64_t)((code * 0x01041040u) >> 24) << (2 * k);
+    }
+    for (; k < len; ++k) {
+        const unsigned c = (unsigned char)s[k];
+        const unsigned y = (c >> 1) & 3u, code = y ^ (y >> 1);              // A 0, C 1, G 2, T 3
+        if (c != (unsigned char)"ACGT"[code]) return false;
+        v |= (uint64_t)code << (2 * k);
+    }
+    out = v;
+    return true;
+}
+
+inline int mismatches2(uint64_t x, uint64_t y, int chars) {             // over the lowest `chars` characters
+    const uint64_t z = x ^ y, m = chars >= 32 ? ~0ull : ((1ull << (2 * chars)) - 1);
+    return __builtin_popcountll((z | (z >> 1)) & 0x5555555555555555ull & m);
+}
+
+// distance() on packed contexts: every shifted comparison is a shift, an XOR and a popcount.
+inline Dist distance_packed(uint64_t a, uint64_t b, int len, int max_gap) {
+    const int plain = mismatches2(a, b, len);
+    int best_a = 0, gap_a = 0, best_b = 0, gap_b = 0;
+    for (int g = 1; g <= max_gap; ++g) {
+        int da, db;
+        if (g <= len) {
+            const int keep = len - g;
+            da = (keep ? mismatches2(a, g >= 32 ? 0 : (b >> (2 * g)), keep) : 0) + g;   // a[0, keep) against b[g, len)
+            db = (keep ? mismatches2(g >= 32 ? 0 : (a >> (2 * g)), b, keep) : 0) + g;   // a[g, len) against b[0, keep)
+        } else {
+            da = db = plain + g;                     // substr(0, len-g) wraps to the whole string when g > len
+        }
+        if (g == 1 || da < best_a) { best_a = da; gap_a = g; }
+        if (g == 1 || db < best_b) { best_b = db; gap_b = g; }
+    }
+    if (plain < best_a && plain < best_b) return {plain, 0};
+    if (best_a < best_b) return {best_a - gap_a, gap_a};
+    return {best_b - gap_b, -gap_b};
+}
+
 Dist distance(const char *a, const char *b, int len, int max_gap) {
+    uint64_t pa, pb;
+    if (max_gap > 0 && len >= 1 && len <= 32 && pack2(a, len, pa) && pack2(b, len, pb)) return distance_packed(pa, pb, len, max_gap);
     const int plain = hamming_right(a, len, b, len);
     if (max_gap <= 0) return {plain, 0};
     int best_a = 0, gap_a = 0, best_b = 0, gap_b = 0;
@@ -64,49 +118,73 @@ bool starts_with_run(const char *s, int len, int k) {
     return true;
 }
 
-void append_event(std::string &o, const char *l0, const char *l1, int len, Dist d) {   // :1102-1144
-    o += "type:";
-    o += d.gap != 0 ? "_INDEL_event:" : "_SNP_event:";
-    if (d.gap == 0) { o += l0[len - 1]; o += '/'; o += l1[len - 1]; }
-    else if (d.gap > 0) { o.append(l0 + len - d.gap, (size_t)d.gap); o += '/'; }
-    else { o += '/'; o.append(l1 + len + d.gap, (size_t)(-d.gap)); }
+// Growable text buffer with unchecked appends after ensure(): the formatter writes a few hundred
+// bytes per record, and std::string's per-character capacity checks were half of its time.
+// Buffers are kept (with their touched pages) in a process-wide pool between calls.
+struct TextBuf {
+    char *p = nullptr;
+    size_t n = 0, cap = 0;
+    TextBuf() = default;
+    TextBuf(const TextBuf &) = delete;
+    TextBuf &operator=(const TextBuf &) = delete;
+    TextBuf(TextBuf &&o) noexcept : p(o.p), n(o.n), cap(o.cap) { o.p = nullptr; o.n = o.cap = 0; }
+    ~TextBuf() { std::free(p); }
+    void ensure(size_t extra) {
+        if (n + extra <= cap) return;
+        size_t want = std::max(cap * 2, n + extra + (1u << 16));
+        p = static_cast<char *>(std::realloc(p, want));
+        cap = want;
+    }
+    void put(char c) { p[n++] = c; }
+    void put(const char *s, size_t len) { std::memcpy(p + n, s, len); n += len; }
+    template <size_t N> void lit(const char (&s)[N]) { std::memcpy(p + n, s, N - 1); n += N - 1; }
+    void uint(uint64_t v) {
+        char buf[24];
+        int k = 0;
+        do { buf[k++] = (char)('0' + v % 10); v /= 10; } while (v);
+        while (k) p[n++] = buf[--k];
+    }
+    void sint(int v) {
+        if (v < 0) { p[n++] = '-'; uint((uint64_t)(-(int64_t)v)); } else uint((uint64_t)v);
+    }
+};
+
+void append_event(TextBuf &o, const char *l0, const char *l1, int len, Dist d) {   // :1102-1144
+    o.lit("type:");
+    if (d.gap != 0) o.lit("_INDEL_event:"); else o.lit("_SNP_event:");
+    if (d.gap == 0) { o.put(l0[len - 1]); o.put('/'); o.put(l1[len - 1]); }
+    else if (d.gap > 0) { o.put(l0 + len - d.gap, (size_t)d.gap); o.put('/'); }
+    else { o.put('/'); o.put(l1 + len + d.gap, (size_t)(-d.gap)); }
 }
 
 // Header with a placeholder for the cluster number: numbering is sequential over the whole run
 // (cluster_nr, ebwt2InDel.cpp:1250/1328), so record ranges are formatted in parallel with local
 // cluster indices and the numbers are filled in once the per-range totals are known.
 struct Piece {
-    std::string text;                                   // '\x01' marks where a cluster number goes
+    TextBuf text;                                       // '\x01' marks where a cluster number goes
     std::vector<std::pair<size_t, uint64_t>> marks;     // (offset of the placeholder, local cluster index)
     uint64_t clusters = 0, events = 0;
 };
 
-inline void append_uint(std::string &o, uint64_t v) {
-    char buf[24];
-    int n = 0;
-    do { buf[n++] = (char)('0' + v % 10); v /= 10; } while (v);
-    while (n) o += buf[--n];
-}
-
-inline void append_int(std::string &o, int v) {
-    if (v < 0) { o += '-'; append_uint(o, (uint64_t)(-(int64_t)v)); } else append_uint(o, (uint64_t)v);
-}
-
 void append_header(Piece &o, uint64_t local_cluster, uint64_t id, int right_len, int cov) {
-    o.text += ">cluster:";
-    o.marks.emplace_back(o.text.size(), local_cluster);
-    o.text += '\x01';
-    o.text += "_id:";      append_uint(o.text, id);
-    o.text += "_right:";   append_int(o.text, right_len);
-    o.text += "_cov:";     append_int(o.text, cov);
-    o.text += '_';
+    o.text.lit(">cluster:");
+    o.marks.emplace_back(o.text.n, local_cluster);
+    o.text.put('\x01');
+    o.text.lit("_id:");      o.text.uint(id);
+    o.text.lit("_right:");   o.text.sint(right_len);
+    o.text.lit("_cov:");     o.text.sint(cov);
+    o.text.put('_');
 }
 
 void format_range(const e2i_call_rec *recs, const char *left, const char *right, uint64_t r0, uint64_t r1,
                   const e2i_params *p, int two_samples, Piece &out) {
     const int kl = p->k_left, kr = p->k_right;
-    std::string &o = out.text;
-    o.reserve((size_t)(r1 - r0) * 2 * (size_t)(kl + kr + 72));
+    TextBuf &o = out.text;
+    o.n = 0;
+    out.marks.clear();
+    out.clusters = out.events = 0;
+    const size_t line_max = 160 + (size_t)std::max(0, p->max_gap) + (size_t)kl + (size_t)kr;   // one header + sequence line
+    o.ensure((size_t)(r1 - r0) * 2 * (size_t)(kl + kr + 72) + line_max);
     out.marks.reserve((size_t)(r1 - r0) * 2);
     uint64_t cluster = 0;                               // local index; global number = first + cluster
     for (uint64_t r = r0; r < r1; ++r) {
@@ -130,14 +208,15 @@ void format_range(const e2i_call_rec *recs, const char *left, const char *right,
                 uint64_t id = 1;
                 for (int g = 0; g < ng; ++g) {
                     const char *me = L + good[g] * kl;
+                    o.ensure(line_max);
                     append_header(out, cluster, id++, rlen, rec.support[good[g]]);
                     const char *x = g == 0 ? me : L + good[g - 1] * kl;   // :1299-1307
                     const char *y = L + good[1] * kl;
                     append_event(o, x, y, kl, distance(x, y, kl, p->max_gap));
-                    o += '\n';
-                    o.append(me, (size_t)kl);
-                    o.append(R, (size_t)rlen);
-                    o += '\n';
+                    o.put('\n');
+                    o.put(me, (size_t)kl);
+                    o.put(R, (size_t)rlen);
+                    o.put('\n');
                     out.events++;
                 }
             }
@@ -156,15 +235,16 @@ void format_range(const e2i_call_rec *recs, const char *left, const char *right,
                 if (d.mism > p->max_snvs) continue;
                 found = true;
                 for (int side = 0; side < 2; ++side) {
+                    o.ensure(line_max);
                     append_header(out, cluster, id, rlen, side ? s1 : s0);
                     append_event(o, l0, l1, kl, d);
-                    o += '\n';
+                    o.put('\n');
                     int skip = 0;
                     if (side == 0 && d.gap < 0) skip = -d.gap;           // :1199
                     if (side == 1 && d.gap > 0) skip = d.gap;            // :1233
-                    o.append((side ? l1 : l0) + skip, (size_t)(kl - skip));
-                    o.append(R, (size_t)rlen);
-                    o += '\n';
+                    o.put((side ? l1 : l0) + skip, (size_t)(kl - skip));
+                    o.put(R, (size_t)rlen);
+                    o.put('\n');
                 }
                 id++;
             }
@@ -236,7 +316,14 @@ extern "C" int e2i_snp_format(const e2i_call_rec *recs, const char *left, const 
     unsigned hw = std::thread::hardware_concurrency();
     if (hw == 0) hw = 1;
     const uint64_t nt = std::max<uint64_t>(1, std::min<uint64_t>({(uint64_t)hw, 64, n_recs / 2048}));
-    std::vector<Piece> pieces(nt);
+    // formatter buffers survive between calls (their pages stay touched); a concurrent caller gets fresh ones
+    static std::mutex pool_mutex;
+    static std::vector<Piece> pool;
+    std::vector<Piece> local;
+    std::unique_lock<std::mutex> hold(pool_mutex, std::try_to_lock);
+    std::vector<Piece> &pieces = hold.owns_lock() ? pool : local;
+    if (pieces.size() < nt) pieces.resize(nt);
+    const auto t_a = std::chrono::steady_clock::now();
     {
         std::vector<std::thread> th;
         for (uint64_t t = 1; t < nt; ++t)
@@ -244,13 +331,14 @@ extern "C" int e2i_snp_format(const e2i_call_rec *recs, const char *left, const 
         format_range(recs, left, right, 0, n_recs / nt, p, two_samples, pieces[0]);
         for (auto &x : th) x.join();
     }
+    const auto t_b = std::chrono::steady_clock::now();
     // global cluster numbers and output offsets
     std::vector<uint64_t> start(nt + 1, first);
     std::vector<size_t> off(nt + 1, 0);
     uint64_t events = 0;
     for (uint64_t t = 0; t < nt; ++t) {
         start[t + 1] = start[t] + pieces[t].clusters;
-        size_t len = pieces[t].text.size() - pieces[t].marks.size();
+        size_t len = pieces[t].text.n - pieces[t].marks.size();
         for (const auto &m : pieces[t].marks) len += (size_t)digits10(start[t] + m.second);
         off[t + 1] = off[t] + len;
         events += pieces[t].events;
@@ -262,7 +350,7 @@ extern "C" int e2i_snp_format(const e2i_call_rec *recs, const char *left, const 
         char *w = buf + off[t];
         size_t pos = 0;
         for (const auto &m : pc.marks) {
-            std::memcpy(w, pc.text.data() + pos, m.first - pos);
+            std::memcpy(w, pc.text.p + pos, m.first - pos);
             w += m.first - pos;
             char num[24];
             const int nd = std::snprintf(num, sizeof num, "%llu", (unsigned long long)(start[t] + m.second));
@@ -270,13 +358,18 @@ extern "C" int e2i_snp_format(const e2i_call_rec *recs, const char *left, const 
             w += nd;
             pos = m.first + 1;
         }
-        std::memcpy(w, pc.text.data() + pos, pc.text.size() - pos);
+        std::memcpy(w, pc.text.p + pos, pc.text.n - pos);
     };
     {
         std::vector<std::thread> th;
         for (uint64_t t = 1; t < nt; ++t) th.emplace_back(emit, t);
         emit(0);
         for (auto &x : th) x.join();
+    }
+    if (std::getenv("E2I_DEBUG")) {
+        const auto t_c = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[e2i] format: %llu threads, pass 1 %.1f ms, numbering + copy %.1f ms, %zu bytes\n", (unsigned long long)nt,
+                     std::chrono::duration<double, std::milli>(t_b - t_a).count(), std::chrono::duration<double, std::milli>(t_c - t_b).count(), off[nt]);
     }
     buf[off[nt]] = 0;
     *snp = buf;
