@@ -180,17 +180,6 @@ def _host_u8(a):
     return a, a.ctypes.data
 
 
-def _ptr(x):
-    """Device pointer of a torch CUDA tensor, host pointer of a numpy array, or a raw int."""
-    if x is None:
-        return None
-    if isinstance(x, int):
-        return x
-    if hasattr(x, "data_ptr"):
-        return x.data_ptr()
-    return x.ctypes.data
-
-
 class SnpText:
     """The .snp text returned by the library (malloc'ed by libe2i, freed with the object).
     `bytes(x)` / `x.tobytes()` copies it out; `len(x)` and `x.view()` do not."""

@@ -102,3 +102,21 @@ def test_world2_gloo_host_logic():
     assert len(ret) == world
     for r in range(world):
         assert ret[r] == (True, True, True, True), (r, ret[r])
+
+
+def test_slice_and_cut_helpers():
+    """index_slices: tile-aligned, equal-sized, cover [0, n) in order; position_cuts: monotone cover."""
+    from ebwt2indel_b200 import distributed as dd
+    for n in (1, 127, 128, 16384, 16385, 1 << 20, 1000003, 15_100_000_000):
+        for world in (1, 2, 3, 4, 8):
+            slices, per = dd.index_slices(n, world)
+            assert len(slices) == world and slices[0][0] == 0 and slices[-1][1] == n
+            tiles = (n // 128 + 1 + 127) // 128
+            assert per * world >= tiles
+            for r, (lo, hi) in enumerate(slices):
+                assert lo <= hi <= n and lo % dd.TILE == 0 or lo == n
+                if r:
+                    assert lo == slices[r - 1][1]
+                assert hi - lo <= per * dd.TILE
+            cuts = dd.position_cuts(n, world)
+            assert cuts[0] == 0 and cuts[-1] == n and all(a <= b for a, b in zip(cuts, cuts[1:]))
