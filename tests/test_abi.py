@@ -182,3 +182,18 @@ def test_filter_snp_matches_reference_tool(e2i, oracle):
                     mine = subprocess.run([my_tool, f.name] + args, capture_output=True).stdout
                 assert ref == got == mine, (name, m, M)
     assert len(e2i.filter_snp(load_golden("m1_default")["snp"], 5)) > 0
+
+
+def test_cli_text_identical_to_reference_binary():
+    """Help text and the missing-file message, byte for byte against the compiled reference (no GPU needed:
+    both programs print and exit before touching the input, ebwt2InDel.cpp:76-103, 1748-1753)."""
+    ref = os.path.join(ROOT, "oracle", "_ref", "ebwt2InDel")
+    if not os.access(ref, os.X_OK):
+        pytest.skip("compiled reference absent")
+    mine = os.path.join(ROOT, "bin", "ebwt2InDel")
+    for argv in ([], ["-h", "x"], ["-1", "/nonexistent.ebwt", "-o", "/tmp/e2i_x.snp"],
+                 ["-1", os.path.join(ROOT, "README.md"), "-2", "/nonexistent2", "-o", "/tmp/e2i_x.snp"],
+                 ["-1", os.path.join(ROOT, "README.md"), "-2", os.path.join(ROOT, "README.md"), "-d", "x", "-o", "/tmp/e2i_x.snp"]):
+        a = subprocess.run([ref] + argv, capture_output=True)
+        b = subprocess.run([mine] + argv, capture_output=True)
+        assert a.stdout == b.stdout and a.returncode == b.returncode, argv
