@@ -895,6 +895,207 @@ expand_leaves_kernel(const NavArgs a, const Segs in) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// Phase 2 sweep, persistent warp-specialised form (same structure as expand_nodes_persistent: the
+// one-tile-per-CTA leaf kernel spent most of its warp time waiting behind the ordered look-back,
+// profiles/r01_ncu_leaves_c4s16_raw.csv).  Leaves are sparse in position space, so there is no
+// staged index window: the two (four) rank queries of a leaf read global memory.
+// ---------------------------------------------------------------------------------------------
+template <bool TWO>
+struct LeafSmem {
+    static constexpr int RU = TWO ? 4 : 2;            // uint4 per record
+    uint4 child[4][kCompThreads * RU];                // parked children of the pending tile, per symbol
+    uint4 recbuf[kCompThreads * RU];                  // records of the next tile (LDGSTS, slot = thread)
+    unsigned long long base[4];
+    unsigned long long stat[C_NCOUNTERS];
+    uint32_t agg[4];
+    uint32_t pend_tile;
+    uint32_t seq_posted, seq_done;
+    uint32_t tile;
+    uint32_t wpk[kCompThreads / 32];
+};
+
+template <bool TWO>
+__global__ void __launch_bounds__(kPersistThreads, TWO ? 2 : 3)
+expand_leaves_persistent(const NavArgs a, const Segs in) {
+    constexpr int WORDS = TWO ? 8 : 4;
+    constexpr int RU = TWO ? 4 : 2;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    LeafSmem<TWO> &sm = *reinterpret_cast<LeafSmem<TWO> *>(smem_raw);
+    volatile uint32_t *v_posted = &sm.seq_posted, *v_done = &sm.seq_done;
+    volatile unsigned long long *v_base = sm.base;
+
+    if (threadIdx.x == 0) { sm.seq_posted = 0; sm.seq_done = 0; }
+    __syncthreads();
+
+    if (threadIdx.x >= kCompThreads) {
+        // ------------------------------- scan warp (as in expand_nodes_persistent) -------------------------------
+        const int lane = threadIdx.x & 31;
+        uint32_t seen = 0;
+        while (true) {
+            uint32_t p = *v_posted;
+            while (p == seen) { __nanosleep(40); p = *v_posted; }
+            if (p == kExitSeq) break;
+            seen = p;
+            __threadfence_block();
+            const uint32_t tile = *(volatile uint32_t *)&sm.pend_tile;
+            uint32_t agg[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) agg[c] = ((volatile uint32_t *)sm.agg)[c];
+            unsigned long long excl[4];
+            lookback4(a.desc, a.epoch, tile, agg, excl);
+            if (lane < 4) {
+                unsigned long long e = 0, g2 = 0;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) if (lane == c) { e = excl[c]; g2 = agg[c]; }
+                v_base[lane] = e;
+                if (tile == a.n_tiles - 1) ((volatile unsigned long long *)a.host->out_count)[lane] = e + g2;
+            }
+            if (tile == a.n_tiles - 1) {                   // tell the host that the counts of this sweep are final
+                __threadfence_system();
+                __syncwarp();
+                if (lane == 0) *(volatile unsigned long long *)&a.host->seq = a.seq;
+            }
+            __threadfence_block();
+            __syncwarp();
+            if (lane == 0) *v_done = seen;
+        }
+        return;
+    }
+
+    // --------------------------------- compute warps ---------------------------------
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t my_seq = 0;
+
+    auto flush_pending = [&]() {
+        while (*v_done != my_seq) { }
+        __threadfence_block();
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const uint32_t n16 = ((volatile uint32_t *)sm.agg)[c] * RU;
+            uint4 *dst = reinterpret_cast<uint4 *>(a.out[c]) + v_base[c] * RU;
+            for (uint32_t i = threadIdx.x; i < n16; i += kCompThreads) dst[i] = sm.child[c][i];
+        }
+    };
+    auto prefetch_records = [&](uint32_t tl) {
+        const uint32_t g = tl * kCompThreads + threadIdx.x;
+        if (tl < a.n_tiles && g < in.total) {
+            const uint4 *rec = reinterpret_cast<const uint4 *>(seg_record(in, g, WORDS));
+#pragma unroll
+            for (int k = 0; k < RU; ++k) cp_async16(&sm.recbuf[threadIdx.x * RU + k], rec + k);
+        }
+    };
+    if (threadIdx.x == 0) sm.tile = atomicAdd(a.ticket, 1u);
+    bar_compute();
+    uint32_t tile = sm.tile;
+    prefetch_records(tile);
+    while (tile < a.n_tiles) {
+        uint32_t nxt = 0;
+        if (threadIdx.x == 0) nxt = atomicAdd(a.ticket, 1u);
+        if (threadIdx.x < C_NCOUNTERS) sm.stat[threadIdx.x] = 0;
+        const uint32_t g = tile * kCompThreads + threadIdx.x;
+        const bool active = g < in.total;
+        uint64_t f1 = 0, s1 = 0, f2 = 0, s2 = 0, depth = 0;
+        cp_async_wait_all();                               // this thread's own record has landed
+        if (active) {
+            const ulonglong2 *rec = reinterpret_cast<const ulonglong2 *>(&sm.recbuf[threadIdx.x * RU]);
+            const ulonglong2 x = rec[0], y = rec[1];
+            f1 = x.x; s1 = x.y; depth = y.x;
+            if (TWO) { const ulonglong2 z = rec[2]; f2 = z.x; s2 = z.y; }
+        }
+        unsigned long long st_lcp = 0, st_da = 0;
+        uint32_t st_rank = 0;
+        if (active && a.write) {
+            // update_LCP_leaf (:344-355) / update_DA (:394-425) at merged coordinates
+            const uint64_t start1 = f1 + f2, start2 = f2 + s1, end = s1 + s2;
+            if (end > start1) st_lcp = end - start1 - 1;
+            const uint32_t pat = (depth >= a.K ? 0x55555555u : 0u) | (depth >= a.k_right ? 0xaaaaaaaau : 0u);
+            if (end > start1 + 1) fill_bits(a.thr, 2 * (start1 + 1), 2 * end, pat);
+            if (TWO) {
+                st_da = end - start1;
+                fill_bits(a.da, start2, end, 0xffffffffu);
+            }
+        }
+        // next_leaves (dna_bwt.hpp:358-379; two BWTs: ebwt2InDel.cpp:452-472): LF(range) = 2 ranks per BWT
+        uint64_t lo1[4] = {0, 0, 0, 0}, hi1[4] = {0, 0, 0, 0}, lo2[4] = {0, 0, 0, 0}, hi2[4] = {0, 0, 0, 0};
+        if (active) {
+            rank4(a.ix1, f1, lo1);
+            st_rank++;
+            if (s1 > f1) { rank4(a.ix1, s1, hi1); st_rank++; }
+            else { hi1[0] = lo1[0]; hi1[1] = lo1[1]; hi1[2] = lo1[2]; hi1[3] = lo1[3]; }
+            if (TWO) {
+                rank4(a.ix2, f2, lo2);
+                st_rank++;
+                if (s2 > f2) { rank4(a.ix2, s2, hi2); st_rank++; }
+                else { hi2[0] = lo2[0]; hi2[1] = lo2[1]; hi2[2] = lo2[2]; hi2[3] = lo2[3]; }
+            }
+        }
+        uint32_t vm = 0, packed = 0, before[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const bool v = active && ((hi1[c] - lo1[c]) + (hi2[c] - lo2[c]) >= 2);
+            const uint32_t bal = __ballot_sync(0xffffffffu, v);
+            before[c] = __popc(bal & ((1u << lane) - 1u));
+            packed |= (uint32_t)__popc(bal) << (8 * c);
+            if (v) vm |= 1u << c;
+        }
+        if (lane == 0) sm.wpk[warp] = packed;
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) {
+            st_lcp += __shfl_xor_sync(0xffffffffu, st_lcp, s);
+            if (TWO) st_da += __shfl_xor_sync(0xffffffffu, st_da, s);
+        }
+        st_rank = __reduce_add_sync(0xffffffffu, st_rank);
+        if (threadIdx.x == 0) sm.tile = nxt;
+        bar_compute();                                     // counters reset, per-warp counts and the next ticket are visible
+        const uint32_t next_tile = sm.tile;
+        prefetch_records(next_tile);
+        if (lane == 0) {
+            if (st_lcp) atomicAdd(&sm.stat[C_LCP], st_lcp);
+            if (st_rank) atomicAdd(&sm.stat[C_RANK], (unsigned long long)st_rank);
+            if (TWO && st_da) atomicAdd(&sm.stat[C_DA], st_da);
+        }
+        if (my_seq) flush_pending();
+        bar_compute();                                     // child buffer and agg free again; statistics complete
+        uint32_t exw[4] = {0, 0, 0, 0}, tot[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int w = 0; w < kCompThreads / 32; ++w) {
+            const uint32_t pk = sm.wpk[w];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const uint32_t n = (pk >> (8 * c)) & 0xffu;
+                if (w < warp) exw[c] += n;
+                tot[c] += n;
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            if ((vm >> c) & 1u) {
+                ulonglong2 *o = reinterpret_cast<ulonglong2 *>(&sm.child[c][(exw[c] + before[c]) * RU]);
+                o[0] = make_ulonglong2(a.ix1.F[c] + lo1[c], a.ix1.F[c] + hi1[c]);
+                o[1] = make_ulonglong2(depth + 1, 0);
+                if (TWO) {
+                    o[2] = make_ulonglong2(a.ix2.F[c] + lo2[c], a.ix2.F[c] + hi2[c]);
+                    o[3] = make_ulonglong2(0, 0);
+                }
+            }
+        }
+        if (threadIdx.x == 0) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) sm.agg[c] = tot[c];
+            sm.pend_tile = tile;
+        }
+        if (threadIdx.x < C_NCOUNTERS && a.write) stripe_add(a.stripes, tile, threadIdx.x, sm.stat[threadIdx.x]);
+        bar_compute();                                     // children, counts and tile id are in shared memory
+        ++my_seq;
+        if (threadIdx.x == 0) { __threadfence_block(); *v_posted = my_seq; }
+        tile = next_tile;
+    }
+    if (my_seq) flush_pending();
+    bar_compute();
+    if (threadIdx.x == 0) *v_posted = kExitSeq;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Host-side frontier driver
 // ---------------------------------------------------------------------------------------------
 // host-side view of the compact node record (see unpack_node)
@@ -1086,6 +1287,8 @@ extern "C" int e2i_navigate_shard(e2i_ctx *ctx, const e2i_index *b1, const e2i_i
     const bool persistent = !(nk && std::strcmp(nk, "tile") == 0);
     E2I_CUDA_TRY(cudaFuncSetAttribute(expand_nodes_persistent<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PersistSmem<false>)));
     E2I_CUDA_TRY(cudaFuncSetAttribute(expand_nodes_persistent<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PersistSmem<true>)));
+    E2I_CUDA_TRY(cudaFuncSetAttribute(expand_leaves_persistent<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LeafSmem<false>)));
+    E2I_CUDA_TRY(cudaFuncSetAttribute(expand_leaves_persistent<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LeafSmem<true>)));
     if (const char *cv = std::getenv("E2I_CARVEOUT")) {
         const int pct = atoi(cv);
         E2I_CUDA_TRY(cudaFuncSetAttribute(expand_nodes_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
@@ -1199,7 +1402,11 @@ extern "C" int e2i_navigate_shard(e2i_ctx *ctx, const e2i_index *b1, const e2i_i
         root.frame->side = 0;
         root.frame->p = rootmem;
         auto launch = [&](NavArgs &a, const Segs &segs, uint32_t n_tiles) {
-            if (leaves) {
+            if (leaves && persistent) {
+                const uint32_t grid = std::min<uint32_t>(n_tiles, (uint32_t)ctx->sm_count * (two ? 2u : 3u));
+                if (two) expand_leaves_persistent<true><<<grid, kPersistThreads, sizeof(LeafSmem<true>), s>>>(a, segs);
+                else expand_leaves_persistent<false><<<grid, kPersistThreads, sizeof(LeafSmem<false>), s>>>(a, segs);
+            } else if (leaves) {
                 if (two) expand_leaves_kernel<true><<<n_tiles, kNavThreads, 0, s>>>(a, segs);
                 else expand_leaves_kernel<false><<<n_tiles, kNavThreads, 0, s>>>(a, segs);
             } else if (persistent) {
