@@ -30,35 +30,7 @@ sys.path.insert(0, ROOT)
 METRIC = "suffix_tree_nodes_per_s"
 UNIT = "nodes/s"
 
-# SURVEY.md §8(d) / BASELINE.json configs.  `scale` < 1 shrinks genome length and variant counts
-# together (same coverage, read length and variant density) -- used for bounded CPU samples.
-CONFIGS = {
-    "C1": dict(mode=1, genome=1_000_000, snps=1000, indels=200, cov=20, read_len=100, revcomp=True, seed=1,
-               desc="mode -1: 1 Mbp random diploid (1k SNPs, 200 indels), 20x 100bp + revcomp, n=40.4M"),
-    "C2": dict(mode=3, genome=5_000_000, snps=5000, indels=1000, cov=50, read_len=100, revcomp=True, seed=2,
-               desc="mode -d: two 5 Mbp individuals, 50x 100bp + revcomp each, merged eBWT + DA, n=1.01G"),
-    "C3": dict(mode=2, genome=50_000_000, snps=50_000, indels=10_000, cov=30, read_len=150, revcomp=False, seed=3,
-               desc="mode -2: two eBWTs of 50 Mbp genomes, 30x 150bp, n=1.51G each"),
-    "C4": dict(mode=1, genome=250_000_000, snps=250_000, indels=50_000, cov=30, read_len=150, revcomp=True, seed=4,
-               desc="mode -1: 250 Mbp diploid, 30x 150bp + revcomp, n=15.1G"),
-    "C5": dict(mode=1, meta=True, species=10, strains=10, genome=10_000_000, snp_rate=0.001, cov=10, read_len=100, revcomp=True,
-               seed=5, snps=0, indels=0,
-               desc="mode -1: metagenome, 10 species x 10 strains x 10 Mbp (0.1% SNPs between strains, log-normal abundances), "
-                    "10x mean 100bp + revcomp, n=20.2G"),
-    # intermediate mode -1 sizes (same shape as C4) used while the C4 pipeline is brought up
-    "C4s16": dict(mode=1, genome=15_625_000, snps=15_625, indels=3_125, cov=30, read_len=150, revcomp=True, seed=4,
-                  desc="mode -1: 1/16 of C4 (15.6 Mbp diploid, 30x 150bp + revcomp), n=0.94G"),
-    "C4s4": dict(mode=1, genome=62_500_000, snps=62_500, indels=12_500, cov=30, read_len=150, revcomp=True, seed=4,
-                 desc="mode -1: 1/4 of C4 (62.5 Mbp diploid, 30x 150bp + revcomp), n=3.8G"),
-}
-
-
-def scaled(cfg: dict, scale: float) -> dict:
-    c = dict(cfg)
-    c["genome"] = max(2000, int(cfg["genome"] * scale))
-    c["snps"] = max(1, int(cfg["snps"] * scale))
-    c["indels"] = max(1, int(cfg["indels"] * scale))
-    return c
+from ebwt2indel_b200.workloads import CONFIGS, scaled  # noqa: E402  (SURVEY.md §8(d) / BASELINE.json configs)
 
 
 def make_workload(cfg: dict, device, ctx=None):
