@@ -45,12 +45,14 @@ _WALL_FIELDS = ("ms_format", "ms_wall")
 class Stats(C.Structure):
     _fields_ = ([(k, C.c_uint64) for k in _U64_FIELDS] + [("clust_sizes", C.c_uint64 * 201)] +
                 [(k, C.c_uint64) for k in _WORK_FIELDS] + [(k, C.c_double) for k in _MS_FIELDS] +
-                [(k, C.c_uint64) for k in _IO_FIELDS] + [(k, C.c_double) for k in _WALL_FIELDS])
+                [(k, C.c_uint64) for k in _IO_FIELDS] + [(k, C.c_double) for k in _WALL_FIELDS] +
+                [("da_values_leaves", C.c_uint64)])
 
     def as_dict(self):
         d = {k: int(getattr(self, k)) for k in _U64_FIELDS + _WORK_FIELDS + _IO_FIELDS}
         d.update({k: float(getattr(self, k)) for k in _MS_FIELDS + _WALL_FIELDS})
         d["clust_sizes"] = list(self.clust_sizes)
+        d["da_values_leaves"] = int(self.da_values_leaves)
         return d
 
 

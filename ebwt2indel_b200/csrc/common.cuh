@@ -86,6 +86,7 @@ struct e2i_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;
+    cudaMemPool_t pool = nullptr;  // the context's own stream-ordered pool (freed blocks stay cached until e2i_trim)
     cudaEvent_t ev[8] = {};
     int sm_count = 148;
     uint64_t frontier_budget = 0;
@@ -96,7 +97,7 @@ struct e2i_ctx {
     unsigned long long *desc = nullptr;
     size_t desc_words = 0;
     uint32_t epoch = 0;
-    void *ctl = nullptr;        // device ring of per-sweep ticket counters, see navigate.cu
+    void *ctl = nullptr;        // device ring of per-sweep control blocks (64 bytes each), see navigate.cu
     void *ctl_host = nullptr;   // page-locked, device-mapped block the sweeps report their counts to
     uint32_t ticket_next = 0;
     unsigned long long sweep_seq = 0;
@@ -110,7 +111,7 @@ struct e2i_ctx {
 namespace e2i {
 template <typename T>
 inline cudaError_t dmalloc(e2i_ctx *ctx, T **p, size_t bytes) {
-    return cudaMallocAsync(reinterpret_cast<void **>(p), bytes ? bytes : 16, ctx->stream);
+    return cudaMallocFromPoolAsync(reinterpret_cast<void **>(p), bytes ? bytes : 16, ctx->pool, ctx->stream);
 }
 inline void dfree(e2i_ctx *ctx, void *p) {
     if (p) cudaFreeAsync(p, ctx->stream);

@@ -93,14 +93,19 @@ extern "C" int e2i_create(int device, e2i_ctx **out) {
     ctx->sm_count = prop.multiProcessorCount;
     E2I_CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     E2I_CUDA_TRY(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
-    {   // keep freed blocks cached in the device's stream-ordered pool (released by e2i_destroy / e2i_trim)
-        cudaMemPool_t mp;
-        E2I_CUDA_TRY(cudaDeviceGetDefaultMemPool(&mp, device));
+    {   // a pool of our own (the process-wide default pool is left alone); freed blocks stay cached in it
+        // until e2i_trim / e2i_destroy
+        cudaMemPoolProps props = {};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = device;
+        E2I_CUDA_TRY(cudaMemPoolCreate(&ctx->pool, &props));
         uint64_t thr = UINT64_MAX;
-        E2I_CUDA_TRY(cudaMemPoolSetAttribute(mp, cudaMemPoolAttrReleaseThreshold, &thr));
+        E2I_CUDA_TRY(cudaMemPoolSetAttribute(ctx->pool, cudaMemPoolAttrReleaseThreshold, &thr));
     }
     for (auto &ev : ctx->ev) E2I_CUDA_TRY(cudaEventCreate(&ev));
-    E2I_CUDA_TRY(cudaMalloc(&ctx->ctl, 16384 * sizeof(uint32_t)));
+    E2I_CUDA_TRY(cudaMalloc(&ctx->ctl, 16384 * 64));   // kSweepSlots x sizeof(SweepDev), navigate.cu
     E2I_CUDA_TRY(cudaHostAlloc(&ctx->ctl_host, 4096, cudaHostAllocMapped | cudaHostAllocPortable));
     std::memset(ctx->ctl_host, 0, 4096);
     *out = ctx;
@@ -119,6 +124,7 @@ extern "C" void e2i_destroy(e2i_ctx *ctx) {
     for (auto &ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->pool) cudaMemPoolDestroy(ctx->pool);
     delete ctx;
 }
 
@@ -130,9 +136,7 @@ extern "C" int e2i_trim(e2i_ctx *ctx) {
     ctx->arena_bytes = 0;
     ctx->arena.reset(nullptr, 0);
     E2I_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-    cudaMemPool_t mp;
-    E2I_CUDA_TRY(cudaDeviceGetDefaultMemPool(&mp, ctx->device));
-    E2I_CUDA_TRY(cudaMemPoolTrimTo(mp, 0));
+    E2I_CUDA_TRY(cudaMemPoolTrimTo(ctx->pool, 0));
     return E2I_OK;
 }
 

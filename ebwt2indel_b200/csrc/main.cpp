@@ -204,7 +204,7 @@ int main(int argc, char **argv) {
     const uint64_t n = n1 + n2;
     cout << "done." << endl;
     cout << "\nPhase 2/4: " << (two ? "merging eBWTs." : "navigating suffix tree leaves.") << endl;
-    if (two) cout << "Computed " << st.da_values << "/" << n << " DA values." << endl;   // :758 prints the leaf-pass share; the total is below
+    if (two) cout << "Computed " << st.da_values_leaves << "/" << n << " DA values." << endl;   // :757, the leaf pass
     cout << "Computed " << st.lcp_values_leaves << "/" << n << " LCP threshold values." << endl;
     cout << "Processed " << st.leaves << " suffix-tree leaves." << endl << endl;
     cout << "Phase 3/4: computing LCP minima." << endl;

@@ -86,6 +86,7 @@ typedef struct {
     /* host wall-clock milliseconds (e2i_run / e2i_run_device only) */
     double ms_format;            /* e2i_snp_format */
     double ms_wall;              /* the whole call */
+    uint64_t da_values_leaves;   /* "Computed N/n DA values." of the leaf pass (mode -2) :757 */
 } e2i_stats;
 
 /* One analysed cluster that passed the allele filter (and, with two samples, can emit a pair).

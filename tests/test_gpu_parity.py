@@ -388,13 +388,3 @@ def test_large_inputs_size_independent_properties(gpu_ctx, e2i, name, scale):
     # (5)
     nums = [int(x) for x in re.findall(rb">cluster:(\d+)_", snp)]
     assert nums == sorted(nums) and nums[0] == 1 and nums[-1] == st.clusters_out
-
-
-def test_one_tile_per_cta_node_kernel_matches(gpu_ctx, e2i, monkeypatch):
-    """E2I_NODE_KERNEL=tile selects the non-persistent node kernel kept for A/B measurements: same results."""
-    monkeypatch.setenv("E2I_NODE_KERNEL", "tile")
-    for name in ("m1_default", "m3_flags", "m2_default"):
-        g = load_golden(name)
-        snp, st = gpu_ctx.run(g["bwt1"], g["bwt2"], g["da"], _case_params(e2i, g))
-        assert snp == g["snp"], name
-        assert st.nodes == g["counters"]["nodes"]
