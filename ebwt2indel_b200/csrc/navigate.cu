@@ -8,18 +8,26 @@
 //
 // B200 design.  Every LCP / DA bit has exactly one writer, so traversal order is free.  The
 // frontier is swept breadth-first, and every sweep keeps its nodes SORTED BY SUFFIX-ARRAY
-// POSITION: the children cW of a sorted frontier are appended, in tile order, to four queues
-// (one per c); A-queue ++ C-queue ++ G-queue ++ T-queue is again sorted because LF is monotone
-// per symbol.  A sorted frontier turns the reference's random rank gathers into one
-// near-sequential pass over the 64-byte index blocks per sweep (neighbouring nodes share blocks
-// and DRAM pages) and makes the bit updates land in neighbouring words.  Ordered appends use a
-// single-pass decoupled look-back (lookback.cuh).  When a sweep would not fit the frontier budget
-// it is cut into position-contiguous chunks that are finished depth-first (bounded memory).
+// POSITION: the children cW of a sorted frontier go to four queues (one per c), each in input
+// order; A-queue ++ C-queue ++ G-queue ++ T-queue is again sorted because LF is monotone per
+// symbol.  A sorted frontier turns the reference's random rank gathers into one near-sequential
+// pass over the 64-byte index blocks per sweep (neighbouring nodes share blocks and DRAM pages)
+// and makes the bit updates land in neighbouring words.
+//
+// No cross-CTA (or cross-warp) dependency inside a sweep.  The input of a sweep is cut into RUNS
+// of consecutive records; a warp takes a run by ticket and writes the children of queue c to a
+// region of the output frame that belongs to (c, run) alone -- a node has at most one child per
+// symbol, so the region is as large as the run.  The frame is therefore "gappy": a tiny kernel
+// (frame_index_kernel) scans the per-(queue, run) counts after the sweep and the next sweep
+// addresses records by global index through that prefix array.  This replaces an ordered append by
+// decoupled look-back, whose resolution latency (hundreds of tiles in flight) was the critical path
+// of round 1's kernel; a warp now synchronises with nobody but itself.  When a sweep would not fit
+// the frontier budget it is cut into index ranges that are finished depth-first (bounded memory).
 //
 // Work mapping.  One thread per internal node (per node pair in mode -2): it walks the node's <= 6
 // distinct boundaries, turns the rank differences into the five sub-interval sizes of each child
-// cW, keeps the children with >= 2 non-empty sub-intervals (number_of_children >= 2) and appends
-// them in order.  Leaves: one thread per leaf (two ranks per BWT).  All nodes of a sweep have the
+// cW, keeps the children with >= 2 non-empty sub-intervals (number_of_children >= 2) and writes
+// them in lane order.  Leaves: one thread per leaf (two ranks per BWT).  All nodes of a sweep have the
 // same depth, so the depth is a launch argument, not part of the records.
 //
 // Records.  Internal node, WIDE form (top of the tree): 48 bytes = {base, s0} {s1, s2} {s3, s4} as
@@ -33,13 +41,17 @@
 #include <memory>
 
 #include "common.cuh"
-#include "lookback.cuh"
 
 namespace e2i {
 
-constexpr int kCompThreads = 256;                     // 8 compute warps: one node (pair) / leaf (pair) per thread and tile
-constexpr int kPersistThreads = kCompThreads + 32;    // + the scan warp
-constexpr int kStageBlocks = 512;                     // index blocks staged in shared memory per CTA (32 KB)
+constexpr int kNavWarps = 4;                          // warps per CTA; every warp works on its own
+constexpr int kNavThreads = kNavWarps * 32;
+constexpr int kWarpStage = 64;                        // index blocks staged in shared memory per warp (4 KB)
+constexpr int kMaxRun = 1024;                         // records per run (multiple of 32), upper bound
+#ifndef E2I_NODE_CTAS
+#define E2I_NODE_CTAS 7                               // resident CTAs per SM the one-BWT kernels are compiled for
+#endif
+constexpr int kNodeCtas = E2I_NODE_CTAS, kPairCtas = 4;
 constexpr int kStripes = 128;                         // striped statistics counters (avoid single-address atomics)
 enum { C_LCP = 0, C_NMIN, C_RANK, C_BITUPD, C_DA, C_NCOUNTERS = 8 };
 #ifndef E2I_SMALL_LIMIT
@@ -47,18 +59,16 @@ enum { C_LCP = 0, C_NMIN, C_RANK, C_BITUPD, C_DA, C_NCOUNTERS = 8 };
 #endif
 constexpr uint64_t kSmallLimit = E2I_SMALL_LIMIT;
 static_assert(kSmallLimit <= 65536, "SMALL records hold 16-bit sizes");
-constexpr uint32_t kExitTile = 0xffffffffu;
 
 // Per-sweep control.  Device side: one zeroed 64-byte block per sweep (a ring, so no per-sweep
-// memset): tile ticket, exit counter, the four child totals, the largest input node.  Host side: a
-// page-locked, device-mapped block that the LAST CTA to leave the sweep fills in, followed by the
-// sweep's sequence number; the host polls that word instead of a copy + stream synchronisation.
+// memset): run ticket and the largest input node.  Host side: a page-locked, device-mapped block
+// that frame_index_kernel fills in after the sweep, followed by the sweep's sequence number; the
+// host polls that word instead of a copy + stream synchronisation.
 constexpr uint32_t kSweepSlots = 16384;
 struct SweepDev {
-    uint32_t ticket, done;
-    unsigned long long counts[4];
+    uint32_t ticket, pad0;
     unsigned long long maxsz;
-    unsigned long long pad[2];
+    unsigned long long pad[6];
 };
 static_assert(sizeof(SweepDev) == 64, "one sweep slot per 64 bytes");
 struct HostCtl {
@@ -67,10 +77,22 @@ struct HostCtl {
     unsigned long long seq;
 };
 
-struct Segs {                 // a position-sorted run of records given as <= 4 segments
-    const uint4 *p[4];
-    uint32_t end[4];          // cumulative record counts
-    uint32_t total;
+// A frame: the records one sweep produced.  Queue c, run k owns the slots
+// base + ((c * K + k) * run_cap ...) and holds cnt[c * K + k] records; P is the exclusive prefix of
+// cnt in (queue, run) order (4K + 1 entries), so global index g lives in the entry j with
+// P[j] <= g < P[j+1]; hint[t] = the entry that holds global index 256 t.
+struct FrameIn {
+    const uint4 *base;
+    const uint32_t *P;
+    const uint32_t *hint;
+    uint32_t K, run_cap;
+    uint32_t g_lo, g_hi;      // this sweep reads the records [g_lo, g_hi)
+};
+struct FrameOut {
+    uint4 *base;
+    uint32_t *cnt;
+    uint32_t *gsum;           // sums of cnt over groups of 256 consecutive entries (group_sum_kernel)
+    uint32_t K, run_cap;      // runs of this sweep's input, records per run (multiple of 32)
 };
 
 struct NavArgs {
@@ -79,25 +101,10 @@ struct NavArgs {
     uint32_t *minima;         // 1 bit per merged position
     uint32_t *da;             // 1 bit per merged position (mode -2)
     unsigned long long *stripes;
-    unsigned long long *desc;
     SweepDev *sweep;          // this sweep's device control block
-    HostCtl *host;            // mapped page-locked result block
-    unsigned long long seq;   // sequence number of this sweep
-    uint4 *out[4];
-    uint32_t epoch;
-    uint32_t n_tiles;
     uint32_t bits;            // (depth >= K) | (depth >= k_right) << 1 for the records of this sweep
     int write;                // 0: expand only (redundant top of the tree on shards != 0)
 };
-
-__device__ __forceinline__ const uint4 *seg_record(const Segs &s, uint32_t g, int ru) {
-    int k = 0;
-    uint32_t start = 0;
-#pragma unroll
-    for (int i = 0; i < 3; ++i)
-        if (g >= s.end[i]) { k = i + 1; start = s.end[i]; }
-    return s.p[k] + (size_t)(g - start) * ru;
-}
 
 // set bits [lo, hi) of a u32 bit array, keeping only those selected by the 32-bit periodic pattern
 __device__ __forceinline__ void fill_bits(uint32_t *words, uint64_t lo, uint64_t hi, uint32_t pattern) {
@@ -123,121 +130,31 @@ struct WordAcc {
     __device__ __forceinline__ void flush() { if (m) atomicOr(words + w, m); m = 0; }
 };
 
-// named barriers: 1 = the compute warps among themselves; 2 = "prefix of the pending tile resolved"
-// (scan warp arrives, compute warps wait); 3 = "a tile was posted" (compute warps arrive, scan warp
-// waits).  Waiting warps are descheduled by the hardware instead of spinning on shared memory.
-__device__ __forceinline__ void bar_compute() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
-__device__ __forceinline__ void bar_prefix_wait() { asm volatile("bar.sync 2, 288;" ::: "memory"); }
-__device__ __forceinline__ void bar_prefix_arrive() { asm volatile("bar.arrive 2, 288;" ::: "memory"); }
-__device__ __forceinline__ void bar_post_wait() { asm volatile("bar.sync 3, 288;" ::: "memory"); }
-__device__ __forceinline__ void bar_post_arrive() { asm volatile("bar.arrive 3, 288;" ::: "memory"); }
-
-// ---- the part of a sweep kernel that does not depend on what a record is ------------------------
-struct SweepShared {
-    unsigned long long base[4];                       // resolved exclusive prefix of the pending tile
-    uint32_t agg[4];                                  // child counts of the pending tile
-    uint32_t pend_tile;
-    uint32_t tile;                                    // next ticket, handed from thread 0 to the CTA
-    uint32_t wpk[kCompThreads / 32];                  // per-warp child counts, 4 x 8 bit
-    uint32_t rng[4];
+// ---- reading a gappy frame by global index ---------------------------------------------------------
+struct Cursor {               // per lane: the entry (queue c, run k) that holds the lane's current record
+    uint32_t j, c, k, pj, pj1;
 };
 
-// Scan warp: publishes the counts of every posted tile at once, resolves its exclusive prefix by
-// look-back while the compute warps already work on the next tile, and hands the four base slots
-// back.  The last CTA to leave the sweep reports the totals to the host.
-__device__ __forceinline__ void scan_warp_loop(const NavArgs &a, SweepShared &sh) {
-    const int lane = threadIdx.x & 31;
-    while (true) {
-        bar_post_wait();
-        const uint32_t tile = *(volatile uint32_t *)&sh.pend_tile;
-        if (tile == kExitTile) break;
-        uint32_t agg[4];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) agg[c] = ((volatile uint32_t *)sh.agg)[c];
-        unsigned long long excl[4];
-        lookback4(a.desc, a.epoch, tile, agg, excl);
-        if (lane < 4) {
-            unsigned long long e = 0, g2 = 0;
-#pragma unroll
-            for (int c = 0; c < 4; ++c) if (lane == c) { e = excl[c]; g2 = agg[c]; }
-            ((volatile unsigned long long *)sh.base)[lane] = e;
-            if (tile == a.n_tiles - 1) ((volatile unsigned long long *)a.sweep->counts)[lane] = e + g2;
-        }
-        __threadfence_block();
-        __syncwarp();
-        bar_prefix_arrive();
-    }
-    // every counter of this CTA is out (the compute warps flushed before posting the exit)
-    if (lane == 0) {
-        __threadfence();
-        const uint32_t done = atomicAdd(&a.sweep->done, 1u);
-        if (done == gridDim.x - 1) {
-            __threadfence();
-#pragma unroll
-            for (int c = 0; c < 4; ++c)
-                ((volatile unsigned long long *)a.host->out_count)[c] = ((volatile unsigned long long *)a.sweep->counts)[c];
-            *(volatile unsigned long long *)&a.host->maxsz = *(volatile unsigned long long *)&a.sweep->maxsz;
-            __threadfence_system();
-            *(volatile unsigned long long *)&a.host->seq = a.seq;
-        }
+__device__ __forceinline__ void cursor_open(const FrameIn &in, Cursor &cur, uint32_t g) {
+    cur.j = __ldg(in.hint + (g >> 8));
+    cur.c = cur.j / in.K;
+    cur.k = cur.j - cur.c * in.K;
+    cur.pj = __ldg(in.P + cur.j);
+    cur.pj1 = __ldg(in.P + cur.j + 1);
+}
+
+// move to the entry that holds g (g never decreases, g < P[4K])
+__device__ __forceinline__ void cursor_seek(const FrameIn &in, Cursor &cur, uint32_t g) {
+    while (g >= cur.pj1) {
+        ++cur.j;
+        if (++cur.k == in.K) { cur.k = 0; ++cur.c; }
+        cur.pj = cur.pj1;
+        cur.pj1 = __ldg(in.P + cur.j + 1);
     }
 }
 
-// children of the pending tile: shared memory -> their resolved global slots (coalesced 16-byte stores)
-template <int RU>
-__device__ __forceinline__ void flush_pending(const NavArgs &a, SweepShared &sh, uint4 (*child)[kCompThreads * RU]) {
-    bar_prefix_wait();
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-        const uint32_t n16 = sh.agg[c] * RU;
-        uint4 *dst = a.out[c] + sh.base[c] * RU;
-        for (uint32_t i = threadIdx.x; i < n16; i += kCompThreads) dst[i] = child[c][i];
-    }
-}
-
-// ballot the four validity flags of the warp's threads: position of this thread's children inside the
-// warp (before[]), the validity mask, and the per-warp counts (4 x 8 bit) in shared memory
-__device__ __forceinline__ uint32_t warp_child_slots(SweepShared &sh, const bool (&valid)[4], uint32_t (&before)[4]) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t vm = 0, packed = 0;
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-        const uint32_t bal = __ballot_sync(0xffffffffu, valid[c]);
-        before[c] = __popc(bal & ((1u << lane) - 1u));
-        packed |= (uint32_t)__popc(bal) << (8 * c);
-        if (valid[c]) vm |= 1u << c;
-    }
-    if (lane == 0) sh.wpk[warp] = packed;
-    return vm;
-}
-
-// exclusive prefix of the per-warp counts for this warp (exw) and the tile totals (tot), by shuffles
-__device__ __forceinline__ void tile_child_prefix(const SweepShared &sh, uint32_t (&exw)[4], uint32_t (&tot)[4]) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t mine = lane < kCompThreads / 32 ? sh.wpk[lane] : 0u;
-    uint32_t lo = (mine & 0xffu) | (((mine >> 8) & 0xffu) << 16);          // A, C as 16-bit fields (<= 256 per tile)
-    uint32_t hi = ((mine >> 16) & 0xffu) | ((mine >> 24) << 16);           // G, T
-    const uint32_t mlo = lo, mhi = hi;
-#pragma unroll
-    for (int s = 1; s < kCompThreads / 32; s <<= 1) {
-        const uint32_t ylo = __shfl_up_sync(0xffffffffu, lo, s), yhi = __shfl_up_sync(0xffffffffu, hi, s);
-        if (lane >= s) { lo += ylo; hi += yhi; }
-    }
-    const uint32_t elo = __shfl_sync(0xffffffffu, lo - mlo, warp), ehi = __shfl_sync(0xffffffffu, hi - mhi, warp);
-    const uint32_t tlo = __shfl_sync(0xffffffffu, lo, kCompThreads / 32 - 1), thi = __shfl_sync(0xffffffffu, hi, kCompThreads / 32 - 1);
-    exw[0] = elo & 0xffffu; exw[1] = elo >> 16; exw[2] = ehi & 0xffffu; exw[3] = ehi >> 16;
-    tot[0] = tlo & 0xffffu; tot[1] = tlo >> 16; tot[2] = thi & 0xffffu; tot[3] = thi >> 16;
-}
-
-__device__ __forceinline__ void post_tile(SweepShared &sh, uint32_t tile, const uint32_t (&tot)[4]) {
-    if (threadIdx.x == 0) {
-#pragma unroll
-        for (int c = 0; c < 4; ++c) sh.agg[c] = tot[c];
-        sh.pend_tile = tile;
-    }
-    bar_compute();                                    // children, counts and tile id are in shared memory
-    __threadfence_block();
-    bar_post_arrive();
+__device__ __forceinline__ const uint4 *cursor_record(const FrameIn &in, const Cursor &cur, uint32_t g, int ru) {
+    return in.base + (((size_t)cur.c * in.K + cur.k) * in.run_cap + (g - cur.pj)) * ru;
 }
 
 // end-of-kernel flush of the per-thread statistics (one atomic per warp and counter)
@@ -245,14 +162,14 @@ __device__ __forceinline__ void flush_stat(const NavArgs &a, int which, unsigned
 #pragma unroll
     for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
     if ((threadIdx.x & 31) == 0 && v)
-        atomicAdd(a.stripes + (size_t)((blockIdx.x * 8 + (threadIdx.x >> 5)) & (kStripes - 1)) * C_NCOUNTERS + which, v);
+        atomicAdd(a.stripes + (size_t)((blockIdx.x * kNavWarps + (threadIdx.x >> 5)) & (kStripes - 1)) * C_NCOUNTERS + which, v);
 }
 
 // ---- staged index blocks ---------------------------------------------------------------------------
-// Where the rank queries of a tile read their index blocks.  WINDOW: the tile's whole block range
+// Where the rank queries of a warp's 32 nodes read their index blocks.  WINDOW: their whole block range
 // [origin, origin + n) sits in shared memory (dense tiles: nodes of one depth are disjoint and sorted).
 // SLOTS: sparse tiles (a traversal shard of a multi-GPU run, the leaf frontier): every thread gets
-// the first and the last block of its own interval, fetched by the whole CTA with 16-byte asynchronous
+// the first and the last block of its own interval, fetched by the whole warp with 16-byte asynchronous
 // copies in which 4 consecutive lanes take one 64-byte block (one L1 wavefront per block instead of
 // one per 16 bytes).  GLOBAL: no staging (WIDE records at the top of the tree, sparse pairs).
 enum { SRC_GLOBAL = 0, SRC_WINDOW = 1, SRC_SLOTS = 2 };
@@ -273,7 +190,7 @@ __device__ __forceinline__ void load_block_smem(const uint4 *stage, uint32_t slo
 
 // #A,#C,#G,#T before relative position rpos, counted from the start of the superblock of origin_blk
 // (mod 2^32: the base cancels in every difference, which is all a node shorter than 2^32 needs).
-// multi_super (CTA-uniform): the tile reaches into a second superblock.
+// multi_super (warp-uniform): the 32 nodes reach into a second superblock.
 __device__ __forceinline__ void rank_rel(const DevIndex &ix, const RankSrc &r, int mode, bool multi_super, uint32_t rpos, uint32_t out[4]) {
     const uint32_t rel = rpos >> kBlockShift;
     uint4 cnt, a, b, t;
@@ -460,203 +377,200 @@ __device__ __forceinline__ void expand_wide(const NavArgs &a, uint64_t base1, co
     }
 }
 
-// SLOTS staging: every thread has announced up to two block ids in need[2 * tid], need[2 * tid + 1]
-// (~0u = none); the CTA copies them with 4 consecutive lanes per 64-byte block
-__device__ __forceinline__ void stage_slots(const DevIndex &ix, uint4 *stage, const uint32_t *need) {
+// SLOTS staging: every lane has announced up to two block ids in need[2 * lane], need[2 * lane + 1]
+// (~0u = none); the warp copies them with 4 consecutive lanes per 64-byte block
+__device__ __forceinline__ void stage_slots(const uint4 *blocks, uint4 *stage, const uint32_t *need, int lane) {
 #pragma unroll
-    for (int it = 0; it < kStageBlocks * 4 / kCompThreads; ++it) {
-        const uint32_t k = threadIdx.x + it * kCompThreads;
+    for (int it = 0; it < kWarpStage * 4 / 32; ++it) {
+        const uint32_t k = lane + it * 32;
         const uint32_t slot = k >> 2, blk = need[slot];
-        if (blk != ~0u) cp_async16(&stage[stage_slot(slot, k & 3)], ix.blocks + (size_t)blk * 4 + (k & 3));
+        if (blk != ~0u) cp_async16(&stage[stage_slot(slot, k & 3)], blocks + (size_t)blk * 4 + (k & 3));
     }
 }
 
-__device__ __forceinline__ void stage_window(const DevIndex &ix, uint4 *stage, uint32_t lo_blk, uint32_t n_blk) {
+__device__ __forceinline__ void stage_window(const DevIndex &ix, uint4 *stage, uint32_t lo_blk, uint32_t n_blk, int lane) {
     const uint4 *src = ix.blocks + (size_t)lo_blk * 4;
-    for (uint32_t k = threadIdx.x; k < n_blk * 4; k += kCompThreads) cp_async16(&stage[stage_slot(k >> 2, k & 3)], src + k);
+    for (uint32_t k = lane; k < n_blk * 4; k += 32) cp_async16(&stage[stage_slot(k >> 2, k & 3)], src + k);
+}
+
+// position of this lane's children inside the step (before[c]) and the step's totals (tot[c])
+__device__ __forceinline__ uint32_t warp_child_slots(const bool (&valid)[4], int lane, uint32_t (&before)[4], uint32_t (&tot)[4]) {
+    uint32_t vm = 0;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const uint32_t bal = __ballot_sync(0xffffffffu, valid[c]);
+        before[c] = __popc(bal & ((1u << lane) - 1u));
+        tot[c] = __popc(bal);
+        if (valid[c]) vm |= 1u << c;
+    }
+    return vm;
 }
 
 // ---------------------------------------------------------------------------------------------
-// Phase 3 sweep: internal nodes.  Persistent, warp-specialised: a CTA is 8 compute warps + 1 scan
-// warp and loops over tiles taken by ticket (a tile's predecessors have always started: needed by the
-// look-back).
-//   compute warps  tile t+1: records -> staged index blocks -> bit updates -> ranks -> children in
-//                  registers; THEN flush the children of tile t from shared memory to their final,
-//                  by now resolved, global slots; park the children of t+1 in shared memory and post
-//                  their counts to the scan warp;
-//   scan warp      see scan_warp_loop.
-// Publication is never delayed, so the look-back window stays short; nothing waits unless the
-// prefix of tile t is still unresolved after the whole compute phase of tile t+1, and a warp that
-// waits sits in a hardware barrier instead of polling.
+// Phase 3 sweep: internal nodes.  Persistent grid; every WARP loops over runs taken by ticket and,
+// inside a run, over steps of 32 records:
+//   records (prefetched by LDGSTS during the previous step) -> the warp's index blocks staged in
+//   its 4 KB of shared memory by asynchronous copies, overlapped with the bit updates of the step
+//   -> ranks -> children written straight to the run's own region of the output frame.
 // ---------------------------------------------------------------------------------------------
-template <bool TWO, bool IN_S, bool OUT_S>
+template <bool TWO, bool IN_S>
 struct NodeSmem {
     static constexpr int RIN = (IN_S ? 1 : 3) * (TWO ? 2 : 1);    // uint4 per input record
-    static constexpr int ROUT = (OUT_S ? 1 : 3) * (TWO ? 2 : 1);  // uint4 per output record
-    uint4 stage[IN_S ? kStageBlocks * 4 : 4];         // staged index blocks
-    uint4 child[4][kCompThreads * ROUT];              // parked children of the pending tile, per symbol
-    uint4 recbuf[kCompThreads * RIN];                 // records of the NEXT tile, prefetched by LDGSTS (slot = thread)
-    uint32_t need[IN_S ? kStageBlocks : 4];           // SLOTS staging: block ids wanted by the threads
-    SweepShared sh;
+    uint4 stage[kNavWarps][IN_S ? kWarpStage * 4 : 1];            // staged index blocks, per warp
+    uint4 recbuf[kNavWarps][32 * RIN];                            // records of the next step (slot = lane)
+    uint32_t need[kNavWarps][IN_S ? kWarpStage : 1];              // SLOTS staging: block ids wanted by the lanes
 };
 
 template <bool TWO, bool IN_S, bool OUT_S>
-__global__ void __launch_bounds__(kPersistThreads, IN_S ? (TWO ? 2 : 3) : 1)
-expand_nodes_persistent(const NavArgs a, const Segs in) {
-    using SM = NodeSmem<TWO, IN_S, OUT_S>;
+__global__ void __launch_bounds__(kNavThreads, IN_S ? (TWO ? kPairCtas : kNodeCtas) : 1)
+expand_nodes_kernel(const NavArgs a, const FrameIn in, const FrameOut out) {
+    using SM = NodeSmem<TWO, IN_S>;
     using W = typename std::conditional<IN_S, uint32_t, uint64_t>::type;
-    constexpr int RIN = SM::RIN, ROUT = SM::ROUT, RSIDE_IN = IN_S ? 1 : 3, RSIDE_OUT = OUT_S ? 1 : 3;
-    constexpr int STAGE = TWO ? kStageBlocks / 2 : kStageBlocks;           // blocks staged per BWT
-    extern __shared__ __align__(1024) unsigned char smem_raw[];
-    SM &sm = *reinterpret_cast<SM *>(smem_raw);
-    SweepShared &sh = sm.sh;
+    constexpr int RIN = SM::RIN, RSIDE_IN = IN_S ? 1 : 3, RSIDE_OUT = OUT_S ? 1 : 3, ROUT = RSIDE_OUT * (TWO ? 2 : 1);
+    constexpr int STAGE = TWO ? kWarpStage / 2 : kWarpStage;               // blocks staged per BWT
+    __shared__ __align__(1024) SM sm;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint4 *stage1 = sm.stage[warp], *stage2 = sm.stage[warp] + (IN_S ? STAGE * 4 : 0);
+    uint4 *recbuf = sm.recbuf[warp] + lane * RIN;
+    uint32_t *need = sm.need[warp];
 
-    if (threadIdx.x == 0) sh.pend_tile = 0;
-    __syncthreads();
-    if (threadIdx.x >= kCompThreads) { scan_warp_loop(a, sh); return; }
-
-    // --------------------------------- compute warps ---------------------------------
-    const int lane = threadIdx.x & 31;
-    uint32_t my_seq = 0;                    // tiles this CTA has posted so far
-    NodeStat st;
+    uint32_t st_lcp = 0, st_min = 0, st_rank = 0, st_upd = 0, st_da = 0;
     uint64_t max_size = 0;
-    uint4 *stage1 = sm.stage, *stage2 = sm.stage + (IN_S ? STAGE * 4 : 0);
-
-    // software pipeline: the ticket and the records of tile t+1 are fetched while tile t is processed
-    auto prefetch_records = [&](uint32_t tl) {
-        const uint32_t g = tl * kCompThreads + threadIdx.x;
-        if (tl < a.n_tiles && g < in.total) {
-            const uint4 *rec = seg_record(in, g, RIN);
+    // the first run of a warp is its own index (no atomic: small sweeps never touch the ticket), the
+    // following ones are taken by ticket
+    uint32_t next_run = blockIdx.x * kNavWarps + warp;
+    while (true) {
+        const uint32_t run = __shfl_sync(0xffffffffu, next_run, 0);
+        if (run >= out.K) break;
+        if (lane == 0) next_run = gridDim.x * kNavWarps + atomicAdd(&a.sweep->ticket, 1u);   // its latency hides behind this run
+        const uint32_t g_begin = in.g_lo + run * out.run_cap, g_end = min(in.g_hi, g_begin + out.run_cap);
+        Cursor cur;
+        cursor_open(in, cur, g_begin);
+        // the record of the first step
+        if (g_begin + lane < g_end) {
+            cursor_seek(in, cur, g_begin + lane);
+            const uint4 *rec = cursor_record(in, cur, g_begin + lane, RIN);
 #pragma unroll
-            for (int k = 0; k < RIN; ++k) cp_async16(&sm.recbuf[threadIdx.x * RIN + k], rec + k);
+            for (int k = 0; k < RIN; ++k) cp_async16(recbuf + k, rec + k);
         }
-    };
-    if (threadIdx.x == 0) sh.tile = atomicAdd(&a.sweep->ticket, 1u);
-    bar_compute();
-    uint32_t tile = sh.tile;
-    prefetch_records(tile);
-    while (tile < a.n_tiles) {
-        uint32_t nxt = 0;
-        if (threadIdx.x == 0) nxt = atomicAdd(&a.sweep->ticket, 1u);       // its latency hides behind this tile
-        const uint32_t g = tile * kCompThreads + threadIdx.x;
-        const bool active = g < in.total;
-
-        uint64_t base1 = 0, base2 = 0;
-        W s1[5] = {0, 0, 0, 0, 0}, s2[5] = {0, 0, 0, 0, 0};
-        cp_async_wait_all();                                                // this thread's own record has landed
-        if (active) {
-            load_node<IN_S, W>(&sm.recbuf[threadIdx.x * RIN], base1, s1);
-            if (TWO) load_node<IN_S, W>(&sm.recbuf[threadIdx.x * RIN + RSIDE_IN], base2, s2);
-        }
-        const uint64_t size1 = (uint64_t)s1[0] + s1[1] + s1[2] + s1[3] + s1[4], size2 = (uint64_t)s2[0] + s2[1] + s2[2] + s2[3] + s2[4];
-        max_size = max(max_size, max(size1, size2));
-
-        // ---- stage the index blocks of the tile in shared memory (SMALL records only) ----
-        int mode = SRC_GLOBAL;
-        bool multi_super = false;
-        const uint32_t fb1 = (uint32_t)(base1 >> kBlockShift), fb2 = (uint32_t)(base2 >> kBlockShift);
-        RankSrc r1{stage1, fb1, 0u, 0u}, r2{stage2, fb2, 0u, 0u};
-        if (IN_S) {
-            const uint32_t last_active = min((uint32_t)kCompThreads, in.total - tile * kCompThreads) - 1;
-            const uint32_t lb1 = (uint32_t)((base1 + size1) >> kBlockShift), lb2 = (uint32_t)((base2 + size2) >> kBlockShift);
-            if (threadIdx.x == 0) { sh.rng[0] = fb1; if (TWO) sh.rng[2] = fb2; }
-            if (threadIdx.x == last_active) { sh.rng[1] = lb1; if (TWO) sh.rng[3] = lb2; }
-            if (!TWO) {                                                     // candidates for SLOTS staging
-                sm.need[2 * threadIdx.x] = active ? fb1 : ~0u;
-                sm.need[2 * threadIdx.x + 1] = (active && lb1 != fb1) ? lb1 : ~0u;
+        uint32_t run_cnt[4] = {0, 0, 0, 0};
+        for (uint32_t g0 = g_begin; g0 < g_end; g0 += 32) {
+            const uint32_t g = g0 + lane;
+            const bool active = g < g_end;
+            uint64_t base1 = 0, base2 = 0;
+            W s1[5] = {0, 0, 0, 0, 0}, s2[5] = {0, 0, 0, 0, 0};
+            cp_async_wait_all();                                            // this lane's own record has landed
+            if (active) {
+                load_node<IN_S, W>(recbuf, base1, s1);
+                if (TWO) load_node<IN_S, W>(recbuf + RSIDE_IN, base2, s2);
             }
-            bar_compute();
-            // nodes of one depth are disjoint and sorted: the tile touches the block range [lo, hi]
-            const uint32_t lo1 = sh.rng[0], hi1 = sh.rng[1], lo2 = TWO ? sh.rng[2] : 0u, hi2 = TWO ? sh.rng[3] : 0u;
-            const uint32_t span1 = hi1 - lo1 + 1, span2 = TWO ? hi2 - lo2 + 1 : 0u;
-            constexpr uint32_t sbs = kSuperShift - kBlockShift;
-            multi_super = (lo1 >> sbs) != (hi1 >> sbs) || (TWO && (lo2 >> sbs) != (hi2 >> sbs));
-            if (span1 <= (uint32_t)STAGE && span2 <= (uint32_t)STAGE) {
-                mode = SRC_WINDOW;
-                stage_window(a.ix1, stage1, lo1, span1);
-                if (TWO) stage_window(a.ix2, stage2, lo2, span2);
-                r1.slot0 = fb1 - lo1;
-                r2.slot0 = fb2 - lo2;
-            } else if (!TWO) {
-                mode = SRC_SLOTS;
-                stage_slots(a.ix1, stage1, sm.need);
-                r1.slot0 = 2 * threadIdx.x;
-                r1.d1 = lb1 - fb1;
+            const uint64_t size1 = (uint64_t)s1[0] + s1[1] + s1[2] + s1[3] + s1[4], size2 = (uint64_t)s2[0] + s2[1] + s2[2] + s2[3] + s2[4];
+            max_size = max(max_size, max(size1, size2));
+
+            // ---- stage the index blocks of the step in the warp's shared memory (SMALL records only) ----
+            int mode = SRC_GLOBAL;
+            bool multi_super = false;
+            const uint32_t fb1 = (uint32_t)(base1 >> kBlockShift), fb2 = (uint32_t)(base2 >> kBlockShift);
+            RankSrc r1{stage1, fb1, 0u, 0u}, r2{stage2, fb2, 0u, 0u};
+            if (IN_S) {
+                const int last_active = (int)min(32u, g_end - g0) - 1;
+                const uint32_t lb1 = (uint32_t)((base1 + size1) >> kBlockShift), lb2 = (uint32_t)((base2 + size2) >> kBlockShift);
+                // nodes of one depth are disjoint and sorted: the step touches the block range [lo, hi]
+                const uint32_t lo1 = __shfl_sync(0xffffffffu, fb1, 0), hi1 = __shfl_sync(0xffffffffu, lb1, last_active);
+                const uint32_t lo2 = TWO ? __shfl_sync(0xffffffffu, fb2, 0) : 0u, hi2 = TWO ? __shfl_sync(0xffffffffu, lb2, last_active) : 0u;
+                const uint32_t span1 = hi1 - lo1 + 1, span2 = TWO ? hi2 - lo2 + 1 : 0u;
+                constexpr uint32_t sbs = kSuperShift - kBlockShift;
+                multi_super = (lo1 >> sbs) != (hi1 >> sbs) || (TWO && (lo2 >> sbs) != (hi2 >> sbs));
+                __syncwarp();                                               // the previous step's reads of the staging buffer are over
+                if (span1 <= (uint32_t)STAGE && span2 <= (uint32_t)STAGE) {
+                    mode = SRC_WINDOW;
+                    stage_window(a.ix1, stage1, lo1, span1, lane);
+                    if (TWO) stage_window(a.ix2, stage2, lo2, span2, lane);
+                    r1.slot0 = fb1 - lo1;
+                    r2.slot0 = fb2 - lo2;
+                } else if (!TWO) {
+                    mode = SRC_SLOTS;
+                    need[2 * lane] = active ? fb1 : ~0u;
+                    need[2 * lane + 1] = (active && lb1 != fb1) ? lb1 : ~0u;
+                    __syncwarp();
+                    stage_slots(a.ix1.blocks, stage1, need, lane);
+                    r1.slot0 = 2 * lane;
+                    r1.d1 = lb1 - fb1;
+                }
             }
-        }
-        const uint32_t rpos1 = (uint32_t)base1 & (kBlockSyms - 1), rpos2 = (uint32_t)base2 & (kBlockSyms - 1);
+            const uint32_t rpos1 = (uint32_t)base1 & (kBlockSyms - 1), rpos2 = (uint32_t)base2 & (kBlockSyms - 1);
 
-        // ---- bit updates on the merged node, while the copies are in flight ----
-        if (active && a.write) node_bit_updates<TWO, W>(a, base1 + base2, s1, s2, st);
-        if (threadIdx.x == 0) sh.tile = nxt;
-        cp_async_wait_all();
-        bar_compute();
-        const uint32_t next_tile = sh.tile;
-        prefetch_records(next_tile);                                         // overlaps with the rank phase below
-
-        // ---- ranks -> children; child c is right-maximal iff >= 2 of its 5 gaps are non-empty ----
-        ChildSide<W> k1, k2;
-        uint32_t nzp = 0;
-        if (active) {
-            if constexpr (IN_S) expand_small<TWO>(a, mode, multi_super, r1, r2, base1, rpos1, s1, base2, rpos2, s2, k1, k2, nzp, st.rank);
-            else expand_wide<TWO>(a, base1, s1, base2, s2, k1, k2, nzp, st.rank);
-        }
-        bool valid[4];
+            // ---- bit updates on the merged node, while the copies are in flight ----
+            if (active && a.write) {
+                NodeStat st;
+                node_bit_updates<TWO, W>(a, base1 + base2, s1, s2, st);
+                st_lcp += st.lcp; st_min += st.nmin; st_upd += st.upd; st_da += st.da;
+            }
+            cp_async_wait_all();
+            __syncwarp();                                                   // every lane's copies are visible to the warp
+            // the record of the next step: overlaps with the rank phase below
+            if (g + 32 < g_end) {
+                cursor_seek(in, cur, g + 32);
+                const uint4 *rec = cursor_record(in, cur, g + 32, RIN);
 #pragma unroll
-        for (int c = 0; c < 4; ++c) valid[c] = ((nzp >> (8 * c)) & 0xffu) >= 2u;
-        uint32_t before[4];
-        const uint32_t vm = warp_child_slots(sh, valid, before);
-        // the staged blocks and the per-warp counts are complete; the previous tile's children can leave
-        if (my_seq) flush_pending<ROUT>(a, sh, sm.child);
-        bar_compute();                                   // wpk visible; child buffer and agg free again
-        uint32_t exw[4], tot[4];
-        tile_child_prefix(sh, exw, tot);
-        if (vm) {
+                for (int k = 0; k < RIN; ++k) cp_async16(recbuf + k, rec + k);
+            }
+
+            // ---- ranks -> children; child c is right-maximal iff >= 2 of its 5 gaps are non-empty ----
+            ChildSide<W> k1, k2;
+            uint32_t nzp = 0;
+            if (active) {
+                if constexpr (IN_S) expand_small<TWO>(a, mode, multi_super, r1, r2, base1, rpos1, s1, base2, rpos2, s2, k1, k2, nzp, st_rank);
+                else expand_wide<TWO>(a, base1, s1, base2, s2, k1, k2, nzp, st_rank);
+            }
+            bool valid[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) valid[c] = ((nzp >> (8 * c)) & 0xffu) >= 2u;
+            uint32_t before[4], tot[4];
+            const uint32_t vm = warp_child_slots(valid, lane, before, tot);
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
                 if ((vm >> c) & 1u) {
-                    uint4 *dst = &sm.child[c][(exw[c] + before[c]) * ROUT];
+                    uint4 *dst = out.base + (((size_t)c * out.K + run) * out.run_cap + run_cnt[c] + before[c]) * ROUT;
                     store_child<OUT_S, W>(dst, k1, c);
                     if (TWO) store_child<OUT_S, W>(dst + RSIDE_OUT, k2, c);
                 }
+                run_cnt[c] += tot[c];
             }
         }
-        post_tile(sh, tile, tot);
-        ++my_seq;
-        tile = next_tile;
+        if (lane < 4) {
+            uint32_t v = 0;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) if (lane == c) v = run_cnt[c];
+            out.cnt[(size_t)lane * out.K + run] = v;
+        }
     }
-    if (my_seq) flush_pending<ROUT>(a, sh, sm.child);
     if (a.write) {
-        flush_stat(a, C_LCP, st.lcp);
-        flush_stat(a, C_NMIN, st.nmin);
-        flush_stat(a, C_RANK, st.rank);
-        flush_stat(a, C_BITUPD, st.upd);
-        if (TWO) flush_stat(a, C_DA, st.da);
+        flush_stat(a, C_LCP, st_lcp);
+        flush_stat(a, C_NMIN, st_min);
+        flush_stat(a, C_RANK, st_rank);
+        flush_stat(a, C_BITUPD, st_upd);
+        if (TWO) flush_stat(a, C_DA, st_da);
     }
 #pragma unroll
     for (int s = 16; s > 0; s >>= 1) max_size = max(max_size, (uint64_t)__shfl_xor_sync(0xffffffffu, (unsigned long long)max_size, s));
     if (lane == 0 && max_size) atomicMax(&a.sweep->maxsz, (unsigned long long)max_size);
-    __threadfence();                                      // statistics and children are out before the CTA counts as done
-    const uint32_t none[4] = {0, 0, 0, 0};
-    post_tile(sh, kExitTile, none);
 }
 
 // ---------------------------------------------------------------------------------------------
 // Phase 2 sweep: leaves (intervals of W#).  One thread per leaf (pair); record = 16 bytes
-// {first, second} (a pair: 32 bytes).  Same persistent compute-warps + scan-warp structure.  Leaves
-// are sparse in position space: the two blocks of a leaf are staged per thread (SLOTS).
+// {first, second} (a pair: 32 bytes).  Same warp-per-run structure.  Leaves are sparse in position
+// space: the two blocks of a leaf are staged per lane (SLOTS).
 // ---------------------------------------------------------------------------------------------
 template <bool TWO>
 struct LeafSmem {
     static constexpr int RU = TWO ? 2 : 1;            // uint4 per record
-    uint4 stage[kStageBlocks * 4];
-    uint4 child[4][kCompThreads * RU];
-    uint4 recbuf[kCompThreads * RU];
-    uint32_t need[kStageBlocks];
-    SweepShared sh;
+    uint4 stage[kNavWarps][kWarpStage * 4];
+    uint4 recbuf[kNavWarps][32 * RU];
+    uint32_t need[kNavWarps][kWarpStage];
 };
 
-// rank at an absolute position whose block is staged in `slot` (SLOTS staging of the leaf kernel)
+// rank at an absolute position whose block is staged in `slot`
 __device__ __forceinline__ void rank_slot(const DevIndex &ix, const uint4 *stage, uint32_t slot, uint64_t pos, uint64_t out[4]) {
     uint4 cnt, a, b, t;
     load_block_smem(stage, slot, cnt, a, b, t);
@@ -673,135 +587,203 @@ __device__ __forceinline__ void rank_slot(const DevIndex &ix, const uint4 *stage
 }
 
 template <bool TWO>
-__global__ void __launch_bounds__(kPersistThreads, TWO ? 2 : 3)
-expand_leaves_persistent(const NavArgs a, const Segs in) {
+__global__ void __launch_bounds__(kNavThreads, TWO ? kPairCtas : kNodeCtas)
+expand_leaves_kernel(const NavArgs a, const FrameIn in, const FrameOut out) {
     constexpr int RU = TWO ? 2 : 1;
-    extern __shared__ __align__(1024) unsigned char smem_raw[];
-    LeafSmem<TWO> &sm = *reinterpret_cast<LeafSmem<TWO> *>(smem_raw);
-    SweepShared &sh = sm.sh;
+    __shared__ __align__(1024) LeafSmem<TWO> sm;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint4 *stage = sm.stage[warp];
+    uint4 *recbuf = sm.recbuf[warp] + lane * RU;
+    uint32_t *need = sm.need[warp];
 
-    if (threadIdx.x == 0) sh.pend_tile = 0;
-    __syncthreads();
-    if (threadIdx.x >= kCompThreads) { scan_warp_loop(a, sh); return; }
-
-    uint32_t my_seq = 0;
     unsigned long long st_lcp = 0, st_da = 0;
     uint32_t st_rank = 0;
-    auto prefetch_records = [&](uint32_t tl) {
-        const uint32_t g = tl * kCompThreads + threadIdx.x;
-        if (tl < a.n_tiles && g < in.total) {
-            const uint4 *rec = seg_record(in, g, RU);
+    // the first run of a warp is its own index (no atomic: small sweeps never touch the ticket), the
+    // following ones are taken by ticket
+    uint32_t next_run = blockIdx.x * kNavWarps + warp;
+    while (true) {
+        const uint32_t run = __shfl_sync(0xffffffffu, next_run, 0);
+        if (run >= out.K) break;
+        if (lane == 0) next_run = gridDim.x * kNavWarps + atomicAdd(&a.sweep->ticket, 1u);   // its latency hides behind this run
+        const uint32_t g_begin = in.g_lo + run * out.run_cap, g_end = min(in.g_hi, g_begin + out.run_cap);
+        Cursor cur;
+        cursor_open(in, cur, g_begin);
+        if (g_begin + lane < g_end) {
+            cursor_seek(in, cur, g_begin + lane);
+            const uint4 *rec = cursor_record(in, cur, g_begin + lane, RU);
 #pragma unroll
-            for (int k = 0; k < RU; ++k) cp_async16(&sm.recbuf[threadIdx.x * RU + k], rec + k);
+            for (int k = 0; k < RU; ++k) cp_async16(recbuf + k, rec + k);
         }
-    };
-    if (threadIdx.x == 0) sh.tile = atomicAdd(&a.sweep->ticket, 1u);
-    bar_compute();
-    uint32_t tile = sh.tile;
-    prefetch_records(tile);
-    while (tile < a.n_tiles) {
-        uint32_t nxt = 0;
-        if (threadIdx.x == 0) nxt = atomicAdd(&a.sweep->ticket, 1u);
-        const uint32_t g = tile * kCompThreads + threadIdx.x;
-        const bool active = g < in.total;
-        uint64_t f1 = 0, s1 = 0, f2 = 0, s2 = 0;
-        cp_async_wait_all();                               // this thread's own record has landed
-        if (active) {
-            const ulonglong2 *rec = reinterpret_cast<const ulonglong2 *>(&sm.recbuf[threadIdx.x * RU]);
-            const ulonglong2 x = rec[0];
-            f1 = x.x; s1 = x.y;
-            if (TWO) { const ulonglong2 z = rec[1]; f2 = z.x; s2 = z.y; }
-        }
-        // the (up to) two index blocks per BWT this leaf (pair) needs: slots 2t, 2t+1 (TWO: one BWT each,
-        // the second boundary of a side reads HBM unless it shares the block of the first)
-        const uint32_t fb1 = (uint32_t)(f1 >> kBlockShift), lb1 = (uint32_t)(s1 >> kBlockShift);
-        const uint32_t fb2 = (uint32_t)(f2 >> kBlockShift), lb2 = (uint32_t)(s2 >> kBlockShift);
-        if (!TWO) {
-            sm.need[2 * threadIdx.x] = active ? fb1 : ~0u;
-            sm.need[2 * threadIdx.x + 1] = (active && lb1 != fb1) ? lb1 : ~0u;
-        } else {
-            sm.need[2 * threadIdx.x] = active ? fb1 : ~0u;
-            sm.need[2 * threadIdx.x + 1] = active ? fb2 : ~0u;
-        }
-        bar_compute();
-        if (!TWO) {
-            stage_slots(a.ix1, sm.stage, sm.need);
-        } else {                                           // even slots come from BWT 1, odd slots from BWT 2
+        uint32_t run_cnt[4] = {0, 0, 0, 0};
+        for (uint32_t g0 = g_begin; g0 < g_end; g0 += 32) {
+            const uint32_t g = g0 + lane;
+            const bool active = g < g_end;
+            uint64_t f1 = 0, s1 = 0, f2 = 0, s2 = 0;
+            cp_async_wait_all();                           // this lane's own record has landed
+            if (active) {
+                const ulonglong2 *rec = reinterpret_cast<const ulonglong2 *>(recbuf);
+                const ulonglong2 x = rec[0];
+                f1 = x.x; s1 = x.y;
+                if (TWO) { const ulonglong2 z = rec[1]; f2 = z.x; s2 = z.y; }
+            }
+            // the (up to) two index blocks this leaf (pair) needs: slots 2 lane, 2 lane + 1 (TWO: one BWT each,
+            // the second boundary of a side reads HBM unless it shares the block of the first)
+            const uint32_t fb1 = (uint32_t)(f1 >> kBlockShift), lb1 = (uint32_t)(s1 >> kBlockShift);
+            const uint32_t fb2 = (uint32_t)(f2 >> kBlockShift), lb2 = (uint32_t)(s2 >> kBlockShift);
+            __syncwarp();                                  // the previous step's reads of the staging buffer are over
+            need[2 * lane] = active ? fb1 : ~0u;
+            if (!TWO) need[2 * lane + 1] = (active && lb1 != fb1) ? lb1 : ~0u;
+            else need[2 * lane + 1] = active ? fb2 : ~0u;
+            __syncwarp();
+            if (!TWO) {
+                stage_slots(a.ix1.blocks, stage, need, lane);
+            } else {                                       // even slots come from BWT 1, odd slots from BWT 2
 #pragma unroll
-            for (int it = 0; it < kStageBlocks * 4 / kCompThreads; ++it) {
-                const uint32_t k = threadIdx.x + it * kCompThreads;
-                const uint32_t slot = k >> 2, blk = sm.need[slot];
-                const uint4 *src = (slot & 1u) ? a.ix2.blocks : a.ix1.blocks;
-                if (blk != ~0u) cp_async16(&sm.stage[stage_slot(slot, k & 3)], src + (size_t)blk * 4 + (k & 3));
+                for (int it = 0; it < kWarpStage * 4 / 32; ++it) {
+                    const uint32_t k = lane + it * 32;
+                    const uint32_t slot = k >> 2, blk = need[slot];
+                    const uint4 *src = (slot & 1u) ? a.ix2.blocks : a.ix1.blocks;
+                    if (blk != ~0u) cp_async16(&stage[stage_slot(slot, k & 3)], src + (size_t)blk * 4 + (k & 3));
+                }
             }
-        }
-        if (active && a.write) {
-            // update_LCP_leaf (:344-355) / update_DA (:394-425) at merged coordinates
-            const uint64_t start1 = f1 + f2, start2 = f2 + s1, end = s1 + s2;
-            if (end > start1) st_lcp += end - start1 - 1;
-            const uint32_t pat = ((a.bits & 1u) ? 0x55555555u : 0u) | ((a.bits & 2u) ? 0xaaaaaaaau : 0u);
-            if (end > start1 + 1) fill_bits(a.thr, 2 * (start1 + 1), 2 * end, pat);
-            if (TWO) {
-                st_da += end - start1;
-                fill_bits(a.da, start2, end, 0xffffffffu);
+            if (active && a.write) {
+                // update_LCP_leaf (:344-355) / update_DA (:394-425) at merged coordinates
+                const uint64_t start1 = f1 + f2, start2 = f2 + s1, end = s1 + s2;
+                if (end > start1) st_lcp += end - start1 - 1;
+                const uint32_t pat = ((a.bits & 1u) ? 0x55555555u : 0u) | ((a.bits & 2u) ? 0xaaaaaaaau : 0u);
+                if (end > start1 + 1) fill_bits(a.thr, 2 * (start1 + 1), 2 * end, pat);
+                if (TWO) {
+                    st_da += end - start1;
+                    fill_bits(a.da, start2, end, 0xffffffffu);
+                }
             }
-        }
-        if (threadIdx.x == 0) sh.tile = nxt;
-        cp_async_wait_all();
-        bar_compute();                                     // staged blocks and the next ticket are visible
-        const uint32_t next_tile = sh.tile;
-        prefetch_records(next_tile);
-        // next_leaves (dna_bwt.hpp:358-379; two BWTs: ebwt2InDel.cpp:452-472): LF(range) = 2 ranks per BWT
-        uint64_t lo1[4] = {0, 0, 0, 0}, hi1[4] = {0, 0, 0, 0}, lo2[4] = {0, 0, 0, 0}, hi2[4] = {0, 0, 0, 0};
-        if (active) {
-            rank_slot(a.ix1, sm.stage, 2 * threadIdx.x, f1, lo1);
-            st_rank++;
-            if (s1 > f1) {
-                if (lb1 == fb1) rank_slot(a.ix1, sm.stage, 2 * threadIdx.x, s1, hi1);
-                else if (!TWO) rank_slot(a.ix1, sm.stage, 2 * threadIdx.x + 1, s1, hi1);
-                else rank4(a.ix1, s1, hi1);
+            cp_async_wait_all();
+            __syncwarp();
+            if (g + 32 < g_end) {
+                cursor_seek(in, cur, g + 32);
+                const uint4 *rec = cursor_record(in, cur, g + 32, RU);
+#pragma unroll
+                for (int k = 0; k < RU; ++k) cp_async16(recbuf + k, rec + k);
+            }
+            // next_leaves (dna_bwt.hpp:358-379; two BWTs: ebwt2InDel.cpp:452-472): LF(range) = 2 ranks per BWT
+            uint64_t lo1[4] = {0, 0, 0, 0}, hi1[4] = {0, 0, 0, 0}, lo2[4] = {0, 0, 0, 0}, hi2[4] = {0, 0, 0, 0};
+            if (active) {
+                rank_slot(a.ix1, stage, 2 * lane, f1, lo1);
                 st_rank++;
-            } else { hi1[0] = lo1[0]; hi1[1] = lo1[1]; hi1[2] = lo1[2]; hi1[3] = lo1[3]; }
-            if (TWO) {
-                rank_slot(a.ix2, sm.stage, 2 * threadIdx.x + 1, f2, lo2);
-                st_rank++;
-                if (s2 > f2) {
-                    if (lb2 == fb2) rank_slot(a.ix2, sm.stage, 2 * threadIdx.x + 1, s2, hi2);
-                    else rank4(a.ix2, s2, hi2);
+                if (s1 > f1) {
+                    if (lb1 == fb1) rank_slot(a.ix1, stage, 2 * lane, s1, hi1);
+                    else if (!TWO) rank_slot(a.ix1, stage, 2 * lane + 1, s1, hi1);
+                    else rank4(a.ix1, s1, hi1);
                     st_rank++;
-                } else { hi2[0] = lo2[0]; hi2[1] = lo2[1]; hi2[2] = lo2[2]; hi2[3] = lo2[3]; }
+                } else { hi1[0] = lo1[0]; hi1[1] = lo1[1]; hi1[2] = lo1[2]; hi1[3] = lo1[3]; }
+                if (TWO) {
+                    rank_slot(a.ix2, stage, 2 * lane + 1, f2, lo2);
+                    st_rank++;
+                    if (s2 > f2) {
+                        if (lb2 == fb2) rank_slot(a.ix2, stage, 2 * lane + 1, s2, hi2);
+                        else rank4(a.ix2, s2, hi2);
+                        st_rank++;
+                    } else { hi2[0] = lo2[0]; hi2[1] = lo2[1]; hi2[2] = lo2[2]; hi2[3] = lo2[3]; }
+                }
+            }
+            bool valid[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) valid[c] = active && ((hi1[c] - lo1[c]) + (hi2[c] - lo2[c]) >= 2);
+            uint32_t before[4], tot[4];
+            const uint32_t vm = warp_child_slots(valid, lane, before, tot);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                if ((vm >> c) & 1u) {
+                    ulonglong2 *o = reinterpret_cast<ulonglong2 *>(out.base + (((size_t)c * out.K + run) * out.run_cap + run_cnt[c] + before[c]) * RU);
+                    o[0] = make_ulonglong2(a.ix1.F[c] + lo1[c], a.ix1.F[c] + hi1[c]);
+                    if (TWO) o[1] = make_ulonglong2(a.ix2.F[c] + lo2[c], a.ix2.F[c] + hi2[c]);
+                }
+                run_cnt[c] += tot[c];
             }
         }
-        bool valid[4];
+        if (lane < 4) {
+            uint32_t v = 0;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) valid[c] = active && ((hi1[c] - lo1[c]) + (hi2[c] - lo2[c]) >= 2);
-        uint32_t before[4];
-        const uint32_t vm = warp_child_slots(sh, valid, before);
-        if (my_seq) flush_pending<RU>(a, sh, sm.child);
-        bar_compute();                                     // child buffer and agg free again
-        uint32_t exw[4], tot[4];
-        tile_child_prefix(sh, exw, tot);
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            if ((vm >> c) & 1u) {
-                ulonglong2 *o = reinterpret_cast<ulonglong2 *>(&sm.child[c][(exw[c] + before[c]) * RU]);
-                o[0] = make_ulonglong2(a.ix1.F[c] + lo1[c], a.ix1.F[c] + hi1[c]);
-                if (TWO) o[1] = make_ulonglong2(a.ix2.F[c] + lo2[c], a.ix2.F[c] + hi2[c]);
-            }
+            for (int c = 0; c < 4; ++c) if (lane == c) v = run_cnt[c];
+            out.cnt[(size_t)lane * out.K + run] = v;
         }
-        post_tile(sh, tile, tot);
-        ++my_seq;
-        tile = next_tile;
     }
-    if (my_seq) flush_pending<RU>(a, sh, sm.child);
     if (a.write) {
         flush_stat(a, C_LCP, st_lcp);
         flush_stat(a, C_RANK, st_rank);
         if (TWO) flush_stat(a, C_DA, st_da);
     }
-    __threadfence();
-    const uint32_t none[4] = {0, 0, 0, 0};
-    post_tile(sh, kExitTile, none);
+}
+
+// ---------------------------------------------------------------------------------------------
+// After a sweep: exclusive prefix of the per-(queue, run) counts, the hints of the next sweep's reads
+// and the total for the host.  One CTA per group of 256 entries: group_sum_kernel adds up every group,
+// frame_index_kernel takes the sum of the groups before its own as offset and scans its 256 entries.
+// ---------------------------------------------------------------------------------------------
+constexpr int kIndexThreads = 256;
+__global__ void __launch_bounds__(kIndexThreads)
+group_sum_kernel(const uint32_t *__restrict__ cnt, uint32_t n_entries, uint32_t *__restrict__ gsum) {
+    __shared__ uint32_t s_warp[kIndexThreads / 32];
+    const uint32_t j = blockIdx.x * kIndexThreads + threadIdx.x;
+    uint32_t v = j < n_entries ? cnt[j] : 0u;
+    v = __reduce_add_sync(0xffffffffu, v);
+    if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+        for (int w = 0; w < kIndexThreads / 32; ++w) t += s_warp[w];
+        gsum[blockIdx.x] = t;
+    }
+}
+
+__global__ void __launch_bounds__(kIndexThreads)
+frame_index_kernel(const uint32_t *__restrict__ cnt, const uint32_t *__restrict__ gsum, uint32_t n_entries,
+                   uint32_t *__restrict__ P, uint32_t *__restrict__ hint, const SweepDev *sweep, HostCtl *host, unsigned long long seq) {
+    __shared__ unsigned long long s_warp[kIndexThreads / 32];
+    __shared__ unsigned long long s_off;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // offset of this group
+    unsigned long long part = 0;
+    for (uint32_t i = threadIdx.x; i < blockIdx.x; i += kIndexThreads) part += gsum[i];
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) part += __shfl_xor_sync(0xffffffffu, part, s);
+    if (lane == 0) s_warp[warp] = part;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long t = 0;
+        for (int w = 0; w < kIndexThreads / 32; ++w) t += s_warp[w];
+        s_off = t;
+    }
+    __syncthreads();
+    const unsigned long long off = s_off;
+    __syncthreads();
+    // scan of the group's entries
+    const uint32_t j = blockIdx.x * kIndexThreads + threadIdx.x;
+    const uint32_t c = j < n_entries ? cnt[j] : 0u;
+    uint32_t incl = c;
+#pragma unroll
+    for (int s = 1; s < 32; s <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, incl, s);
+        if (lane >= s) incl += y;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    unsigned long long p = off + incl - c;
+    for (int w = 0; w < warp; ++w) p += s_warp[w];
+    if (j < n_entries) {
+        P[j] = (uint32_t)p;
+        // every multiple of 256 inside [p, p + c) starts a hint
+        for (unsigned long long t = (p + 255) >> 8; (t << 8) < p + c; ++t) hint[t] = j;
+    }
+    if (j == n_entries - 1) {                             // the last entry knows the total
+        const unsigned long long total = p + c;
+        P[n_entries] = (uint32_t)total;
+        hint[(total + 255) >> 8] = n_entries - 1;         // sentinel: upper bound of the last partial group
+        ((volatile unsigned long long *)host->out_count)[0] = total;
+        *(volatile unsigned long long *)&host->maxsz = sweep->maxsz;
+        __threadfence_system();
+        *(volatile unsigned long long *)&host->seq = seq;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -828,36 +810,46 @@ struct Frame {
     ~Frame() { if (p) arena->free(side, p); }
 };
 
-struct Chunk {
-    uint4 *p[4];
-    uint64_t cnt[4];
+// layout of one frame inside its arena block: records, then cnt[4K], P[4K+1], hint[]
+struct FrameLayout {
+    uint32_t K, run_cap;
+    size_t rec_bytes, cnt_off, gsum_off, p_off, hint_off, total_bytes;
+    FrameLayout(uint64_t n_in, uint32_t run, int ru_out) {
+        run_cap = run;
+        K = (uint32_t)((n_in + run - 1) / run);
+        rec_bytes = (size_t)4 * K * run_cap * ru_out * sizeof(uint4);
+        cnt_off = (rec_bytes + 255) & ~(size_t)255;
+        gsum_off = cnt_off + (((size_t)4 * K * 4 + 255) & ~(size_t)255);
+        p_off = gsum_off + ((((size_t)4 * K / 256 + 1) * 4 + 255) & ~(size_t)255);
+        hint_off = p_off + ((((size_t)4 * K + 1) * 4 + 255) & ~(size_t)255);
+        total_bytes = hint_off + ((((size_t)4 * K * run_cap / 256 + 2) * 4 + 255) & ~(size_t)255);
+    }
+};
+
+struct Chunk {                          // records [g_lo, g_hi) of a frame
+    FrameIn in{};
     int level = 0;                      // tree depth of the records (selects the arena end of the next frame)
     bool small = false;                 // record form (internal nodes)
     uint64_t bound = ~0ull;             // upper bound on the size of any node of the chunk
     std::shared_ptr<Frame> frame;
-    uint64_t total() const { return cnt[0] + cnt[1] + cnt[2] + cnt[3]; }
+    uint64_t total() const { return (uint64_t)in.g_hi - in.g_lo; }
 };
 
 struct SweepStats {
     uint64_t items = 0, sweeps = 0, max_chunk = 0;
     double ms_alloc = 0, ms_sync = 0, ms_max_alloc = 0, ms_max_sync = 0;   // host wall time (E2I_DEBUG)
+    double ms_sweep = 0, ms_index = 0;                                    // device time of the two kernels (E2I_DEBUG)
 };
 
 static inline double now_ms() {
     return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
-// Cut the first `take` records off a chunk (position-contiguous prefix); ru = uint4 per record.
-static Chunk split_head(Chunk &c, uint64_t take, int ru) {
+// Cut the first `take` records off a chunk (position-contiguous prefix).
+static Chunk split_head(Chunk &c, uint64_t take) {
     Chunk head = c;
-    uint64_t left = take;
-    for (int s = 0; s < 4; ++s) {
-        const uint64_t k = std::min<uint64_t>(left, c.cnt[s]);
-        head.cnt[s] = k;
-        c.p[s] += k * ru;
-        c.cnt[s] -= k;
-        left -= k;
-    }
+    head.in.g_hi = c.in.g_lo + (uint32_t)take;
+    c.in.g_lo = head.in.g_hi;
     return head;
 }
 
@@ -866,6 +858,8 @@ struct PassCfg {
     uint64_t budget;          // bytes of the frame arena
     uint64_t depth_hint;      // expected depth of the traversal below a cut level
     uint32_t K, k_right;
+    uint32_t resident_warps;  // warps the persistent grid keeps in flight
+    uint32_t runs_per_warp;   // runs a warp should get in a large sweep
 };
 
 template <typename Launch>
@@ -884,28 +878,32 @@ static int run_frontier(e2i_ctx *ctx, Chunk root, const PassCfg &cfg, NavArgs &a
         }
         // record forms: the children of nodes shorter than kSmallLimit are shorter than kSmallLimit
         const bool in_small = !cfg.leaves && cur.small, out_small = !cfg.leaves && cur.bound < kSmallLimit;
-        const int ru_in = cfg.leaves ? (cfg.two ? 2 : 1) : node_rec_u4(in_small, cfg.two);
         const int ru_out = cfg.leaves ? (cfg.two ? 2 : 1) : node_rec_u4(out_small, cfg.two);
-        const double out_bytes = 16.0 * ru_out * 4;      // four queues, each sized for every input record
+        const double out_bytes = 16.0 * ru_out * 4 + 1;  // four queues, each with room for every input record
         // max_chunk: largest chunk swept whole (two of its frames fit the arena: level-synchronous case).
         // split_chunk: chunk size once a level has to be cut (depth-first case): a path of such chunks down
         // to the deepest level must fit the arena next to the frame that is being cut.
-        const uint64_t max_chunk = std::max<uint64_t>(65536, (uint64_t)((double)cfg.budget / (out_bytes * 2.5)));
+        const uint64_t max_chunk = std::min<uint64_t>(1ull << 30, std::max<uint64_t>(65536, (uint64_t)((double)cfg.budget / (out_bytes * 2.5))));
         const uint64_t split_chunk = std::max<uint64_t>(256, std::min<uint64_t>(max_chunk, (uint64_t)((double)cfg.budget * 0.45 / (out_bytes * (double)cfg.depth_hint))));
-        Chunk work;
         uint64_t take = cur.total() <= max_chunk ? cur.total() : std::min<uint64_t>(cur.total(), split_chunk);
         void *mem = nullptr;
         const double ta = now_ms();
+        uint32_t run_len = 32;
         while (true) {   // shrink the chunk until its output frame fits the pool
-            mem = ctx->arena.alloc((cur.level + 1) & 1, take * 4 * ru_out * sizeof(uint4));
+            // runs: a few per resident warp (the first is the warp's own index, the others are taken by
+            // ticket, which evens out the tail), between 32 and kMaxRun records each
+            run_len = (uint32_t)std::min<uint64_t>(kMaxRun, std::max<uint64_t>(32, (take / ((uint64_t)cfg.resident_warps * cfg.runs_per_warp) + 31) / 32 * 32));
+            const FrameLayout lay(take, run_len, ru_out);
+            mem = ctx->arena.alloc((cur.level + 1) & 1, lay.total_bytes);
             if (mem) break;
             if (take <= 256) { set_error("frontier memory exhausted (arena %llu bytes, %llu in use): raise the frontier budget",
                                           (unsigned long long)ctx->arena.size(), (unsigned long long)ctx->arena.in_use()); return E2I_ERR_MEMORY; }
             take /= 2;
         }
         { const double d = now_ms() - ta; ss.ms_alloc += d; ss.ms_max_alloc = std::max(ss.ms_max_alloc, d); }
+        Chunk work;
         if (take < cur.total()) {
-            work = split_head(cur, take, ru_in);
+            work = split_head(cur, take);
             stack.push_back(std::move(cur));
         } else {
             work = std::move(cur);
@@ -914,54 +912,44 @@ static int run_frontier(e2i_ctx *ctx, Chunk root, const PassCfg &cfg, NavArgs &a
         frame->arena = &ctx->arena;
         frame->side = (work.level + 1) & 1;
         frame->p = mem;
-        Segs segs;
-        uint32_t acc = 0;
-        for (int s = 0; s < 4; ++s) {
-            segs.p[s] = work.p[s];
-            acc += (uint32_t)work.cnt[s];
-            segs.end[s] = acc;
-        }
-        segs.total = acc;
-        const uint32_t n_tiles = (acc + kCompThreads - 1) / kCompThreads;
-        if ((size_t)n_tiles * kLb4Words > ctx->desc_words) {
-            dfree(ctx, ctx->desc);
-            ctx->desc = nullptr;
-            ctx->desc_words = (size_t)n_tiles * kLb4Words * 3 / 2 + 1024;
-            E2I_CUDA_TRY(dmalloc(ctx, &ctx->desc, ctx->desc_words * 8));
-            E2I_CUDA_TRY(cudaMemsetAsync(ctx->desc, 0, ctx->desc_words * 8, ctx->stream));
-            ctx->epoch = 0;
-        }
-        if (++ctx->epoch >= 0xffffu) {
-            E2I_CUDA_TRY(cudaMemsetAsync(ctx->desc, 0, ctx->desc_words * 8, ctx->stream));
-            ctx->epoch = 1;
-        }
-        for (int c = 0; c < 4; ++c) args.out[c] = reinterpret_cast<uint4 *>(mem) + (size_t)c * take * ru_out;
-        args.desc = ctx->desc;
-        args.epoch = ctx->epoch;
-        args.n_tiles = n_tiles;
+        const FrameLayout lay(take, run_len, ru_out);
+        char *fb = static_cast<char *>(mem);
+        FrameOut fo;
+        fo.base = reinterpret_cast<uint4 *>(fb);
+        fo.cnt = reinterpret_cast<uint32_t *>(fb + lay.cnt_off);
+        fo.gsum = reinterpret_cast<uint32_t *>(fb + lay.gsum_off);
+        fo.K = lay.K;
+        fo.run_cap = lay.run_cap;
+        uint32_t *P = reinterpret_cast<uint32_t *>(fb + lay.p_off), *hint = reinterpret_cast<uint32_t *>(fb + lay.hint_off);
         if (ctx->ticket_next == kSweepSlots) {           // ring of sweep control blocks used up: zero it again
             E2I_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
             E2I_CUDA_TRY(cudaMemsetAsync(ctx->ctl, 0, kSweepSlots * sizeof(SweepDev), ctx->stream));
             ctx->ticket_next = 0;
         }
         args.sweep = reinterpret_cast<SweepDev *>(ctx->ctl) + ctx->ticket_next++;
-        args.host = hctl;
-        args.seq = ++ctx->sweep_seq;
         const uint64_t depth = (uint64_t)work.level;     // every record of a sweep has this depth
         args.bits = (depth >= cfg.K ? 1u : 0u) | (depth >= cfg.k_right ? 2u : 0u);
-        launch(args, segs, n_tiles, in_small, out_small);
+        const unsigned long long seq = ++ctx->sweep_seq;
+        static const bool debug = std::getenv("E2I_DEBUG") != nullptr;
+        if (debug) cudaEventRecord(ctx->ev[4], ctx->stream);
+        const uint32_t n_groups = (4 * fo.K + kIndexThreads - 1) / kIndexThreads;
+        launch(args, work.in, fo, in_small, out_small);
+        if (debug) cudaEventRecord(ctx->ev[5], ctx->stream);
+        group_sum_kernel<<<n_groups, kIndexThreads, 0, ctx->stream>>>(fo.cnt, 4 * fo.K, fo.gsum);
+        frame_index_kernel<<<n_groups, kIndexThreads, 0, ctx->stream>>>(fo.cnt, fo.gsum, 4 * fo.K, P, hint, args.sweep, hctl, seq);
+        if (debug) cudaEventRecord(ctx->ev[6], ctx->stream);
         E2I_CUDA_TRY(cudaGetLastError());
-        ctx->n_launch++;
+        ctx->n_launch += 3;
         ctx->n_d2h += sizeof(HostCtl);
         const double tsy = now_ms();
-        {   // wait for the totals (written by the last CTA to leave): poll the mapped sequence word
+        {   // wait for the totals: poll the mapped sequence word
             volatile unsigned long long *seqp = &hctl->seq;
             unsigned spins = 0;
-            while (*seqp != args.seq) {
+            while (*seqp != seq) {
                 if ((++spins & 0xfffu) == 0) {
                     const cudaError_t q = cudaStreamQuery(ctx->stream);
                     if (q == cudaSuccess) {
-                        if (*seqp == args.seq) break;
+                        if (*seqp == seq) break;
                         set_error("traversal sweep finished without publishing its counts");
                         return E2I_ERR_CUDA;
                     }
@@ -971,18 +959,49 @@ static int run_frontier(e2i_ctx *ctx, Chunk root, const PassCfg &cfg, NavArgs &a
             std::atomic_thread_fence(std::memory_order_acquire);
         }
         { const double d = now_ms() - tsy; ss.ms_sync += d; ss.ms_max_sync = std::max(ss.ms_max_sync, d); }
-        ss.items += acc;
+        if (debug) {
+            float m1 = 0, m2 = 0;
+            cudaEventSynchronize(ctx->ev[6]);
+            cudaEventElapsedTime(&m1, ctx->ev[4], ctx->ev[5]);
+            cudaEventElapsedTime(&m2, ctx->ev[5], ctx->ev[6]);
+            ss.ms_sweep += m1; ss.ms_index += m2;
+        }
+        ss.items += take;
         ss.sweeps++;
-        ss.max_chunk = std::max<uint64_t>(ss.max_chunk, acc);
+        ss.max_chunk = std::max<uint64_t>(ss.max_chunk, take);
+        const uint64_t n_out = ((volatile unsigned long long *)hctl->out_count)[0];
         Chunk next;
         next.frame = frame;
         next.level = work.level + 1;
         next.small = out_small;
         next.bound = cfg.leaves ? ~0ull : std::min<uint64_t>(work.bound, ((volatile unsigned long long *)&hctl->maxsz)[0]);
-        for (int c = 0; c < 4; ++c) { next.p[c] = args.out[c]; next.cnt[c] = ((volatile unsigned long long *)hctl->out_count)[c]; }
+        next.in.base = fo.base;
+        next.in.P = P;
+        next.in.hint = hint;
+        next.in.K = fo.K;
+        next.in.run_cap = fo.run_cap;
+        next.in.g_lo = 0;
+        next.in.g_hi = (uint32_t)n_out;
         work.frame.reset();
-        if (next.total()) stack.push_back(std::move(next));
+        if (n_out) stack.push_back(std::move(next));
     }
+    return E2I_OK;
+}
+
+// records [g_lo, g_hi) of a chunk copied to the host in order (sharding: the frames involved are small)
+static int fetch_chunk(e2i_ctx *ctx, const Chunk &c, int ru, std::vector<uint64_t> &host) {
+    const uint32_t n_entries = 4 * c.in.K;
+    std::vector<uint32_t> P(n_entries + 1);
+    E2I_CUDA_TRY(cudaMemcpyAsync(P.data(), c.in.P, P.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    E2I_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    host.resize((size_t)c.total() * ru * 2);
+    for (uint32_t j = 0; j < n_entries; ++j) {
+        const uint64_t lo = std::max<uint64_t>(P[j], c.in.g_lo), hi = std::min<uint64_t>(P[j + 1], c.in.g_hi);
+        if (lo >= hi) continue;
+        const uint4 *src = c.in.base + ((size_t)j * c.in.run_cap + (lo - P[j])) * ru;   // entry j = (queue, run) in order
+        E2I_CUDA_TRY(cudaMemcpyAsync(host.data() + (lo - c.in.g_lo) * ru * 2, src, (hi - lo) * ru * 16, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    E2I_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     return E2I_OK;
 }
 
@@ -991,25 +1010,6 @@ static int run_frontier(e2i_ctx *ctx, Chunk root, const PassCfg &cfg, NavArgs &a
 using namespace e2i;
 
 static uint64_t padded_words32(uint64_t bits) { return ((bits + 31) / 32 + 63) / 64 * 64 + 64; }
-
-namespace {
-template <bool TWO, bool IN_S, bool OUT_S>
-cudaError_t launch_nodes(const NavArgs &a, const Segs &segs, uint32_t grid, cudaStream_t s) {
-    constexpr size_t smem = sizeof(NodeSmem<TWO, IN_S, OUT_S>);
-    const cudaError_t e = cudaFuncSetAttribute(expand_nodes_persistent<TWO, IN_S, OUT_S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    expand_nodes_persistent<TWO, IN_S, OUT_S><<<grid, kPersistThreads, smem, s>>>(a, segs);
-    return cudaSuccess;
-}
-template <bool TWO>
-cudaError_t launch_leaves(const NavArgs &a, const Segs &segs, uint32_t grid, cudaStream_t s) {
-    constexpr size_t smem = sizeof(LeafSmem<TWO>);
-    const cudaError_t e = cudaFuncSetAttribute(expand_leaves_persistent<TWO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    expand_leaves_persistent<TWO><<<grid, kPersistThreads, smem, s>>>(a, segs);
-    return cudaSuccess;
-}
-}  // namespace
 
 extern "C" int e2i_navigate_shard(e2i_ctx *ctx, const e2i_index *b1, const e2i_index *b2, const e2i_params *p,
                                   int shard, int n_shards, e2i_lcpbits **out, e2i_bits **da_out, e2i_stats *st) {
@@ -1097,6 +1097,14 @@ extern "C" int e2i_navigate_shard(e2i_ctx *ctx, const e2i_index *b1, const e2i_i
     // equal cumulated interval length, and every shard finishes its slice independently.  The cut
     // depends only on the input and n_shards (never on a rank's free memory), so all shards agree on it.
     const uint64_t kDealItems = 4096ull * (uint64_t)n_shards;
+    {   // the sweep kernels use ~20 KB of static shared memory per CTA and want 4-7 CTAs per SM: ask for the large carveout
+        const int pct = (int)cudaSharedmemCarveoutMaxShared;
+        TRYF(cudaFuncSetAttribute(expand_nodes_kernel<false, true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+        TRYF(cudaFuncSetAttribute(expand_nodes_kernel<true, true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+        TRYF(cudaFuncSetAttribute(expand_leaves_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+        TRYF(cudaFuncSetAttribute(expand_leaves_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+    }
+    const uint32_t ctas_per_sm = two ? (uint32_t)kPairCtas : (uint32_t)kNodeCtas;
 
     auto run_pass = [&](bool leaves, SweepStats &ss) -> int {
         PassCfg cfg;
@@ -1107,10 +1115,16 @@ extern "C" int e2i_navigate_shard(e2i_ctx *ctx, const e2i_index *b1, const e2i_i
         cfg.depth_hint = leaves ? 1024 : st->levels_leaves + 16;
         cfg.K = (uint32_t)p->K;
         cfg.k_right = (uint32_t)p->k_right;
+        cfg.resident_warps = (uint32_t)ctx->sm_count * ctas_per_sm * kNavWarps;
+        cfg.runs_per_warp = leaves ? 1u : 4u;
+        if (const char *e = std::getenv(leaves ? "E2I_RUNS_LEAVES" : "E2I_RUNS_NODES")) cfg.runs_per_warp = (uint32_t)std::max(1, atoi(e));
+        // the root frame: one record, one run
         const int ru_root = leaves ? (two ? 2 : 1) : node_rec_u4(false, two);
-        void *rootmem = ctx->arena.alloc(0, (size_t)ru_root * 16);
+        const size_t root_bytes = 1024;
+        char *rootmem = static_cast<char *>(ctx->arena.alloc(0, root_bytes));
         if (!rootmem) { set_error("frontier arena too small"); return E2I_ERR_MEMORY; }
-        uint64_t rec[12] = {0};
+        uint64_t hostroot[root_bytes / 8] = {0};
+        uint64_t *rec = hostroot;
         if (leaves) {                                   // first_leaf (dna_bwt.hpp:313-317)
             rec[0] = 0; rec[1] = b1->F[0];
             if (two) { rec[2] = 0; rec[3] = b2->F[0]; }
@@ -1118,46 +1132,50 @@ extern "C" int e2i_navigate_shard(e2i_ctx *ctx, const e2i_index *b1, const e2i_i
             pack_wide_host(rec, 0, b1->F, b1->n);
             if (two) pack_wide_host(rec + 6, 0, b2->F, b2->n);
         }
-        E2I_CUDA_TRY(cudaMemcpyAsync(rootmem, rec, (size_t)ru_root * 16, cudaMemcpyHostToDevice, s));
+        uint32_t *hp = reinterpret_cast<uint32_t *>(hostroot) + 128;     // byte 512: P[5] = {0,1,1,1,1}, byte 640: hint[2] = {0, 3}
+        hp[0] = 0; hp[1] = hp[2] = hp[3] = hp[4] = 1;
+        hp[32] = 0; hp[33] = 3;
+        E2I_CUDA_TRY(cudaMemcpyAsync(rootmem, hostroot, root_bytes, cudaMemcpyHostToDevice, s));
+        (void)ru_root;
         Chunk root{};
-        root.p[0] = reinterpret_cast<uint4 *>(rootmem);
-        root.cnt[0] = 1;
+        root.in.base = reinterpret_cast<uint4 *>(rootmem);
+        root.in.P = reinterpret_cast<uint32_t *>(rootmem + 512);
+        root.in.hint = reinterpret_cast<uint32_t *>(rootmem + 640);
+        root.in.K = 1;
+        root.in.run_cap = 1;
+        root.in.g_lo = 0;
+        root.in.g_hi = 1;
         root.small = false;
         root.bound = std::max<uint64_t>(b1->n, two ? b2->n : 0);
         root.frame = std::make_shared<Frame>();
         root.frame->arena = &ctx->arena;
         root.frame->side = 0;
         root.frame->p = rootmem;
-        cudaError_t launch_err = cudaSuccess;
-        auto launch = [&](NavArgs &a, const Segs &segs, uint32_t n_tiles, bool in_small, bool out_small) {
-            cudaError_t e;
+        auto launch = [&](NavArgs &a, const FrameIn &fi, const FrameOut &fo, bool in_small, bool out_small) {
+            const uint32_t want = (fo.K + kNavWarps - 1) / kNavWarps;
             if (leaves) {
-                const uint32_t grid = std::min<uint32_t>(n_tiles, (uint32_t)ctx->sm_count * (two ? 2u : 3u));
-                e = two ? launch_leaves<true>(a, segs, grid, s) : launch_leaves<false>(a, segs, grid, s);
+                const uint32_t grid = std::min<uint32_t>(want, (uint32_t)ctx->sm_count * ctas_per_sm);
+                if (two) expand_leaves_kernel<true><<<grid, kNavThreads, 0, s>>>(a, fi, fo);
+                else expand_leaves_kernel<false><<<grid, kNavThreads, 0, s>>>(a, fi, fo);
             } else if (in_small) {
-                const uint32_t grid = std::min<uint32_t>(n_tiles, (uint32_t)ctx->sm_count * (two ? 2u : 3u));
-                e = two ? launch_nodes<true, true, true>(a, segs, grid, s) : launch_nodes<false, true, true>(a, segs, grid, s);
+                const uint32_t grid = std::min<uint32_t>(want, (uint32_t)ctx->sm_count * ctas_per_sm);
+                if (two) expand_nodes_kernel<true, true, true><<<grid, kNavThreads, 0, s>>>(a, fi, fo);
+                else expand_nodes_kernel<false, true, true><<<grid, kNavThreads, 0, s>>>(a, fi, fo);
             } else {
-                const uint32_t grid = std::min<uint32_t>(n_tiles, (uint32_t)ctx->sm_count);
-                if (out_small) e = two ? launch_nodes<true, false, true>(a, segs, grid, s) : launch_nodes<false, false, true>(a, segs, grid, s);
-                else e = two ? launch_nodes<true, false, false>(a, segs, grid, s) : launch_nodes<false, false, false>(a, segs, grid, s);
+                const uint32_t grid = std::min<uint32_t>(want, (uint32_t)ctx->sm_count * 2);
+                if (out_small) { if (two) expand_nodes_kernel<true, false, true><<<grid, kNavThreads, 0, s>>>(a, fi, fo); else expand_nodes_kernel<false, false, true><<<grid, kNavThreads, 0, s>>>(a, fi, fo); }
+                else { if (two) expand_nodes_kernel<true, false, false><<<grid, kNavThreads, 0, s>>>(a, fi, fo); else expand_nodes_kernel<false, false, false><<<grid, kNavThreads, 0, s>>>(a, fi, fo); }
             }
-            if (e != cudaSuccess) launch_err = e;
-        };
-        auto run = [&](Chunk c, SweepStats &stats, uint64_t stop_at, std::vector<Chunk> *stopped) -> int {
-            const int rc = run_frontier(ctx, std::move(c), cfg, args, launch, stats, stop_at, stopped);
-            if (rc == E2I_OK && launch_err != cudaSuccess) { set_error("kernel configuration failed: %s", cudaGetErrorString(launch_err)); return E2I_ERR_CUDA; }
-            return rc;
         };
         if (n_shards == 1) {
             args.write = 1;
-            return run(std::move(root), ss, 0, nullptr);
+            return run_frontier(ctx, std::move(root), cfg, args, launch, ss, 0, nullptr);
         }
         // shared top of the tree
         std::vector<Chunk> dealt;
         args.write = shard == 0;
         SweepStats top;
-        E2I_TRY(run(std::move(root), top, kDealItems, &dealt));
+        E2I_TRY(run_frontier(ctx, std::move(root), cfg, args, launch, top, kDealItems, &dealt));
         if (shard == 0) { ss.items += top.items; ss.sweeps += top.sweeps; ss.max_chunk = std::max(ss.max_chunk, top.max_chunk); }
         args.write = 1;
         for (Chunk &c : dealt) {
@@ -1165,14 +1183,8 @@ extern "C" int e2i_navigate_shard(e2i_ctx *ctx, const e2i_index *b1, const e2i_i
             const int ru = leaves ? (two ? 2 : 1) : node_rec_u4(c.small, two);
             const int words = ru * 2, side_words = words / (two ? 2 : 1);
             const uint64_t tot = c.total();
-            std::vector<uint64_t> host((size_t)tot * words);
-            uint64_t off = 0;
-            for (int q = 0; q < 4; ++q) {
-                if (!c.cnt[q]) continue;
-                E2I_CUDA_TRY(cudaMemcpyAsync(host.data() + off * words, c.p[q], c.cnt[q] * words * 8, cudaMemcpyDeviceToHost, s));
-                off += c.cnt[q];
-            }
-            E2I_CUDA_TRY(cudaStreamSynchronize(s));
+            std::vector<uint64_t> host;
+            E2I_TRY(fetch_chunk(ctx, c, ru, host));
             auto weight = [&](uint64_t i) -> uint64_t {
                 const uint64_t *r = host.data() + i * words;
                 if (leaves) return (r[1] - r[0]) + (two ? r[3] - r[2] : 0) + 1;
@@ -1190,11 +1202,10 @@ extern "C" int e2i_navigate_shard(e2i_ctx *ctx, const e2i_index *b1, const e2i_i
                 acc += weight(i);
             }
             if (!have_lo || lo >= hi) continue;
-            Chunk mine = c;
-            (void)split_head(mine, lo, ru);             // drop [0, lo)
-            Chunk part = split_head(mine, hi - lo, ru);
-            part.frame = c.frame;
-            E2I_TRY(run(std::move(part), ss, 0, nullptr));
+            Chunk part = c;
+            part.in.g_lo = c.in.g_lo + (uint32_t)lo;
+            part.in.g_hi = c.in.g_lo + (uint32_t)hi;
+            E2I_TRY(run_frontier(ctx, std::move(part), cfg, args, launch, ss, 0, nullptr));
         }
         return E2I_OK;
     };
@@ -1236,9 +1247,9 @@ extern "C" int e2i_navigate_shard(e2i_ctx *ctx, const e2i_index *b1, const e2i_i
     st->bit_updates += tot[C_BITUPD];
     st->max_frontier = std::max<uint64_t>(st->max_frontier, sn.max_chunk);
     if (std::getenv("E2I_DEBUG"))
-        std::fprintf(stderr, "[e2i] leaves: %llu sweeps, alloc %.2f ms (max %.2f), sync %.2f ms (max %.2f) | nodes: %llu sweeps, alloc %.2f ms (max %.2f), sync %.2f ms (max %.2f)\n",
-                     (unsigned long long)sl.sweeps, sl.ms_alloc, sl.ms_max_alloc, sl.ms_sync, sl.ms_max_sync,
-                     (unsigned long long)sn.sweeps, sn.ms_alloc, sn.ms_max_alloc, sn.ms_sync, sn.ms_max_sync);
+        std::fprintf(stderr, "[e2i] leaves: %llu sweeps, alloc %.2f ms, sync %.2f ms (max %.2f), kernels %.2f + index %.2f ms | nodes: %llu sweeps, alloc %.2f ms, sync %.2f ms (max %.2f), kernels %.2f + index %.2f ms\n",
+                     (unsigned long long)sl.sweeps, sl.ms_alloc, sl.ms_sync, sl.ms_max_sync, sl.ms_sweep, sl.ms_index,
+                     (unsigned long long)sn.sweeps, sn.ms_alloc, sn.ms_sync, sn.ms_max_sync, sn.ms_sweep, sn.ms_index);
     float ms = 0;
     TRYF(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
     st->ms_leaves += ms;
