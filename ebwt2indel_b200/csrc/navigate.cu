@@ -191,12 +191,13 @@ __device__ __forceinline__ void load_block_smem(const uint4 *stage, uint32_t slo
 // #A,#C,#G,#T before relative position rpos, counted from the start of the superblock of origin_blk
 // (mod 2^32: the base cancels in every difference, which is all a node shorter than 2^32 needs).
 // multi_super (warp-uniform): the 32 nodes reach into a second superblock.
-__device__ __forceinline__ void rank_rel(const DevIndex &ix, const RankSrc &r, int mode, bool multi_super, uint32_t rpos, uint32_t out[4]) {
+template <int MODE>
+__device__ __forceinline__ void rank_rel(const DevIndex &ix, const RankSrc &r, bool multi_super, uint32_t rpos, uint32_t out[4]) {
     const uint32_t rel = rpos >> kBlockShift;
     uint4 cnt, a, b, t;
-    if (mode == SRC_WINDOW) {
+    if (MODE == SRC_WINDOW) {
         load_block_smem(r.stage, r.slot0 + rel, cnt, a, b, t);
-    } else if (mode == SRC_SLOTS && (rel == 0 || rel == r.d1)) {
+    } else if (MODE == SRC_SLOTS && (rel == 0 || rel == r.d1)) {
         load_block_smem(r.stage, r.slot0 + (rel != 0), cnt, a, b, t);
     } else {
         const uint4 *p = ix.blocks + (size_t)(r.origin_blk + rel) * 4;
@@ -291,38 +292,47 @@ __device__ __forceinline__ void node_bit_updates(const NavArgs &a, uint64_t mbas
     mn.flush();
 }
 
-// turn the ranks at one boundary into the sizes of sub-interval j of every child; nzp counts, per
-// symbol, the non-empty sub-intervals (union over both BWTs, include.hpp:784-792)
+// Turn the ranks at one boundary into the sizes of sub-interval j of every child.  Child c is
+// right-maximal iff >= 2 of its 5 sub-intervals are non-empty in the union of both BWTs
+// (number_of_children, include.hpp:760-792), i.e. iff the sum of the (summed) sizes exceeds their
+// maximum: Gaps keeps both per symbol.
+template <typename W>
+struct Gaps {
+    W sum[4] = {0, 0, 0, 0}, mx[4] = {0, 0, 0, 0};
+    __device__ __forceinline__ bool valid(int c) const { return sum[c] > mx[c]; }
+};
+
 template <bool TWO, typename W>
 __device__ __forceinline__ void take_boundary(int j, const W (&cur1)[4], W (&prev1)[4], const W (&cur2)[4], W (&prev2)[4],
-                                              ChildSide<W> &k1, ChildSide<W> &k2, uint32_t &nzp) {
+                                              ChildSide<W> &k1, ChildSide<W> &k2, Gaps<W> &gp) {
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
         const W d1 = cur1[c] - prev1[c];
-        W any = d1;
+        W e = d1;
         k1.sz[j][c] = d1;
         prev1[c] = cur1[c];
         if (TWO) {
             const W d2 = cur2[c] - prev2[c];
-            any |= d2;
+            e += d2;
             k2.sz[j][c] = d2;
             prev2[c] = cur2[c];
         }
-        nzp += (any != 0 ? 1u : 0u) << (8 * c);
+        gp.sum[c] += e;
+        gp.mx[c] = max(gp.mx[c], e);
     }
 }
 
 // LF(sa_node) (dna_bwt.hpp:323-356) for one SMALL node (pair): ranks at the distinct boundaries (equal
 // neighbours reuse the previous result, :334-347) in 32-bit arithmetic relative to the staged blocks.
-template <bool TWO>
-__device__ __forceinline__ void expand_small(const NavArgs &a, int mode, bool multi_super, const RankSrc &r1, const RankSrc &r2,
+template <bool TWO, int MODE>
+__device__ __forceinline__ void expand_small(const NavArgs &a, bool multi_super, const RankSrc &r1, const RankSrc &r2,
                                              uint64_t base1, uint32_t rpos1, const uint32_t (&s1)[5],
                                              uint64_t base2, uint32_t rpos2, const uint32_t (&s2)[5],
-                                             ChildSide<uint32_t> &k1, ChildSide<uint32_t> &k2, uint32_t &nzp, uint32_t &st_rank) {
+                                             ChildSide<uint32_t> &k1, ChildSide<uint32_t> &k2, Gaps<uint32_t> &gp, uint32_t &st_rank) {
     uint32_t prev1[4], cur1[4], prev2[4] = {0, 0, 0, 0}, cur2[4] = {0, 0, 0, 0};
-    rank_rel(a.ix1, r1, mode, multi_super, rpos1, prev1);
+    rank_rel<MODE>(a.ix1, r1, multi_super, rpos1, prev1);
     st_rank++;
-    if (TWO) { rank_rel(a.ix2, r2, mode, multi_super, rpos2, prev2); st_rank++; }
+    if (TWO) { rank_rel<MODE>(a.ix2, r2, multi_super, rpos2, prev2); st_rank++; }
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
         // prev is relative to the superblock of the node's first block, which is the superblock of `base`
@@ -338,21 +348,21 @@ __device__ __forceinline__ void expand_small(const NavArgs &a, int mode, bool mu
 #pragma unroll
     for (int j = 0; j < 5; ++j) {
         rpos1 += s1[j];
-        if (s1[j]) { rank_rel(a.ix1, r1, mode, multi_super, rpos1, cur1); st_rank++; }
+        if (s1[j]) { rank_rel<MODE>(a.ix1, r1, multi_super, rpos1, cur1); st_rank++; }
         else { cur1[0] = prev1[0]; cur1[1] = prev1[1]; cur1[2] = prev1[2]; cur1[3] = prev1[3]; }
         if (TWO) {
             rpos2 += s2[j];
-            if (s2[j]) { rank_rel(a.ix2, r2, mode, multi_super, rpos2, cur2); st_rank++; }
+            if (s2[j]) { rank_rel<MODE>(a.ix2, r2, multi_super, rpos2, cur2); st_rank++; }
             else { cur2[0] = prev2[0]; cur2[1] = prev2[1]; cur2[2] = prev2[2]; cur2[3] = prev2[3]; }
         }
-        take_boundary<TWO, uint32_t>(j, cur1, prev1, cur2, prev2, k1, k2, nzp);
+        take_boundary<TWO, uint32_t>(j, cur1, prev1, cur2, prev2, k1, k2, gp);
     }
 }
 
 // the same for a WIDE node (pair): absolute 64-bit ranks read from HBM
 template <bool TWO>
 __device__ __forceinline__ void expand_wide(const NavArgs &a, uint64_t base1, const uint64_t (&s1)[5], uint64_t base2, const uint64_t (&s2)[5],
-                                            ChildSide<uint64_t> &k1, ChildSide<uint64_t> &k2, uint32_t &nzp, uint32_t &st_rank) {
+                                            ChildSide<uint64_t> &k1, ChildSide<uint64_t> &k2, Gaps<uint64_t> &gp, uint32_t &st_rank) {
     uint64_t prev1[4], cur1[4], prev2[4] = {0, 0, 0, 0}, cur2[4] = {0, 0, 0, 0};
     rank4(a.ix1, base1, prev1);
     st_rank++;
@@ -373,7 +383,7 @@ __device__ __forceinline__ void expand_wide(const NavArgs &a, uint64_t base1, co
             if (s2[j]) { rank4(a.ix2, b2, cur2); st_rank++; }
             else { cur2[0] = prev2[0]; cur2[1] = prev2[1]; cur2[2] = prev2[2]; cur2[3] = prev2[3]; }
         }
-        take_boundary<TWO, uint64_t>(j, cur1, prev1, cur2, prev2, k1, k2, nzp);
+        take_boundary<TWO, uint64_t>(j, cur1, prev1, cur2, prev2, k1, k2, gp);
     }
 }
 
@@ -454,6 +464,9 @@ expand_nodes_kernel(const NavArgs a, const FrameIn in, const FrameOut out) {
             for (int k = 0; k < RIN; ++k) cp_async16(recbuf + k, rec + k);
         }
         uint32_t run_cnt[4] = {0, 0, 0, 0};
+        uint4 *region[4];                                 // next free slot of the run's region, per queue
+#pragma unroll
+        for (int c = 0; c < 4; ++c) region[c] = out.base + (((size_t)c * out.K + run) * out.run_cap) * ROUT;
         for (uint32_t g0 = g_begin; g0 < g_end; g0 += 32) {
             const uint32_t g = g0 + lane;
             const bool active = g < g_end;
@@ -518,23 +531,29 @@ expand_nodes_kernel(const NavArgs a, const FrameIn in, const FrameOut out) {
 
             // ---- ranks -> children; child c is right-maximal iff >= 2 of its 5 gaps are non-empty ----
             ChildSide<W> k1, k2;
-            uint32_t nzp = 0;
+            Gaps<W> gp;
             if (active) {
-                if constexpr (IN_S) expand_small<TWO>(a, mode, multi_super, r1, r2, base1, rpos1, s1, base2, rpos2, s2, k1, k2, nzp, st_rank);
-                else expand_wide<TWO>(a, base1, s1, base2, s2, k1, k2, nzp, st_rank);
+                if constexpr (IN_S) {
+                    if (mode == SRC_WINDOW) expand_small<TWO, SRC_WINDOW>(a, multi_super, r1, r2, base1, rpos1, s1, base2, rpos2, s2, k1, k2, gp, st_rank);
+                    else if (mode == SRC_SLOTS) expand_small<TWO, SRC_SLOTS>(a, multi_super, r1, r2, base1, rpos1, s1, base2, rpos2, s2, k1, k2, gp, st_rank);
+                    else expand_small<TWO, SRC_GLOBAL>(a, multi_super, r1, r2, base1, rpos1, s1, base2, rpos2, s2, k1, k2, gp, st_rank);
+                } else {
+                    expand_wide<TWO>(a, base1, s1, base2, s2, k1, k2, gp, st_rank);
+                }
             }
             bool valid[4];
 #pragma unroll
-            for (int c = 0; c < 4; ++c) valid[c] = ((nzp >> (8 * c)) & 0xffu) >= 2u;
+            for (int c = 0; c < 4; ++c) valid[c] = gp.valid(c);
             uint32_t before[4], tot[4];
             const uint32_t vm = warp_child_slots(valid, lane, before, tot);
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
                 if ((vm >> c) & 1u) {
-                    uint4 *dst = out.base + (((size_t)c * out.K + run) * out.run_cap + run_cnt[c] + before[c]) * ROUT;
+                    uint4 *dst = region[c] + before[c] * ROUT;
                     store_child<OUT_S, W>(dst, k1, c);
                     if (TWO) store_child<OUT_S, W>(dst + RSIDE_OUT, k2, c);
                 }
+                region[c] += tot[c] * ROUT;
                 run_cnt[c] += tot[c];
             }
         }
