@@ -390,7 +390,7 @@ def main():
             n_t = h.numel()
             if n_t < world * 4 * dd.TILE:
                 return h.to(device, non_blocking=True), None, n_t
-            lo, hi = dd.index_slices(n_t, world)[0][rank]
+            lo, hi, _ = dd.index_slices(n_t, world)[0][rank]
             return h[lo:hi].to(device, non_blocking=True), n_t, hi - lo
         d1, t1, c1 = up(h1)
         d2, t2, c2 = up(h2)

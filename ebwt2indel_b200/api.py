@@ -69,7 +69,7 @@ assert CALL_REC_DTYPE.itemsize == C.sizeof(CallRec) == 56
 SYMBOLS = (
     "e2i_last_error", "e2i_version", "e2i_params_default", "e2i_params_resolve", "e2i_create", "e2i_destroy",
     "e2i_set_frontier_budget", "e2i_trim", "e2i_stream", "e2i_host_alloc", "e2i_host_free", "e2i_index_build", "e2i_index_build_device",
-    "e2i_index_slice_align", "e2i_index_alloc", "e2i_index_slice_count", "e2i_index_slice_super",
+    "e2i_index_slice_align", "e2i_index_super_count", "e2i_index_alloc", "e2i_index_slice_count", "e2i_index_slice_super",
     "e2i_index_slice_pack", "e2i_index_finish", "e2i_index_device", "e2i_index_free", "e2i_index_size", "e2i_index_F", "e2i_index_bytes", "e2i_rank_batch", "e2i_access_batch",
     "e2i_fl_batch", "e2i_rank_batch_device", "e2i_da_load", "e2i_da_load_device", "e2i_bits_fetch",
     "e2i_bits_size", "e2i_bits_free", "e2i_navigate", "e2i_navigate_shard", "e2i_lcpbits_fetch",
@@ -106,8 +106,9 @@ def lib():
         "e2i_index_build": (C.c_int, [vp, u8p, u64, C.c_uint8, C.POINTER(vp), C.POINTER(u64)]),
         "e2i_index_build_device": (C.c_int, [vp, u8p, u64, C.c_uint8, C.POINTER(vp), C.POINTER(u64)]),
         "e2i_index_slice_align": (u64, []),
+        "e2i_index_super_count": (u64, [vp]),
         "e2i_index_alloc": (C.c_int, [vp, u64, C.c_uint8, u64, C.POINTER(vp)]),
-        "e2i_index_slice_count": (C.c_int, [vp, vp, u8p, u64, u64, u64p, C.POINTER(u64)]),
+        "e2i_index_slice_count": (C.c_int, [vp, vp, u8p, u64, u64, u64, u64p, C.POINTER(u64)]),
         "e2i_index_slice_super": (C.c_int, [vp, vp, u64p, u64p]),
         "e2i_index_slice_pack": (C.c_int, [vp, vp, u8p, u64p, u64p]),
         "e2i_index_finish": (C.c_int, [vp, u64p]),
@@ -407,17 +408,24 @@ class Index:
         return out
 
     # ---- slice-wise construction (multi-GPU) ----
-    def slice_count(self, dev_slice, begin: int) -> np.ndarray:
+    def slice_count(self, dev_slice, begin: int, n_tiles: int) -> np.ndarray:
+        """Counts of one slice; n_tiles = tiles the slice owns (0 = empty slice), see distributed.index_slices."""
         counts = np.zeros(4, dtype=np.uint64)
         bad = C.c_uint64(0)
         rc = lib().e2i_index_slice_count(self.ctx.h, self.h, dev_slice.data_ptr() if dev_slice.numel() else None, begin,
-                                         dev_slice.numel(), counts.ctypes.data, C.byref(bad))
+                                         dev_slice.numel(), n_tiles, counts.ctypes.data, C.byref(bad))
         if rc == E2I_ERR_SYMBOL:
             raise ValueError(f"forbidden symbol at position {bad.value}")
         _check(rc)
         return counts
 
-    def slice_super(self, before: np.ndarray, n_super: int) -> np.ndarray:
+    @property
+    def n_super(self) -> int:
+        """Entries of the superblock table (one per 2^16 symbols)."""
+        return int(lib().e2i_index_super_count(self.h))
+
+    def slice_super(self, before: np.ndarray, n_super: int | None = None) -> np.ndarray:
+        n_super = self.n_super if n_super is None else n_super
         before = np.ascontiguousarray(before, dtype=np.uint64)
         out = np.zeros(n_super * 4, dtype=np.uint64)
         _check(lib().e2i_index_slice_super(self.ctx.h, self.h, before.ctypes.data, out.ctypes.data))

@@ -106,9 +106,9 @@ __device__ __forceinline__ void hist_da_words(const DevIndex &ix, const uint32_t
         uint32_t m = 0xffffffffu;
         if (w == w0) m &= 0xffffffffu << (begin & 31);
         if (w == w1 && (end & 31)) m &= 0xffffffffu >> (32 - (end & 31));
-        const uint32_t *blk = blocks32 + (w >> 2) * 16;      // [0..3] counters, [4..7] plane 0, [8..11] plane 1, [12..15] TERM plane
-        const int k = (int)(w & 3);
-        const uint32_t pa = __ldg(blk + 4 + k), pb = __ldg(blk + 8 + k), d = __ldg(da + w);
+        const uint32_t *blk = blocks32 + (w >> 1) * 8;       // [0..1] counters, [2..3] plane a, [4..5] plane b, [6..7] TERM plane
+        const int k = (int)(w & 1);
+        const uint32_t pa = __ldg(blk + 2 + k), pb = __ldg(blk + 4 + k), d = __ldg(da + w);
         const uint32_t m1 = m & d, m0 = m & ~d;
         c0[0] += __popc(m0 & ~pa & ~pb); c0[1] += __popc(m0 & pa & ~pb); c0[2] += __popc(m0 & ~pa & pb); c0[3] += __popc(m0 & pa & pb);
         c1[0] += __popc(m1 & ~pa & ~pb); c1[1] += __popc(m1 & pa & ~pb); c1[2] += __popc(m1 & ~pa & pb); c1[3] += __popc(m1 & pa & pb);

@@ -1,13 +1,17 @@
 // common.cuh -- shared host/device definitions of libe2i (B200 / sm_100a).
 //
 // HBM layout of the rank-indexed BWT (replaces dna_string, /root/reference/internal/dna_string.hpp):
-//   one 64-byte block per 128 symbols = 4 x uint4:
-//     [0] four u32 counts of A,C,G,T before the block, relative to the 2^32-symbol superblock
-//     [1] plane 0 (bit 0 of the code)   [2] plane 1 (bit 1 of the code)   [3] TERM plane
-//   symbol j of the block sits at bit j%32 of word j/32 of each plane (A=00, C=01, G=10, T=11;
-//   TERM has its TERM-plane bit set and 00 in the others).  A superblock table (4 x u64 absolute
-//   counts per 2^32 symbols) lifts the u32 counters to 64-bit positions.  One rank query =
-//   one aligned 64-byte fetch (two 32-byte sectors) + 16 popcounts.
+//   one 32-byte block per 64 symbols = 2 x uint4 -- exactly one DRAM sector:
+//     [0] = { #A | #C << 16, #G | #T << 16, plane a bits 0-31, plane a bits 32-63 }
+//     [1] = { plane b bits 0-31, plane b bits 32-63, TERM plane bits 0-31, TERM plane bits 32-63 }
+//   symbol j of the block sits at bit j of each plane (A=00, C=01, G=10, T=11 as (b,a); TERM has its
+//   TERM-plane bit set and 00 in the others).  The four 16-bit counters hold the occurrences BEFORE
+//   THE MIDDLE of the block (position 32), relative to the start of its 2^16-symbol superblock, so a
+//   rank query popcounts one masked 32-bit word per plane -- upwards or downwards from the middle --
+//   instead of up to four: 4 POPC per query (POPC is a quarter-rate instruction and was the limiter
+//   of the 64-byte / 128-symbol layout of round 1).  A superblock table (4 x u64 absolute counts
+//   per 2^16 symbols, 0.05 % of the index) lifts the counters to 64-bit positions.  Same 4 bits per
+//   symbol as the reference's dna_string; one rank query = one aligned 32-byte sector + 4 popcounts.
 #pragma once
 
 #include <cuda_runtime.h>
@@ -24,16 +28,18 @@
 
 namespace e2i {
 
-constexpr int kBlockSyms = 128;          // symbols per index block
-constexpr int kBlockShift = 7;
-constexpr int kSuperShift = 32;          // symbols per superblock = 2^32
-constexpr int kTileSyms = 16384;         // symbols per index-build tile (128 blocks)
+constexpr int kBlockSyms = 64;           // symbols per index block
+constexpr int kBlockShift = 6;
+constexpr int kBlockU4 = 2;              // uint4 per block
+constexpr int kSuperShift = 16;          // symbols per superblock = 2^16
+constexpr int kTileSyms = 16384;         // symbols per index-build tile (256 blocks)
 constexpr int kTileShift = 14;
+constexpr int kTileBlocks = kTileSyms / kBlockSyms;
 constexpr int kSuperTileShift = kSuperShift - kTileShift;
 
 struct DevIndex {
-    const uint4 *blocks;      // 4 x uint4 per block
-    const uint64_t *super;    // 4 x u64 per superblock
+    const uint4 *blocks;      // 2 x uint4 per block
+    const uint64_t *super;    // 4 x u64 per superblock (absolute counts at its start)
     uint64_t n;
     uint64_t F[4];            // F_A, F_C, F_G, F_T (dna_bwt.hpp:412-415)
 };
@@ -130,7 +136,7 @@ struct Accounting {            // adds what a call launched / copied to its e2i_
 
 struct e2i_index {
     e2i_ctx *ctx = nullptr;
-    uint4 *blocks = nullptr;
+    uint4 *blocks = nullptr;      // kBlockU4 x uint4 per block
     uint64_t *super = nullptr;
     uint64_t n = 0, n_blocks = 0, n_super = 0, bytes = 0;
     uint64_t F[4] = {0, 0, 0, 0};
@@ -183,66 +189,34 @@ __device__ __forceinline__ uint32_t low_mask(int t) {
     return m;
 }
 
-__device__ __forceinline__ uint32_t prefix_mask32(int off, int word) {
-    // bits of `word` (32 symbols) that lie before block offset `off`
-    return low_mask(off - 32 * word);
-}
-
-// #A,#C,#G,#T among the first `off` symbols of a block given its three planes
-__device__ __forceinline__ void block_popc(const uint4 a, const uint4 b, const uint4 t, int off, uint32_t out[4]) {
-    const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w}, tw[4] = {t.x, t.y, t.z, t.w};
-    uint32_t nN = 0, nC = 0, nG = 0, nT = 0;
+// #A,#C,#G,#T before offset `off` (0..63) of a block, relative to the block's superblock: the counters
+// hold the counts before the middle, the masked half-word is added (off >= 32) or subtracted
+__device__ __forceinline__ void block_rank(const uint4 lo, const uint4 hi, int off, uint32_t out[4]) {
+    const bool up = off >= 32;
+    const uint32_t a = up ? lo.w : lo.z, b = up ? hi.y : hi.x, t = up ? hi.w : hi.z;
+    const uint32_t lm = low_mask(off & 31);               // the bits of the half that lie before `off`
+    const uint32_t nt = ~t & (up ? lm : ~lm);             // non-terminators between the middle and `off`
+    const uint32_t pn = __popc(nt), pa = __popc(nt & a), pb = __popc(nt & b), pab = __popc(nt & a & b);
+    const uint32_t v[4] = {pn - pa - pb + pab, pa - pab, pb - pab, pab};
+    const uint32_t c[4] = {lo.x & 0xffffu, lo.x >> 16, lo.y & 0xffffu, lo.y >> 16};
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const uint32_t nt = ~tw[k] & low_mask(off - 32 * k);
-        nN += __popc(nt);
-        nC += __popc(nt & aw[k]);
-        nG += __popc(nt & bw[k]);
-        nT += __popc(nt & aw[k] & bw[k]);
-    }
-    nC -= nT;
-    nG -= nT;
-    out[0] = nN - nC - nG - nT;
-    out[1] = nC;
-    out[2] = nG;
-    out[3] = nT;
+    for (int k = 0; k < 4; ++k) out[k] = up ? c[k] + v[k] : c[k] - v[k];
 }
 
-// Index blocks staged in shared memory: block r of the window lives at stage[4r .. 4r+3] with its
-// four 16-byte quarters XOR-swizzled by (r >> 1) & 3, so that lanes reading the same quarter of
-// eight consecutive blocks hit eight different bank groups.
-__device__ __forceinline__ int stage_slot(uint32_t r, int q) { return (int)(r * 4 + (q ^ ((r >> 1) & 3))); }
+// Index blocks staged in shared memory: slot r lives at stage[2r], stage[2r+1] with its two 16-byte
+// halves swapped when bit 2 of r is set, so that lanes reading the same half of random slots spread
+// over all eight 16-byte bank groups.
+__device__ __forceinline__ int stage_slot(uint32_t r, int h) { return (int)(r * 2 + (h ^ ((r >> 2) & 1))); }
 
-// a2: parallel_rank (dna_string.hpp:140-152): #A,#C,#G,#T in [0, i), 0 <= i <= n, in W arithmetic:
-// W = uint64_t gives absolute counts; W = uint32_t gives them modulo 2^32, which is all that a
-// DIFFERENCE of two ranks less than 2^32 apart needs (half the integer work of the 64-bit form).
-// Blocks [blk_lo, blk_lo + n_staged) are read from the shared-memory window, the others from HBM.
-template <typename W>
-__device__ __forceinline__ void rank4w(const DevIndex &ix, const uint4 *stage, uint32_t blk_lo, uint32_t n_staged,
-                                       uint64_t i, W out[4]) {
-    const uint32_t blk = (uint32_t)(i >> kBlockShift);      // n < 2^39
-    const uint32_t rel = blk - blk_lo;                       // wraps to a huge value below the window
-    uint4 cnt, a, b, t;
-    if (rel < n_staged) {
-        cnt = stage[stage_slot(rel, 0)]; a = stage[stage_slot(rel, 1)]; b = stage[stage_slot(rel, 2)]; t = stage[stage_slot(rel, 3)];
-    } else {
-        const uint4 *p = ix.blocks + (size_t)blk * 4;
-        cnt = __ldg(p); a = __ldg(p + 1); b = __ldg(p + 2); t = __ldg(p + 3);
-    }
-    uint32_t pc[4];
-    block_popc(a, b, t, (int)((uint32_t)i & (kBlockSyms - 1)), pc);
-    out[0] = (W)cnt.x + pc[0];
-    out[1] = (W)cnt.y + pc[1];
-    out[2] = (W)cnt.z + pc[2];
-    out[3] = (W)cnt.w + pc[3];
-    if (ix.n >> kSuperShift) {                               // more than one superblock: add its base counts
-        const uint64_t *sb = ix.super + (i >> kSuperShift) * 4;
-        out[0] += (W)sb[0]; out[1] += (W)sb[1]; out[2] += (W)sb[2]; out[3] += (W)sb[3];
-    }
-}
-
+// a2: parallel_rank (dna_string.hpp:140-152): #A,#C,#G,#T in [0, i), 0 <= i <= n, read from HBM
 __device__ __forceinline__ void rank4(const DevIndex &ix, uint64_t i, uint64_t out[4]) {
-    rank4w<uint64_t>(ix, nullptr, 0u, 0u, i, out);
+    const uint4 *p = ix.blocks + (i >> kBlockShift) * kBlockU4;
+    const uint4 lo = __ldg(p), hi = __ldg(p + 1);
+    uint32_t r[4];
+    block_rank(lo, hi, (int)((uint32_t)i & (kBlockSyms - 1)), r);
+    const ulonglong2 *sb = reinterpret_cast<const ulonglong2 *>(ix.super + (i >> kSuperShift) * 4);
+    const ulonglong2 s0 = __ldg(sb), s1 = __ldg(sb + 1);
+    out[0] = s0.x + r[0]; out[1] = s0.y + r[1]; out[2] = s1.x + r[2]; out[3] = s1.y + r[3];
 }
 
 // 16-byte asynchronous global -> shared copy (LDGSTS), L2-only caching
@@ -252,17 +226,17 @@ __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-// single-symbol count before block `blk` (absolute)
-__device__ __forceinline__ uint64_t block_count(const DevIndex &ix, uint64_t blk, int c) {
-    const uint32_t *cnt = reinterpret_cast<const uint32_t *>(ix.blocks + blk * 4);
+// occurrences of symbol c before the MIDDLE of block `blk` (absolute)
+__device__ __forceinline__ uint64_t mid_count(const DevIndex &ix, uint64_t blk, int c) {
+    const uint16_t *cnt = reinterpret_cast<const uint16_t *>(ix.blocks + blk * kBlockU4);
     return ix.super[(blk >> (kSuperShift - kBlockShift)) * 4 + c] + __ldg(cnt + c);
 }
 
 // a3: operator[] (dna_string.hpp:113-135): code 0..3 = A,C,G,T, 4 = TERM
 __device__ __forceinline__ int access_code(const DevIndex &ix, uint64_t i) {
-    const uint32_t *w = reinterpret_cast<const uint32_t *>(ix.blocks + (i >> kBlockShift) * 4);
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(ix.blocks + (i >> kBlockShift) * kBlockU4);
     const int off = (int)(i & (kBlockSyms - 1)), k = off >> 5, sh = off & 31;
-    const uint32_t a = (__ldg(w + 4 + k) >> sh) & 1u, b = (__ldg(w + 8 + k) >> sh) & 1u, t = (__ldg(w + 12 + k) >> sh) & 1u;
+    const uint32_t a = (__ldg(w + 2 + k) >> sh) & 1u, b = (__ldg(w + 4 + k) >> sh) & 1u, t = (__ldg(w + 6 + k) >> sh) & 1u;
     return t ? 4 : (int)(a | (b << 1));
 }
 
@@ -271,26 +245,33 @@ __device__ __forceinline__ int f_code(const DevIndex &ix, uint64_t i) {
     return i < ix.F[0] ? 4 : i < ix.F[1] ? 0 : i < ix.F[2] ? 1 : i < ix.F[3] ? 2 : 3;
 }
 
+// the 32 symbols of half h (0 = first, 1 = second) of block blk that equal c, as a bit mask
+__device__ __forceinline__ uint32_t half_mask(const DevIndex &ix, uint64_t blk, int h, int c) {
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(ix.blocks + blk * kBlockU4);
+    const uint32_t a = __ldg(w + 2 + h), b = __ldg(w + 4 + h), t = __ldg(w + 6 + h);
+    return ~t & ((c & 1) ? a : ~a) & ((c & 2) ? b : ~b);
+}
+
 // a4: select (dna_string.hpp:182-188, 254-272): position of the r-th (0-based) symbol c.
-// Binary search on the interleaved block counters, then a bit select inside the block.
+// Binary search on the mid-block counters (last block whose middle has at most r occurrences before
+// it), then a bit select in the 64 symbols from that middle to the next one.
 __device__ __forceinline__ uint64_t select_sym(const DevIndex &ix, uint64_t r, int c) {
-    uint64_t lo = 0, hi = ix.n >> kBlockShift;  // last block whose count <= r lies in [lo, hi]
+    if (mid_count(ix, 0, c) > r) {                        // inside the first half of block 0
+        const uint32_t m = half_mask(ix, 0, 0, c);
+        return (uint64_t)__fns(m, 0, (int)r + 1);
+    }
+    uint64_t lo = 0, hi = ix.n >> kBlockShift;            // last block with mid_count <= r lies in [lo, hi]
     while (lo < hi) {
         const uint64_t mid = (lo + hi + 1) >> 1;
-        if (block_count(ix, mid, c) <= r) lo = mid; else hi = mid - 1;
+        if (mid_count(ix, mid, c) <= r) lo = mid; else hi = mid - 1;
     }
-    uint32_t k = (uint32_t)(r - block_count(ix, lo, c));  // k-th occurrence inside block lo
-    const uint4 *p = ix.blocks + lo * 4;
-    const uint4 a = __ldg(p + 1), b = __ldg(p + 2), t = __ldg(p + 3);
-    const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w}, tw[4] = {t.x, t.y, t.z, t.w};
-#pragma unroll
-    for (int w = 0; w < 4; ++w) {
-        const uint32_t m = ~tw[w] & ((c & 1) ? aw[w] : ~aw[w]) & ((c & 2) ? bw[w] : ~bw[w]);
-        const uint32_t pc = __popc(m);
-        if (k < pc) return (lo << kBlockShift) + 32 * w + __fns(m, 0, (int)k + 1);
-        k -= pc;
-    }
-    return ~0ull;  // unreachable for r < #c
+    uint32_t k = (uint32_t)(r - mid_count(ix, lo, c));    // k-th occurrence at or after the middle of block lo
+    const uint32_t m1 = half_mask(ix, lo, 1, c);
+    const uint32_t p1 = __popc(m1);
+    if (k < p1) return (lo << kBlockShift) + 32 + __fns(m1, 0, (int)k + 1);
+    k -= p1;
+    const uint32_t m2 = half_mask(ix, lo + 1, 0, c);
+    return ((lo + 1) << kBlockShift) + __fns(m2, 0, (int)k + 1);   // exists for r < #c
 }
 
 // FL (dna_bwt.hpp:115-133); the caller guarantees F(i) != TERM

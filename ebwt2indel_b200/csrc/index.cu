@@ -3,7 +3,7 @@
 // Replaces dna_string(path, TERM) + build_rank_support (/root/reference/internal/dna_string.hpp:
 // 55-110, 275-315, 320-369) and the F-array scan of dna_bwt(path, TERM) (dna_bwt.hpp:36-62).
 // Three streaming kernels: count symbols per 16384-symbol tile, scan the tile totals, pack
-// (second read of the ASCII, one write of the 64-byte blocks).  HBM traffic: 2n read + n/2 write.
+// (second read of the ASCII, one write of the 32-byte blocks).  HBM traffic: 2n read + n/2 write.
 #include "common.cuh"
 
 namespace e2i {
@@ -47,7 +47,7 @@ __device__ __forceinline__ Piece encode_piece(uint4 v, uint64_t pos0, uint64_t n
         if (ok != live && pc.bad < 0) pc.bad = 4 * q + ((__ffs((int)(~ok & live)) - 1) >> 3);
         pc.p0 |= gather4(isC | isT) << (4 * q);
         pc.p1 |= gather4(isG | isT) << (4 * q);
-        pc.pt |= gather4(isX) << (4 * q);
+        pc.pt |= gather4(isX | ~live) << (4 * q);                       // positions past the end count as terminators: never as A
         pc.cnt += (uint32_t)__popc(isA & 0x01010101u) | ((uint32_t)__popc(isC & 0x01010101u) << 8) |
                   ((uint32_t)__popc(isG & 0x01010101u) << 16) | ((uint32_t)__popc(isT & 0x01010101u) << 24);
     }
@@ -152,7 +152,7 @@ scan_tiles_kernel(const uint4 *__restrict__ tile_cnt, uint64_t n_tiles, ulonglon
     if (threadIdx.x < 4) totals[threadIdx.x] = s_carry[threadIdx.x];
 }
 
-// Kernel 3: pack one tile (128 blocks) per CTA iteration.
+// Kernel 3: pack one tile (256 blocks of 64 symbols) per CTA iteration.
 __global__ void __launch_bounds__(kBuildThreads)
 pack_tiles_kernel(const uint8_t *__restrict__ ascii, uint64_t n, uint32_t term, uint64_t tile0, uint64_t n_tiles,
                   const ulonglong4 *__restrict__ tile_prefix, const ulonglong4 base,
@@ -162,18 +162,23 @@ pack_tiles_kernel(const uint8_t *__restrict__ ascii, uint64_t n, uint32_t term, 
     // tile_prefix is local to the slice and `base` holds the counts before it.  Whole-string build:
     // tile0 = 0, base = 0, super_in = nullptr (superblock entries are written here).  Slice build:
     // super_in = the complete table of absolute counts at the superblock starts.
+    static_assert(kTileBlocks == kBuildThreads, "one thread per block in the per-block scan");
     ascii -= tile0 << kTileShift;
     __shared__ uint16_t s_plane[3][kPiecesPerTile];
     __shared__ uint32_t s_cnt[kPiecesPerTile];
-    __shared__ unsigned long long s_blk[kTileSyms / kBlockSyms];      // exclusive per-block prefix, 4 x 16 bit
-    __shared__ unsigned long long s_wsum[4];
+    __shared__ unsigned long long s_mid[kTileBlocks];                 // counts before the middle of each block, 4 x 16 bit, tile-relative
+    __shared__ unsigned long long s_wsum[kBuildThreads / 32];
+    auto widen = [](uint32_t c) {
+        return (unsigned long long)(c & 0xffu) | ((unsigned long long)((c >> 8) & 0xffu) << 16) |
+               ((unsigned long long)((c >> 16) & 0xffu) << 32) | ((unsigned long long)(c >> 24) << 48);
+    };
     for (uint64_t lt = blockIdx.x; lt < n_tiles; lt += gridDim.x) {
         const uint64_t tile = tile0 + lt;
 #pragma unroll
         for (int it = 0; it < kPiecesPerThread; ++it) {
             const int piece = it * kBuildThreads + threadIdx.x;
             const uint64_t pos0 = (tile << kTileShift) + (uint64_t)piece * 16;
-            Piece pc{0, 0, 0, 0, -1};
+            Piece pc{0, 0, 0xffffu, 0, -1};                                   // past the end: terminator bits, no counts
             if (pos0 < n) pc = encode_piece(load_piece(ascii, pos0, n), pos0, n, term);
             s_plane[0][piece] = (uint16_t)pc.p0;
             s_plane[1][piece] = (uint16_t)pc.p1;
@@ -181,29 +186,22 @@ pack_tiles_kernel(const uint8_t *__restrict__ ascii, uint64_t n, uint32_t term, 
             s_cnt[piece] = pc.cnt;
         }
         __syncthreads();
-        // per-block totals (8 pieces each) and their exclusive scan over the 128 blocks of the tile
+        // per-block totals (4 pieces each) and their exclusive scan over the 256 blocks of the tile
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-        unsigned long long mine = 0, incl = 0;
-        if (threadIdx.x < 128) {
+        const unsigned long long half = widen(s_cnt[threadIdx.x * 4]) + widen(s_cnt[threadIdx.x * 4 + 1]);
+        const unsigned long long mine = half + widen(s_cnt[threadIdx.x * 4 + 2]) + widen(s_cnt[threadIdx.x * 4 + 3]);
+        unsigned long long incl = mine;
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const uint32_t c = s_cnt[threadIdx.x * 8 + k];
-                mine += (unsigned long long)(c & 0xffu) | ((unsigned long long)((c >> 8) & 0xffu) << 16) |
-                        ((unsigned long long)((c >> 16) & 0xffu) << 32) | ((unsigned long long)(c >> 24) << 48);
-            }
-            incl = mine;
-#pragma unroll
-            for (int s = 1; s < 32; s <<= 1) {
-                const unsigned long long y = __shfl_up_sync(0xffffffffu, incl, s);
-                if (lane >= s) incl += y;
-            }
-            if (lane == 31) s_wsum[warp] = incl;
+        for (int s = 1; s < 32; s <<= 1) {
+            const unsigned long long y = __shfl_up_sync(0xffffffffu, incl, s);
+            if (lane >= s) incl += y;
         }
+        if (lane == 31) s_wsum[warp] = incl;
         __syncthreads();
-        if (threadIdx.x < 128) {
+        {
             unsigned long long off = 0;
             for (int w = 0; w < warp; ++w) off += s_wsum[w];
-            s_blk[threadIdx.x] = off + incl - mine;
+            s_mid[threadIdx.x] = off + incl - mine + half;           // 16-bit fields: a tile has 16384 symbols
         }
         __syncthreads();
         ulonglong4 tp = tile_prefix[lt], sp;
@@ -218,25 +216,27 @@ pack_tiles_kernel(const uint8_t *__restrict__ ascii, uint64_t n, uint32_t term, 
                 s[0] = tp.x; s[1] = tp.y; s[2] = tp.z; s[3] = tp.w;
             }
         }
-        // 128 blocks x 4 uint4 = 512 uint4 per tile, written coalesced
-        uint4 *out = blocks + (tile << (kTileShift - kBlockShift)) * 4;
+        // 256 blocks x 2 uint4 = 512 uint4 per tile, written coalesced
+        uint4 *out = blocks + (tile << (kTileShift - kBlockShift)) * kBlockU4;
 #pragma unroll
         for (int it = 0; it < 2; ++it) {
             const int q = it * kBuildThreads + threadIdx.x;
-            const int blk = q >> 2, part = q & 3;
+            const int blk = q >> 1, part = q & 1;
             uint4 v;
             if (part == 0) {
-                const unsigned long long e = s_blk[blk];
-                v.x = (uint32_t)(tp.x - sp.x) + (uint32_t)(e & 0xffff);
-                v.y = (uint32_t)(tp.y - sp.y) + (uint32_t)((e >> 16) & 0xffff);
-                v.z = (uint32_t)(tp.z - sp.z) + (uint32_t)((e >> 32) & 0xffff);
-                v.w = (uint32_t)(tp.w - sp.w) + (uint32_t)(e >> 48);
+                const unsigned long long e = s_mid[blk];
+                const uint16_t *pl = s_plane[0] + blk * 4;
+                // counts before the middle of the block, relative to the superblock start (< 2^16)
+                v.x = ((uint32_t)(tp.x - sp.x) + (uint32_t)(e & 0xffff)) | (((uint32_t)(tp.y - sp.y) + (uint32_t)((e >> 16) & 0xffff)) << 16);
+                v.y = ((uint32_t)(tp.z - sp.z) + (uint32_t)((e >> 32) & 0xffff)) | (((uint32_t)(tp.w - sp.w) + (uint32_t)(e >> 48)) << 16);
+                v.z = pl[0] | ((uint32_t)pl[1] << 16);
+                v.w = pl[2] | ((uint32_t)pl[3] << 16);
             } else {
-                const uint16_t *pl = s_plane[part - 1] + blk * 8;
-                v.x = pl[0] | ((uint32_t)pl[1] << 16);
-                v.y = pl[2] | ((uint32_t)pl[3] << 16);
-                v.z = pl[4] | ((uint32_t)pl[5] << 16);
-                v.w = pl[6] | ((uint32_t)pl[7] << 16);
+                const uint16_t *pb = s_plane[1] + blk * 4, *pt = s_plane[2] + blk * 4;
+                v.x = pb[0] | ((uint32_t)pb[1] << 16);
+                v.y = pb[2] | ((uint32_t)pb[3] << 16);
+                v.z = pt[0] | ((uint32_t)pt[1] << 16);
+                v.w = pt[2] | ((uint32_t)pt[3] << 16);
             }
             out[q] = v;
         }
@@ -305,9 +305,9 @@ extern "C" int e2i_index_build_device(e2i_ctx *ctx, const uint8_t *dev_ascii, ui
     ix->n = n;
     ix->term = term;
     ix->n_blocks = n / kBlockSyms + 1;                       // rank(n) must be addressable (dna_string.hpp:62)
-    const uint64_t n_tiles = (ix->n_blocks + 127) / 128;
+    const uint64_t n_tiles = (ix->n_blocks + kTileBlocks - 1) / kTileBlocks;
     ix->n_super = (n >> kSuperShift) + 1;
-    const size_t blk_bytes = n_tiles * 128 * 64;
+    const size_t blk_bytes = n_tiles * kTileBlocks * kBlockU4 * sizeof(uint4);
     ix->bytes = blk_bytes + ix->n_super * 32;
     uint4 *tile_cnt = nullptr;
     ulonglong4 *tile_prefix = nullptr;
@@ -363,10 +363,10 @@ extern "C" int e2i_index_alloc(e2i_ctx *ctx, uint64_t n, uint8_t term, uint64_t 
     ix->n = n;
     ix->term = term;
     ix->n_blocks = n / kBlockSyms + 1;
-    uint64_t n_tiles = (ix->n_blocks + 127) / 128;
+    uint64_t n_tiles = (ix->n_blocks + kTileBlocks - 1) / kTileBlocks;
     n_tiles = (n_tiles + tile_multiple - 1) / tile_multiple * tile_multiple;   // equal slices for the all-gather
     ix->n_super = (n >> kSuperShift) + 1;
-    const size_t blk_bytes = n_tiles * 128 * 64;
+    const size_t blk_bytes = n_tiles * kTileBlocks * kBlockU4 * sizeof(uint4);
     ix->bytes = blk_bytes + ix->n_super * 32;
     if (dmalloc(ctx, &ix->blocks, blk_bytes) != cudaSuccess || dmalloc(ctx, &ix->super, ix->n_super * 32) != cudaSuccess) {
         cudaGetLastError();
@@ -379,18 +379,24 @@ extern "C" int e2i_index_alloc(e2i_ctx *ctx, uint64_t n, uint8_t term, uint64_t 
 }
 
 extern "C" int e2i_index_slice_count(e2i_ctx *ctx, e2i_index *ix, const uint8_t *dev_slice, uint64_t begin, uint64_t len,
-                                     uint64_t counts[4], uint64_t *bad_pos) {
+                                     uint64_t n_tiles, uint64_t counts[4], uint64_t *bad_pos) {
     if (!ctx || !ix || !counts || (len && !dev_slice)) { set_error("e2i_index_slice_count: null argument"); return E2I_ERR_ARG; }
-    if ((begin & (kTileSyms - 1)) || begin + len > ix->n || (reinterpret_cast<uintptr_t>(dev_slice) & 15)) { set_error("e2i_index_slice_count: slice must start on a multiple of %d symbols, lie inside the string and be 16-byte aligned", kTileSyms); return E2I_ERR_ARG; }
+    const uint64_t all_tiles = (ix->n_blocks + kTileBlocks - 1) / kTileBlocks;
+    if (n_tiles && ((begin & (kTileSyms - 1)) || begin + len > ix->n || (reinterpret_cast<uintptr_t>(dev_slice) & 15) ||
+                    (begin >> kTileShift) + n_tiles > all_tiles || len > n_tiles * kTileSyms)) {
+        set_error("e2i_index_slice_count: slice must start on a multiple of %d symbols, lie inside the string and be 16-byte aligned", kTileSyms);
+        return E2I_ERR_ARG;
+    }
     E2I_CUDA_TRY(cudaSetDevice(ctx->device));
     cudaStream_t s = ctx->stream;
     dfree(ctx, ix->slice_cnt); dfree(ctx, ix->slice_prefix);
     ix->slice_cnt = nullptr; ix->slice_prefix = nullptr;
-    ix->slice_begin = begin;
-    ix->slice_len = len;
-    // the slice that reaches n also owns the block that makes rank(n) addressable
-    const uint64_t end = begin + len;
-    ix->slice_tiles = end == ix->n ? (ix->n_blocks + 127) / 128 - (begin >> kTileShift) : (len + kTileSyms - 1) >> kTileShift;
+    ix->slice_begin = n_tiles ? begin : 0;
+    ix->slice_len = n_tiles ? len : 0;
+    // n_tiles: the tiles this slice owns; the owner of the last tile also packs the block that makes rank(n)
+    // addressable (that tile may hold no symbol at all).  An empty slice (n_tiles == 0) does nothing.
+    ix->slice_tiles = n_tiles;
+    const uint64_t end = ix->slice_begin + ix->slice_len;
     const uint64_t nt = ix->slice_tiles;
     for (int k = 0; k < 4; ++k) counts[k] = 0;
     if (nt == 0) return E2I_OK;
@@ -418,19 +424,22 @@ extern "C" int e2i_index_slice_count(e2i_ctx *ctx, e2i_index *ix, const uint8_t 
     return E2I_OK;
 }
 
+extern "C" uint64_t e2i_index_super_count(const e2i_index *ix) { return ix ? ix->n_super : 0; }
+
 extern "C" int e2i_index_slice_super(e2i_ctx *ctx, e2i_index *ix, const uint64_t before[4], uint64_t *host_super) {
     if (!ctx || !ix || !before || !host_super) { set_error("e2i_index_slice_super: null argument"); return E2I_ERR_ARG; }
     E2I_CUDA_TRY(cudaSetDevice(ctx->device));
-    const uint64_t tile0 = ix->slice_begin >> kTileShift;
-    for (uint64_t sb = 0; sb < ix->n_super; ++sb) {
-        uint64_t *o = host_super + sb * 4;
-        o[0] = o[1] = o[2] = o[3] = 0;
-        const uint64_t tile = sb << kSuperTileShift;              // first tile of the superblock
-        if (tile < tile0 || tile >= tile0 + ix->slice_tiles) continue;
-        unsigned long long tp[4];
-        E2I_CUDA_TRY(cudaMemcpy(tp, static_cast<ulonglong4 *>(ix->slice_prefix) + (tile - tile0), sizeof tp, cudaMemcpyDeviceToHost));
-        for (int k = 0; k < 4; ++k) o[k] = before[k] + tp[k];
-    }
+    std::memset(host_super, 0, ix->n_super * 32);
+    const uint64_t tile0 = ix->slice_begin >> kTileShift, step = 1ull << kSuperTileShift;
+    // superblocks that start inside this slice: tiles tile0 <= sb * step < tile0 + slice_tiles
+    const uint64_t sb_lo = (tile0 + step - 1) / step, sb_hi = std::min<uint64_t>(ix->n_super, (tile0 + ix->slice_tiles + step - 1) / step);
+    if (sb_lo >= sb_hi || ix->slice_tiles == 0) return E2I_OK;
+    // one strided copy: the prefix entry (32 bytes) of every `step`-th tile
+    E2I_CUDA_TRY(cudaMemcpy2DAsync(host_super + sb_lo * 4, 32, static_cast<ulonglong4 *>(ix->slice_prefix) + (sb_lo * step - tile0), 32 * step, 32,
+                                   sb_hi - sb_lo, cudaMemcpyDeviceToHost, ctx->stream));
+    E2I_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    for (uint64_t sb = sb_lo; sb < sb_hi; ++sb)
+        for (int k = 0; k < 4; ++k) host_super[sb * 4 + k] += before[k];
     return E2I_OK;
 }
 

@@ -46,7 +46,7 @@ namespace e2i {
 
 constexpr int kNavWarps = 4;                          // warps per CTA; every warp works on its own
 constexpr int kNavThreads = kNavWarps * 32;
-constexpr int kWarpStage = 64;                        // index blocks staged in shared memory per warp (4 KB)
+constexpr int kWarpStage = 128;                       // index blocks staged in shared memory per warp (4 KB)
 constexpr int kMaxRun = 1024;                         // records per run (multiple of 32), upper bound
 #ifndef E2I_NODE_CTAS
 #define E2I_NODE_CTAS 7                               // resident CTAs per SM the one-BWT kernels are compiled for
@@ -182,10 +182,10 @@ struct RankSrc {               // per thread and BWT: relative position 0 = star
     uint32_t d1;               // SLOTS: relative index of the second staged block (0 = none)
 };
 
-__device__ __forceinline__ void load_block_smem(const uint4 *stage, uint32_t slot, uint4 &cnt, uint4 &a, uint4 &b, uint4 &t) {
-    const uint32_t sw = (slot >> 1) & 3u;
-    const uint4 *p = stage + slot * 4;
-    cnt = p[sw]; a = p[1u ^ sw]; b = p[2u ^ sw]; t = p[3u ^ sw];
+__device__ __forceinline__ void load_block_smem(const uint4 *stage, uint32_t slot, uint4 &lo, uint4 &hi) {
+    const uint32_t sw = (slot >> 2) & 1u;
+    const uint4 *p = stage + slot * 2;
+    lo = p[sw]; hi = p[1u ^ sw];
 }
 
 // #A,#C,#G,#T before relative position rpos, counted from the start of the superblock of origin_blk
@@ -194,21 +194,16 @@ __device__ __forceinline__ void load_block_smem(const uint4 *stage, uint32_t slo
 template <int MODE>
 __device__ __forceinline__ void rank_rel(const DevIndex &ix, const RankSrc &r, bool multi_super, uint32_t rpos, uint32_t out[4]) {
     const uint32_t rel = rpos >> kBlockShift;
-    uint4 cnt, a, b, t;
+    uint4 lo, hi;
     if (MODE == SRC_WINDOW) {
-        load_block_smem(r.stage, r.slot0 + rel, cnt, a, b, t);
+        load_block_smem(r.stage, r.slot0 + rel, lo, hi);
     } else if (MODE == SRC_SLOTS && (rel == 0 || rel == r.d1)) {
-        load_block_smem(r.stage, r.slot0 + (rel != 0), cnt, a, b, t);
+        load_block_smem(r.stage, r.slot0 + (rel != 0), lo, hi);
     } else {
-        const uint4 *p = ix.blocks + (size_t)(r.origin_blk + rel) * 4;
-        cnt = __ldg(p); a = __ldg(p + 1); b = __ldg(p + 2); t = __ldg(p + 3);
+        const uint4 *p = ix.blocks + (size_t)(r.origin_blk + rel) * kBlockU4;
+        lo = __ldg(p); hi = __ldg(p + 1);
     }
-    uint32_t pc[4];
-    block_popc(a, b, t, (int)(rpos & (kBlockSyms - 1)), pc);
-    out[0] = cnt.x + pc[0];
-    out[1] = cnt.y + pc[1];
-    out[2] = cnt.z + pc[2];
-    out[3] = cnt.w + pc[3];
+    block_rank(lo, hi, (int)(rpos & (kBlockSyms - 1)), out);
     if (multi_super) {                                   // the interval may reach into the next superblock
         const uint32_t sb = (r.origin_blk + rel) >> (kSuperShift - kBlockShift), sb0 = r.origin_blk >> (kSuperShift - kBlockShift);
         if (sb != sb0) {
@@ -336,14 +331,8 @@ __device__ __forceinline__ void expand_small(const NavArgs &a, bool multi_super,
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
         // prev is relative to the superblock of the node's first block, which is the superblock of `base`
-        uint64_t b1 = a.ix1.F[c] + prev1[c];
-        if (a.ix1.n >> kSuperShift) b1 += a.ix1.super[(base1 >> kSuperShift) * 4 + c];
-        k1.base[c] = b1;
-        if (TWO) {
-            uint64_t b2 = a.ix2.F[c] + prev2[c];
-            if (a.ix2.n >> kSuperShift) b2 += a.ix2.super[(base2 >> kSuperShift) * 4 + c];
-            k2.base[c] = b2;
-        }
+        k1.base[c] = a.ix1.F[c] + prev1[c] + __ldg(a.ix1.super + (base1 >> kSuperShift) * 4 + c);
+        if (TWO) k2.base[c] = a.ix2.F[c] + prev2[c] + __ldg(a.ix2.super + (base2 >> kSuperShift) * 4 + c);
     }
 #pragma unroll
     for (int j = 0; j < 5; ++j) {
@@ -388,19 +377,19 @@ __device__ __forceinline__ void expand_wide(const NavArgs &a, uint64_t base1, co
 }
 
 // SLOTS staging: every lane has announced up to two block ids in need[2 * lane], need[2 * lane + 1]
-// (~0u = none); the warp copies them with 4 consecutive lanes per 64-byte block
+// (~0u = none); the warp copies them with 2 consecutive lanes per 32-byte block
 __device__ __forceinline__ void stage_slots(const uint4 *blocks, uint4 *stage, const uint32_t *need, int lane) {
 #pragma unroll
-    for (int it = 0; it < kWarpStage * 4 / 32; ++it) {
+    for (int it = 0; it < 64 * kBlockU4 / 32; ++it) {
         const uint32_t k = lane + it * 32;
-        const uint32_t slot = k >> 2, blk = need[slot];
-        if (blk != ~0u) cp_async16(&stage[stage_slot(slot, k & 3)], blocks + (size_t)blk * 4 + (k & 3));
+        const uint32_t slot = k >> 1, blk = need[slot];
+        if (blk != ~0u) cp_async16(&stage[stage_slot(slot, k & 1)], blocks + (size_t)blk * kBlockU4 + (k & 1));
     }
 }
 
 __device__ __forceinline__ void stage_window(const DevIndex &ix, uint4 *stage, uint32_t lo_blk, uint32_t n_blk, int lane) {
-    const uint4 *src = ix.blocks + (size_t)lo_blk * 4;
-    for (uint32_t k = lane; k < n_blk * 4; k += 32) cp_async16(&stage[stage_slot(k >> 2, k & 3)], src + k);
+    const uint4 *src = ix.blocks + (size_t)lo_blk * kBlockU4;
+    for (uint32_t k = lane; k < n_blk * kBlockU4; k += 32) cp_async16(&stage[stage_slot(k >> 1, k & 1)], src + k);
 }
 
 // position of this lane's children inside the step (before[c]) and the step's totals (tot[c])
@@ -426,9 +415,9 @@ __device__ __forceinline__ uint32_t warp_child_slots(const bool (&valid)[4], int
 template <bool TWO, bool IN_S>
 struct NodeSmem {
     static constexpr int RIN = (IN_S ? 1 : 3) * (TWO ? 2 : 1);    // uint4 per input record
-    uint4 stage[kNavWarps][IN_S ? kWarpStage * 4 : 1];            // staged index blocks, per warp
+    uint4 stage[kNavWarps][IN_S ? kWarpStage * kBlockU4 : 1];     // staged index blocks, per warp
     uint4 recbuf[kNavWarps][32 * RIN];                            // records of the next step (slot = lane)
-    uint32_t need[kNavWarps][IN_S ? kWarpStage : 1];              // SLOTS staging: block ids wanted by the lanes
+    uint32_t need[kNavWarps][IN_S ? 64 : 1];                      // SLOTS staging: block ids wanted by the lanes
 };
 
 template <bool TWO, bool IN_S, bool OUT_S>
@@ -440,7 +429,7 @@ expand_nodes_kernel(const NavArgs a, const FrameIn in, const FrameOut out) {
     constexpr int STAGE = TWO ? kWarpStage / 2 : kWarpStage;               // blocks staged per BWT
     __shared__ __align__(1024) SM sm;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint4 *stage1 = sm.stage[warp], *stage2 = sm.stage[warp] + (IN_S ? STAGE * 4 : 0);
+    uint4 *stage1 = sm.stage[warp], *stage2 = sm.stage[warp] + (IN_S ? STAGE * kBlockU4 : 0);
     uint4 *recbuf = sm.recbuf[warp] + lane * RIN;
     uint32_t *need = sm.need[warp];
 
@@ -584,25 +573,19 @@ expand_nodes_kernel(const NavArgs a, const FrameIn in, const FrameOut out) {
 template <bool TWO>
 struct LeafSmem {
     static constexpr int RU = TWO ? 2 : 1;            // uint4 per record
-    uint4 stage[kNavWarps][kWarpStage * 4];
+    uint4 stage[kNavWarps][64 * kBlockU4];            // two blocks per lane
     uint4 recbuf[kNavWarps][32 * RU];
-    uint32_t need[kNavWarps][kWarpStage];
+    uint32_t need[kNavWarps][64];
 };
 
 // rank at an absolute position whose block is staged in `slot`
 __device__ __forceinline__ void rank_slot(const DevIndex &ix, const uint4 *stage, uint32_t slot, uint64_t pos, uint64_t out[4]) {
-    uint4 cnt, a, b, t;
-    load_block_smem(stage, slot, cnt, a, b, t);
-    uint32_t pc[4];
-    block_popc(a, b, t, (int)((uint32_t)pos & (kBlockSyms - 1)), pc);
-    out[0] = (uint64_t)cnt.x + pc[0];
-    out[1] = (uint64_t)cnt.y + pc[1];
-    out[2] = (uint64_t)cnt.z + pc[2];
-    out[3] = (uint64_t)cnt.w + pc[3];
-    if (ix.n >> kSuperShift) {
-        const uint64_t *sb = ix.super + (pos >> kSuperShift) * 4;
-        out[0] += sb[0]; out[1] += sb[1]; out[2] += sb[2]; out[3] += sb[3];
-    }
+    uint4 lo, hi;
+    load_block_smem(stage, slot, lo, hi);
+    uint32_t r[4];
+    block_rank(lo, hi, (int)((uint32_t)pos & (kBlockSyms - 1)), r);
+    const uint64_t *sb = ix.super + (pos >> kSuperShift) * 4;
+    out[0] = sb[0] + r[0]; out[1] = sb[1] + r[1]; out[2] = sb[2] + r[2]; out[3] = sb[3] + r[3];
 }
 
 template <bool TWO>
@@ -658,11 +641,11 @@ expand_leaves_kernel(const NavArgs a, const FrameIn in, const FrameOut out) {
                 stage_slots(a.ix1.blocks, stage, need, lane);
             } else {                                       // even slots come from BWT 1, odd slots from BWT 2
 #pragma unroll
-                for (int it = 0; it < kWarpStage * 4 / 32; ++it) {
+                for (int it = 0; it < 64 * kBlockU4 / 32; ++it) {
                     const uint32_t k = lane + it * 32;
-                    const uint32_t slot = k >> 2, blk = need[slot];
+                    const uint32_t slot = k >> 1, blk = need[slot];
                     const uint4 *src = (slot & 1u) ? a.ix2.blocks : a.ix1.blocks;
-                    if (blk != ~0u) cp_async16(&stage[stage_slot(slot, k & 3)], src + (size_t)blk * 4 + (k & 3));
+                    if (blk != ~0u) cp_async16(&stage[stage_slot(slot, k & 1)], src + (size_t)blk * kBlockU4 + (k & 1));
                 }
             }
             if (active && a.write) {

@@ -38,37 +38,60 @@ TILE = 16384            # e2i_index_slice_align(): slices of the index start on 
 
 
 def index_slices(n: int, world: int):
-    """Tile-aligned, equally sized slices of [0, n) for the slice-wise index build: (begin, end) per rank."""
-    tiles = (n // 128 + 1 + 127) // 128
+    """Slices of [0, n) for the slice-wise index build.  The string is cut into tiles of TILE symbols;
+    the last tile may hold no symbol at all (it carries the block that makes rank(n) addressable).  Every
+    rank owns `per` consecutive tiles -- fewer, possibly none, at the end.  Returns ([(begin, end,
+    n_tiles) per rank], per): begin is tile-aligned, an empty rank gets (0, 0, 0), and every tile,
+    the last one included, has exactly one owner."""
+    tiles = (n // 64 + 1 + 255) // 256
     per = (tiles + world - 1) // world
-    return [(min(n, r * per * TILE), min(n, (r + 1) * per * TILE)) for r in range(world)], per
+    out = []
+    for r in range(world):
+        t_lo, t_hi = min(tiles, r * per), min(tiles, (r + 1) * per)
+        if t_hi <= t_lo:
+            out.append((0, 0, 0))
+        else:
+            out.append((min(n, t_lo * TILE), min(n, t_hi * TILE), t_hi - t_lo))
+    return out, per
+
+
+def all_ranks_ok(ok: bool, device, group=None) -> bool:
+    """True iff `ok` on every rank: exchanged BEFORE the next collective so that all ranks fail together."""
+    t = torch.tensor([0 if ok else 1], dtype=torch.int32, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return int(t[0]) == 0
 
 
 def build_index_sharded(ctx, bwt_slice, n: int, term: int, rank: int, world: int, group=None):
     """Index of the whole string from one ASCII slice per rank.
 
     Every rank counts and packs its own tile-aligned slice (bwt_slice = CUDA uint8 tensor holding
-    positions index_slices(n, world)[rank]); symbol totals and the superblock table are exchanged
-    (a few integers), then the block ranges are all-gathered over NVLink.  Bit-identical to
-    ctx.index(whole string)."""
+    positions index_slices(n, world)[rank]); symbol totals and the superblock table are exchanged,
+    then the block ranges are all-gathered over NVLink.  Bit-identical to ctx.index(whole string).
+    A forbidden symbol on any rank raises ValueError on every rank."""
     device = bwt_slice.device
     slices, per = index_slices(n, world)
-    begin, end = slices[rank]
+    begin, end, n_tiles = slices[rank]
     assert bwt_slice.numel() == end - begin
     ix = ctx.index_alloc(n, term, tile_multiple=world)
-    counts = ix.slice_count(bwt_slice, begin)
+    err = None
+    try:
+        counts = ix.slice_count(bwt_slice, begin, n_tiles)
+    except ValueError as e:            # forbidden symbol in this rank's slice
+        err, counts = e, np.zeros(4, dtype=np.uint64)
+    if not all_ranks_ok(err is None, device, group):
+        raise err if err is not None else ValueError("forbidden symbol in another rank's slice of the input BWT")
     mine = torch.from_numpy(counts.astype(np.int64)).to(device)
     allc = [torch.zeros_like(mine) for _ in range(world)]
     dist.all_gather(allc, mine, group=group)
     allc = torch.stack(allc).cpu().numpy().astype(np.uint64)
     before = allc[:rank].sum(axis=0) if rank else np.zeros(4, dtype=np.uint64)
-    n_super = (n >> 32) + 1
-    sup = torch.from_numpy(ix.slice_super(before, n_super).astype(np.int64)).to(device)
+    sup = torch.from_numpy(ix.slice_super(before).astype(np.int64)).to(device)
     dist.all_reduce(sup, op=dist.ReduceOp.SUM, group=group)
     ix.slice_pack(bwt_slice, before, sup.cpu().numpy().astype(np.uint64))
     ptr, nbytes = ix.device_blocks()
     full = wrap_device_words(ptr, nbytes // 4, device)
-    per_words = per * 128 * 64 // 4
+    per_words = per * TILE // 2 // 4
     assert per_words * world == full.numel()
     dist.all_gather_into_tensor(full, full[rank * per_words:(rank + 1) * per_words], group=group)
     ix.finish(allc.sum(axis=0))
@@ -199,7 +222,7 @@ def run_sharded(ctx, api, bwt1, bwt2, da, params, rank: int, world: int, group=N
         n_t = t.numel()
         if world == 1 or n_t < world * 4 * TILE:
             return ctx.index(t, term)
-        lo, hi = index_slices(n_t, world)[0][rank]
+        lo, hi, _ = index_slices(n_t, world)[0][rank]
         return build_index_sharded(ctx, t[lo:hi], n_t, term, rank, world, group)
 
     b1 = make_index(bwt1, n1)

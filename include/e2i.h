@@ -143,13 +143,16 @@ uint64_t e2i_index_bytes(const e2i_index *ix);                  /* HBM footprint
  *      (all-gather over NVLink, ebwt2indel_b200/distributed.py) and e2i_index_finish sets F.
  *      Same result as e2i_index_build_device on the whole string.
  *      tile_multiple: the block array is padded to a multiple of that many slices' worth of tiles.
- *      slice_count: counts[4] = #A,#C,#G,#T of the slice.  slice_super: host_super[n_super*4]
+ *      slice_count: counts[4] = #A,#C,#G,#T of the slice; n_tiles = the tiles of e2i_index_slice_align()
+ *      symbols the slice owns (the last tile of the string may hold no symbol, only the block that makes
+ *      rank(n) addressable; exactly one slice owns it); n_tiles = 0: an empty slice, nothing to do.  slice_super: host_super[n_super*4]
  *      receives the superblock entries this slice owns (zeros elsewhere) given the counts before
  *      the slice; the SUM over ranks is the complete table that slice_pack takes. --------------- */
 uint64_t e2i_index_slice_align(void);
+uint64_t e2i_index_super_count(const e2i_index *ix);   /* entries (4 x u64 each) of the superblock table */
 int e2i_index_alloc(e2i_ctx *ctx, uint64_t n, uint8_t term, uint64_t tile_multiple, e2i_index **out);
 int e2i_index_slice_count(e2i_ctx *ctx, e2i_index *ix, const uint8_t *dev_slice, uint64_t begin, uint64_t len,
-                          uint64_t counts[4], uint64_t *bad_pos);
+                          uint64_t n_tiles, uint64_t counts[4], uint64_t *bad_pos);
 int e2i_index_slice_super(e2i_ctx *ctx, e2i_index *ix, const uint64_t before[4], uint64_t *host_super);
 int e2i_index_slice_pack(e2i_ctx *ctx, e2i_index *ix, const uint8_t *dev_slice, const uint64_t before[4],
                          const uint64_t *host_super);

@@ -105,18 +105,23 @@ def test_world2_gloo_host_logic():
 
 
 def test_slice_and_cut_helpers():
-    """index_slices: tile-aligned, equal-sized, cover [0, n) in order; position_cuts: monotone cover."""
+    """index_slices: tile-aligned, every tile (the symbol-free tail tile included) has exactly one owner,
+    symbols are covered in order, empty ranks are (0, 0, 0); position_cuts: monotone cover."""
     from ebwt2indel_b200 import distributed as dd
-    for n in (1, 127, 128, 16384, 16385, 1 << 20, 1000003, 15_100_000_000):
+    for n in (1, 127, 128, 16384, 16385, 2 * 16384, 40 * 16384 + 5, 1 << 20, 1000003, 1 << 32, 15_100_000_000):
         for world in (1, 2, 3, 4, 8):
             slices, per = dd.index_slices(n, world)
-            assert len(slices) == world and slices[0][0] == 0 and slices[-1][1] == n
-            tiles = (n // 128 + 1 + 127) // 128
-            assert per * world >= tiles
-            for r, (lo, hi) in enumerate(slices):
-                assert lo <= hi <= n and lo % dd.TILE == 0 or lo == n
-                if r:
-                    assert lo == slices[r - 1][1]
-                assert hi - lo <= per * dd.TILE
+            tiles = (n // 64 + 1 + 255) // 256
+            assert len(slices) == world and per * world >= tiles
+            assert sum(s[2] for s in slices) == tiles                      # one owner per tile
+            pos, tile = 0, 0
+            for lo, hi, nt in slices:
+                if nt == 0:
+                    assert (lo, hi) == (0, 0)
+                    continue
+                assert lo % dd.TILE == 0 and lo == min(n, tile * dd.TILE) and lo == pos and lo <= hi <= n
+                assert hi - lo <= nt * dd.TILE and nt <= per
+                pos, tile = hi, tile + nt
+            assert pos == n and tile == tiles
             cuts = dd.position_cuts(n, world)
             assert cuts[0] == 0 and cuts[-1] == n and all(a <= b for a, b in zip(cuts, cuts[1:]))

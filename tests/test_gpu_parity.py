@@ -275,7 +275,7 @@ def test_gpu_ebwt_builder_matches_reference_builders(gpu_ctx):
     torch.cuda.synchronize()
 
 
-@pytest.mark.parametrize("n,world", [(200000, 2), (1 << 20, 3), (1000003, 8)])
+@pytest.mark.parametrize("n,world", [(200000, 2), (1 << 20, 3), (1000003, 8), (40 * 16384 + 5, 8), (4 * 65536, 2)])
 def test_slicewise_index_build_equals_whole_build(gpu_ctx, oracle, n, world):
     """Multi-GPU index construction, emulated on one GPU: every 'rank' counts and packs its own
     tile-aligned slice, the block ranges are put together, and the result answers rank queries
@@ -286,17 +286,16 @@ def test_slicewise_index_build_equals_whole_build(gpu_ctx, oracle, n, world):
     dev = torch.from_numpy(bwt.copy()).cuda()
     slices, per = dd.index_slices(n, world)
     parts = [gpu_ctx.index_alloc(n, ord("#"), tile_multiple=world) for _ in range(world)]
-    counts = np.stack([parts[r].slice_count(dev[slices[r][0]:slices[r][1]], slices[r][0]) for r in range(world)])
-    n_super = (n >> 32) + 1
-    sup = np.zeros(n_super * 4, dtype=np.uint64)
+    counts = np.stack([parts[r].slice_count(dev[slices[r][0]:slices[r][1]], slices[r][0], slices[r][2]) for r in range(world)])
+    sup = np.zeros(parts[0].n_super * 4, dtype=np.uint64)
     for r in range(world):
-        sup += parts[r].slice_super(counts[:r].sum(axis=0), n_super)
+        sup += parts[r].slice_super(counts[:r].sum(axis=0))
     views = []
     for r in range(world):
         parts[r].slice_pack(dev[slices[r][0]:slices[r][1]], counts[:r].sum(axis=0), sup)
         ptr, nbytes = parts[r].device_blocks()
         views.append(dd.wrap_device_words(ptr, nbytes // 4, dev.device))
-    w = per * 128 * 64 // 4
+    w = per * dd.TILE // 2 // 4
     for r in range(1, world):
         views[0][r * w:(r + 1) * w].copy_(views[r][r * w:(r + 1) * w])   # the all-gather, by hand
     torch.cuda.synchronize()
