@@ -5,7 +5,7 @@ CXX ?= g++
 ARCH := -gencode arch=compute_100a,code=sm_100a
 NVFLAGS := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC,-Wall,-Wno-unused-function -Iinclude -Iebwt2indel_b200/csrc
 CSRC := ebwt2indel_b200/csrc
-OBJ := build/context.o build/index.o build/navigate.o build/call.o build/snp_format.o
+OBJ := build/context.o build/index.o build/navigate.o build/call.o build/multi.o build/snp_format.o
 LIB := ebwt2indel_b200/libe2i.so
 TOOLS := ebwt2indel_b200/libe2i_tools.so
 BIN := bin/ebwt2InDel

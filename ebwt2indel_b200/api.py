@@ -75,7 +75,7 @@ SYMBOLS = (
     "e2i_bits_size", "e2i_bits_free", "e2i_navigate", "e2i_navigate_shard", "e2i_lcpbits_fetch",
     "e2i_lcpbits_device", "e2i_bits_device", "e2i_lcpbits_free", "e2i_call", "e2i_calls_count",
     "e2i_calls_fetch", "e2i_calls_view", "e2i_calls_free", "e2i_snp_format", "e2i_snp_count", "e2i_filter_snp", "e2i_distance", "e2i_buffer_free", "e2i_run",
-    "e2i_run_device",
+    "e2i_run_device", "e2i_run_multi", "e2i_enable_peers", "e2i_or_allreduce",
 )
 
 _lib = None
@@ -144,6 +144,9 @@ def lib():
         "e2i_buffer_free": (None, [vp]),
         "e2i_run": (C.c_int, [vp, u8p, u64, u8p, u64, u8p, PP, C.POINTER(vp), C.POINTER(C.c_size_t), PS]),
         "e2i_run_device": (C.c_int, [vp, u8p, u64, u8p, u64, u8p, PP, C.POINTER(vp), C.POINTER(C.c_size_t), PS]),
+        "e2i_run_multi": (C.c_int, [C.POINTER(C.c_int), C.c_int, u8p, u64, u8p, u64, u8p, PP, u64, C.POINTER(vp), C.POINTER(C.c_size_t), PS]),
+        "e2i_enable_peers": (C.c_int, [C.POINTER(vp), C.c_int]),
+        "e2i_or_allreduce": (C.c_int, [vp, C.POINTER(vp), C.c_int, C.c_int, u64]),
     }
     assert set(sig) == set(SYMBOLS)
     for name, (res, args) in sig.items():
@@ -349,6 +352,32 @@ class Context:
         _check(rc)
         text = SnpText(out, ln.value)
         return (text.tobytes() if copy else text), st
+
+
+def run_multi(devices, bwt1, bwt2=None, da=None, params: Params | None = None, frontier_bytes: int = 0, copy: bool = True):
+    """Whole path on several GPUs of this box from ONE process (e2i_run_multi): host inputs (numpy / bytes).
+    Returns (.snp bytes or SnpText, Stats)."""
+    p = params or default_params()
+    st = Stats()
+    keep = []
+
+    def arg(x):
+        if x is None:
+            return None, 0
+        a, ptr = _host_u8(np.frombuffer(x, dtype=np.uint8) if isinstance(x, (bytes, bytearray)) else x)
+        keep.append(a)
+        return ptr, len(a)
+    p1, n1 = arg(bwt1)
+    p2, n2 = arg(bwt2)
+    pd, _ = arg(da)
+    devs = (C.c_int * len(devices))(*devices)
+    out, ln = C.c_void_p(), C.c_size_t()
+    rc = lib().e2i_run_multi(devs, len(devices), p1, n1, p2, n2, pd, C.byref(p), frontier_bytes, C.byref(out), C.byref(ln), C.byref(st))
+    if rc == E2I_ERR_SYMBOL:
+        raise ValueError(lib().e2i_last_error().decode())
+    _check(rc)
+    text = SnpText(out, ln.value)
+    return (text.tobytes() if copy else text), st
 
 
 def filter_snp(snp: bytes, m: int, M: int = 0) -> bytes:

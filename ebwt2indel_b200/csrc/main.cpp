@@ -18,6 +18,7 @@
 #include <cstring>
 #include <iostream>
 #include <string>
+#include <vector>
 
 #include "e2i.h"
 
@@ -156,14 +157,29 @@ int main(int argc, char **argv) {
     else cout << "Maximum number of variants per genomic position per sample: unlimited." << endl;
     cout << endl;
 
+    // GPUs: E2I_DEVICE=<id> (default 0) runs on one GPU; E2I_GPUS=<N> (devices 0..N-1) or E2I_DEVICES=<id,id,...>
+    // runs the same job on several GPUs of this box from this one process (the reference's way to use more
+    // hardware is the wrapper pebwt2InDel.sh, which splits the reads and loses cross-piece coverage).
     int device = 0;
     if (const char *dv = std::getenv("E2I_DEVICE")) device = atoi(dv);
-    e2i_ctx *ctx = nullptr;
-    if (e2i_create(device, &ctx) != E2I_OK) {
-        cout << "Error: " << e2i_last_error() << endl;
-        return 2;
+    std::vector<int> devices;
+    if (const char *dl = std::getenv("E2I_DEVICES")) {
+        for (const char *q = dl; *q;) { devices.push_back(atoi(q)); while (*q && *q != ',') ++q; if (*q == ',') ++q; }
+    } else if (const char *ng = std::getenv("E2I_GPUS")) {
+        for (int i = 0; i < atoi(ng); ++i) devices.push_back(i);
     }
-    if (const char *fb = std::getenv("E2I_FRONTIER_BYTES")) e2i_set_frontier_budget(ctx, strtoull(fb, nullptr, 10));
+    const bool multi = devices.size() > 1;
+    uint64_t frontier_bytes = 0;
+    if (const char *fb = std::getenv("E2I_FRONTIER_BYTES")) frontier_bytes = strtoull(fb, nullptr, 10);
+    e2i_ctx *ctx = nullptr;
+    if (!multi) {
+        if (devices.size() == 1) device = devices[0];
+        if (e2i_create(device, &ctx) != E2I_OK) {
+            cout << "Error: " << e2i_last_error() << endl;
+            return 2;
+        }
+        if (frontier_bytes) e2i_set_frontier_budget(ctx, frontier_bytes);
+    }
 
     const bool two = !input2.empty(), with_da = !input_da.empty();
     cout << (two ? "Phase 1/4: loading and indexing eBWTs ... " : "Phase 1/4: loading and indexing eBWT ... ") << std::flush;
@@ -192,7 +208,8 @@ int main(int argc, char **argv) {
     std::memset(&st, 0, sizeof st);
     char *snp = nullptr;
     size_t snp_len = 0;
-    const int rc = e2i_run(ctx, b1, n1, b2, n2, da, &p, &snp, &snp_len, &st);
+    const int rc = multi ? e2i_run_multi(devices.data(), (int)devices.size(), b1, n1, b2, n2, da, &p, frontier_bytes, &snp, &snp_len, &st)
+                         : e2i_run(ctx, b1, n1, b2, n2, da, &p, &snp, &snp_len, &st);
     if (rc == E2I_ERR_SYMBOL) {   // locate the byte on the host only on this error path
         check_symbols(b1, n1);
         if (two) check_symbols(b2, n2);

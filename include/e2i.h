@@ -234,6 +234,22 @@ int e2i_run(e2i_ctx *ctx, const uint8_t *host_bwt1, uint64_t n1, const uint8_t *
 int e2i_run_device(e2i_ctx *ctx, const uint8_t *dev_bwt1, uint64_t n1, const uint8_t *dev_bwt2, uint64_t n2,
                    const uint8_t *dev_da, const e2i_params *p, char **snp, size_t *snp_len, e2i_stats *st);
 
+/* ---- several GPUs of one box, one process (replaces the parallel wrapper pebwt2InDel.sh:45-88 without its
+ *      loss of cross-piece coverage: the output equals the single-GPU run's).  e2i_run_multi: the whole path
+ *      on devices[0..n_devices); one host thread and one context per GPU inside the call; the index is built
+ *      slice-wise and replicated through peer copies, the traversal is sharded, the bit vectors are OR-combined
+ *      by e2i_or_allreduce over peer memory, phase 4 runs per suffix-array range.  frontier_budget: bytes per
+ *      GPU (0 = what is free).
+ *      e2i_enable_peers: mutual peer access (device + memory pool) between the contexts of ONE process.
+ *      e2i_or_allreduce: rank's share of the OR of dev_words[0..n_ranks) (words32 32-bit words each, a
+ *      multiple of 4): its 1/n_ranks slice is read from every peer, combined and stored back to every peer;
+ *      the caller synchronises the ranks before (all inputs written) and after (all slices done). ------------ */
+int e2i_run_multi(const int *devices, int n_devices, const uint8_t *host_bwt1, uint64_t n1, const uint8_t *host_bwt2,
+                  uint64_t n2, const uint8_t *host_da, const e2i_params *p, uint64_t frontier_budget,
+                  char **snp, size_t *snp_len, e2i_stats *st);
+int e2i_enable_peers(e2i_ctx **ctxs, int n);
+int e2i_or_allreduce(e2i_ctx *ctx, void *const *dev_words, int n_ranks, int rank, uint64_t words32);
+
 #ifdef __cplusplus
 }
 #endif

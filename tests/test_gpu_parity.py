@@ -387,3 +387,38 @@ def test_large_inputs_size_independent_properties(gpu_ctx, e2i, name, scale):
     # (5)
     nums = [int(x) for x in re.findall(rb">cluster:(\d+)_", snp)]
     assert nums == sorted(nums) and nums[0] == 1 and nums[-1] == st.clusters_out
+
+
+@pytest.mark.parametrize("devices", [[0, 0], [0, 0, 0]])
+def test_multi_gpu_single_process_matches(e2i, oracle, devices):
+    """e2i_run_multi (what bin/ebwt2InDel runs with E2I_GPUS / E2I_DEVICES): one process, one thread and one
+    context per rank, slice-wise index + peer copies, sharded traversal, OR-combine kernel over peer pointers,
+    phase 4 per suffix-array range.  Ranks on one device here (the logic does not care): the text and the
+    counters equal the reference's in all three modes, and a mid-size seeded input equals the oracle."""
+    from ebwt2indel_b200 import synth
+    for name in ("m1_default", "m1_flags", "m2_default", "m3_default", "m2_flags", "m1_short_reads"):
+        g = load_golden(name)
+        snp, st = e2i.run_multi(devices, g["bwt1"], g["bwt2"], g["da"], _case_params(e2i, g))
+        assert snp == g["snp"], name
+        for k, v in g["counters"].items():
+            assert getattr(st, k) == v, (name, k)
+    reads = synth.diploid_reads(150000, 300, 60, 20, 100, seed=77)          # n = 6 M: the shards get real work
+    bwt, _ = synth.ebwt_bcr_numpy(reads)
+    snp, st = e2i.run_multi(devices, bwt, None, None, e2i.default_params())
+    osnp, ost = oracle.run(bwt, None, None, oracle.default_params())
+    assert snp == osnp and len(snp) > 0
+    for k in COUNTERS + ("events",):
+        assert getattr(st, k) == getattr(ost, k), k
+
+
+def test_cli_multi_gpu_env(tmp_path):
+    """bin/ebwt2InDel with E2I_DEVICES=0,0: same .snp bytes as the reference."""
+    exe = os.path.join(ROOT, "bin", "ebwt2InDel")
+    g = load_golden("m3_default")
+    f1, f3, out = tmp_path / "a.ebwt", tmp_path / "da.txt", tmp_path / "o.snp"
+    g["bwt1"].tofile(f1)
+    g["da"].tofile(f3)
+    r = subprocess.run([exe, "-1", str(f1), "-d", str(f3), "-o", str(out)], capture_output=True, text=True,
+                       env=dict(os.environ, E2I_DEVICES="0,0"))
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert out.read_bytes() == g["snp"]
