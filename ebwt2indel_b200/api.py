@@ -75,7 +75,7 @@ SYMBOLS = (
     "e2i_bits_size", "e2i_bits_free", "e2i_navigate", "e2i_navigate_shard", "e2i_lcpbits_fetch",
     "e2i_lcpbits_device", "e2i_bits_device", "e2i_lcpbits_free", "e2i_call", "e2i_calls_count",
     "e2i_calls_fetch", "e2i_calls_view", "e2i_calls_free", "e2i_snp_format", "e2i_snp_count", "e2i_filter_snp", "e2i_distance", "e2i_buffer_free", "e2i_run",
-    "e2i_run_device", "e2i_run_multi", "e2i_enable_peers", "e2i_or_allreduce",
+    "e2i_run_device", "e2i_run_files", "e2i_index_build_file", "e2i_da_load_file", "e2i_index_save", "e2i_index_load", "e2i_run_multi", "e2i_enable_peers", "e2i_or_allreduce",
 )
 
 _lib = None
@@ -144,6 +144,11 @@ def lib():
         "e2i_buffer_free": (None, [vp]),
         "e2i_run": (C.c_int, [vp, u8p, u64, u8p, u64, u8p, PP, C.POINTER(vp), C.POINTER(C.c_size_t), PS]),
         "e2i_run_device": (C.c_int, [vp, u8p, u64, u8p, u64, u8p, PP, C.POINTER(vp), C.POINTER(C.c_size_t), PS]),
+        "e2i_run_files": (C.c_int, [vp, C.c_char_p, C.c_char_p, C.c_char_p, PP, C.POINTER(vp), C.POINTER(C.c_size_t), PS, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)]),
+        "e2i_index_build_file": (C.c_int, [vp, C.c_char_p, C.c_uint8, C.POINTER(vp), C.POINTER(u64)]),
+        "e2i_da_load_file": (C.c_int, [vp, C.c_char_p, u64, C.POINTER(vp)]),
+        "e2i_index_save": (C.c_int, [vp, C.c_char_p]),
+        "e2i_index_load": (C.c_int, [vp, C.c_char_p, C.POINTER(vp)]),
         "e2i_run_multi": (C.c_int, [C.POINTER(C.c_int), C.c_int, u8p, u64, u8p, u64, u8p, PP, u64, C.POINTER(vp), C.POINTER(C.c_size_t), PS]),
         "e2i_enable_peers": (C.c_int, [C.POINTER(vp), C.c_int]),
         "e2i_or_allreduce": (C.c_int, [vp, C.POINTER(vp), C.c_int, C.c_int, u64]),
@@ -258,6 +263,40 @@ class Context:
             raise ValueError(f"forbidden symbol at position {bad.value}")
         _check(rc)
         return Index(self, h)
+
+    def index_file(self, path: str, term: int = ord("#")) -> "Index":
+        """Streaming ingest of an ASCII eBWT file (reader thread -> page-locked ring -> copy stream -> counting)."""
+        h, bad = C.c_void_p(), C.c_uint64(0)
+        rc = lib().e2i_index_build_file(self.h, os.fsencode(path), term, C.byref(h), C.byref(bad))
+        if rc == E2I_ERR_SYMBOL:
+            raise ValueError(f"forbidden symbol at position {bad.value}")
+        _check(rc)
+        return Index(self, h)
+
+    def index_load(self, path: str) -> "Index":
+        """Packed-index sidecar written by Index.save()."""
+        h = C.c_void_p()
+        _check(lib().e2i_index_load(self.h, os.fsencode(path), C.byref(h)))
+        return Index(self, h)
+
+    def document_array_file(self, path: str, n: int) -> "Bits":
+        h = C.c_void_p()
+        _check(lib().e2i_da_load_file(self.h, os.fsencode(path), n, C.byref(h)))
+        return Bits(self, h)
+
+    def run_files(self, path1: str, path2: str | None = None, path_da: str | None = None, params: Params | None = None, copy: bool = True):
+        """Whole path from files (e2i_run_files).  Returns (.snp bytes or SnpText, Stats)."""
+        p = params or default_params()
+        st = Stats()
+        out, ln = C.c_void_p(), C.c_size_t()
+        bad = (C.c_uint64 * 2)()
+        rc = lib().e2i_run_files(self.h, os.fsencode(path1), os.fsencode(path2) if path2 else None, os.fsencode(path_da) if path_da else None,
+                                 C.byref(p), C.byref(out), C.byref(ln), C.byref(st), None, None, bad)
+        if rc == E2I_ERR_SYMBOL:
+            raise ValueError(lib().e2i_last_error().decode())
+        _check(rc)
+        text = SnpText(out, ln.value)
+        return (text.tobytes() if copy else text), st
 
     def index_alloc(self, n: int, term: int = ord("#"), tile_multiple: int = 1) -> "Index":
         """Empty index for slice-wise construction (Index.slice_count / slice_super / slice_pack / finish)."""
@@ -435,6 +474,10 @@ class Index:
         out = np.zeros(4, dtype=np.uint64)
         _check(lib().e2i_index_F(self.h, out.ctypes.data))
         return out
+
+    def save(self, path: str):
+        """Write the packed index (as it lies in HBM) to `path`; Context.index_load reads it back."""
+        _check(lib().e2i_index_save(self.h, os.fsencode(path)))
 
     # ---- slice-wise construction (multi-GPU) ----
     def slice_count(self, dev_slice, begin: int, n_tiles: int) -> np.ndarray:

@@ -107,6 +107,8 @@ struct e2i_ctx {
     void *ctl_host = nullptr;   // page-locked, device-mapped block the sweeps report their counts to
     uint32_t ticket_next = 0;
     unsigned long long sweep_seq = 0;
+    void *ring[4] = {};         // page-locked ring of the streaming file ingest (index.cu)
+    float last_h2d_ms = 0;      // copy-stream time of the last streamed upload
     void *pinned = nullptr;     // page-locked staging of the call records
     size_t pinned_bytes = 0;
     uint64_t pinned_gen = 0;

@@ -4,6 +4,8 @@
 // e2i_run replaces run_one_dataset / run_two_datasets / run_two_datasets_da
 // (/root/reference/ebwt2InDel.cpp:1584-1674, 1344-1465, 1471-1579): load + index the eBWT(s),
 // traverse (phases 2-3), scan clusters and extract contexts (phase 4), format the .snp text.
+#include <sys/stat.h>
+
 #include <algorithm>
 #include <chrono>
 
@@ -121,6 +123,7 @@ extern "C" void e2i_destroy(e2i_ctx *ctx) {
     cudaFree(ctx->ctl);
     cudaFreeHost(ctx->ctl_host);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    for (void *r : ctx->ring) if (r) cudaFreeHost(r);
     for (auto &ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
@@ -149,123 +152,139 @@ extern "C" int e2i_set_frontier_budget(e2i_ctx *ctx, uint64_t bytes) {
 }
 
 // ---- whole path ------------------------------------------------------------------------------
-static int run_on_device(e2i_ctx *ctx, const uint8_t *dev_bwt1, uint64_t n1, const uint8_t *dev_bwt2, uint64_t n2,
-                         const uint8_t *dev_da, const e2i_params *p, char **snp, size_t *snp_len, e2i_stats *st,
-                         void (*release_inputs)(void *), void *release_arg) {
-    e2i_index *b1 = nullptr, *b2 = nullptr;
-    e2i_bits *da = nullptr, *da_nav = nullptr;
+namespace {
+// phases 2-4 + text on indexes that already exist
+int run_with_indexes(e2i_ctx *ctx, e2i_index *b1, e2i_index *b2, e2i_bits *da, const e2i_params *p, char **snp, size_t *snp_len, e2i_stats *st) {
+    e2i_bits *da_nav = nullptr;
     e2i_lcpbits *lcp = nullptr;
     e2i_calls *calls = nullptr;
-    auto cleanup = [&] {
-        e2i_calls_free(calls); e2i_lcpbits_free(lcp); e2i_bits_free(da); e2i_bits_free(da_nav);
-        e2i_index_free(b1); e2i_index_free(b2);
-    };
-    cudaStream_t s = ctx->stream;
     const auto w0 = std::chrono::steady_clock::now();
-    cudaEventRecord(ctx->ev[6], s);
-    uint64_t bad = 0;
-    Accounting *acct = new Accounting(ctx, st);
-    int rc = e2i_index_build_device(ctx, dev_bwt1, n1, (uint8_t)p->term, &b1, &bad);
-    if (rc == E2I_OK && dev_bwt2) rc = e2i_index_build_device(ctx, dev_bwt2, n2, (uint8_t)p->term, &b2, &bad);
-    if (rc == E2I_OK && dev_da) rc = e2i_da_load_device(ctx, dev_da, n1, &da);
-    delete acct;   // index + DA build only; navigate and call account for themselves
-    cudaEventRecord(ctx->ev[7], s);
-    if (rc == E2I_OK) {
-        cudaEventSynchronize(ctx->ev[7]);
-        float ms = 0;
-        cudaEventElapsedTime(&ms, ctx->ev[6], ctx->ev[7]);
-        st->ms_index += ms;
-    }
-    if (release_inputs) release_inputs(release_arg);   // the ASCII copies are dead once the index exists
-    if (rc == E2I_OK) rc = e2i_navigate(ctx, b1, b2, p, &lcp, b2 ? &da_nav : nullptr, st);
+    int rc = e2i_navigate(ctx, b1, b2, p, &lcp, b2 ? &da_nav : nullptr, st);
     if (rc == E2I_OK) rc = e2i_call(ctx, b1, b2, b2 ? da_nav : da, lcp, p, 0, UINT64_MAX, &calls, st);
     if (std::getenv("E2I_DEBUG")) {
-        cudaStreamSynchronize(s);
+        cudaStreamSynchronize(ctx->stream);
         std::fprintf(stderr, "[e2i] run: %.1f ms of host wall time before formatting (phases: index %.1f leaves %.1f nodes %.1f call %.1f)\n",
                      std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - w0).count(),
                      st->ms_index, st->ms_leaves, st->ms_nodes, st->ms_call);
     }
     const auto w1 = std::chrono::steady_clock::now();
     if (rc == E2I_OK)
-        rc = e2i_snp_format(calls->recs, calls->left, calls->right, calls->n, p,
-                            (b2 || da) ? 1 : 0, 1, snp, snp_len, st);
-    const auto w2 = std::chrono::steady_clock::now();
-    cleanup();
-    st->ms_format += std::chrono::duration<double, std::milli>(w2 - w1).count();
-    st->ms_wall += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - w0).count();
+        rc = e2i_snp_format(calls->recs, calls->left, calls->right, calls->n, p, (b2 || da) ? 1 : 0, 1, snp, snp_len, st);
+    st->ms_format += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - w1).count();
+    e2i_calls_free(calls);
+    e2i_lcpbits_free(lcp);
+    e2i_bits_free(da_nav);
     return rc;
 }
+
+// the index of one input: from the packed sidecar when E2I_INDEX_CACHE is set and a valid one exists, else
+// streamed from the ASCII file (and saved as a sidecar when the cache is on)
+int index_from_file(e2i_ctx *ctx, const char *path, uint8_t term, e2i_index **out, uint64_t *bad) {
+    const char *cache = std::getenv("E2I_INDEX_CACHE");
+    const bool use_cache = cache && *cache && std::strcmp(cache, "0") != 0;
+    const std::string side = std::string(path) + ".e2ix";
+    if (use_cache) {
+        struct stat a, b;
+        if (::stat(path, &a) == 0 && ::stat(side.c_str(), &b) == 0 && b.st_mtime >= a.st_mtime) {
+            e2i_index *ix = nullptr;
+            if (e2i_index_load(ctx, side.c_str(), &ix) == E2I_OK) {
+                if (e2i_index_size(ix) == (uint64_t)a.st_size && ix->term == term) { *out = ix; return E2I_OK; }
+                e2i_index_free(ix);
+            }
+        }
+    }
+    E2I_TRY(e2i_index_build_file(ctx, path, term, out, bad));
+    if (use_cache && e2i_index_save(*out, side.c_str()) != E2I_OK)
+        std::fprintf(stderr, "[e2i] warning: %s\n", e2i_last_error());
+    return E2I_OK;
+}
+
+struct IndexTimer {             // device time of the index phase (uploads overlap with the counting pass)
+    e2i_ctx *ctx; e2i_stats *st;
+    IndexTimer(e2i_ctx *c, e2i_stats *s) : ctx(c), st(s) { cudaEventRecord(ctx->ev[6], ctx->stream); }
+    void stop() {
+        cudaEventRecord(ctx->ev[7], ctx->stream);
+        if (cudaEventSynchronize(ctx->ev[7]) == cudaSuccess) { float ms = 0; if (cudaEventElapsedTime(&ms, ctx->ev[6], ctx->ev[7]) == cudaSuccess) st->ms_index += ms; }
+    }
+};
+}  // namespace
 
 extern "C" int e2i_run_device(e2i_ctx *ctx, const uint8_t *dev_bwt1, uint64_t n1, const uint8_t *dev_bwt2, uint64_t n2,
                               const uint8_t *dev_da, const e2i_params *p, char **snp, size_t *snp_len, e2i_stats *st) {
     if (!ctx || !dev_bwt1 || !p || !snp || !snp_len || !st) { set_error("e2i_run_device: null argument"); return E2I_ERR_ARG; }
     if (dev_bwt2 && dev_da) { set_error("Document array (-d) can only be used with one input BWT file (-1)"); return E2I_ERR_ARG; }
     E2I_CUDA_TRY(cudaSetDevice(ctx->device));
-    return run_on_device(ctx, dev_bwt1, n1, dev_bwt2, n2, dev_da, p, snp, snp_len, st, nullptr, nullptr);
+    const auto w0 = std::chrono::steady_clock::now();
+    e2i_index *b1 = nullptr, *b2 = nullptr;
+    e2i_bits *da = nullptr;
+    uint64_t bad = 0;
+    int rc;
+    {
+        Accounting acct(ctx, st);
+        IndexTimer t(ctx, st);
+        rc = e2i_index_build_device(ctx, dev_bwt1, n1, (uint8_t)p->term, &b1, &bad);
+        if (rc == E2I_OK && dev_bwt2) rc = e2i_index_build_device(ctx, dev_bwt2, n2, (uint8_t)p->term, &b2, &bad);
+        if (rc == E2I_OK && dev_da) rc = e2i_da_load_device(ctx, dev_da, n1, &da);
+        t.stop();
+    }
+    if (rc == E2I_OK) rc = run_with_indexes(ctx, b1, b2, da, p, snp, snp_len, st);
+    e2i_bits_free(da); e2i_index_free(b1); e2i_index_free(b2);
+    st->ms_wall += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - w0).count();
+    return rc;
 }
-
-namespace {
-struct HostInputs {
-    uint8_t *d1 = nullptr, *d2 = nullptr, *dd = nullptr;
-};
-struct HostInputsRef { HostInputs *in; e2i_ctx *ctx; };
-void free_inputs(void *arg) {
-    HostInputsRef *r = static_cast<HostInputsRef *>(arg);
-    HostInputs *h = r->in;
-    dfree(r->ctx, h->d1); dfree(r->ctx, h->d2); dfree(r->ctx, h->dd);
-    h->d1 = h->d2 = h->dd = nullptr;
-}
-}  // namespace
 
 extern "C" int e2i_run(e2i_ctx *ctx, const uint8_t *host_bwt1, uint64_t n1, const uint8_t *host_bwt2, uint64_t n2,
                        const uint8_t *host_da, const e2i_params *p, char **snp, size_t *snp_len, e2i_stats *st) {
     if (!ctx || !host_bwt1 || !p || !snp || !snp_len || !st) { set_error("e2i_run: null argument"); return E2I_ERR_ARG; }
     if (host_bwt2 && host_da) { set_error("Document array (-d) can only be used with one input BWT file (-1)"); return E2I_ERR_ARG; }
     E2I_CUDA_TRY(cudaSetDevice(ctx->device));
-    cudaStream_t s = ctx->stream;
-    HostInputs in;
-    HostInputsRef ref{&in, ctx};
-    auto fail = [&](cudaError_t e) { set_error("e2i_run: %s", cudaGetErrorString(e)); free_inputs(&ref); return E2I_ERR_CUDA; };
-    // One stream by default (a single copy engine saturates the link on an idle host).  With
-    // E2I_H2D_STREAMS=2 large inputs go up as 256 MB pieces alternating between the context's two
-    // streams; measurements on a shared host were too noisy to prefer either (profiles/e2e_time.py).
-    const char *hs = std::getenv("E2I_H2D_STREAMS");
-    const int n_streams = hs ? std::max(1, std::min(2, atoi(hs))) : 1;
-    cudaEvent_t ev_copy = nullptr;
-    auto upload = [&](uint8_t *dst, const uint8_t *src, uint64_t n) -> cudaError_t {
-        const uint64_t piece = 256ull << 20;
-        if (n_streams == 1 || n <= piece) return cudaMemcpyAsync(dst, src, n, cudaMemcpyHostToDevice, s);
-        int k = 0;
-        for (uint64_t off = 0; off < n; off += piece, ++k) {
-            const cudaError_t ce = cudaMemcpyAsync(dst + off, src + off, std::min(piece, n - off), cudaMemcpyHostToDevice,
-                                                   (k & 1) ? ctx->copy_stream : s);
-            if (ce != cudaSuccess) return ce;
-        }
-        return cudaSuccess;
-    };
-    cudaError_t e = cudaEventRecord(ctx->ev[6], s);
-    if (e == cudaSuccess) e = dmalloc(ctx, &in.d1, n1 + 16);
-    if (e == cudaSuccess && host_bwt2) e = dmalloc(ctx, &in.d2, n2 + 16);
-    if (e == cudaSuccess && host_da) e = dmalloc(ctx, &in.dd, n1 + 16);
-    // the second stream must not start before the allocations (stream-ordered) are done on the first
-    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev_copy, cudaEventDisableTiming);
-    if (e == cudaSuccess) e = cudaEventRecord(ev_copy, s);
-    if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->copy_stream, ev_copy, 0);
-    if (e == cudaSuccess) e = upload(in.d1, host_bwt1, n1);
-    if (e == cudaSuccess && host_bwt2) e = upload(in.d2, host_bwt2, n2);
-    if (e == cudaSuccess && host_da) e = upload(in.dd, host_da, n1);
-    if (e == cudaSuccess) e = cudaEventRecord(ev_copy, ctx->copy_stream);       // join the second stream
-    if (e == cudaSuccess) e = cudaStreamWaitEvent(s, ev_copy, 0);
-    if (e == cudaSuccess) e = cudaEventRecord(ctx->ev[7], s);
-    if (e == cudaSuccess) e = cudaEventSynchronize(ctx->ev[7]);
-    if (e != cudaSuccess) return fail(e);
-    if (ev_copy) cudaEventDestroy(ev_copy);
-    float ms = 0;
-    cudaEventElapsedTime(&ms, ctx->ev[6], ctx->ev[7]);
-    st->ms_h2d += ms;
-    st->h2d_bytes += n1 + (host_bwt2 ? n2 : 0) + (host_da ? n1 : 0);
-    const int rc = run_on_device(ctx, in.d1, n1, in.d2, n2, in.dd, p, snp, snp_len, st, free_inputs, &ref);
-    free_inputs(&ref);
+    const auto w0 = std::chrono::steady_clock::now();
+    e2i_index *b1 = nullptr, *b2 = nullptr;
+    e2i_bits *da = nullptr;
+    uint64_t bad = 0;
+    int rc;
+    {   // the eBWT goes up in chunks on the copy stream while the counting pass of the index build follows it
+        Accounting acct(ctx, st);
+        IndexTimer t(ctx, st);
+        rc = e2i_index_build(ctx, host_bwt1, n1, (uint8_t)p->term, &b1, &bad);
+        st->ms_h2d += ctx->last_h2d_ms;
+        if (rc == E2I_OK && host_bwt2) { rc = e2i_index_build(ctx, host_bwt2, n2, (uint8_t)p->term, &b2, &bad); st->ms_h2d += ctx->last_h2d_ms; }
+        if (rc == E2I_OK && host_da) rc = e2i_da_load(ctx, host_da, n1, &da);
+        t.stop();
+    }
+    if (rc == E2I_OK) rc = run_with_indexes(ctx, b1, b2, da, p, snp, snp_len, st);
+    e2i_bits_free(da); e2i_index_free(b1); e2i_index_free(b2);
+    st->ms_wall += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - w0).count();
+    return rc;
+}
+
+// The whole path from files: what bin/ebwt2InDel calls.  Disk reads, PCIe copies and the counting pass of the
+// index build overlap (e2i_index_build_file); with E2I_INDEX_CACHE=1 the packed index is kept next to the
+// input as <file>.e2ix and later runs upload that instead (half the bytes, no build).
+extern "C" int e2i_run_files(e2i_ctx *ctx, const char *path_bwt1, const char *path_bwt2, const char *path_da, const e2i_params *p,
+                             char **snp, size_t *snp_len, e2i_stats *st, uint64_t *n1_out, uint64_t *n2_out, uint64_t *bad_pos) {
+    if (!ctx || !path_bwt1 || !p || !snp || !snp_len || !st) { set_error("e2i_run_files: null argument"); return E2I_ERR_ARG; }
+    if (path_bwt2 && path_da) { set_error("Document array (-d) can only be used with one input BWT file (-1)"); return E2I_ERR_ARG; }
+    E2I_CUDA_TRY(cudaSetDevice(ctx->device));
+    const auto w0 = std::chrono::steady_clock::now();
+    e2i_index *b1 = nullptr, *b2 = nullptr;
+    e2i_bits *da = nullptr;
+    uint64_t bad = 0;
+    int rc, which = 1;
+    {
+        Accounting acct(ctx, st);
+        IndexTimer t(ctx, st);
+        rc = index_from_file(ctx, path_bwt1, (uint8_t)p->term, &b1, &bad);
+        if (rc == E2I_OK && path_bwt2) { which = 2; rc = index_from_file(ctx, path_bwt2, (uint8_t)p->term, &b2, &bad); }
+        if (rc == E2I_OK && path_da) rc = e2i_da_load_file(ctx, path_da, b1->n, &da);
+        t.stop();
+    }
+    if (rc == E2I_ERR_SYMBOL && bad_pos) { bad_pos[0] = bad; bad_pos[1] = (uint64_t)which; }
+    if (n1_out) *n1_out = b1 ? b1->n : 0;
+    if (n2_out) *n2_out = b2 ? b2->n : 0;
+    if (rc == E2I_OK) rc = run_with_indexes(ctx, b1, b2, da, p, snp, snp_len, st);
+    e2i_bits_free(da); e2i_index_free(b1); e2i_index_free(b2);
+    st->ms_wall += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - w0).count();
     return rc;
 }
 

@@ -4,6 +4,15 @@
 // 55-110, 275-315, 320-369) and the F-array scan of dna_bwt(path, TERM) (dna_bwt.hpp:36-62).
 // Three streaming kernels: count symbols per 16384-symbol tile, scan the tile totals, pack
 // (second read of the ASCII, one write of the 32-byte blocks).  HBM traffic: 2n read + n/2 write.
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <condition_variable>
+#include <mutex>
+#include <thread>
+
 #include "common.cuh"
 
 namespace e2i {
@@ -294,62 +303,101 @@ using namespace e2i;
 // =================================================================================================
 // C ABI
 // =================================================================================================
+// ---- whole-string build in three steps, so that the counting pass can follow the data as it arrives ----
+namespace {
+struct IndexBuild {
+    e2i_index *ix = nullptr;
+    uint4 *tile_cnt = nullptr;
+    ulonglong4 *tile_prefix = nullptr;
+    unsigned long long *scal = nullptr;    // [0..3] totals, [4] position of the first forbidden symbol
+    uint64_t n_tiles = 0;
+};
+
+void index_abort(e2i_ctx *ctx, IndexBuild &b) {
+    dfree(ctx, b.tile_cnt); dfree(ctx, b.tile_prefix); dfree(ctx, b.scal);
+    e2i_index_free(b.ix);
+    b = IndexBuild();
+}
+
+int index_begin(e2i_ctx *ctx, uint64_t n, uint8_t term, IndexBuild &b) {
+    cudaStream_t s = ctx->stream;
+    e2i_index *ix = new e2i_index();
+    b.ix = ix;
+    ix->ctx = ctx;
+    ix->n = n;
+    ix->term = term;
+    ix->n_blocks = n / kBlockSyms + 1;                       // rank(n) must be addressable (dna_string.hpp:62)
+    b.n_tiles = (ix->n_blocks + kTileBlocks - 1) / kTileBlocks;
+    ix->n_super = (n >> kSuperShift) + 1;
+    const size_t blk_bytes = b.n_tiles * kTileBlocks * kBlockU4 * sizeof(uint4);
+    ix->bytes = blk_bytes + ix->n_super * 32;
+    const unsigned long long init[5] = {0, 0, 0, 0, ~0ull};
+    cudaError_t e = dmalloc(ctx, &ix->blocks, blk_bytes);
+    if (e == cudaSuccess) e = dmalloc(ctx, &ix->super, ix->n_super * 32);
+    if (e == cudaSuccess) e = dmalloc(ctx, &b.tile_cnt, b.n_tiles * sizeof(uint4));
+    if (e == cudaSuccess) e = dmalloc(ctx, &b.tile_prefix, b.n_tiles * sizeof(ulonglong4));
+    if (e == cudaSuccess) e = dmalloc(ctx, &b.scal, 5 * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMemsetAsync(b.tile_cnt, 0, b.n_tiles * sizeof(uint4), s);   // the last tile may hold no symbol
+    if (e == cudaSuccess) e = cudaMemcpyAsync(b.scal, init, sizeof init, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);      // `init` lives on this stack frame
+    if (e != cudaSuccess) { set_error("index build: %s", cudaGetErrorString(e)); cudaGetLastError(); index_abort(ctx, b); return E2I_ERR_CUDA; }
+    ctx->n_h2d += sizeof init;
+    return E2I_OK;
+}
+
+// count the symbols of tiles [tile0, tile0 + nt); dev_ascii = the string's first byte, valid up to position `end`
+int index_count(e2i_ctx *ctx, IndexBuild &b, const uint8_t *dev_ascii, uint64_t tile0, uint64_t nt, uint64_t end) {
+    if (!nt) return E2I_OK;
+    const int grid = (int)std::min<uint64_t>(nt, (uint64_t)ctx->sm_count * 16);
+    count_tiles_kernel<<<grid, kBuildThreads, 0, ctx->stream>>>(dev_ascii + (tile0 << kTileShift), end, b.ix->term, tile0, nt, b.tile_cnt + tile0, b.scal + 4);
+    E2I_CUDA_TRY(cudaGetLastError());
+    ctx->n_launch++;
+    return E2I_OK;
+}
+
+int index_finish(e2i_ctx *ctx, IndexBuild &b, const uint8_t *dev_ascii, e2i_index **out, uint64_t *bad_pos) {
+    cudaStream_t s = ctx->stream;
+    e2i_index *ix = b.ix;
+    const int grid = (int)std::min<uint64_t>(b.n_tiles, (uint64_t)ctx->sm_count * 16);
+    scan_tiles_kernel<<<1, kScanThreads, 0, s>>>(b.tile_cnt, b.n_tiles, b.tile_prefix, b.scal);
+    pack_tiles_kernel<<<grid, kBuildThreads, 0, s>>>(dev_ascii, ix->n, ix->term, 0, b.n_tiles, b.tile_prefix, make_ulonglong4(0, 0, 0, 0), nullptr,
+                                                     ix->blocks, reinterpret_cast<unsigned long long *>(ix->super));
+    unsigned long long res[5];
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(res, b.scal, sizeof res, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) { set_error("index build: %s", cudaGetErrorString(e)); index_abort(ctx, b); return E2I_ERR_CUDA; }
+    ctx->n_launch += 2;
+    ctx->n_d2h += sizeof res;
+    if (res[4] != ~0ull) {
+        if (bad_pos) *bad_pos = res[4];
+        set_error("forbidden character at position %llu: only A,C,G,T and the terminator (ASCII %d) are admitted in the input BWT",
+                  res[4], (int)ix->term);
+        index_abort(ctx, b);
+        return E2I_ERR_SYMBOL;
+    }
+    const uint64_t acgt = res[0] + res[1] + res[2] + res[3];
+    ix->F[0] = ix->n - acgt;                                  // dna_bwt.hpp:51-60
+    ix->F[1] = ix->F[0] + res[0];
+    ix->F[2] = ix->F[1] + res[1];
+    ix->F[3] = ix->F[2] + res[2];
+    dfree(ctx, b.tile_cnt); dfree(ctx, b.tile_prefix); dfree(ctx, b.scal);
+    *out = ix;
+    b = IndexBuild();
+    return E2I_OK;
+}
+}  // namespace
+
 extern "C" int e2i_index_build_device(e2i_ctx *ctx, const uint8_t *dev_ascii, uint64_t n, uint8_t term,
                                       e2i_index **out, uint64_t *bad_pos) {
     if (!ctx || !out || (n && !dev_ascii)) { set_error("e2i_index_build_device: null argument"); return E2I_ERR_ARG; }
     if (reinterpret_cast<uintptr_t>(dev_ascii) & 15) { set_error("e2i_index_build_device: input must be 16-byte aligned"); return E2I_ERR_ARG; }
     E2I_CUDA_TRY(cudaSetDevice(ctx->device));
-    cudaStream_t s = ctx->stream;
-    e2i_index *ix = new e2i_index();
-    ix->ctx = ctx;
-    ix->n = n;
-    ix->term = term;
-    ix->n_blocks = n / kBlockSyms + 1;                       // rank(n) must be addressable (dna_string.hpp:62)
-    const uint64_t n_tiles = (ix->n_blocks + kTileBlocks - 1) / kTileBlocks;
-    ix->n_super = (n >> kSuperShift) + 1;
-    const size_t blk_bytes = n_tiles * kTileBlocks * kBlockU4 * sizeof(uint4);
-    ix->bytes = blk_bytes + ix->n_super * 32;
-    uint4 *tile_cnt = nullptr;
-    ulonglong4 *tile_prefix = nullptr;
-    unsigned long long *scal = nullptr;  // [0..3] totals, [4] bad position
-    auto fail = [&](int rc) { dfree(ctx, tile_cnt); dfree(ctx, tile_prefix); dfree(ctx, scal); e2i_index_free(ix); return rc; };
-#define TRYF(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { set_error("CUDA error %s at %s:%d: %s", cudaGetErrorName(_e), __FILE__, __LINE__, cudaGetErrorString(_e)); return fail(E2I_ERR_CUDA); } } while (0)
-    TRYF(dmalloc(ctx, &ix->blocks, blk_bytes));
-    TRYF(dmalloc(ctx, &ix->super, ix->n_super * 32));
-    TRYF(dmalloc(ctx, &tile_cnt, n_tiles * sizeof(uint4)));
-    TRYF(dmalloc(ctx, &tile_prefix, n_tiles * sizeof(ulonglong4)));
-    TRYF(dmalloc(ctx, &scal, 5 * sizeof(unsigned long long)));
-    unsigned long long init[5] = {0, 0, 0, 0, ~0ull};
-    TRYF(cudaMemcpyAsync(scal, init, sizeof init, cudaMemcpyHostToDevice, s));
-    const int grid = (int)std::min<uint64_t>(n_tiles, (uint64_t)ctx->sm_count * 16);
-    count_tiles_kernel<<<grid, kBuildThreads, 0, s>>>(dev_ascii, n, term, 0, n_tiles, tile_cnt, scal + 4);
-    scan_tiles_kernel<<<1, kScanThreads, 0, s>>>(tile_cnt, n_tiles, tile_prefix, scal);
-    pack_tiles_kernel<<<grid, kBuildThreads, 0, s>>>(dev_ascii, n, term, 0, n_tiles, tile_prefix, make_ulonglong4(0, 0, 0, 0), nullptr,
-                                                     ix->blocks, reinterpret_cast<unsigned long long *>(ix->super));
-    TRYF(cudaGetLastError());
-    ctx->n_launch += 3;
-    ctx->n_h2d += sizeof init;
-    ctx->n_d2h += 5 * sizeof(unsigned long long);
-    unsigned long long res[5];
-    TRYF(cudaMemcpyAsync(res, scal, sizeof res, cudaMemcpyDeviceToHost, s));
-    TRYF(cudaStreamSynchronize(s));
-#undef TRYF
-    dfree(ctx, tile_cnt); dfree(ctx, tile_prefix); dfree(ctx, scal);
-    tile_cnt = nullptr; tile_prefix = nullptr; scal = nullptr;
-    if (res[4] != ~0ull) {
-        if (bad_pos) *bad_pos = res[4];
-        set_error("forbidden character at position %llu: only A,C,G,T and the terminator (ASCII %d) are admitted in the input BWT",
-                  res[4], (int)term);
-        e2i_index_free(ix);
-        return E2I_ERR_SYMBOL;
-    }
-    const uint64_t acgt = res[0] + res[1] + res[2] + res[3];
-    ix->F[0] = n - acgt;                                      // dna_bwt.hpp:51-60
-    ix->F[1] = ix->F[0] + res[0];
-    ix->F[2] = ix->F[1] + res[1];
-    ix->F[3] = ix->F[2] + res[2];
-    *out = ix;
-    return E2I_OK;
+    IndexBuild b;
+    E2I_TRY(index_begin(ctx, n, term, b));
+    const int rc = index_count(ctx, b, dev_ascii, 0, (n + kTileSyms - 1) >> kTileShift, n);
+    if (rc != E2I_OK) { index_abort(ctx, b); return rc; }
+    return index_finish(ctx, b, dev_ascii, out, bad_pos);
 }
 
 // ---- slice-wise construction (multi-GPU): every rank packs the blocks of one tile-aligned slice ----
@@ -483,18 +531,287 @@ extern "C" int e2i_index_device(const e2i_index *ix, void **dev_blocks, uint64_t
     return E2I_OK;
 }
 
+// ---- streaming ingest: the eBWT goes up in chunks on the copy stream while the counting
+//      pass follows it on the compute stream; with a file as the source a reader thread fills a ring of
+//      page-locked buffers, so disk reads, PCIe copies and the counting kernels overlap.  Replaces the
+//      byte-at-a-time loop of dna_string.hpp:82-101. ---------------------------------------------------
+namespace {
+constexpr uint64_t kChunk = 64ull << 20;                  // multiple of the tile size
+constexpr int kRing = 4;
+
+struct Uploader {                                           // H2D of consecutive chunks + counting behind them
+    e2i_ctx *ctx;
+    IndexBuild *b;
+    uint8_t *dev;
+    uint64_t n, off = 0;
+    cudaEvent_t ev[kRing] = {};
+    int k = 0;
+    int init() { for (auto &e : ev) E2I_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); return E2I_OK; }
+    ~Uploader() { for (auto &e : ev) if (e) cudaEventDestroy(e); }
+    // host must stay valid until event `slot` (returned) has completed
+    int push(const uint8_t *host, uint64_t len, int *slot) {
+        const int sl = k++ % kRing;
+        E2I_CUDA_TRY(cudaMemcpyAsync(dev + off, host, len, cudaMemcpyHostToDevice, ctx->copy_stream));
+        E2I_CUDA_TRY(cudaEventRecord(ev[sl], ctx->copy_stream));
+        E2I_CUDA_TRY(cudaStreamWaitEvent(ctx->stream, ev[sl], 0));
+        ctx->n_h2d += len;
+        // chunks are tile-aligned except the last: count the tiles this chunk completes
+        const uint64_t t0 = off >> kTileShift, t1 = (off + len + kTileSyms - 1) >> kTileShift;
+        E2I_TRY(index_count(ctx, *b, dev, t0, t1 - t0, off + len));
+        off += len;
+        if (slot) *slot = sl;
+        return E2I_OK;
+    }
+};
+}  // namespace
+
 extern "C" int e2i_index_build(e2i_ctx *ctx, const uint8_t *host_ascii, uint64_t n, uint8_t term,
                                e2i_index **out, uint64_t *bad_pos) {
     if (!ctx || !out || (n && !host_ascii)) { set_error("e2i_index_build: null argument"); return E2I_ERR_ARG; }
     E2I_CUDA_TRY(cudaSetDevice(ctx->device));
     uint8_t *d = nullptr;
     E2I_CUDA_TRY(dmalloc(ctx, &d, n + 16));
-    cudaError_t e = cudaMemcpyAsync(d, host_ascii, n, cudaMemcpyHostToDevice, ctx->stream);
-    if (e != cudaSuccess) { dfree(ctx, d); set_error("H2D copy failed: %s", cudaGetErrorString(e)); return E2I_ERR_CUDA; }
-    ctx->n_h2d += n;
-    const int rc = e2i_index_build_device(ctx, d, n, term, out, bad_pos);
+    IndexBuild b;
+    int rc = index_begin(ctx, n, term, b);
+    if (rc != E2I_OK) { dfree(ctx, d); return rc; }
+    // the copy stream must not run ahead of the allocations made on the compute stream
+    Uploader up{ctx, &b, d, n};
+    rc = up.init();
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
+    if (rc == E2I_OK && (cudaEventCreate(&t0) != cudaSuccess || cudaEventCreate(&t1) != cudaSuccess)) rc = E2I_ERR_CUDA;
+    if (rc == E2I_OK && cudaEventRecord(up.ev[0], ctx->stream) == cudaSuccess) cudaStreamWaitEvent(ctx->copy_stream, up.ev[0], 0);
+    if (rc == E2I_OK) cudaEventRecord(t0, ctx->copy_stream);
+    for (uint64_t off = 0; rc == E2I_OK && off < n; off += kChunk) rc = up.push(host_ascii + off, std::min(kChunk, n - off), nullptr);
+    if (rc == E2I_OK) cudaEventRecord(t1, ctx->copy_stream);
+    if (rc == E2I_OK) rc = index_finish(ctx, b, d, out, bad_pos); else index_abort(ctx, b);
+    if (t0 && t1 && rc == E2I_OK) { float ms = 0; if (cudaEventElapsedTime(&ms, t0, t1) == cudaSuccess) ctx->last_h2d_ms = ms; }
+    if (t0) cudaEventDestroy(t0);
+    if (t1) cudaEventDestroy(t1);
+    cudaStreamSynchronize(ctx->copy_stream);
     dfree(ctx, d);
     return rc;
+}
+
+namespace {
+// A file streamed through a ring of page-locked buffers by a reader thread.  `total` bytes are delivered:
+// the file's bytes, then (DA semantics, ebwt2InDel.cpp:1503-1508) copies of its last byte.
+struct FileStream {
+    int fd = -1;
+    uint64_t size = 0, total = 0;
+    uint8_t *buf[kRing] = {};
+    uint64_t len[kRing] = {};
+    std::mutex m;
+    std::condition_variable cv;
+    uint64_t filled = 0, released = 0;      // chunks produced / chunks whose buffer may be reused
+    bool failed = false;
+    std::thread th;
+    void reader() {
+        const uint64_t n_chunks = (total + kChunk - 1) / kChunk;
+        uint8_t last = 0;
+        for (uint64_t c = 0; c < n_chunks; ++c) {
+            {
+                std::unique_lock<std::mutex> lk(m);
+                cv.wait(lk, [&] { return c < released + kRing; });
+            }
+            const int sl = (int)(c % kRing);
+            const uint64_t off = c * kChunk, want = std::min(kChunk, total - off);
+            uint64_t got = 0;
+            while (off + got < size && got < want) {
+                const ssize_t r = ::pread(fd, buf[sl] + got, (size_t)std::min<uint64_t>(want - got, size - off - got), (off_t)(off + got));
+                if (r <= 0) { std::lock_guard<std::mutex> lk(m); failed = true; cv.notify_all(); return; }
+                got += (uint64_t)r;
+            }
+            if (got) last = buf[sl][got - 1];
+            if (got < want) std::memset(buf[sl] + got, last, want - got);
+            {
+                std::lock_guard<std::mutex> lk(m);
+                len[sl] = want;
+                ++filled;
+            }
+            cv.notify_all();
+        }
+    }
+    int open(e2i_ctx *ctx, const char *path, uint64_t want_total) {
+        fd = ::open(path, O_RDONLY);
+        struct stat sb;
+        if (fd < 0 || ::fstat(fd, &sb) != 0) { set_error("could not read file %s", path); return E2I_ERR_IO; }
+        size = (uint64_t)sb.st_size;
+        total = want_total ? want_total : size;
+        if (!ctx->ring[0]) {
+            for (int i = 0; i < kRing; ++i)
+                if (cudaMallocHost(&ctx->ring[i], kChunk) != cudaSuccess) { cudaGetLastError(); set_error("cannot page-lock the ingest ring"); return E2I_ERR_MEMORY; }
+        }
+        for (int i = 0; i < kRing; ++i) buf[i] = static_cast<uint8_t *>(ctx->ring[i]);
+#ifdef POSIX_FADV_SEQUENTIAL
+        ::posix_fadvise(fd, 0, 0, POSIX_FADV_SEQUENTIAL);
+#endif
+        th = std::thread([this] { reader(); });
+        return E2I_OK;
+    }
+    // next filled chunk (blocks); false on a read error
+    bool next(uint64_t c, const uint8_t **p, uint64_t *l) {
+        std::unique_lock<std::mutex> lk(m);
+        cv.wait(lk, [&] { return failed || filled > c; });
+        if (failed) return false;
+        *p = buf[c % kRing];
+        *l = len[c % kRing];
+        return true;
+    }
+    void release() { { std::lock_guard<std::mutex> lk(m); ++released; } cv.notify_all(); }
+    ~FileStream() {
+        { std::lock_guard<std::mutex> lk(m); released = ~0ull >> 1; }
+        cv.notify_all();
+        if (th.joinable()) th.join();
+        if (fd >= 0) ::close(fd);
+    }
+};
+}  // namespace
+
+extern "C" int e2i_index_build_file(e2i_ctx *ctx, const char *path, uint8_t term, e2i_index **out, uint64_t *bad_pos) {
+    if (!ctx || !path || !out) { set_error("e2i_index_build_file: null argument"); return E2I_ERR_ARG; }
+    E2I_CUDA_TRY(cudaSetDevice(ctx->device));
+    FileStream fs;
+    E2I_TRY(fs.open(ctx, path, 0));
+    const uint64_t n = fs.total;
+    uint8_t *d = nullptr;
+    E2I_CUDA_TRY(dmalloc(ctx, &d, n + 16));
+    IndexBuild b;
+    int rc = index_begin(ctx, n, term, b);
+    if (rc != E2I_OK) { dfree(ctx, d); return rc; }
+    Uploader up{ctx, &b, d, n};
+    rc = up.init();
+    if (rc == E2I_OK && cudaEventRecord(up.ev[0], ctx->stream) == cudaSuccess) cudaStreamWaitEvent(ctx->copy_stream, up.ev[0], 0);
+    const uint64_t n_chunks = (n + kChunk - 1) / kChunk;
+    std::vector<int> slot_of(n_chunks, 0);
+    for (uint64_t c = 0; rc == E2I_OK && c < n_chunks; ++c) {
+        const uint8_t *p;
+        uint64_t l;
+        if (!fs.next(c, &p, &l)) { set_error("read error on %s", path); rc = E2I_ERR_IO; break; }
+        int sl = 0;
+        rc = up.push(p, l, &sl);
+        slot_of[c] = sl;
+        // the buffer of chunk c - (kRing - 2) is free once its copy has completed
+        if (rc == E2I_OK && c + 2 >= (uint64_t)kRing) { cudaEventSynchronize(up.ev[slot_of[c + 2 - kRing]]); fs.release(); }
+    }
+    cudaStreamSynchronize(ctx->copy_stream);
+    if (rc == E2I_OK) rc = index_finish(ctx, b, d, out, bad_pos); else index_abort(ctx, b);
+    dfree(ctx, d);
+    return rc;
+}
+
+// document array from a file, streamed the same way; a file shorter than n repeats its last byte
+extern "C" int e2i_da_load_file(e2i_ctx *ctx, const char *path, uint64_t n, e2i_bits **out) {
+    if (!ctx || !path || !out) { set_error("e2i_da_load_file: null argument"); return E2I_ERR_ARG; }
+    E2I_CUDA_TRY(cudaSetDevice(ctx->device));
+    FileStream fs;
+    E2I_TRY(fs.open(ctx, path, n));
+    uint8_t *d = nullptr;
+    E2I_CUDA_TRY(dmalloc(ctx, &d, n + 16));
+    cudaEvent_t ev[kRing] = {};
+    int rc = E2I_OK;
+    for (auto &e : ev) if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) rc = E2I_ERR_CUDA;
+    if (rc == E2I_OK && cudaEventRecord(ev[0], ctx->stream) == cudaSuccess) cudaStreamWaitEvent(ctx->copy_stream, ev[0], 0);
+    const uint64_t n_chunks = (n + kChunk - 1) / kChunk;
+    for (uint64_t c = 0; rc == E2I_OK && c < n_chunks; ++c) {
+        const uint8_t *p;
+        uint64_t l;
+        if (!fs.next(c, &p, &l)) { set_error("read error on %s", path); rc = E2I_ERR_IO; break; }
+        if (cudaMemcpyAsync(d + c * kChunk, p, l, cudaMemcpyHostToDevice, ctx->copy_stream) != cudaSuccess) { rc = E2I_ERR_CUDA; break; }
+        cudaEventRecord(ev[c % kRing], ctx->copy_stream);
+        ctx->n_h2d += l;
+        if (c + 2 >= (uint64_t)kRing) { cudaEventSynchronize(ev[(c + 2 - kRing) % kRing]); fs.release(); }
+    }
+    cudaStreamSynchronize(ctx->copy_stream);
+    for (auto &e : ev) if (e) cudaEventDestroy(e);
+    if (rc == E2I_OK) rc = e2i_da_load_device(ctx, d, n, out);
+    dfree(ctx, d);
+    return rc;
+}
+
+// ---- packed-index sidecar: the index as it lies in HBM, so that a later run uploads n/2 bytes and skips the
+//      build.  Replaces the reference's (unused) serialize / load, dna_bwt.hpp:238-289, dna_string.hpp:205-243.
+namespace {
+struct SidecarHeader {
+    char magic[8];              // "E2IIDX02"
+    uint64_t n, n_blocks, n_super, blk_bytes, F[4];
+    uint32_t term, block_syms, super_shift, pad;
+};
+}  // namespace
+
+extern "C" int e2i_index_save(const e2i_index *ix, const char *path) {
+    if (!ix || !path) { set_error("e2i_index_save: null argument"); return E2I_ERR_ARG; }
+    E2I_CUDA_TRY(cudaSetDevice(ix->ctx->device));
+    SidecarHeader h = {};
+    std::memcpy(h.magic, "E2IIDX02", 8);
+    h.n = ix->n; h.n_blocks = ix->n_blocks; h.n_super = ix->n_super; h.blk_bytes = ix->bytes - ix->n_super * 32;
+    for (int i = 0; i < 4; ++i) h.F[i] = ix->F[i];
+    h.term = ix->term; h.block_syms = kBlockSyms; h.super_shift = kSuperShift;
+    FILE *f = std::fopen(path, "wb");
+    if (!f) { set_error("could not write %s", path); return E2I_ERR_IO; }
+    bool ok = std::fwrite(&h, sizeof h, 1, f) == 1;
+    std::vector<uint8_t> host((size_t)kChunk);
+    auto dump = [&](const void *dev, uint64_t bytes) {
+        for (uint64_t off = 0; ok && off < bytes; off += kChunk) {
+            const uint64_t l = std::min(kChunk, bytes - off);
+            ok = cudaMemcpy(host.data(), static_cast<const char *>(dev) + off, l, cudaMemcpyDeviceToHost) == cudaSuccess &&
+                 std::fwrite(host.data(), 1, l, f) == l;
+        }
+    };
+    dump(ix->super, ix->n_super * 32);
+    dump(ix->blocks, h.blk_bytes);
+    ok = (std::fclose(f) == 0) && ok;
+    if (!ok) { set_error("could not write %s", path); return E2I_ERR_IO; }
+    return E2I_OK;
+}
+
+extern "C" int e2i_index_load(e2i_ctx *ctx, const char *path, e2i_index **out) {
+    if (!ctx || !path || !out) { set_error("e2i_index_load: null argument"); return E2I_ERR_ARG; }
+    E2I_CUDA_TRY(cudaSetDevice(ctx->device));
+    FileStream fs;
+    E2I_TRY(fs.open(ctx, path, 0));
+    const uint8_t *p;
+    uint64_t l;
+    SidecarHeader h;
+    if (fs.total < sizeof h || !fs.next(0, &p, &l)) { set_error("%s is not a packed index", path); return E2I_ERR_IO; }
+    std::memcpy(&h, p, sizeof h);
+    if (std::memcmp(h.magic, "E2IIDX02", 8) != 0 || h.block_syms != (uint32_t)kBlockSyms || h.super_shift != (uint32_t)kSuperShift ||
+        fs.total != sizeof h + h.n_super * 32 + h.blk_bytes || h.n_blocks != h.n / kBlockSyms + 1) {
+        set_error("%s is not a packed index of this library version", path);
+        return E2I_ERR_IO;
+    }
+    e2i_index *ix = new e2i_index();
+    ix->ctx = ctx; ix->n = h.n; ix->n_blocks = h.n_blocks; ix->n_super = h.n_super; ix->term = (uint8_t)h.term;
+    ix->bytes = h.blk_bytes + h.n_super * 32;
+    for (int i = 0; i < 4; ++i) ix->F[i] = h.F[i];
+    if (dmalloc(ctx, &ix->blocks, h.blk_bytes) != cudaSuccess || dmalloc(ctx, &ix->super, h.n_super * 32) != cudaSuccess ||
+        cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+        cudaGetLastError(); set_error("e2i_index_load: out of device memory"); e2i_index_free(ix); return E2I_ERR_MEMORY;
+    }
+    // the payload [super | blocks] follows the header; chunks go up as they arrive
+    cudaEvent_t ev[kRing] = {};
+    int rc = E2I_OK;
+    for (auto &e : ev) if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) rc = E2I_ERR_CUDA;
+    const uint64_t s_bytes = h.n_super * 32, n_chunks = (fs.total + kChunk - 1) / kChunk;
+    for (uint64_t c = 0; rc == E2I_OK && c < n_chunks; ++c) {
+        if (c && !fs.next(c, &p, &l)) { set_error("read error on %s", path); rc = E2I_ERR_IO; break; }
+        uint64_t lo = c * kChunk, hi = lo + l;                       // file range of this chunk
+        const uint64_t pay0 = sizeof h;
+        auto copy = [&](uint64_t f0, uint64_t f1, char *dst_base, uint64_t dst_f0) {   // file range [f0,f1) ∩ chunk -> device
+            const uint64_t a = std::max(lo, f0), b2 = std::min(hi, f1);
+            if (a >= b2 || rc != E2I_OK) return;
+            if (cudaMemcpyAsync(dst_base + (a - dst_f0), p + (a - lo), b2 - a, cudaMemcpyHostToDevice, ctx->copy_stream) != cudaSuccess) rc = E2I_ERR_CUDA;
+            ctx->n_h2d += b2 - a;
+        };
+        copy(pay0, pay0 + s_bytes, reinterpret_cast<char *>(ix->super), pay0);
+        copy(pay0 + s_bytes, fs.total, reinterpret_cast<char *>(ix->blocks), pay0 + s_bytes);
+        cudaEventRecord(ev[c % kRing], ctx->copy_stream);
+        if (c + 2 >= (uint64_t)kRing) { cudaEventSynchronize(ev[(c + 2 - kRing) % kRing]); fs.release(); }
+    }
+    cudaStreamSynchronize(ctx->copy_stream);
+    for (auto &e : ev) if (e) cudaEventDestroy(e);
+    if (rc != E2I_OK) { if (rc == E2I_ERR_CUDA) set_error("e2i_index_load: copy failed"); e2i_index_free(ix); return rc; }
+    *out = ix;
+    return E2I_OK;
 }
 
 extern "C" void e2i_index_free(e2i_index *ix) {

@@ -186,33 +186,46 @@ int main(int argc, char **argv) {
     const auto t0 = std::chrono::steady_clock::now();
     uint8_t *b1 = nullptr, *b2 = nullptr, *da = nullptr;
     uint64_t n1 = 0, n2 = 0, nd = 0;
-    if (!read_file(input1, &b1, &n1, 0) || (two && !read_file(input2, &b2, &n2, 0)) ||
-        (with_da && !read_file(input_da, &da, &nd, n1))) {
-        cout << "Error: could not read the input files (" << e2i_last_error() << ")" << endl;
-        return 2;
-    }
     // forbidden symbols: same message and exit code as dna_string.hpp:90-96
-    auto check_symbols = [&](const uint8_t *b, uint64_t n) {
-        for (uint64_t i = 0; i < n; ++i) {
-            const uint8_t c = b[i];
-            if (c != 'A' && c != 'C' && c != 'G' && c != 'T' && c != (uint8_t)p.term) {
-                cout << "Error while reading file: read forbidden character '" << (char)c << "' (ASCII code " << int((char)c) << ")." << endl
-                     << "Only A,C,G,T, and " << (char)p.term << " are admitted in the input BWT!" << endl
-                     << "If the unknown character is the terminator, you can solve the problem by adding option \"-t " << int((char)c) << "\"." << endl;
-                std::exit(1);
-            }
-        }
+    auto forbidden = [&](uint8_t c) {
+        cout << "Error while reading file: read forbidden character '" << (char)c << "' (ASCII code " << int((char)c) << ")." << endl
+             << "Only A,C,G,T, and " << (char)p.term << " are admitted in the input BWT!" << endl
+             << "If the unknown character is the terminator, you can solve the problem by adding option \"-t " << int((char)c) << "\"." << endl;
+        std::exit(1);
     };
-
     e2i_stats st;
     std::memset(&st, 0, sizeof st);
     char *snp = nullptr;
     size_t snp_len = 0;
-    const int rc = multi ? e2i_run_multi(devices.data(), (int)devices.size(), b1, n1, b2, n2, da, &p, frontier_bytes, &snp, &snp_len, &st)
-                         : e2i_run(ctx, b1, n1, b2, n2, da, &p, &snp, &snp_len, &st);
-    if (rc == E2I_ERR_SYMBOL) {   // locate the byte on the host only on this error path
-        check_symbols(b1, n1);
-        if (two) check_symbols(b2, n2);
+    int rc;
+    if (!multi) {
+        // one GPU: the files are streamed (reader thread -> page-locked ring -> copy stream -> counting pass)
+        uint64_t bad[2] = {0, 0};
+        rc = e2i_run_files(ctx, input1.c_str(), two ? input2.c_str() : nullptr, with_da ? input_da.c_str() : nullptr, &p,
+                           &snp, &snp_len, &st, &n1, &n2, bad);
+        if (rc == E2I_ERR_SYMBOL) {                   // fetch the byte on this error path only
+            const string &f = bad[1] == 2 ? input2 : input1;
+            const int fd = ::open(f.c_str(), O_RDONLY);
+            uint8_t c = 0;
+            if (fd >= 0 && ::pread(fd, &c, 1, (off_t)bad[0]) == 1) forbidden(c);
+        }
+    } else {
+        if (!read_file(input1, &b1, &n1, 0) || (two && !read_file(input2, &b2, &n2, 0)) ||
+            (with_da && !read_file(input_da, &da, &nd, n1))) {
+            cout << "Error: could not read the input files (" << e2i_last_error() << ")" << endl;
+            return 2;
+        }
+        rc = e2i_run_multi(devices.data(), (int)devices.size(), b1, n1, b2, n2, da, &p, frontier_bytes, &snp, &snp_len, &st);
+        if (rc == E2I_ERR_SYMBOL) {
+            auto check_symbols = [&](const uint8_t *b, uint64_t n) {
+                for (uint64_t i = 0; i < n; ++i) {
+                    const uint8_t c = b[i];
+                    if (c != 'A' && c != 'C' && c != 'G' && c != 'T' && c != (uint8_t)p.term) forbidden(c);
+                }
+            };
+            check_symbols(b1, n1);
+            if (two) check_symbols(b2, n2);
+        }
     }
     if (rc != E2I_OK) {
         cout << "Error: " << e2i_last_error() << endl;

@@ -311,7 +311,8 @@ extern "C" int e2i_snp_format(const e2i_call_rec *recs, const char *left, const 
                               const e2i_params *p, int two_samples, uint64_t first_cluster_nr,
                               char **snp, size_t *snp_len, e2i_stats *st) {
     if (!p || !snp || !snp_len || (n_recs && (!recs || !left || !right))) { e2i::set_error("e2i_snp_format: null argument"); return E2I_ERR_ARG; }
-    if (p->max_gap > p->k_left) { e2i::set_error("e2i_snp_format: max_gap (-g) must not exceed k_left (-L)"); return E2I_ERR_ARG; }
+    // -g larger than -L is accepted like the reference does (its substr(0, len - g) wraps to the whole string,
+    // ebwt2InDel.cpp:208-219; such a gap never wins, see distance())
     const uint64_t first = first_cluster_nr ? first_cluster_nr : 1;
     unsigned hw = std::thread::hardware_concurrency();
     if (hw == 0) hw = 1;

@@ -130,9 +130,8 @@ def format_sharded(api, recs, left, right, params, two_samples: bool, rank: int,
 
 def gather_bytes(view, rank: int, world: int, device, group=None):
     """Concatenation of every rank's bytes on rank 0 (rank order) as a uint8 numpy array.
-    Sizes are exchanged first; every rank > 0 sends exactly its bytes and rank 0 receives them
-    (NCCL point-to-point over NVLink on GPUs, gloo on CPU) into consecutive slices of ONE
-    page-locked host buffer that is kept across calls, so each side copies the text once."""
+    Sizes are exchanged first; then ONE gather collective of pieces padded to the largest size (NCCL over
+    NVLink on GPUs, gloo on CPU) and one copy per piece into a page-locked host buffer kept across calls."""
     global _pinned
     view = memoryview(view).cast("B") if len(view) else memoryview(b"")
     size = torch.tensor([len(view)], dtype=torch.int64, device=device)
@@ -140,26 +139,25 @@ def gather_bytes(view, rank: int, world: int, device, group=None):
     dist.all_gather(sizes, size, group=group)
     sizes = [int(s) for s in sizes]
     cuda = torch.device(device).type == "cuda"
-    src = torch.from_numpy(np.frombuffer(view, dtype=np.uint8)) if len(view) else torch.empty(0, dtype=torch.uint8)
+    pad = max(max(sizes), 1)
+    mine = torch.empty(pad, dtype=torch.uint8, device=device)
+    if len(view):
+        mine[:len(view)].copy_(torch.from_numpy(np.frombuffer(view, dtype=np.uint8)), non_blocking=True)
+    parts = [torch.empty(pad, dtype=torch.uint8, device=device) for _ in range(world)] if rank == 0 else None
+    dist.gather(mine, parts, dst=0, group=group)
     if rank != 0:
-        if sizes[rank]:
-            dist.send(src.to(device) if cuda else src.clone(), dst=0, group=group)
         return None
     total = sum(sizes)
     if _pinned is None or _pinned.numel() < total:
         _pinned = torch.empty(max(total, 1) * 5 // 4, dtype=torch.uint8, pin_memory=cuda)
     out = _pinned[:max(total, 1)]
-    out[:sizes[0]].copy_(src)
-    off = sizes[0]
-    for r in range(1, world):
+    off = 0
+    for r in range(world):
         if sizes[r]:
-            if cuda:
-                stage = torch.empty(sizes[r], dtype=torch.uint8, device=device)
-                dist.recv(stage, src=r, group=group)
-                out[off:off + sizes[r]].copy_(stage)
-            else:
-                dist.recv(out[off:off + sizes[r]], src=r, group=group)
+            out[off:off + sizes[r]].copy_(parts[r][:sizes[r]], non_blocking=True)
         off += sizes[r]
+    if cuda:
+        torch.cuda.synchronize(device)
     return out[:total].numpy()
 
 

@@ -230,6 +230,19 @@ void e2i_buffer_free(void *p);
  *      run_two_datasets :1344, run_two_datasets_da :1471).  host_bwt2 / host_da may be NULL. -- */
 int e2i_run(e2i_ctx *ctx, const uint8_t *host_bwt1, uint64_t n1, const uint8_t *host_bwt2, uint64_t n2,
             const uint8_t *host_da, const e2i_params *p, char **snp, size_t *snp_len, e2i_stats *st);
+/* The same from files (what bin/ebwt2InDel calls): streaming ingest -- a reader thread fills a ring of page-
+ * locked buffers, the chunks go up on a copy stream and the counting pass of the index build follows them, so
+ * disk reads, PCIe copies and kernels overlap (replaces the byte-at-a-time loops of dna_string.hpp:82-101 and
+ * ebwt2InDel.cpp:1503-1508; a DA file shorter than the eBWT repeats its last byte like that loop does).  With
+ * the environment variable E2I_INDEX_CACHE=1 the packed index is kept as <file>.e2ix and reused by later runs
+ * (e2i_index_save / e2i_index_load: the reference's unused serialize / load, dna_bwt.hpp:238-289).
+ * n1_out / n2_out: the eBWT lengths; bad_pos[2]: on E2I_ERR_SYMBOL the position and the input (1 or 2). */
+int e2i_run_files(e2i_ctx *ctx, const char *path_bwt1, const char *path_bwt2, const char *path_da, const e2i_params *p,
+                  char **snp, size_t *snp_len, e2i_stats *st, uint64_t *n1_out, uint64_t *n2_out, uint64_t *bad_pos);
+int e2i_index_build_file(e2i_ctx *ctx, const char *path, uint8_t term, e2i_index **out, uint64_t *bad_pos);
+int e2i_da_load_file(e2i_ctx *ctx, const char *path, uint64_t n, e2i_bits **out);
+int e2i_index_save(const e2i_index *ix, const char *path);
+int e2i_index_load(e2i_ctx *ctx, const char *path, e2i_index **out);
 /* same, inputs already resident in HBM (kernel-side throughput in bench.py) */
 int e2i_run_device(e2i_ctx *ctx, const uint8_t *dev_bwt1, uint64_t n1, const uint8_t *dev_bwt2, uint64_t n2,
                    const uint8_t *dev_da, const e2i_params *p, char **snp, size_t *snp_len, e2i_stats *st);

@@ -690,7 +690,7 @@ static void call_two(const orc_bwt *b1, const orc_bwt *b2, const uint64_t *da, c
 /* cluster scan: run_one_dataset (:1609-1655), run_two_datasets (:1395-1445), run_two_datasets_da (:1510-1560) */
 int orc_call(const orc_bwt *b1, const orc_bwt *b2, const uint64_t *da, const uint64_t *thr,
              const uint64_t *minima, const orc_params *p, char **snp, size_t *snp_len, orc_stats *st) {
-    if (p->k_left >= MAX_CTX || p->k_right >= MAX_CTX || p->k_left < 1 || p->max_gap > p->k_left) return 2;
+    if (p->k_left >= MAX_CTX || p->k_right >= MAX_CTX || p->k_left < 1) return 2;   /* -g > -L is accepted like the reference (orc_distance) */
     orc_bwt *m1 = (orc_bwt *)b1, *m2 = (orc_bwt *)b2;
     m1->rank_calls = &st->rank_call;
     if (m2) m2->rank_calls = &st->rank_call;

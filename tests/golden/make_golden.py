@@ -64,5 +64,42 @@ def main():
     save("m2_flags", b0, b1, flags=("-m", 2, "-L", 24, "-R", 20, "-k", 12, "-g", 6, "-q", 2))
 
 
+def save_stdout():
+    """tests/golden/<case>.stdout.txt: what the reference prints (progress percentages dropped, file names
+    replaced by placeholders) -- the CLI drop-in test diffs bin/ebwt2InDel's stdout against it."""
+    import re
+    import subprocess
+    import tempfile
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from conftest import golden_names, load_golden
+    inv = {v: k for k, v in FLAG_FIELD.items()}
+    for name in golden_names():
+        g = load_golden(name)
+        with tempfile.TemporaryDirectory() as d:
+            names = {}
+            cmd = [ob.REF_BIN]
+            for key, flag, fn in (("bwt1", "-1", "a.ebwt"), ("bwt2", "-2", "b.ebwt"), ("da", "-d", "da.txt")):
+                if g[key] is not None:
+                    path = os.path.join(d, fn)
+                    g[key].tofile(path)
+                    cmd += [flag, path]
+                    names[path] = "<" + key + ">"
+            out = os.path.join(d, "out.snp")
+            names[out] = "<out>"
+            for k, v in g["flags"].items():
+                cmd += [inv[k], str(v)]
+            text = subprocess.run(cmd + ["-o", out], capture_output=True, text=True, check=True).stdout
+        for path, ph in names.items():
+            text = text.replace(path, ph)
+        lines = [ln for ln in text.split("\n") if not re.match(r"^\s*(LCP: )?\d+(\.\d+)?%", ln) and "%" not in ln[:10]]
+        with open(os.path.join(HERE, name + ".stdout.txt"), "w") as f:
+            f.write("\n".join(lines))
+        print(name, len(lines), "stdout lines")
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "stdout":
+        save_stdout()
+    else:
+        main()
+        save_stdout()

@@ -225,37 +225,110 @@ def test_small_frontier_budget_gives_same_result(e2i):
     assert st.nodes == g["counters"]["nodes"]
 
 
-def test_cli_drop_in(tmp_path):
-    """bin/ebwt2InDel with the reference's argv: same .snp bytes, same counter lines."""
+def _run_cli(tmp_path, g, env=None):
     exe = os.path.join(ROOT, "bin", "ebwt2InDel")
-    for name in ("m1_flags", "m3_default", "m2_default", "m1_term36"):
+    f1 = tmp_path / "a.ebwt"
+    g["bwt1"].tofile(f1)
+    cmd, names = [exe, "-1", str(f1)], {str(f1): "<bwt1>"}
+    if g["bwt2"] is not None:
+        f2 = tmp_path / "b.ebwt"
+        g["bwt2"].tofile(f2)
+        cmd += ["-2", str(f2)]
+        names[str(f2)] = "<bwt2>"
+    if g["da"] is not None:
+        f3 = tmp_path / "da.txt"
+        g["da"].tofile(f3)
+        cmd += ["-d", str(f3)]
+        names[str(f3)] = "<da>"
+    out = tmp_path / "out.snp"
+    names[str(out)] = "<out>"
+    inv = {v: k for k, v in {"-L": "k_left", "-R": "k_right", "-k": "K", "-g": "max_gap", "-v": "max_snvs",
+                             "-m": "mcov_out", "-c": "complexity", "-q": "max_variants_per_position",
+                             "-t": "term"}.items()}
+    for k, v in g["flags"].items():
+        cmd += [inv[k], str(v)]
+    r = subprocess.run(cmd + ["-o", str(out)], capture_output=True, text=True, env=env)
+    text = r.stdout
+    for path, ph in names.items():
+        text = text.replace(path, ph)
+    return r, text, out
+
+
+def test_cli_drop_in(tmp_path):
+    """bin/ebwt2InDel with the reference's argv: same .snp bytes, and the same stdout as the compiled reference
+    line for line (tests/golden/<case>.stdout.txt) -- banner, counters, averages, the cluster-length histogram --
+    except the reference's progress percentages and its 'Max stack depth' lines (a property of its DFS order)."""
+    for name in golden_names():
         g = load_golden(name)
-        f1 = tmp_path / "a.ebwt"
-        g["bwt1"].tofile(f1)
-        cmd = [exe, "-1", str(f1)]
-        if g["bwt2"] is not None:
-            f2 = tmp_path / "b.ebwt"
-            g["bwt2"].tofile(f2)
-            cmd += ["-2", str(f2)]
-        if g["da"] is not None:
-            f3 = tmp_path / "da.txt"
-            g["da"].tofile(f3)
-            cmd += ["-d", str(f3)]
-        out = tmp_path / "out.snp"
-        inv = {v: k for k, v in {"-L": "k_left", "-R": "k_right", "-k": "K", "-g": "max_gap", "-v": "max_snvs",
-                                 "-m": "mcov_out", "-c": "complexity", "-q": "max_variants_per_position",
-                                 "-t": "term"}.items()}
-        for k, v in g["flags"].items():
-            cmd += [inv[k], str(v)]
-        r = subprocess.run(cmd + ["-o", str(out)], capture_output=True, text=True)
+        r, text, out = _run_cli(tmp_path, g)
         assert r.returncode == 0, r.stdout + r.stderr
-        assert out.read_bytes() == g["snp"]
-        assert f"Processed {g['counters']['nodes']} suffix-tree nodes." in r.stdout
-        assert f"Analyzed {g['counters']['n_clusters']} clusters." in r.stdout
+        assert out.read_bytes() == g["snp"], name
+        want = [ln for ln in open(os.path.join(ROOT, "tests", "golden", name + ".stdout.txt")).read().split("\n")
+                if not ln.startswith("Max stack depth")]
+        assert text.split("\n") == want, name
     bad = tmp_path / "bad.ebwt"
     bad.write_bytes(b"ACGTNACGT#")
+    exe = os.path.join(ROOT, "bin", "ebwt2InDel")
     r = subprocess.run([exe, "-1", str(bad), "-o", str(tmp_path / "x.snp")], capture_output=True, text=True)
     assert r.returncode == 1 and "read forbidden character 'N' (ASCII code 78)" in r.stdout
+
+
+def test_streaming_ingest_and_index_sidecar(gpu_ctx, e2i, oracle, tmp_path):
+    """f1: e2i_index_build_file (reader thread -> page-locked ring -> copy stream -> counting pass) gives the
+    index of the in-memory build, for sizes around the 64 MB chunk and the tile size; the packed sidecar
+    (save / load) answers the same queries; e2i_run_files equals e2i_run; a short DA file repeats its last
+    byte (ebwt2InDel.cpp:1503-1508); the CLI reuses the sidecar when E2I_INDEX_CACHE=1."""
+    rng = np.random.default_rng(3)
+    for n in (1, 16384, (64 << 20) - 1, (64 << 20) + 16385, 3 * (64 << 20) + 7):
+        bwt = mixed_bwt(n, seed=n % 1000)
+        f = tmp_path / "x.ebwt"
+        bwt.tofile(f)
+        a, b = gpu_ctx.index_file(str(f)), gpu_ctx.index(bwt)
+        pos = np.unique(np.concatenate([rng.integers(0, n + 1, 3000), [0, n]])).astype(np.uint64)
+        assert np.array_equal(a.F(), b.F()) and np.array_equal(a.rank4(pos), b.rank4(pos))
+        a.save(str(tmp_path / "x.e2ix"))
+        c = gpu_ctx.index_load(str(tmp_path / "x.e2ix"))
+        assert c.n == n and np.array_equal(c.F(), b.F()) and np.array_equal(c.rank4(pos), b.rank4(pos))
+        del a, b, c
+    bad = mixed_bwt(100000, 1).copy()
+    bad[70001] = ord("N")
+    bad.tofile(tmp_path / "bad.ebwt")
+    with pytest.raises(ValueError, match="70001"):
+        gpu_ctx.index_file(str(tmp_path / "bad.ebwt"))
+    for name in ("m1_default", "m2_flags", "m3_default"):
+        g = load_golden(name)
+        paths = {}
+        for key in ("bwt1", "bwt2", "da"):
+            if g[key] is not None:
+                paths[key] = str(tmp_path / (key + ".bin"))
+                g[key].tofile(paths[key])
+        snp, st = gpu_ctx.run_files(paths["bwt1"], paths.get("bwt2"), paths.get("da"), _case_params(e2i, g))
+        assert snp == g["snp"], name
+    # short document array: the missing positions take the value of the last byte
+    g = load_golden("m3_default")
+    n = len(g["bwt1"])
+    cut = n - 1000
+    da_short = g["da"][:cut]
+    da_short.tofile(tmp_path / "short.txt")
+    want = np.concatenate([da_short, np.full(n - cut, da_short[-1], dtype=np.uint8)])
+    bits = gpu_ctx.document_array_file(str(tmp_path / "short.txt"), n).fetch()
+    assert np.array_equal(bits, gpu_ctx.document_array(want).fetch())
+    # CLI with the sidecar cache: first run writes it, second run loads it; same output
+    g = load_golden("m1_default")
+    env = dict(os.environ, E2I_INDEX_CACHE="1")
+    for _ in range(2):
+        r, _, out = _run_cli(tmp_path, g, env)
+        assert r.returncode == 0 and out.read_bytes() == g["snp"]
+        assert os.path.exists(str(tmp_path / "a.ebwt") + ".e2ix")
+
+
+def test_gap_longer_than_left_context_is_accepted(gpu_ctx, e2i, oracle):
+    """-g > -L: accepted like the reference (its substr wraps, ebwt2InDel.cpp:208-219); same text as the oracle."""
+    g = load_golden("m3_default")
+    kw = {"k_left": 12, "max_gap": 20, "k_right": 10, "K": 8, "complexity": 6}
+    snp, _ = gpu_ctx.run(g["bwt1"], None, g["da"], e2i.default_params(**kw))
+    osnp, _ = oracle.run(g["bwt1"], None, g["da"], oracle.default_params(**kw))
+    assert snp == osnp and len(snp) > 0
 
 
 def test_gpu_ebwt_builder_matches_reference_builders(gpu_ctx):

@@ -5,10 +5,12 @@ other vector under tests/golden/ was produced by the compiled, unmodified refere
 (tests/golden/make_golden.py).  When the compiled reference is present (build container) the
 oracle is also compared with it live on fresh seeded inputs.
 """
+import os
+
 import numpy as np
 import pytest
 
-from conftest import golden_names, load_golden, resolved_fields
+from conftest import ROOT, golden_names, load_golden, resolved_fields
 
 
 def test_distance_known_answer(oracle):
@@ -94,3 +96,16 @@ def test_bcr_builder_matches_naive():
     a, oa = synth.ebwt_naive(reads)
     b, ob_ = synth.ebwt_bcr_numpy(reads)
     assert np.array_equal(a, b) and np.array_equal(oa, ob_)
+
+
+@pytest.mark.skipif(not os.access(os.path.join(ROOT, "oracle", "_ref", "ebwt2InDel"), os.X_OK), reason="compiled reference absent")
+def test_gap_longer_than_left_context_like_reference(oracle):
+    """-g > -L: the reference accepts it (its substr(0, len - g) wraps to the whole string, ebwt2InDel.cpp:208-219);
+    the oracle gives the same bytes, in modes -1 and -d."""
+    for name in ("m1_default", "m3_default"):
+        g = load_golden(name)
+        flags = ("-L", 12, "-g", 20, "-R", 10, "-k", 8, "-c", 6)
+        kw = {"k_left": 12, "max_gap": 20, "k_right": 10, "K": 8, "complexity": 6}
+        want, _ = oracle.run_ref(g["bwt1"], g["bwt2"], g["da"], flags)
+        snp, _ = oracle.run(g["bwt1"], g["bwt2"], g["da"], oracle.default_params(**kw))
+        assert snp == want and len(snp) > 0
