@@ -47,6 +47,10 @@ namespace e2i {
 constexpr int kNavWarps = 4;                          // warps per CTA; every warp works on its own
 constexpr int kNavThreads = kNavWarps * 32;
 constexpr int kWarpStage = 128;                       // index blocks staged in shared memory per warp (4 KB)
+#ifndef E2I_WINDOW_MAX
+#define E2I_WINDOW_MAX 96
+#endif
+constexpr int kWindowMax = E2I_WINDOW_MAX;             // longest block range staged as one window (one BWT)
 constexpr int kMaxRun = 1024;                         // records per run (multiple of 32), upper bound
 #ifndef E2I_NODE_CTAS
 #define E2I_NODE_CTAS 7                               // resident CTAs per SM the one-BWT kernels are compiled for
@@ -484,7 +488,9 @@ expand_nodes_kernel(const NavArgs a, const FrameIn in, const FrameOut out) {
                 constexpr uint32_t sbs = kSuperShift - kBlockShift;
                 multi_super = (lo1 >> sbs) != (hi1 >> sbs) || (TWO && (lo2 >> sbs) != (hi2 >> sbs));
                 __syncwarp();                                               // the previous step's reads of the staging buffer are over
-                if (span1 <= (uint32_t)STAGE && span2 <= (uint32_t)STAGE) {
+                // WINDOW copies the whole block range, SLOTS at most two blocks per node: the window pays off while
+                // the range is not longer than what SLOTS would fetch (pairs: up to the staging capacity)
+                if (span1 <= (uint32_t)(TWO ? STAGE : kWindowMax) && span2 <= (uint32_t)STAGE) {
                     mode = SRC_WINDOW;
                     stage_window(a.ix1, stage1, lo1, span1, lane);
                     if (TWO) stage_window(a.ix2, stage2, lo2, span2, lane);
