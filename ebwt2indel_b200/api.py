@@ -75,7 +75,7 @@ SYMBOLS = (
     "e2i_bits_size", "e2i_bits_free", "e2i_navigate", "e2i_navigate_shard", "e2i_lcpbits_fetch",
     "e2i_lcpbits_device", "e2i_bits_device", "e2i_lcpbits_free", "e2i_call", "e2i_calls_count",
     "e2i_calls_fetch", "e2i_calls_view", "e2i_calls_free", "e2i_snp_format", "e2i_snp_count", "e2i_filter_snp", "e2i_distance", "e2i_buffer_free", "e2i_run",
-    "e2i_run_device", "e2i_run_files", "e2i_index_build_file", "e2i_da_load_file", "e2i_index_save", "e2i_index_load", "e2i_run_multi", "e2i_enable_peers", "e2i_or_allreduce",
+    "e2i_run_device", "e2i_run_files", "e2i_index_build_file", "e2i_da_load_file", "e2i_index_save", "e2i_index_load", "e2i_ebwt_build", "e2i_run_multi", "e2i_enable_peers", "e2i_or_allreduce",
 )
 
 _lib = None
@@ -149,6 +149,7 @@ def lib():
         "e2i_da_load_file": (C.c_int, [vp, C.c_char_p, u64, C.POINTER(vp)]),
         "e2i_index_save": (C.c_int, [vp, C.c_char_p]),
         "e2i_index_load": (C.c_int, [vp, C.c_char_p, C.POINTER(vp)]),
+        "e2i_ebwt_build": (C.c_int, [vp, u8p, u64, C.c_uint32, u64, C.c_uint8, u8p, u8p]),
         "e2i_run_multi": (C.c_int, [C.POINTER(C.c_int), C.c_int, u8p, u64, u8p, u64, u8p, PP, u64, C.POINTER(vp), C.POINTER(C.c_size_t), PS]),
         "e2i_enable_peers": (C.c_int, [C.POINTER(vp), C.c_int]),
         "e2i_or_allreduce": (C.c_int, [vp, C.POINTER(vp), C.c_int, C.c_int, u64]),
@@ -297,6 +298,20 @@ class Context:
         _check(rc)
         text = SnpText(out, ln.value)
         return (text.tobytes() if copy else text), st
+
+    def ebwt_build(self, reads: np.ndarray, second_from: int | None = None, term: int = ord("#")):
+        """eBWT of an (m, L) uint8 matrix of reads on the GPU (e2i_ebwt_build).  With second_from the reads from that
+        row on belong to the second individual and the ASCII '0'/'1' document array is returned as well."""
+        reads = np.ascontiguousarray(reads, dtype=np.uint8)
+        m, L = reads.shape
+        bwt = np.empty(m * (L + 1), dtype=np.uint8)
+        da = np.empty(m * (L + 1), dtype=np.uint8) if second_from is not None else None
+        rc = lib().e2i_ebwt_build(self.h, reads.ctypes.data, m, L, m if second_from is None else second_from, term,
+                                  bwt.ctypes.data, da.ctypes.data if da is not None else None)
+        if rc == E2I_ERR_SYMBOL:
+            raise ValueError(lib().e2i_last_error().decode())
+        _check(rc)
+        return bwt if da is None else (bwt, da)
 
     def index_alloc(self, n: int, term: int = ord("#"), tile_multiple: int = 1) -> "Index":
         """Empty index for slice-wise construction (Index.slice_count / slice_super / slice_pack / finish)."""

@@ -247,6 +247,15 @@ int e2i_index_load(e2i_ctx *ctx, const char *path, e2i_index **out);
 int e2i_run_device(e2i_ctx *ctx, const uint8_t *dev_bwt1, uint64_t n1, const uint8_t *dev_bwt2, uint64_t n2,
                    const uint8_t *dev_da, const e2i_params *p, char **snp, size_t *snp_len, e2i_stats *st);
 
+/* ---- eBWT (+ document array) construction on the GPU.  The reference takes its input from an
+ *      external builder (BCR_LCP_GSA / egap, README.md:38, 91-92); this entry point makes the chain self-contained.
+ *      host_reads: m x L ASCII matrix (row-major, A/C/G/T only, one fixed length L); reads with index >=
+ *      second_from belong to the second individual (pass m for a single set).  Convention: '#'_i < '#'_j for
+ *      i < j, '#' < A < C < G < T.  host_bwt: m * (L + 1) bytes, caller-allocated; host_da (nullable): the
+ *      document array as ASCII '0' / '1', same size.  bin/ebwt_build is its command line. ---------------------- */
+int e2i_ebwt_build(e2i_ctx *ctx, const uint8_t *host_reads, uint64_t m, uint32_t L, uint64_t second_from, uint8_t term,
+                   uint8_t *host_bwt, uint8_t *host_da);
+
 /* ---- several GPUs of one box, one process (replaces the parallel wrapper pebwt2InDel.sh:45-88 without its
  *      loss of cross-piece coverage: the output equals the single-GPU run's).  e2i_run_multi: the whole path
  *      on devices[0..n_devices); one host thread and one context per GPU inside the call; the index is built

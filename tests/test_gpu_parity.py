@@ -495,3 +495,35 @@ def test_cli_multi_gpu_env(tmp_path):
                        env=dict(os.environ, E2I_DEVICES="0,0"))
     assert r.returncode == 0, r.stdout + r.stderr
     assert out.read_bytes() == g["snp"]
+
+
+def test_product_ebwt_builder(gpu_ctx, e2i, tmp_path):
+    """f2: e2i_ebwt_build / bin/ebwt_build (GPU BCR on the product's own index + rank kernels) give the eBWT and
+    the document array of the naive suffix sort, and ebwt2InDel on their output equals the golden .snp."""
+    from ebwt2indel_b200 import synth
+    reads = synth.diploid_reads(3000, 8, 3, 20, 50, seed=31)
+    want, _ = synth.ebwt_naive(reads)
+    assert np.array_equal(gpu_ctx.ebwt_build(reads), want)
+    r0, r1 = synth.two_individuals_reads(2000, 6, 2, 16, 40, seed=32)
+    m, da = synth.merged_ebwt_da(r0, r1)
+    bwt, got_da = gpu_ctx.ebwt_build(np.concatenate([r0, r1]), second_from=len(r0))
+    assert np.array_equal(bwt, m) and np.array_equal(got_da, da)
+    with pytest.raises(ValueError, match="read 3 at offset 7"):
+        bad = reads.copy()
+        bad[3, 7] = ord("N")
+        gpu_ctx.ebwt_build(bad)
+    # command line: FASTA in, -r adds the reverse complements; then the whole chain reads -> eBWT -> .snp
+    fwd = synth.read_plan([synth.random_genome(4000, np.random.default_rng(5))], 1200, 60, np.random.default_rng(6), revcomp=False).materialize()
+    fa = tmp_path / "reads.fa"
+    with open(fa, "w") as f:
+        for i, r in enumerate(fwd):
+            f.write(f">r{i}\n{r.tobytes().decode()}\n")
+    exe = os.path.join(ROOT, "bin", "ebwt_build")
+    out = tmp_path / "reads.ebwt"
+    r = subprocess.run([exe, "-i", str(fa), "-r", "-o", str(out)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    both = np.concatenate([fwd, synth._COMP[fwd[:, ::-1]]])
+    assert np.array_equal(np.fromfile(out, dtype=np.uint8), synth.ebwt_naive(both)[0])
+    g = load_golden("m1_default")          # its reads are synth.diploid_reads(6000, 14, 5, 24, 100, seed=11)
+    gr = synth.diploid_reads(6000, 14, 5, 24, 100, seed=11)
+    assert np.array_equal(gpu_ctx.ebwt_build(gr), g["bwt1"])
