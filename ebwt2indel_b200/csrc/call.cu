@@ -368,7 +368,7 @@ __global__ void pack_calls_kernel(const CallArgs a, uint64_t n_cand, char *__res
     const uint64_t ci = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (ci >= n_cand) return;
     const Candidate cd = a.cand[ci];
-    e2i_call_rec rec;
+    e2i_call_rec rec = {};                                 // padding bytes included: the records are copied out as bytes
     rec.begin = cd.begin;
     rec.end = cd.end;
     rec.right_len = right_len[ci];
@@ -438,10 +438,11 @@ __global__ void __launch_bounds__(1024) scan_u64_kernel(uint64_t *data, uint64_t
 
 using namespace e2i;
 
+// The directory is rebuilt on every e2i_call (two tiny kernels): the DA words are exposed through
+// e2i_bits_device and are modified in place by the cross-GPU OR-combine, so a cached copy could be stale.
 static int build_da_rank(e2i_ctx *ctx, e2i_bits *da) {
-    if (da->rank512) return E2I_OK;
     const uint64_t n_groups = da->n_words32 / 16;
-    E2I_CUDA_TRY(dmalloc(ctx, &da->rank512, (n_groups + 1) * 8));
+    if (!da->rank512) E2I_CUDA_TRY(dmalloc(ctx, &da->rank512, (n_groups + 1) * 8));
     da_group_popc_kernel<<<(unsigned)((n_groups + 255) / 256), 256, 0, ctx->stream>>>(da->words, n_groups, da->rank512);
     scan_u64_kernel<<<1, 1024, 0, ctx->stream>>>(da->rank512, n_groups);
     E2I_CUDA_TRY(cudaGetLastError());
@@ -490,7 +491,7 @@ extern "C" int e2i_call(e2i_ctx *ctx, const e2i_index *b1, const e2i_index *b2, 
         dfree(ctx, ctx->arena_mem);
         ctx->arena_mem = nullptr;
         ctx->arena_bytes = 0;
-        E2I_CUDA_TRY(dmalloc(ctx, &ctx->arena_mem, 1ull << 30));
+        if (dmalloc(ctx, &ctx->arena_mem, 1ull << 30) != cudaSuccess) { cudaGetLastError(); delete calls; set_error("e2i_call: out of device memory"); return E2I_ERR_MEMORY; }
         ctx->arena_bytes = 1ull << 30;
     }
     char *const abase = static_cast<char *>(ctx->arena_mem);

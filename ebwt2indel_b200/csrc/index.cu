@@ -279,12 +279,12 @@ __global__ void fl_batch_kernel(DevIndex ix, const uint64_t *__restrict__ pos, u
 }
 
 // document array: ASCII '1' -> 1, anything else -> 0 (ebwt2InDel.cpp:1503-1508); 32 positions per thread
-__global__ void da_pack_kernel(const uint8_t *__restrict__ ascii, uint64_t n, uint32_t *__restrict__ words, uint64_t n_words) {
+__global__ void da_pack_kernel(const uint8_t *__restrict__ ascii, uint64_t n, uint32_t *__restrict__ words, uint64_t n_words, bool aligned16) {
     const uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= n_words) return;
     uint32_t bits = 0;
     const uint64_t base = w * 32;
-    if (base + 32 <= n) {
+    if (base + 32 <= n && aligned16) {
         const uint4 a = __ldg(reinterpret_cast<const uint4 *>(ascii + base));
         const uint4 b = __ldg(reinterpret_cast<const uint4 *>(ascii + base + 16));
         const uint32_t v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
@@ -903,7 +903,8 @@ extern "C" int e2i_da_load_device(e2i_ctx *ctx, const uint8_t *dev_ascii01, uint
     if (e == cudaSuccess) e = cudaMemsetAsync(b->words, 0, b->n_words32 * 4, ctx->stream);
     const uint64_t nw = (n + 31) / 32;
     if (e == cudaSuccess && nw) {
-        da_pack_kernel<<<(unsigned)((nw + 255) / 256), 256, 0, ctx->stream>>>(dev_ascii01, n, b->words, nw);
+        da_pack_kernel<<<(unsigned)((nw + 255) / 256), 256, 0, ctx->stream>>>(dev_ascii01, n, b->words, nw,
+                                                                              (reinterpret_cast<uintptr_t>(dev_ascii01) & 15) == 0);   // a sliced tensor may be unaligned: byte loads then
         e = cudaGetLastError();
         ctx->n_launch++;
     }

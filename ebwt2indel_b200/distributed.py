@@ -250,6 +250,10 @@ def run_sharded(ctx, api, bwt1, bwt2, da, params, rank: int, world: int, group=N
     lap("call")
     stats = reduce_stats(st.as_dict(), device, group)
     lap("reduce_stats")
+    # Every LCP position has exactly one writer over all shards ("Computed n/n LCP values", ebwt2InDel.cpp:670);
+    # the SUM all-reduce above is an OR only under that condition, so a violated deal fails loudly here.
+    if stats["lcp_values"] != n or (b2 is not None and stats["da_values"] != n):
+        raise RuntimeError(f"sharded traversal wrote {stats['lcp_values']} LCP values for {n} positions: the shards disagree on the deal")
     snp, events, clusters = format_sharded(api, recs, left, right, params, (b2 is not None or da is not None),
                                            rank, world, device, group)
     lap("format+gather")

@@ -56,3 +56,58 @@ def test_big_case_matches_compiled_reference(gpu_ctx, e2i, name):
             assert st.clust_sizes[i] == v, (name, i)
     del snp
     gpu_ctx.trim()
+
+
+def test_rank_access_beyond_2_32_positions(gpu_ctx):
+    """rank / access / F on a random 5.2 G-symbol string (n > 2^32: 64-bit positions, 79 k superblocks of 2^16)
+    against prefix counts computed independently with torch on the GPU."""
+    import numpy as np
+    import torch
+    n = 5_200_000_123
+    free_b, _ = torch.cuda.mem_get_info()
+    if free_b < 3 * n:
+        pytest.skip("not enough free device memory")
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev)
+    g.manual_seed(7)
+    lut = torch.tensor(list(b"ACGT") * 63 + list(b"####"), dtype=torch.uint8, device=dev)       # ~1.6 % terminators
+    bwt = torch.empty(n, dtype=torch.uint8, device=dev)
+    step = 1 << 28
+    for off in range(0, n, step):
+        k = min(step, n - off)
+        bwt[off:off + k] = lut[torch.randint(0, 256, (k,), device=dev, generator=g)]
+    ix = gpu_ctx.index(bwt)
+    rng = np.random.default_rng(11)
+    pos = np.unique(np.concatenate([rng.integers(0, n + 1, 200_000), [0, 1, n - 1, n, 1 << 32, (1 << 32) - 1, (1 << 32) + 1,
+                                                                        1 << 16, (1 << 16) - 1, 65 * (1 << 16) + 31, 65 * (1 << 16) + 32]])).astype(np.uint64)
+    got = ix.rank4(pos)
+    # independent prefix counts: per-chunk totals, then an exact count inside the chunk of every query
+    tot = torch.zeros((n + step - 1) // step + 1, 4, dtype=torch.int64, device=dev)
+    for c, off in enumerate(range(0, n, step)):
+        chunk = bwt[off:off + step]
+        for s, ch in enumerate(b"ACGT"):
+            tot[c + 1, s] = (chunk == ch).sum()
+    pre = torch.cumsum(tot, 0).cpu().numpy()
+    want = np.zeros_like(got)
+    order = np.argsort(pos)
+    pp = pos.astype(np.int64)
+    for c, off in enumerate(range(0, n, step)):
+        sel = order[(pp[order] >= off) & (pp[order] < off + step)] if off + step < n else order[pp[order] >= off]
+        if not len(sel):
+            continue
+        chunk = bwt[off:off + step]
+        q = torch.from_numpy(pp[sel] - off).to(dev)
+        for s, ch in enumerate(b"ACGT"):
+            cs = torch.cumsum((chunk == ch).to(torch.int32), 0, dtype=torch.int64)
+            inside = torch.where(q > 0, cs[torch.clamp(q - 1, min=0)], torch.zeros_like(q))
+            want[sel, s] = pre[c, s] + inside.cpu().numpy()
+            del cs
+    assert np.array_equal(got, want)
+    F = ix.F()
+    n_term = n - int(pre[-1].sum())
+    assert list(F) == [n_term, n_term + pre[-1, 0], n_term + pre[-1, 0] + pre[-1, 1], n_term + pre[-1, :3].sum()]
+    ipos = pos[pos < n][::40]
+    assert np.array_equal(ix.access(ipos), bwt[torch.from_numpy(ipos.astype(np.int64)).to(dev)].cpu().numpy())
+    del ix, bwt
+    gpu_ctx.trim()
+    torch.cuda.empty_cache()
