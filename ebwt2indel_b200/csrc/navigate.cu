@@ -51,6 +51,11 @@ constexpr int kWarpStage = 128;                       // index blocks staged in 
 #define E2I_WINDOW_MAX 96
 #endif
 constexpr int kWindowMax = E2I_WINDOW_MAX;             // longest block range staged as one window (one BWT)
+#ifndef E2I_WINDOW_TMA
+#define E2I_WINDOW_TMA 0                              // 1: windows are staged by cp.async.bulk + mbarrier (measured slower:
+                                                      // C4 nodes 468 vs 382 ms, profiles/README.md), 0: by LDGSTS
+#endif
+constexpr bool kWindowTma = E2I_WINDOW_TMA != 0;
 constexpr int kMaxRun = 1024;                         // records per run (multiple of 32), upper bound
 #ifndef E2I_NODE_CTAS
 #define E2I_NODE_CTAS 7                               // resident CTAs per SM the one-BWT kernels are compiled for
@@ -191,6 +196,11 @@ __device__ __forceinline__ void load_block_smem(const uint4 *stage, uint32_t slo
     const uint4 *p = stage + slot * 2;
     lo = p[sw]; hi = p[1u ^ sw];
 }
+// a window staged by the bulk-copy engine is a plain image of the block range
+__device__ __forceinline__ void load_block_linear(const uint4 *stage, uint32_t slot, uint4 &lo, uint4 &hi) {
+    const uint4 *p = stage + slot * 2;
+    lo = p[0]; hi = p[1];
+}
 
 // #A,#C,#G,#T before relative position rpos, counted from the start of the superblock of origin_blk
 // (mod 2^32: the base cancels in every difference, which is all a node shorter than 2^32 needs).
@@ -200,7 +210,7 @@ __device__ __forceinline__ void rank_rel(const DevIndex &ix, const RankSrc &r, b
     const uint32_t rel = rpos >> kBlockShift;
     uint4 lo, hi;
     if (MODE == SRC_WINDOW) {
-        load_block_smem(r.stage, r.slot0 + rel, lo, hi);
+        if (kWindowTma) load_block_linear(r.stage, r.slot0 + rel, lo, hi); else load_block_smem(r.stage, r.slot0 + rel, lo, hi);
     } else if (MODE == SRC_SLOTS && (rel == 0 || rel == r.d1)) {
         load_block_smem(r.stage, r.slot0 + (rel != 0), lo, hi);
     } else {
@@ -396,6 +406,34 @@ __device__ __forceinline__ void stage_window(const DevIndex &ix, uint4 *stage, u
     for (uint32_t k = lane; k < n_blk * kBlockU4; k += 32) cp_async16(&stage[stage_slot(k >> 1, k & 1)], src + k);
 }
 
+// ---- the same window staged by the TMA / bulk-copy engine: the block range is one contiguous piece of HBM, so
+//      ONE elected lane issues ONE cp.async.bulk (UBLKCP) per BWT and the warp waits on its own mbarrier; replaces
+//      up to 6 LDGSTS per lane with their address arithmetic ------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(void *smem, const void *gmem, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"((uint32_t)__cvta_generic_to_shared(smem)),
+                 "l"(gmem), "r"(bytes), "r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
+}
+// generic-proxy reads of the staging buffer (previous step) are ordered before the async-proxy writes that follow
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 // position of this lane's children inside the step (before[c]) and the step's totals (tot[c])
 __device__ __forceinline__ uint32_t warp_child_slots(const bool (&valid)[4], int lane, uint32_t (&before)[4], uint32_t (&tot)[4]) {
     uint32_t vm = 0;
@@ -422,6 +460,7 @@ struct NodeSmem {
     uint4 stage[kNavWarps][IN_S ? kWarpStage * kBlockU4 : 1];     // staged index blocks, per warp
     uint4 recbuf[kNavWarps][32 * RIN];                            // records of the next step (slot = lane)
     uint32_t need[kNavWarps][IN_S ? 64 : 1];                      // SLOTS staging: block ids wanted by the lanes
+    uint64_t mbar[kNavWarps];                                     // completion barrier of the warp's bulk copies
 };
 
 template <bool TWO, bool IN_S, bool OUT_S>
@@ -436,6 +475,13 @@ expand_nodes_kernel(const NavArgs a, const FrameIn in, const FrameOut out) {
     uint4 *stage1 = sm.stage[warp], *stage2 = sm.stage[warp] + (IN_S ? STAGE * kBlockU4 : 0);
     uint4 *recbuf = sm.recbuf[warp] + lane * RIN;
     uint32_t *need = sm.need[warp];
+
+    uint64_t *mbar = &sm.mbar[warp];
+    uint32_t mbar_phase = 0;
+    if (IN_S && kWindowTma) {
+        if (lane == 0) mbar_init(mbar, 1);
+        __syncwarp();
+    }
 
     uint32_t st_lcp = 0, st_min = 0, st_rank = 0, st_upd = 0, st_da = 0;
     uint64_t max_size = 0;
@@ -492,8 +538,17 @@ expand_nodes_kernel(const NavArgs a, const FrameIn in, const FrameOut out) {
                 // the range is not longer than what SLOTS would fetch (pairs: up to the staging capacity)
                 if (span1 <= (uint32_t)(TWO ? STAGE : kWindowMax) && span2 <= (uint32_t)STAGE) {
                     mode = SRC_WINDOW;
-                    stage_window(a.ix1, stage1, lo1, span1, lane);
-                    if (TWO) stage_window(a.ix2, stage2, lo2, span2, lane);
+                    if (kWindowTma) {
+                        if (lane == 0) {
+                            fence_proxy_async();
+                            mbar_expect_tx(mbar, (span1 + span2) * (uint32_t)(kBlockU4 * sizeof(uint4)));
+                            bulk_copy_g2s(stage1, a.ix1.blocks + (size_t)lo1 * kBlockU4, span1 * (uint32_t)(kBlockU4 * sizeof(uint4)), mbar);
+                            if (TWO) bulk_copy_g2s(stage2, a.ix2.blocks + (size_t)lo2 * kBlockU4, span2 * (uint32_t)(kBlockU4 * sizeof(uint4)), mbar);
+                        }
+                    } else {
+                        stage_window(a.ix1, stage1, lo1, span1, lane);
+                        if (TWO) stage_window(a.ix2, stage2, lo2, span2, lane);
+                    }
                     r1.slot0 = fb1 - lo1;
                     r2.slot0 = fb2 - lo2;
                 } else if (!TWO) {
@@ -515,6 +570,7 @@ expand_nodes_kernel(const NavArgs a, const FrameIn in, const FrameOut out) {
                 st_lcp += st.lcp; st_min += st.nmin; st_upd += st.upd; st_da += st.da;
             }
             cp_async_wait_all();
+            if (IN_S && kWindowTma && mode == SRC_WINDOW) { mbar_wait(mbar, mbar_phase); mbar_phase ^= 1u; }
             __syncwarp();                                                   // every lane's copies are visible to the warp
             // the record of the next step: overlaps with the rank phase below
             if (g + 32 < g_end) {
