@@ -7,6 +7,7 @@ NVFLAGS := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC,-Wall,-Wno-unused-f
 CSRC := ebwt2indel_b200/csrc
 OBJ := build/context.o build/index.o build/navigate.o build/call.o build/multi.o build/ebwt_build.o build/snp_format.o
 LIB := ebwt2indel_b200/libe2i.so
+LDLIBS := -lrt
 TOOLS := ebwt2indel_b200/libe2i_tools.so
 BIN := bin/ebwt2InDel
 FILTER := bin/filter_snp
@@ -36,7 +37,7 @@ build/snp_format.o: $(CSRC)/snp_format.cpp $(CSRC)/common.cuh include/e2i.h
 	$(NVCC) $(NVFLAGS) -x cu -c $< -o $@
 
 $(LIB): $(OBJ)
-	$(NVCC) $(ARCH) -shared -o $@ $(OBJ)
+	$(NVCC) $(ARCH) -shared -o $@ $(OBJ) $(LDLIBS)
 
 $(BIN): $(CSRC)/main.cpp include/e2i.h $(LIB)
 	@mkdir -p bin

@@ -76,6 +76,7 @@ SYMBOLS = (
     "e2i_lcpbits_device", "e2i_bits_device", "e2i_lcpbits_free", "e2i_call", "e2i_calls_count",
     "e2i_calls_fetch", "e2i_calls_view", "e2i_calls_free", "e2i_snp_format", "e2i_snp_count", "e2i_filter_snp", "e2i_distance", "e2i_buffer_free", "e2i_run",
     "e2i_run_device", "e2i_run_files", "e2i_index_build_file", "e2i_da_load_file", "e2i_index_save", "e2i_index_load", "e2i_ebwt_build", "e2i_run_multi", "e2i_enable_peers", "e2i_or_allreduce",
+    "e2i_navigate_ranged", "e2i_comm_local", "e2i_comm_shm", "e2i_comm_barrier", "e2i_comm_free",
 )
 
 _lib = None
@@ -152,6 +153,11 @@ def lib():
         "e2i_ebwt_build": (C.c_int, [vp, u8p, u64, C.c_uint32, u64, C.c_uint8, u8p, u8p]),
         "e2i_run_multi": (C.c_int, [C.POINTER(C.c_int), C.c_int, u8p, u64, u8p, u64, u8p, PP, u64, C.POINTER(vp), C.POINTER(C.c_size_t), PS]),
         "e2i_enable_peers": (C.c_int, [C.POINTER(vp), C.c_int]),
+        "e2i_navigate_ranged": (C.c_int, [vp, vp, vp, vp, PP, C.POINTER(vp), C.POINTER(vp), PS]),
+        "e2i_comm_local": (C.c_int, [C.c_int, C.POINTER(vp)]),
+        "e2i_comm_shm": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.POINTER(vp)]),
+        "e2i_comm_barrier": (None, [vp]),
+        "e2i_comm_free": (None, [vp]),
         "e2i_or_allreduce": (C.c_int, [vp, C.POINTER(vp), C.c_int, C.c_int, u64]),
     }
     assert set(sig) == set(SYMBOLS)
@@ -338,6 +344,14 @@ class Context:
                                         C.byref(lh), C.byref(dh) if b2 else None, C.byref(st)))
         return LcpBits(self, lh), (Bits(self, dh) if b2 else None), st
 
+    def navigate_ranged(self, comm, b1: "Index", b2: "Index | None" = None, params: Params | None = None, stats: Stats | None = None):
+        """Position-range sharded traversal (e2i_navigate_ranged); comm: a handle made by comm_shm()."""
+        p = params or default_params()
+        st = stats if stats is not None else Stats()
+        lh, dh = C.c_void_p(), C.c_void_p()
+        _check(lib().e2i_navigate_ranged(self.h, comm, b1.h, b2.h if b2 else None, C.byref(p), C.byref(lh), C.byref(dh) if b2 else None, C.byref(st)))
+        return LcpBits(self, lh), (Bits(self, dh) if b2 else None), st
+
     # ---- phase 4 ----
     def call(self, b1, b2, da, lcp, params: Params | None = None, pos_begin: int = 0,
              pos_end: int = 2 ** 64 - 1, stats: Stats | None = None, copy: bool = True):
@@ -432,6 +446,18 @@ def run_multi(devices, bwt1, bwt2=None, da=None, params: Params | None = None, f
     _check(rc)
     text = SnpText(out, ln.value)
     return (text.tobytes() if copy else text), st
+
+
+def comm_shm(name: str, rank: int, world: int):
+    """Communicator over a POSIX shared-memory segment for the processes of one box (e2i_comm_shm)."""
+    h = C.c_void_p()
+    _check(lib().e2i_comm_shm(name.encode(), rank, world, C.byref(h)))
+    return h
+
+
+def comm_free(h):
+    if h:
+        lib().e2i_comm_free(h)
 
 
 def filter_snp(snp: bytes, m: int, M: int = 0) -> bytes:

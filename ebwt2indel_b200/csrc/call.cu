@@ -488,11 +488,7 @@ extern "C" int e2i_call(e2i_ctx *ctx, const e2i_index *b1, const e2i_index *b2, 
     // Phase 4 runs after the traversal, so the frame arena is idle: the control block, the candidate
     // list and the per-candidate outputs are carved out of it (no allocation on this path).
     if (ctx->arena_bytes < (64ull << 20)) {
-        dfree(ctx, ctx->arena_mem);
-        ctx->arena_mem = nullptr;
-        ctx->arena_bytes = 0;
-        if (dmalloc(ctx, &ctx->arena_mem, 1ull << 30) != cudaSuccess) { cudaGetLastError(); delete calls; set_error("e2i_call: out of device memory"); return E2I_ERR_MEMORY; }
-        ctx->arena_bytes = 1ull << 30;
+        if (arena_alloc(ctx, 1ull << 30, false) != cudaSuccess) { cudaGetLastError(); delete calls; set_error("e2i_call: out of device memory"); return E2I_ERR_MEMORY; }
     }
     char *const abase = static_cast<char *>(ctx->arena_mem);
     CallCtl *dctl = reinterpret_cast<CallCtl *>(abase);

@@ -99,6 +99,7 @@ struct e2i_ctx {
     e2i::Arena arena;           // frontier frames (device memory of `arena_mem`)
     void *arena_mem = nullptr;
     size_t arena_bytes = 0;
+    bool arena_ipc = false;     // the arena is a plain cudaMalloc block (exportable by CUDA IPC), not a pool block
     // look-back descriptors shared by all ordered-compaction kernels
     unsigned long long *desc = nullptr;
     size_t desc_words = 0;
@@ -116,6 +117,20 @@ struct e2i_ctx {
     uint64_t n_launch = 0, n_h2d = 0, n_d2h = 0;
 };
 
+// Ranks of a multi-GPU run (threads of one process, or processes of one box): a barrier and one 4 KB publish
+// slot per rank that every rank can read (multi.cu).  Device memory of a peer is addressed through
+// peer_ptr(): the pointer itself between threads of one process, a CUDA IPC mapping between processes.
+struct e2i_comm {
+    int rank = 0, world = 1;
+    virtual ~e2i_comm() {}
+    virtual void barrier() = 0;
+    virtual unsigned char *slot(int r) = 0;                     // 4 KB, written by rank r only, read after a barrier
+    // this process's view of `base`, a device allocation of rank r whose IPC handle is `handle`
+    virtual void *peer_ptr(int r, void *base, const cudaIpcMemHandle_t &handle) = 0;
+    virtual bool needs_ipc() const = 0;
+};
+constexpr size_t kCommSlotBytes = 4096;
+
 namespace e2i {
 template <typename T>
 inline cudaError_t dmalloc(e2i_ctx *ctx, T **p, size_t bytes) {
@@ -123,6 +138,22 @@ inline cudaError_t dmalloc(e2i_ctx *ctx, T **p, size_t bytes) {
 }
 inline void dfree(e2i_ctx *ctx, void *p) {
     if (p) cudaFreeAsync(p, ctx->stream);
+}
+// the frame arena: a pool block normally, a plain cudaMalloc block when peers of other processes must map it
+inline void arena_release(e2i_ctx *ctx) {
+    if (ctx->arena_mem) {
+        if (ctx->arena_ipc) { cudaStreamSynchronize(ctx->stream); cudaFree(ctx->arena_mem); }
+        else dfree(ctx, ctx->arena_mem);
+    }
+    ctx->arena_mem = nullptr;
+    ctx->arena_bytes = 0;
+    ctx->arena_ipc = false;
+}
+inline cudaError_t arena_alloc(e2i_ctx *ctx, size_t bytes, bool ipc) {
+    arena_release(ctx);
+    const cudaError_t e = ipc ? cudaMalloc(&ctx->arena_mem, bytes) : cudaMallocFromPoolAsync(&ctx->arena_mem, bytes, ctx->pool, ctx->stream);
+    if (e == cudaSuccess) { ctx->arena_bytes = bytes; ctx->arena_ipc = ipc; }
+    return e;
 }
 struct Accounting {            // adds what a call launched / copied to its e2i_stats on scope exit
     e2i_ctx *ctx; e2i_stats *st; uint64_t l0, h0, d0;

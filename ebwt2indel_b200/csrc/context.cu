@@ -134,9 +134,7 @@ extern "C" void e2i_destroy(e2i_ctx *ctx) {
 extern "C" int e2i_trim(e2i_ctx *ctx) {
     if (!ctx) { set_error("e2i_trim: null context"); return E2I_ERR_ARG; }
     E2I_CUDA_TRY(cudaSetDevice(ctx->device));
-    dfree(ctx, ctx->arena_mem);
-    ctx->arena_mem = nullptr;
-    ctx->arena_bytes = 0;
+    arena_release(ctx);
     ctx->arena.reset(nullptr, 0);
     E2I_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     E2I_CUDA_TRY(cudaMemPoolTrimTo(ctx->pool, 0));

@@ -13,8 +13,16 @@
 //                result back into every peer's copy -- reduce-scatter and all-gather fused, over P2P loads
 //                and stores, no staging buffer
 //   4. call      phase 4 on the GPU's own suffix-array range; .snp text per range, concatenated in order
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
 #include <algorithm>
+#include <atomic>
 #include <condition_variable>
+#include <map>
+#include <memory>
 #include <mutex>
 #include <thread>
 
@@ -60,6 +68,62 @@ class HostBarrier {
     uint64_t gen_ = 0;
 };
 
+// ---- communicators ------------------------------------------------------------------------------------
+// ranks = threads of this process: a shared barrier, slots in ordinary memory, peer pointers used as they are
+struct LocalShared {
+    explicit LocalShared(int n) : bar(n), slots((size_t)n * kCommSlotBytes, 0) {}
+    HostBarrier bar;
+    std::vector<unsigned char> slots;
+};
+struct LocalComm : e2i_comm {
+    std::shared_ptr<LocalShared> sh;
+    void barrier() override { sh->bar.wait(); }
+    unsigned char *slot(int r) override { return sh->slots.data() + (size_t)r * kCommSlotBytes; }
+    void *peer_ptr(int, void *base, const cudaIpcMemHandle_t &) override { return base; }
+    bool needs_ipc() const override { return false; }
+};
+
+// ranks = processes of one box (torchrun): barrier and slots in a POSIX shared-memory segment, peer device
+// memory mapped through CUDA IPC handles (NVLink P2P between the processes' GPUs)
+struct ShmHeader {
+    std::atomic<uint32_t> ready, arrived, generation, pad;
+};
+struct ShmComm : e2i_comm {
+    std::string name;
+    void *map = nullptr;
+    size_t bytes = 0;
+    std::map<std::string, void *> opened;             // IPC handle bytes -> mapping
+    ShmHeader *hdr() { return static_cast<ShmHeader *>(map); }
+    void barrier() override {
+        ShmHeader *h = hdr();
+        const uint32_t gen = h->generation.load(std::memory_order_acquire);
+        if (h->arrived.fetch_add(1, std::memory_order_acq_rel) + 1 == (uint32_t)world) {
+            h->arrived.store(0, std::memory_order_relaxed);
+            h->generation.store(gen + 1, std::memory_order_release);
+        } else {
+            unsigned spins = 0;
+            while (h->generation.load(std::memory_order_acquire) == gen)
+                if (++spins > 2000) { sched_yield(); spins = 0; }
+        }
+    }
+    unsigned char *slot(int r) override { return static_cast<unsigned char *>(map) + 4096 + (size_t)r * kCommSlotBytes; }
+    void *peer_ptr(int, void *, const cudaIpcMemHandle_t &handle) override {
+        const std::string key(reinterpret_cast<const char *>(&handle), sizeof handle);
+        auto it = opened.find(key);
+        if (it != opened.end()) return it->second;
+        void *p = nullptr;
+        if (cudaIpcOpenMemHandle(&p, handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        opened[key] = p;
+        return p;
+    }
+    bool needs_ipc() const override { return true; }
+    ~ShmComm() override {
+        for (auto &kv : opened) cudaIpcCloseMemHandle(kv.second);
+        if (map) munmap(map, bytes);
+        if (rank == 0 && !name.empty()) shm_unlink(name.c_str());
+    }
+};
+
 // tile-aligned slices of [0, n): every tile (the last one may hold no symbol, only the block that makes
 // rank(n) addressable) has exactly one owner; trailing ranks may be empty
 struct Slice { uint64_t begin, len, tiles; };
@@ -98,6 +162,54 @@ struct MultiShared {
 }  // namespace e2i
 
 using namespace e2i;
+
+extern "C" int e2i_comm_local(int world, e2i_comm **out) {
+    if (!out || world < 1 || world > kMaxGpus) { set_error("e2i_comm_local: bad argument"); return E2I_ERR_ARG; }
+    auto sh = std::make_shared<LocalShared>(world);
+    for (int r = 0; r < world; ++r) {
+        LocalComm *c = new LocalComm();
+        c->rank = r; c->world = world; c->sh = sh;
+        out[r] = c;
+    }
+    return E2I_OK;
+}
+
+extern "C" int e2i_comm_shm(const char *name, int rank, int world, e2i_comm **out) {
+    if (!out || !name || world < 1 || world > kMaxGpus || rank < 0 || rank >= world) { set_error("e2i_comm_shm: bad argument"); return E2I_ERR_ARG; }
+    ShmComm *c = new ShmComm();
+    c->rank = rank; c->world = world; c->name = name;
+    c->bytes = 4096 + (size_t)world * kCommSlotBytes;
+    int fd = -1;
+    if (rank == 0) {
+        shm_unlink(name);
+        fd = shm_open(name, O_CREAT | O_EXCL | O_RDWR, 0600);
+        if (fd >= 0 && ftruncate(fd, (off_t)c->bytes) != 0) { close(fd); fd = -1; }
+    } else {
+        for (int tries = 0; tries < 60000 && fd < 0; ++tries) {       // rank 0 creates the segment
+            fd = shm_open(name, O_RDWR, 0600);
+            if (fd >= 0) { struct stat sb; if (fstat(fd, &sb) != 0 || (size_t)sb.st_size < c->bytes) { close(fd); fd = -1; } }
+            if (fd < 0) usleep(1000);
+        }
+    }
+    if (fd < 0) { set_error("e2i_comm_shm: cannot open shared memory segment %s", name); c->name.clear(); delete c; return E2I_ERR_IO; }
+    c->map = mmap(nullptr, c->bytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+    close(fd);
+    if (c->map == MAP_FAILED) { c->map = nullptr; set_error("e2i_comm_shm: mmap failed"); delete c; return E2I_ERR_IO; }
+    if (rank == 0) {
+        std::memset(c->map, 0, c->bytes);
+        c->hdr()->ready.store(0x600dc0deu, std::memory_order_release);
+    } else {
+        for (int tries = 0; c->hdr()->ready.load(std::memory_order_acquire) != 0x600dc0deu; ++tries) {
+            if (tries > 60000) { set_error("e2i_comm_shm: rank 0 never initialised %s", name); delete c; return E2I_ERR_IO; }
+            usleep(1000);
+        }
+    }
+    *out = c;
+    return E2I_OK;
+}
+
+extern "C" void e2i_comm_barrier(e2i_comm *c) { if (c) c->barrier(); }
+extern "C" void e2i_comm_free(e2i_comm *c) { delete c; }
 
 extern "C" int e2i_enable_peers(e2i_ctx **ctxs, int n) {
     if (!ctxs || n < 1 || n > kMaxGpus) { set_error("e2i_enable_peers: bad argument"); return E2I_ERR_ARG; }
@@ -176,6 +288,12 @@ extern "C" int e2i_run_multi(const int *devices, int n_devices, const uint8_t *h
     if (world > 1) { const int rc = e2i_enable_peers(sh.ctx.data(), world); if (rc != E2I_OK) { destroy_all(); return rc; } }
 
     HostBarrier bar(world);
+    // traversal: position-range sharding with peer pulls by default, E2I_SHARDING=subtree selects the independent
+    // subtree shards of round 1
+    const char *shard_env = std::getenv("E2I_SHARDING");
+    const bool ranged = world > 1 && !(shard_env && std::strcmp(shard_env, "subtree") == 0);
+    std::vector<e2i_comm *> comms((size_t)world, nullptr);
+    if (ranged) { const int rc = e2i_comm_local(world, comms.data()); if (rc != E2I_OK) { destroy_all(); return rc; } }
     const uint64_t n = n1 + (two ? n2 : 0);
     std::vector<Slice> sl[2];
     uint64_t per[2] = {0, 0};
@@ -252,8 +370,12 @@ extern "C" int e2i_run_multi(const int *devices, int n_devices, const uint8_t *h
         { float ms = 0; if (cudaEventElapsedTime(&ms, ctx->ev[6], ctx->ev[7]) == cudaSuccess) st.ms_index += ms; }
         bar.wait();                                      // nobody reads a peer's blocks any more; the indexes are complete
         // ---- 2. traversal shard ----
-        if (!sh.any_failed())
+        if (ranged) {                                    // every rank enters: the traversal has barriers of its own
+            if (sh.any_failed()) { /* all ranks see the same flags here (after the barrier): nobody enters */ }
+            else STEP(e2i_navigate_ranged(ctx, comms[rank], sh.ix[0][rank], two ? sh.ix[1][rank] : nullptr, p, &sh.lcp[rank], two ? &sh.da_nav[rank] : nullptr, &st));
+        } else if (!sh.any_failed()) {
             STEP(e2i_navigate_shard(ctx, sh.ix[0][rank], two ? sh.ix[1][rank] : nullptr, p, rank, world, &sh.lcp[rank], two ? &sh.da_nav[rank] : nullptr, &st));
+        }
         CUDA_STEP(cudaStreamSynchronize(s));
         bar.wait();                                      // every shard's bits are written
         // ---- 3. OR-combine over peer memory ----
@@ -305,6 +427,7 @@ extern "C" int e2i_run_multi(const int *devices, int n_devices, const uint8_t *h
     for (int r = 1; r < world; ++r) th.emplace_back(worker, r);
     worker(0);
     for (auto &t : th) t.join();
+    for (e2i_comm *c : comms) e2i_comm_free(c);
 
     int rc = E2I_OK;
     for (int r = 0; r < world; ++r)

@@ -74,34 +74,59 @@ static_assert(kSmallLimit <= 65536, "SMALL records hold 16-bit sizes");
 // that frame_index_kernel fills in after the sweep, followed by the sweep's sequence number; the
 // host polls that word instead of a copy + stream synchronisation.
 constexpr uint32_t kSweepSlots = 16384;
+constexpr int kMaxDest = 16;                          // destinations of a frame = GPUs of one box
 struct SweepDev {
-    uint32_t ticket, pad0;
+    uint32_t ticket, done;    // run ticket; CTAs of frame_index_kernel that have finished
     unsigned long long maxsz;
     unsigned long long pad[6];
 };
 static_assert(sizeof(SweepDev) == 64, "one sweep slot per 64 bytes");
 struct HostCtl {
-    unsigned long long out_count[4];
-    unsigned long long maxsz;
+    unsigned long long total;                         // records of the frame
+    unsigned long long maxsz;                         // largest node the sweep read
     unsigned long long seq;
+    uint32_t qstart[4 * kMaxDest + 1];                // P[(4h+c)K]: where destination h, queue c starts
 };
 
 // A frame: the records one sweep produced.  Queue c, run k owns the slots
-// base + ((c * K + k) * run_cap ...) and holds cnt[c * K + k] records; P is the exclusive prefix of
-// cnt in (queue, run) order (4K + 1 entries), so global index g lives in the entry j with
-// P[j] <= g < P[j+1]; hint[t] = the entry that holds global index 256 t.
-struct FrameIn {
+// base + ((c * K + k) * run_cap ...) and fills them in input order.  With D destinations (position
+// ranges of D GPUs, D = 1 on one GPU) the children of a region are counted per destination h -- they are
+// sorted by position, so each destination's share is a contiguous piece -- and entry e = (h * 4 + c) * K + k
+// holds cnt[e] records starting off[e] slots into the region.  P is the exclusive prefix of cnt in entry
+// order (4 D K + 1 values), so global index g lives in the entry e with P[e] <= g < P[e+1], and the records
+// of destination h, queue c are the global indices [P[(4h+c)K], P[(4h+c+1)K)).  hint[t] = the entry that
+// holds global index 256 t.
+struct FrameSrc {
     const uint4 *base;
     const uint32_t *P;
+    const uint32_t *off;      // nullptr when the frame has one destination
     const uint32_t *hint;
     uint32_t K, run_cap;
+};
+constexpr int kMaxSeg = 4 * kMaxDest;
+struct Segment {                                      // a piece of one source frame in the sweep's input order
+    uint32_t start, len;      // position in the concatenated input, records
+    uint32_t lo, src;         // first global index in the source frame, source id
+};
+template <bool MULTI> struct FrameInT;
+template <> struct FrameInT<false> {                  // one local frame, read by global index
+    FrameSrc s;
     uint32_t g_lo, g_hi;      // this sweep reads the records [g_lo, g_hi)
 };
+template <> struct FrameInT<true> {                   // pieces of several frames (own and peers'), concatenated in position order
+    uint32_t g_lo, g_hi;
+    uint32_t n_seg, pad;
+    FrameSrc src[kMaxDest];
+    Segment seg[kMaxSeg];
+};
+using FrameIn = FrameInT<false>;
 struct FrameOut {
     uint4 *base;
     uint32_t *cnt;
     uint32_t *gsum;           // sums of cnt over groups of 256 consecutive entries (group_sum_kernel)
     uint32_t K, run_cap;      // runs of this sweep's input, records per run (multiple of 32)
+    uint32_t D, pad;          // destinations
+    uint64_t range_len;       // destination h owns the positions [h * range_len, (h + 1) * range_len)
 };
 
 struct NavArgs {
@@ -139,31 +164,97 @@ struct WordAcc {
     __device__ __forceinline__ void flush() { if (m) atomicOr(words + w, m); m = 0; }
 };
 
-// ---- reading a gappy frame by global index ---------------------------------------------------------
-struct Cursor {               // per lane: the entry (queue c, run k) that holds the lane's current record
+// ---- reading gappy frames by global index ----------------------------------------------------------
+struct Cursor {               // per lane: the entry that holds the lane's current record
     uint32_t j, c, k, pj, pj1;
+    uint32_t s, delta, seg_end, offj;                 // MULTI: segment, source index - position, end of the segment
 };
 
-__device__ __forceinline__ void cursor_open(const FrameIn &in, Cursor &cur, uint32_t g) {
-    cur.j = __ldg(in.hint + (g >> 8));
-    cur.c = cur.j / in.K;
-    cur.k = cur.j - cur.c * in.K;
-    cur.pj = __ldg(in.P + cur.j);
-    cur.pj1 = __ldg(in.P + cur.j + 1);
+__device__ __forceinline__ void cursor_open(const FrameInT<false> &in, Cursor &cur, uint32_t g) {
+    cur.j = __ldg(in.s.hint + (g >> 8));
+    cur.c = cur.j / in.s.K;
+    cur.k = cur.j - cur.c * in.s.K;
+    cur.pj = __ldg(in.s.P + cur.j);
+    cur.pj1 = __ldg(in.s.P + cur.j + 1);
 }
 
-// move to the entry that holds g (g never decreases, g < P[4K])
-__device__ __forceinline__ void cursor_seek(const FrameIn &in, Cursor &cur, uint32_t g) {
+// move to the entry that holds g (g never decreases, g < P[last])
+__device__ __forceinline__ void cursor_seek(const FrameInT<false> &in, Cursor &cur, uint32_t g) {
     while (g >= cur.pj1) {
         ++cur.j;
-        if (++cur.k == in.K) { cur.k = 0; ++cur.c; }
+        if (++cur.k == in.s.K) { cur.k = 0; ++cur.c; }
         cur.pj = cur.pj1;
-        cur.pj1 = __ldg(in.P + cur.j + 1);
+        cur.pj1 = __ldg(in.s.P + cur.j + 1);
     }
 }
 
-__device__ __forceinline__ const uint4 *cursor_record(const FrameIn &in, const Cursor &cur, uint32_t g, int ru) {
-    return in.base + (((size_t)cur.c * in.K + cur.k) * in.run_cap + (g - cur.pj)) * ru;
+__device__ __forceinline__ const uint4 *cursor_record(const FrameInT<false> &in, const Cursor &cur, uint32_t g, int ru) {
+    return in.s.base + (((size_t)cur.c * in.s.K + cur.k) * in.s.run_cap + (g - cur.pj)) * ru;
+}
+
+// MULTI: position g of the concatenated input -> segment -> entry of that segment's source frame
+__device__ __forceinline__ void cursor_enter(const FrameInT<true> &in, Cursor &cur, uint32_t g) {
+    uint32_t s = cur.s;
+    while (g >= in.seg[s].start + in.seg[s].len) ++s;
+    cur.s = s;
+    const Segment sg = in.seg[s];
+    const FrameSrc &f = in.src[sg.src];
+    cur.delta = sg.lo - sg.start;
+    cur.seg_end = sg.start + sg.len;
+    const uint32_t x = g + cur.delta;
+    uint32_t j = __ldg(f.hint + (x >> 8));
+    uint32_t pj = __ldg(f.P + j), pj1 = __ldg(f.P + j + 1);
+    while (x >= pj1) { ++j; pj = pj1; pj1 = __ldg(f.P + j + 1); }
+    cur.j = j; cur.pj = pj; cur.pj1 = pj1;
+    cur.c = (j / f.K) & 3u;
+    cur.k = j % f.K;
+    cur.offj = f.off ? __ldg(f.off + j) : 0u;
+}
+__device__ __forceinline__ void cursor_open(const FrameInT<true> &in, Cursor &cur, uint32_t g) {
+    cur.s = 0;
+    cursor_enter(in, cur, g);
+}
+__device__ __forceinline__ void cursor_seek(const FrameInT<true> &in, Cursor &cur, uint32_t g) {
+    if (g >= cur.seg_end) { cursor_enter(in, cur, g); return; }
+    const uint32_t x = g + cur.delta;
+    if (x >= cur.pj1) {
+        const FrameSrc &f = in.src[in.seg[cur.s].src];
+        while (x >= cur.pj1) {
+            ++cur.j;
+            if (++cur.k == f.K) { cur.k = 0; cur.c = (cur.c + 1) & 3u; }
+            cur.pj = cur.pj1;
+            cur.pj1 = __ldg(f.P + cur.j + 1);
+        }
+        cur.offj = f.off ? __ldg(f.off + cur.j) : 0u;
+    }
+}
+__device__ __forceinline__ const uint4 *cursor_record(const FrameInT<true> &in, const Cursor &cur, uint32_t g, int ru) {
+    const FrameSrc &f = in.src[in.seg[cur.s].src];
+    return f.base + (((size_t)cur.c * f.K + cur.k) * f.run_cap + cur.offj + (g + cur.delta - cur.pj)) * ru;
+}
+
+// ---- MULTI: children of a run counted per destination (position range) ---------------------------------
+// The children of queue c leave a run sorted by position, so the destination never decreases: dcur / dbound
+// (warp-uniform) hold the current destination and the first position beyond it; only a step that crosses a
+// range boundary takes the slow path.
+__device__ __forceinline__ void count_dests(uint32_t *dcnt, uint32_t &dcur, uint64_t &dbound, const FrameOut &out, int lane,
+                                            bool valid, uint64_t pos, uint32_t tot) {
+    const uint32_t over = __ballot_sync(0xffffffffu, valid && pos >= dbound);
+    if (!over) {
+        if (lane == 0 && tot) dcnt[dcur] += tot;
+        return;
+    }
+    uint32_t rest = __ballot_sync(0xffffffffu, valid);
+    while (rest) {
+        const uint32_t ov = __ballot_sync(0xffffffffu, ((rest >> lane) & 1u) && pos >= dbound);
+        const uint32_t below = ov ? (rest & ((1u << (__ffs(ov) - 1)) - 1u)) : rest;
+        if (lane == 0 && below) dcnt[dcur] += __popc(below);
+        rest &= ~below;
+        if (!rest) break;
+        const uint64_t p0 = __shfl_sync(0xffffffffu, (unsigned long long)pos, __ffs(ov) - 1);
+        dcur = (uint32_t)min((uint64_t)(out.D - 1), p0 / out.range_len);
+        dbound = dcur == out.D - 1 ? ~0ull : (uint64_t)(dcur + 1) * out.range_len;
+    }
 }
 
 // end-of-kernel flush of the per-thread statistics (one atomic per warp and counter)
@@ -461,11 +552,12 @@ struct NodeSmem {
     uint4 recbuf[kNavWarps][32 * RIN];                            // records of the next step (slot = lane)
     uint32_t need[kNavWarps][IN_S ? 64 : 1];                      // SLOTS staging: block ids wanted by the lanes
     uint64_t mbar[kNavWarps];                                     // completion barrier of the warp's bulk copies
+    uint32_t dcnt[kNavWarps][4 * kMaxDest];                       // MULTI: children of the current run per (queue, destination)
 };
 
-template <bool TWO, bool IN_S, bool OUT_S>
+template <bool TWO, bool IN_S, bool OUT_S, bool MULTI>
 __global__ void __launch_bounds__(kNavThreads, IN_S ? (TWO ? kPairCtas : kNodeCtas) : 1)
-expand_nodes_kernel(const NavArgs a, const FrameIn in, const FrameOut out) {
+expand_nodes_kernel(const NavArgs a, const __grid_constant__ FrameInT<MULTI> in, const FrameOut out) {
     using SM = NodeSmem<TWO, IN_S>;
     using W = typename std::conditional<IN_S, uint32_t, uint64_t>::type;
     constexpr int RIN = SM::RIN, RSIDE_IN = IN_S ? 1 : 3, RSIDE_OUT = OUT_S ? 1 : 3, ROUT = RSIDE_OUT * (TWO ? 2 : 1);
@@ -506,6 +598,14 @@ expand_nodes_kernel(const NavArgs a, const FrameIn in, const FrameOut out) {
         uint4 *region[4];                                 // next free slot of the run's region, per queue
 #pragma unroll
         for (int c = 0; c < 4; ++c) region[c] = out.base + (((size_t)c * out.K + run) * out.run_cap) * ROUT;
+        uint32_t dcur[4] = {0, 0, 0, 0};                  // MULTI: current destination of every queue
+        uint64_t dbound[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) dbound[c] = out.D > 1 ? out.range_len : ~0ull;
+        if (MULTI) {
+            for (int i = lane; i < 4 * kMaxDest; i += 32) sm.dcnt[warp][i] = 0;
+            __syncwarp();
+        }
         for (uint32_t g0 = g_begin; g0 < g_end; g0 += 32) {
             const uint32_t g = g0 + lane;
             const bool active = g < g_end;
@@ -606,13 +706,24 @@ expand_nodes_kernel(const NavArgs a, const FrameIn in, const FrameOut out) {
                 }
                 region[c] += tot[c] * ROUT;
                 run_cnt[c] += tot[c];
+                if (MULTI) count_dests(sm.dcnt[warp] + c * kMaxDest, dcur[c], dbound[c], out, lane, (vm >> c) & 1u,
+                                       k1.base[c] + (TWO ? k2.base[c] : 0ull), tot[c]);
             }
         }
-        if (lane < 4) {
-            uint32_t v = 0;
+        if (!MULTI) {
+            if (lane < 4) {
+                uint32_t v = 0;
 #pragma unroll
-            for (int c = 0; c < 4; ++c) if (lane == c) v = run_cnt[c];
-            out.cnt[(size_t)lane * out.K + run] = v;
+                for (int c = 0; c < 4; ++c) if (lane == c) v = run_cnt[c];
+                out.cnt[(size_t)lane * out.K + run] = v;
+            }
+        } else {                                          // entry (h, c, run) for every destination h
+            __syncwarp();
+            for (int i = lane; i < 4 * kMaxDest; i += 32) {
+                const uint32_t c = i / kMaxDest, h = i % kMaxDest;
+                if (h < out.D) out.cnt[((size_t)h * 4 + c) * out.K + run] = sm.dcnt[warp][i];
+            }
+            __syncwarp();
         }
     }
     if (a.write) {
@@ -638,6 +749,7 @@ struct LeafSmem {
     uint4 stage[kNavWarps][64 * kBlockU4];            // two blocks per lane
     uint4 recbuf[kNavWarps][32 * RU];
     uint32_t need[kNavWarps][64];
+    uint32_t dcnt[kNavWarps][4 * kMaxDest];           // MULTI: children of the current run per (queue, destination)
 };
 
 // rank at an absolute position whose block is staged in `slot`
@@ -650,9 +762,9 @@ __device__ __forceinline__ void rank_slot(const DevIndex &ix, const uint4 *stage
     out[0] = sb[0] + r[0]; out[1] = sb[1] + r[1]; out[2] = sb[2] + r[2]; out[3] = sb[3] + r[3];
 }
 
-template <bool TWO>
+template <bool TWO, bool MULTI>
 __global__ void __launch_bounds__(kNavThreads, TWO ? kPairCtas : kNodeCtas)
-expand_leaves_kernel(const NavArgs a, const FrameIn in, const FrameOut out) {
+expand_leaves_kernel(const NavArgs a, const __grid_constant__ FrameInT<MULTI> in, const FrameOut out) {
     constexpr int RU = TWO ? 2 : 1;
     __shared__ __align__(1024) LeafSmem<TWO> sm;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -679,6 +791,14 @@ expand_leaves_kernel(const NavArgs a, const FrameIn in, const FrameOut out) {
             for (int k = 0; k < RU; ++k) cp_async16(recbuf + k, rec + k);
         }
         uint32_t run_cnt[4] = {0, 0, 0, 0};
+        uint32_t dcur[4] = {0, 0, 0, 0};
+        uint64_t dbound[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) dbound[c] = out.D > 1 ? out.range_len : ~0ull;
+        if (MULTI) {
+            for (int i = lane; i < 4 * kMaxDest; i += 32) sm.dcnt[warp][i] = 0;
+            __syncwarp();
+        }
         for (uint32_t g0 = g_begin; g0 < g_end; g0 += 32) {
             const uint32_t g = g0 + lane;
             const bool active = g < g_end;
@@ -763,13 +883,25 @@ expand_leaves_kernel(const NavArgs a, const FrameIn in, const FrameOut out) {
                     if (TWO) o[1] = make_ulonglong2(a.ix2.F[c] + lo2[c], a.ix2.F[c] + hi2[c]);
                 }
                 run_cnt[c] += tot[c];
+                // a leaf (pair) lives at the merged position of its first suffix
+                if (MULTI) count_dests(sm.dcnt[warp] + c * kMaxDest, dcur[c], dbound[c], out, lane, (vm >> c) & 1u,
+                                       a.ix1.F[c] + lo1[c] + (TWO ? a.ix2.F[c] + lo2[c] : 0ull), tot[c]);
             }
         }
-        if (lane < 4) {
-            uint32_t v = 0;
+        if (!MULTI) {
+            if (lane < 4) {
+                uint32_t v = 0;
 #pragma unroll
-            for (int c = 0; c < 4; ++c) if (lane == c) v = run_cnt[c];
-            out.cnt[(size_t)lane * out.K + run] = v;
+                for (int c = 0; c < 4; ++c) if (lane == c) v = run_cnt[c];
+                out.cnt[(size_t)lane * out.K + run] = v;
+            }
+        } else {
+            __syncwarp();
+            for (int i = lane; i < 4 * kMaxDest; i += 32) {
+                const uint32_t c = i / kMaxDest, h = i % kMaxDest;
+                if (h < out.D) out.cnt[((size_t)h * 4 + c) * out.K + run] = sm.dcnt[warp][i];
+            }
+            __syncwarp();
         }
     }
     if (a.write) {
@@ -801,8 +933,9 @@ group_sum_kernel(const uint32_t *__restrict__ cnt, uint32_t n_entries, uint32_t 
 }
 
 __global__ void __launch_bounds__(kIndexThreads)
-frame_index_kernel(const uint32_t *__restrict__ cnt, const uint32_t *__restrict__ gsum, uint32_t n_entries,
-                   uint32_t *__restrict__ P, uint32_t *__restrict__ hint, const SweepDev *sweep, HostCtl *host, unsigned long long seq) {
+frame_index_kernel(const uint32_t *__restrict__ cnt, const uint32_t *__restrict__ gsum, uint32_t n_entries, uint32_t K, uint32_t D,
+                   uint32_t *__restrict__ P, uint32_t *__restrict__ off, uint32_t *__restrict__ hint, SweepDev *sweep, HostCtl *host,
+                   unsigned long long seq) {
     __shared__ unsigned long long s_warp[kIndexThreads / 32];
     __shared__ unsigned long long s_off;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -819,7 +952,7 @@ frame_index_kernel(const uint32_t *__restrict__ cnt, const uint32_t *__restrict_
         s_off = t;
     }
     __syncthreads();
-    const unsigned long long off = s_off;
+    const unsigned long long goff = s_off;
     __syncthreads();
     // scan of the group's entries
     const uint32_t j = blockIdx.x * kIndexThreads + threadIdx.x;
@@ -832,21 +965,37 @@ frame_index_kernel(const uint32_t *__restrict__ cnt, const uint32_t *__restrict_
     }
     if (lane == 31) s_warp[warp] = incl;
     __syncthreads();
-    unsigned long long p = off + incl - c;
+    unsigned long long p = goff + incl - c;
     for (int w = 0; w < warp; ++w) p += s_warp[w];
     if (j < n_entries) {
         P[j] = (uint32_t)p;
         // every multiple of 256 inside [p, p + c) starts a hint
         for (unsigned long long t = (p + 255) >> 8; (t << 8) < p + c; ++t) hint[t] = j;
+        if (D > 1) {                                      // slots of the region taken by the destinations before this one
+            const uint32_t h = j / (4 * K), ck = j - h * 4 * K;
+            uint32_t o = 0;
+            for (uint32_t hh = 0; hh < h; ++hh) o += cnt[(size_t)hh * 4 * K + ck];
+            off[j] = o;
+        }
+        if (j % K == 0) ((volatile uint32_t *)host->qstart)[j / K] = (uint32_t)p;
     }
     if (j == n_entries - 1) {                             // the last entry knows the total
         const unsigned long long total = p + c;
         P[n_entries] = (uint32_t)total;
         hint[(total + 255) >> 8] = n_entries - 1;         // sentinel: upper bound of the last partial group
-        ((volatile unsigned long long *)host->out_count)[0] = total;
+        ((volatile uint32_t *)host->qstart)[4 * D] = (uint32_t)total;
+        *(volatile unsigned long long *)&host->total = total;
         *(volatile unsigned long long *)&host->maxsz = sweep->maxsz;
-        __threadfence_system();
-        *(volatile unsigned long long *)&host->seq = seq;
+    }
+    // the sequence number goes out after every CTA's part of the table
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t done = atomicAdd(&sweep->done, 1u);
+        if (done == gridDim.x - 1) {
+            __threadfence_system();
+            *(volatile unsigned long long *)&host->seq = seq;
+        }
     }
 }
 
@@ -874,19 +1023,23 @@ struct Frame {
     ~Frame() { if (p) arena->free(side, p); }
 };
 
-// layout of one frame inside its arena block: records, then cnt[4K], P[4K+1], hint[]
+// layout of one frame inside its arena block: records, then cnt[4DK], gsum[], P[4DK+1], off[4DK], hint[]
 struct FrameLayout {
-    uint32_t K, run_cap;
-    size_t rec_bytes, cnt_off, gsum_off, p_off, hint_off, total_bytes;
-    FrameLayout(uint64_t n_in, uint32_t run, int ru_out) {
+    uint32_t K, run_cap, D;
+    size_t rec_bytes, cnt_off, gsum_off, p_off, off_off, hint_off, total_bytes;
+    FrameLayout(uint64_t n_in, uint32_t run, int ru_out, uint32_t dests = 1) {
+        auto pad = [](size_t b) { return (b + 255) & ~(size_t)255; };
         run_cap = run;
+        D = dests;
         K = (uint32_t)((n_in + run - 1) / run);
+        const size_t ne = (size_t)4 * D * K;
         rec_bytes = (size_t)4 * K * run_cap * ru_out * sizeof(uint4);
-        cnt_off = (rec_bytes + 255) & ~(size_t)255;
-        gsum_off = cnt_off + (((size_t)4 * K * 4 + 255) & ~(size_t)255);
-        p_off = gsum_off + ((((size_t)4 * K / 256 + 1) * 4 + 255) & ~(size_t)255);
-        hint_off = p_off + ((((size_t)4 * K + 1) * 4 + 255) & ~(size_t)255);
-        total_bytes = hint_off + ((((size_t)4 * K * run_cap / 256 + 2) * 4 + 255) & ~(size_t)255);
+        cnt_off = pad(rec_bytes);
+        gsum_off = cnt_off + pad(ne * 4);
+        p_off = gsum_off + pad((ne / 256 + 1) * 4);
+        off_off = p_off + pad((ne + 1) * 4);
+        hint_off = off_off + pad(D > 1 ? ne * 4 : 0);
+        total_bytes = hint_off + pad(((size_t)4 * K * run_cap / 256 + 2) * 4);
     }
 };
 
@@ -978,12 +1131,14 @@ static int run_frontier(e2i_ctx *ctx, Chunk root, const PassCfg &cfg, NavArgs &a
         frame->p = mem;
         const FrameLayout lay(take, run_len, ru_out);
         char *fb = static_cast<char *>(mem);
-        FrameOut fo;
+        FrameOut fo{};
         fo.base = reinterpret_cast<uint4 *>(fb);
         fo.cnt = reinterpret_cast<uint32_t *>(fb + lay.cnt_off);
         fo.gsum = reinterpret_cast<uint32_t *>(fb + lay.gsum_off);
         fo.K = lay.K;
         fo.run_cap = lay.run_cap;
+        fo.D = 1;
+        fo.range_len = ~0ull;
         uint32_t *P = reinterpret_cast<uint32_t *>(fb + lay.p_off), *hint = reinterpret_cast<uint32_t *>(fb + lay.hint_off);
         if (ctx->ticket_next == kSweepSlots) {           // ring of sweep control blocks used up: zero it again
             E2I_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
@@ -1000,7 +1155,7 @@ static int run_frontier(e2i_ctx *ctx, Chunk root, const PassCfg &cfg, NavArgs &a
         launch(args, work.in, fo, in_small, out_small);
         if (debug) cudaEventRecord(ctx->ev[5], ctx->stream);
         group_sum_kernel<<<n_groups, kIndexThreads, 0, ctx->stream>>>(fo.cnt, 4 * fo.K, fo.gsum);
-        frame_index_kernel<<<n_groups, kIndexThreads, 0, ctx->stream>>>(fo.cnt, fo.gsum, 4 * fo.K, P, hint, args.sweep, hctl, seq);
+        frame_index_kernel<<<n_groups, kIndexThreads, 0, ctx->stream>>>(fo.cnt, fo.gsum, 4 * fo.K, fo.K, 1, P, nullptr, hint, args.sweep, hctl, seq);
         if (debug) cudaEventRecord(ctx->ev[6], ctx->stream);
         E2I_CUDA_TRY(cudaGetLastError());
         ctx->n_launch += 3;
@@ -1033,17 +1188,18 @@ static int run_frontier(e2i_ctx *ctx, Chunk root, const PassCfg &cfg, NavArgs &a
         ss.items += take;
         ss.sweeps++;
         ss.max_chunk = std::max<uint64_t>(ss.max_chunk, take);
-        const uint64_t n_out = ((volatile unsigned long long *)hctl->out_count)[0];
+        const uint64_t n_out = *(volatile unsigned long long *)&hctl->total;
         Chunk next;
         next.frame = frame;
         next.level = work.level + 1;
         next.small = out_small;
         next.bound = cfg.leaves ? ~0ull : std::min<uint64_t>(work.bound, ((volatile unsigned long long *)&hctl->maxsz)[0]);
-        next.in.base = fo.base;
-        next.in.P = P;
-        next.in.hint = hint;
-        next.in.K = fo.K;
-        next.in.run_cap = fo.run_cap;
+        next.in.s.base = fo.base;
+        next.in.s.P = P;
+        next.in.s.off = nullptr;
+        next.in.s.hint = hint;
+        next.in.s.K = fo.K;
+        next.in.s.run_cap = fo.run_cap;
         next.in.g_lo = 0;
         next.in.g_hi = (uint32_t)n_out;
         work.frame.reset();
@@ -1054,15 +1210,15 @@ static int run_frontier(e2i_ctx *ctx, Chunk root, const PassCfg &cfg, NavArgs &a
 
 // records [g_lo, g_hi) of a chunk copied to the host in order (sharding: the frames involved are small)
 static int fetch_chunk(e2i_ctx *ctx, const Chunk &c, int ru, std::vector<uint64_t> &host) {
-    const uint32_t n_entries = 4 * c.in.K;
+    const uint32_t n_entries = 4 * c.in.s.K;
     std::vector<uint32_t> P(n_entries + 1);
-    E2I_CUDA_TRY(cudaMemcpyAsync(P.data(), c.in.P, P.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    E2I_CUDA_TRY(cudaMemcpyAsync(P.data(), c.in.s.P, P.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
     E2I_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     host.resize((size_t)c.total() * ru * 2);
     for (uint32_t j = 0; j < n_entries; ++j) {
         const uint64_t lo = std::max<uint64_t>(P[j], c.in.g_lo), hi = std::min<uint64_t>(P[j + 1], c.in.g_hi);
         if (lo >= hi) continue;
-        const uint4 *src = c.in.base + ((size_t)j * c.in.run_cap + (lo - P[j])) * ru;   // entry j = (queue, run) in order
+        const uint4 *src = c.in.s.base + ((size_t)j * c.in.s.run_cap + (lo - P[j])) * ru;   // entry j = (queue, run) in order
         E2I_CUDA_TRY(cudaMemcpyAsync(host.data() + (lo - c.in.g_lo) * ru * 2, src, (hi - lo) * ru * 16, cudaMemcpyDeviceToHost, ctx->stream));
     }
     E2I_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
@@ -1075,8 +1231,12 @@ using namespace e2i;
 
 static uint64_t padded_words32(uint64_t bits) { return ((bits + 31) / 32 + 63) / 64 * 64 + 64; }
 
-extern "C" int e2i_navigate_shard(e2i_ctx *ctx, const e2i_index *b1, const e2i_index *b2, const e2i_params *p,
-                                  int shard, int n_shards, e2i_lcpbits **out, e2i_bits **da_out, e2i_stats *st) {
+// comm == nullptr: this rank traverses the subtrees dealt to `shard` (or everything when n_shards == 1).
+// comm != nullptr: position-range sharding -- rank r processes the nodes (leaves) whose first position lies in
+// its range of the suffix array and pulls its records from the frames of all ranks over peer memory, level
+// by level (run_pass_ranged).
+static int navigate_impl(e2i_ctx *ctx, const e2i_index *b1, const e2i_index *b2, const e2i_params *p, int shard, int n_shards, e2i_comm *comm,
+                         e2i_lcpbits **out, e2i_bits **da_out, e2i_stats *st) {
     if (!ctx || !b1 || !p || !out || !st) { set_error("e2i_navigate: null argument"); return E2I_ERR_ARG; }
     if (b2 && !da_out) { set_error("e2i_navigate: da_out is required with two BWTs"); return E2I_ERR_ARG; }
     if (n_shards < 1 || shard < 0 || shard >= n_shards) { set_error("e2i_navigate: bad shard %d/%d", shard, n_shards); return E2I_ERR_ARG; }
@@ -1126,13 +1286,8 @@ extern "C" int e2i_navigate_shard(e2i_ctx *ctx, const e2i_index *b1, const e2i_i
     uint64_t budget = ctx->frontier_budget ? ctx->frontier_budget : (uint64_t)(free_b * 0.85);
     {   // the frame arena: kept across calls, re-allocated only when this input needs a larger one
         const uint64_t want = std::min<uint64_t>(budget, std::max<uint64_t>(1ull << 30, 4 * n));
-        if (ctx->arena_bytes < want && ctx->arena_bytes < budget) {
-            dfree(ctx, ctx->arena_mem);
-            ctx->arena_mem = nullptr;
-            ctx->arena_bytes = 0;
-            TRYF(dmalloc(ctx, &ctx->arena_mem, want));
-            ctx->arena_bytes = want;
-        }
+        const bool ipc = comm && comm->needs_ipc();
+        if ((ctx->arena_bytes < want && ctx->arena_bytes < budget) || (ipc && !ctx->arena_ipc)) TRYF(arena_alloc(ctx, want, ipc));
         const uint64_t use = ctx->frontier_budget ? std::min<uint64_t>(ctx->arena_bytes, ctx->frontier_budget) : ctx->arena_bytes;
         ctx->arena.reset(static_cast<char *>(ctx->arena_mem), use);
         budget = use;
@@ -1163,10 +1318,10 @@ extern "C" int e2i_navigate_shard(e2i_ctx *ctx, const e2i_index *b1, const e2i_i
     const uint64_t kDealItems = 4096ull * (uint64_t)n_shards;
     {   // the sweep kernels use ~20 KB of static shared memory per CTA and want 4-7 CTAs per SM: ask for the large carveout
         const int pct = (int)cudaSharedmemCarveoutMaxShared;
-        TRYF(cudaFuncSetAttribute(expand_nodes_kernel<false, true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
-        TRYF(cudaFuncSetAttribute(expand_nodes_kernel<true, true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
-        TRYF(cudaFuncSetAttribute(expand_leaves_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
-        TRYF(cudaFuncSetAttribute(expand_leaves_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+        TRYF(cudaFuncSetAttribute(expand_nodes_kernel<false, true, true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+        TRYF(cudaFuncSetAttribute(expand_nodes_kernel<true, true, true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+        TRYF(cudaFuncSetAttribute(expand_leaves_kernel<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+        TRYF(cudaFuncSetAttribute(expand_leaves_kernel<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
     }
     const uint32_t ctas_per_sm = two ? (uint32_t)kPairCtas : (uint32_t)kNodeCtas;
 
@@ -1202,11 +1357,12 @@ extern "C" int e2i_navigate_shard(e2i_ctx *ctx, const e2i_index *b1, const e2i_i
         E2I_CUDA_TRY(cudaMemcpyAsync(rootmem, hostroot, root_bytes, cudaMemcpyHostToDevice, s));
         (void)ru_root;
         Chunk root{};
-        root.in.base = reinterpret_cast<uint4 *>(rootmem);
-        root.in.P = reinterpret_cast<uint32_t *>(rootmem + 512);
-        root.in.hint = reinterpret_cast<uint32_t *>(rootmem + 640);
-        root.in.K = 1;
-        root.in.run_cap = 1;
+        root.in.s.base = reinterpret_cast<uint4 *>(rootmem);
+        root.in.s.P = reinterpret_cast<uint32_t *>(rootmem + 512);
+        root.in.s.off = nullptr;
+        root.in.s.hint = reinterpret_cast<uint32_t *>(rootmem + 640);
+        root.in.s.K = 1;
+        root.in.s.run_cap = 1;
         root.in.g_lo = 0;
         root.in.g_hi = 1;
         root.small = false;
@@ -1219,16 +1375,16 @@ extern "C" int e2i_navigate_shard(e2i_ctx *ctx, const e2i_index *b1, const e2i_i
             const uint32_t want = (fo.K + kNavWarps - 1) / kNavWarps;
             if (leaves) {
                 const uint32_t grid = std::min<uint32_t>(want, (uint32_t)ctx->sm_count * ctas_per_sm);
-                if (two) expand_leaves_kernel<true><<<grid, kNavThreads, 0, s>>>(a, fi, fo);
-                else expand_leaves_kernel<false><<<grid, kNavThreads, 0, s>>>(a, fi, fo);
+                if (two) expand_leaves_kernel<true, false><<<grid, kNavThreads, 0, s>>>(a, fi, fo);
+                else expand_leaves_kernel<false, false><<<grid, kNavThreads, 0, s>>>(a, fi, fo);
             } else if (in_small) {
                 const uint32_t grid = std::min<uint32_t>(want, (uint32_t)ctx->sm_count * ctas_per_sm);
-                if (two) expand_nodes_kernel<true, true, true><<<grid, kNavThreads, 0, s>>>(a, fi, fo);
-                else expand_nodes_kernel<false, true, true><<<grid, kNavThreads, 0, s>>>(a, fi, fo);
+                if (two) expand_nodes_kernel<true, true, true, false><<<grid, kNavThreads, 0, s>>>(a, fi, fo);
+                else expand_nodes_kernel<false, true, true, false><<<grid, kNavThreads, 0, s>>>(a, fi, fo);
             } else {
                 const uint32_t grid = std::min<uint32_t>(want, (uint32_t)ctx->sm_count * 2);
-                if (out_small) { if (two) expand_nodes_kernel<true, false, true><<<grid, kNavThreads, 0, s>>>(a, fi, fo); else expand_nodes_kernel<false, false, true><<<grid, kNavThreads, 0, s>>>(a, fi, fo); }
-                else { if (two) expand_nodes_kernel<true, false, false><<<grid, kNavThreads, 0, s>>>(a, fi, fo); else expand_nodes_kernel<false, false, false><<<grid, kNavThreads, 0, s>>>(a, fi, fo); }
+                if (out_small) { if (two) expand_nodes_kernel<true, false, true, false><<<grid, kNavThreads, 0, s>>>(a, fi, fo); else expand_nodes_kernel<false, false, true, false><<<grid, kNavThreads, 0, s>>>(a, fi, fo); }
+                else { if (two) expand_nodes_kernel<true, false, false, false><<<grid, kNavThreads, 0, s>>>(a, fi, fo); else expand_nodes_kernel<false, false, false, false><<<grid, kNavThreads, 0, s>>>(a, fi, fo); }
             }
         };
         if (n_shards == 1) {
@@ -1274,17 +1430,191 @@ extern "C" int e2i_navigate_shard(e2i_ctx *ctx, const e2i_index *b1, const e2i_i
         return E2I_OK;
     };
 
+    // ---- position-range sharding (comm != nullptr) ------------------------------------------------------
+    // Rank r owns the suffix-array positions [r * range_len, (r + 1) * range_len) and processes the records
+    // whose (merged) first position lies there.  A sweep writes its children into the rank's OWN gappy frame,
+    // counted per destination rank; after the sweep every rank publishes where each (destination, queue)
+    // piece of its frame starts, and the next sweep PULLS its input -- the pieces addressed to it, in
+    // (queue, source rank) order, which is position order -- straight out of the peers' frames over
+    // NVLink (P2P loads in the kernel's record prefetch).  One barrier per level; no collective, no staging.
+    // Every rank's frontier stays as dense as the single-GPU frontier, which is what the subtree deal loses.
+    struct LevelInfo {                                  // what a rank publishes after a sweep (one comm slot)
+        uint64_t total, maxsz;
+        uint64_t rec_off, p_off, off_off, hint_off;     // the frame inside the rank's arena
+        uint32_t K, run_cap, small, error;
+        uint32_t qstart[4 * kMaxDest + 1];
+        void *arena_base;
+        cudaIpcMemHandle_t arena_handle;
+    };
+    static_assert(sizeof(LevelInfo) <= kCommSlotBytes, "LevelInfo must fit a comm slot");
+    auto run_pass_ranged = [&](bool leaves, SweepStats &ss) -> int {
+        const int world = comm->world, me = comm->rank;
+        HostCtl *hctl = reinterpret_cast<HostCtl *>(ctx->ctl_host);
+        const uint64_t range_len = (n + world - 1) / world;
+        const uint32_t resident_warps = (uint32_t)ctx->sm_count * ctas_per_sm * kNavWarps;
+        LevelInfo mine;
+        std::memset(&mine, 0, sizeof mine);
+        mine.arena_base = ctx->arena_mem;
+        if (comm->needs_ipc()) E2I_CUDA_TRY(cudaIpcGetMemHandle(&mine.arena_handle, ctx->arena_mem));
+        mine.K = 1; mine.run_cap = 1;
+        char *const abase = static_cast<char *>(ctx->arena_mem);
+        std::shared_ptr<Frame> f_prev, f_old;
+        // level 0: the root lives on rank 0 (its first position is 0), as a frame with one record
+        if (me == 0) {
+            const int ru_root = leaves ? (two ? 2 : 1) : node_rec_u4(false, two);
+            const FrameLayout lay(1, 1, ru_root, (uint32_t)world);
+            char *mem = static_cast<char *>(ctx->arena.alloc(0, lay.total_bytes));
+            if (!mem) { set_error("frontier arena too small"); return E2I_ERR_MEMORY; }
+            std::vector<uint64_t> host(lay.total_bytes / 8 + 1, 0);
+            uint64_t *rec = host.data();
+            if (leaves) { rec[0] = 0; rec[1] = b1->F[0]; if (two) { rec[2] = 0; rec[3] = b2->F[0]; } }
+            else { pack_wide_host(rec, 0, b1->F, b1->n); if (two) pack_wide_host(rec + 6, 0, b2->F, b2->n); }
+            uint32_t *hp = reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(host.data()) + lay.p_off);
+            const uint32_t ne = 4 * (uint32_t)world;
+            for (uint32_t e = 1; e <= ne; ++e) hp[e] = 1;                  // P = {0, 1, 1, ...}: the record is entry (h=0, c=0, k=0)
+            uint32_t *hh = reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(host.data()) + lay.hint_off);
+            hh[0] = 0; hh[1] = ne - 1;
+            E2I_CUDA_TRY(cudaMemcpyAsync(mem, host.data(), lay.total_bytes, cudaMemcpyHostToDevice, s));
+            E2I_CUDA_TRY(cudaStreamSynchronize(s));
+            f_prev = std::make_shared<Frame>();
+            f_prev->arena = &ctx->arena; f_prev->side = 0; f_prev->p = mem;
+            mine.total = 1;
+            mine.rec_off = (uint64_t)(mem - abase); mine.p_off = mine.rec_off + lay.p_off; mine.off_off = mine.rec_off + lay.off_off;
+            mine.hint_off = mine.rec_off + lay.hint_off;
+            for (uint32_t i = 1; i <= ne; ++i) mine.qstart[i] = 1;
+        }
+        mine.maxsz = std::max<uint64_t>(b1->n, two ? b2->n : 0);
+        mine.small = 0;
+        std::vector<LevelInfo> info((size_t)world);
+        std::vector<char *> peer_base((size_t)world, nullptr);
+        for (int level = 0;; ++level) {
+            std::memcpy(comm->slot(me), &mine, sizeof mine);
+            comm->barrier();                              // every rank has finished the previous sweep and published its frame
+            uint64_t all = 0, bound = 0;
+            uint32_t err = 0;
+            for (int r = 0; r < world; ++r) {
+                std::memcpy(&info[r], comm->slot(r), sizeof(LevelInfo));
+                all += info[r].total; bound = std::max(bound, info[r].maxsz); err |= info[r].error;
+                if (!peer_base[r]) peer_base[r] = static_cast<char *>(r == me ? (void *)abase : comm->peer_ptr(r, info[r].arena_base, info[r].arena_handle));
+                if (!peer_base[r]) { set_error("cannot map the frame arena of rank %d", r); err |= 1; }
+            }
+            comm->barrier();                              // everybody has read the slots: they may be rewritten
+            f_old.reset();                                // the frame of two levels ago is dead on every rank
+            f_old = f_prev;
+            f_prev.reset();
+            if (err) { if (!mine.error) set_error("position-range traversal failed on another rank"); return E2I_ERR_MEMORY; }
+            if (all == 0) break;
+            // my input: for every queue, the pieces the ranks addressed to me, in rank order
+            FrameInT<true> in;
+            std::memset(&in, 0, sizeof in);
+            uint32_t n_in = 0;
+            for (int c = 0; c < 4; ++c) {
+                for (int r = 0; r < world; ++r) {
+                    const uint32_t lo = info[r].qstart[me * 4 + c], hi = info[r].qstart[me * 4 + c + 1];
+                    if (hi <= lo) continue;
+                    Segment &sg = in.seg[in.n_seg++];
+                    sg.start = n_in; sg.len = hi - lo; sg.lo = lo; sg.src = (uint32_t)r;
+                    n_in += hi - lo;
+                }
+            }
+            for (int r = 0; r < world; ++r) {
+                FrameSrc &f = in.src[r];
+                f.base = reinterpret_cast<const uint4 *>(peer_base[r] + info[r].rec_off);
+                f.P = reinterpret_cast<const uint32_t *>(peer_base[r] + info[r].p_off);
+                f.off = reinterpret_cast<const uint32_t *>(peer_base[r] + info[r].off_off);
+                f.hint = reinterpret_cast<const uint32_t *>(peer_base[r] + info[r].hint_off);
+                f.K = info[r].K; f.run_cap = info[r].run_cap;
+            }
+            in.g_lo = 0; in.g_hi = n_in;
+            const bool in_small = !leaves && info[0].small, out_small = !leaves && bound < kSmallLimit;
+            std::memset(&mine, 0, sizeof mine);
+            mine.arena_base = ctx->arena_mem;
+            mine.K = 1; mine.run_cap = 1; mine.small = out_small; mine.maxsz = 0;
+            if (n_in == 0) continue;                      // nothing for me on this level (I still keep the barriers company)
+            const int ru_out = leaves ? (two ? 2 : 1) : node_rec_u4(out_small, two);
+            const uint32_t run_len = (uint32_t)std::min<uint64_t>(kMaxRun, std::max<uint64_t>(32, (n_in / ((uint64_t)resident_warps * (leaves ? 1 : 4)) + 31) / 32 * 32));
+            const FrameLayout lay(n_in, run_len, ru_out, (uint32_t)world);
+            char *mem = static_cast<char *>(ctx->arena.alloc((level + 1) & 1, lay.total_bytes));
+            if (!mem) {
+                set_error("frontier memory exhausted in the position-range traversal (arena %llu bytes, level of %u records): raise the frontier budget",
+                          (unsigned long long)ctx->arena.size(), n_in);
+                mine.error = 1;
+                continue;                                 // the other ranks learn about it at the next barrier
+            }
+            f_prev = std::make_shared<Frame>();
+            f_prev->arena = &ctx->arena; f_prev->side = (level + 1) & 1; f_prev->p = mem;
+            FrameOut fo{};
+            fo.base = reinterpret_cast<uint4 *>(mem);
+            fo.cnt = reinterpret_cast<uint32_t *>(mem + lay.cnt_off);
+            fo.gsum = reinterpret_cast<uint32_t *>(mem + lay.gsum_off);
+            fo.K = lay.K; fo.run_cap = lay.run_cap; fo.D = (uint32_t)world; fo.range_len = range_len;
+            uint32_t *P = reinterpret_cast<uint32_t *>(mem + lay.p_off), *off = reinterpret_cast<uint32_t *>(mem + lay.off_off),
+                     *hint = reinterpret_cast<uint32_t *>(mem + lay.hint_off);
+            if (ctx->ticket_next == kSweepSlots) {
+                E2I_CUDA_TRY(cudaStreamSynchronize(s));
+                E2I_CUDA_TRY(cudaMemsetAsync(ctx->ctl, 0, kSweepSlots * sizeof(SweepDev), s));
+                ctx->ticket_next = 0;
+            }
+            args.sweep = reinterpret_cast<SweepDev *>(ctx->ctl) + ctx->ticket_next++;
+            args.bits = ((uint64_t)level >= (uint64_t)p->K ? 1u : 0u) | ((uint64_t)level >= (uint64_t)p->k_right ? 2u : 0u);
+            args.write = 1;
+            const unsigned long long seq = ++ctx->sweep_seq;
+            const uint32_t grid = std::min<uint32_t>((fo.K + kNavWarps - 1) / kNavWarps, (uint32_t)ctx->sm_count * ctas_per_sm);
+            if (leaves) {
+                if (two) expand_leaves_kernel<true, true><<<grid, kNavThreads, 0, s>>>(args, in, fo);
+                else expand_leaves_kernel<false, true><<<grid, kNavThreads, 0, s>>>(args, in, fo);
+            } else if (in_small) {
+                if (two) expand_nodes_kernel<true, true, true, true><<<grid, kNavThreads, 0, s>>>(args, in, fo);
+                else expand_nodes_kernel<false, true, true, true><<<grid, kNavThreads, 0, s>>>(args, in, fo);
+            } else if (out_small) {
+                if (two) expand_nodes_kernel<true, false, true, true><<<grid, kNavThreads, 0, s>>>(args, in, fo);
+                else expand_nodes_kernel<false, false, true, true><<<grid, kNavThreads, 0, s>>>(args, in, fo);
+            } else {
+                if (two) expand_nodes_kernel<true, false, false, true><<<grid, kNavThreads, 0, s>>>(args, in, fo);
+                else expand_nodes_kernel<false, false, false, true><<<grid, kNavThreads, 0, s>>>(args, in, fo);
+            }
+            const uint32_t n_entries = 4 * fo.D * fo.K, n_groups = (n_entries + kIndexThreads - 1) / kIndexThreads;
+            group_sum_kernel<<<n_groups, kIndexThreads, 0, s>>>(fo.cnt, n_entries, fo.gsum);
+            frame_index_kernel<<<n_groups, kIndexThreads, 0, s>>>(fo.cnt, fo.gsum, n_entries, fo.K, fo.D, P, off, hint, args.sweep, hctl, seq);
+            E2I_CUDA_TRY(cudaGetLastError());
+            ctx->n_launch += 3;
+            ctx->n_d2h += sizeof(HostCtl);
+            {
+                volatile unsigned long long *seqp = &hctl->seq;
+                unsigned spins = 0;
+                while (*seqp != seq) {
+                    if ((++spins & 0xfffu) == 0) {
+                        const cudaError_t q = cudaStreamQuery(s);
+                        if (q == cudaSuccess) { if (*seqp == seq) break; set_error("traversal sweep finished without publishing its counts"); return E2I_ERR_CUDA; }
+                        if (q != cudaErrorNotReady) { set_error("CUDA error in a traversal sweep: %s", cudaGetErrorString(q)); return E2I_ERR_CUDA; }
+                    }
+                }
+                std::atomic_thread_fence(std::memory_order_acquire);
+            }
+            ss.items += n_in;
+            ss.sweeps++;
+            ss.max_chunk = std::max<uint64_t>(ss.max_chunk, n_in);
+            mine.total = *(volatile unsigned long long *)&hctl->total;
+            mine.maxsz = leaves ? 0 : *(volatile unsigned long long *)&hctl->maxsz;
+            mine.rec_off = (uint64_t)(mem - abase); mine.p_off = mine.rec_off + lay.p_off; mine.off_off = mine.rec_off + lay.off_off;
+            mine.hint_off = mine.rec_off + lay.hint_off;
+            mine.K = fo.K; mine.run_cap = fo.run_cap;
+            for (uint32_t i = 0; i <= 4 * fo.D; ++i) mine.qstart[i] = ((volatile uint32_t *)hctl->qstart)[i];
+        }
+        return E2I_OK;
+    };
+
     unsigned long long tot[C_NCOUNTERS];
     // ---- Phase 2: leaves ----
     TRYF(cudaMemsetAsync(stripes, 0, stripe_bytes, s));
     TRYF(cudaEventRecord(ctx->ev[0], s));
     SweepStats sl;
-    int rc = run_pass(true, sl);
+    int rc = comm ? run_pass_ranged(true, sl) : run_pass(true, sl);
     if (rc != E2I_OK) return fail(rc);
     TRYF(cudaEventRecord(ctx->ev[1], s));
     rc = sum_stripes(tot);
     if (rc != E2I_OK) return fail(rc);
-    const uint64_t first = shard == 0 ? 1 : 0;          // lcp_values starts at 1 (ebwt2InDel.cpp:575)
+    const uint64_t first = (comm ? comm->rank : shard) == 0 ? 1 : 0;          // lcp_values starts at 1 (ebwt2InDel.cpp:575)
     st->leaves += sl.items;
     st->levels_leaves += sl.sweeps;
     st->rank_leaves += tot[C_RANK];
@@ -1297,7 +1627,7 @@ extern "C" int e2i_navigate_shard(e2i_ctx *ctx, const e2i_index *b1, const e2i_i
     TRYF(cudaMemsetAsync(stripes, 0, stripe_bytes, s));
     TRYF(cudaEventRecord(ctx->ev[2], s));
     SweepStats sn;
-    rc = run_pass(false, sn);
+    rc = comm ? run_pass_ranged(false, sn) : run_pass(false, sn);
     if (rc != E2I_OK) return fail(rc);
     TRYF(cudaEventRecord(ctx->ev[3], s));
     rc = sum_stripes(tot);
@@ -1326,9 +1656,21 @@ extern "C" int e2i_navigate_shard(e2i_ctx *ctx, const e2i_index *b1, const e2i_i
     return E2I_OK;
 }
 
+extern "C" int e2i_navigate_shard(e2i_ctx *ctx, const e2i_index *b1, const e2i_index *b2, const e2i_params *p,
+                                  int shard, int n_shards, e2i_lcpbits **out, e2i_bits **da_out, e2i_stats *st) {
+    return navigate_impl(ctx, b1, b2, p, shard, n_shards, nullptr, out, da_out, st);
+}
+
 extern "C" int e2i_navigate(e2i_ctx *ctx, const e2i_index *b1, const e2i_index *b2, const e2i_params *p,
                             e2i_lcpbits **out, e2i_bits **da_out, e2i_stats *st) {
-    return e2i_navigate_shard(ctx, b1, b2, p, 0, 1, out, da_out, st);
+    return navigate_impl(ctx, b1, b2, p, 0, 1, nullptr, out, da_out, st);
+}
+
+extern "C" int e2i_navigate_ranged(e2i_ctx *ctx, e2i_comm *comm, const e2i_index *b1, const e2i_index *b2, const e2i_params *p,
+                                   e2i_lcpbits **out, e2i_bits **da_out, e2i_stats *st) {
+    if (!comm || comm->world < 1 || comm->world > kMaxDest) { set_error("e2i_navigate_ranged: bad communicator"); return E2I_ERR_ARG; }
+    if (comm->world == 1) return navigate_impl(ctx, b1, b2, p, 0, 1, nullptr, out, da_out, st);
+    return navigate_impl(ctx, b1, b2, p, 0, 1, comm, out, da_out, st);
 }
 
 extern "C" int e2i_lcpbits_fetch(e2i_ctx *ctx, const e2i_lcpbits *l, uint64_t *host_thr_words, uint64_t *host_min_words) {

@@ -35,6 +35,7 @@ typedef struct e2i_ctx e2i_ctx;         /* device + streams + scratch */
 typedef struct e2i_index e2i_index;     /* rank-indexed BWT in HBM: replaces dna_bwt_t (internal/dna_bwt.hpp:24-420) */
 typedef struct e2i_bits e2i_bits;       /* packed bitvector in HBM: replaces vector<bool> DA (ebwt2InDel.cpp:58) */
 typedef struct e2i_lcpbits e2i_lcpbits; /* LCP_threshold (2n bits) + LCP_minima (n bits) (ebwt2InDel.cpp:56-57) */
+typedef struct e2i_comm e2i_comm;       /* ranks of a multi-GPU run: barrier + publish slots + peer memory mapping */
 typedef struct e2i_calls e2i_calls;     /* per-cluster variant records, SA order (variant_t / variant_single_t, :115-141) */
 
 /* Resolved parameters: the globals of ebwt2InDel.cpp:20-74 after the "0 means default" rule (:1740-1746). */
@@ -270,6 +271,19 @@ int e2i_run_multi(const int *devices, int n_devices, const uint8_t *host_bwt1, u
                   uint64_t n2, const uint8_t *host_da, const e2i_params *p, uint64_t frontier_budget,
                   char **snp, size_t *snp_len, e2i_stats *st);
 int e2i_enable_peers(e2i_ctx **ctxs, int n);
+/* Position-range sharded traversal (the dense alternative to e2i_navigate_shard): rank r of `comm`
+ * processes the nodes / leaves whose first suffix-array position lies in its 1/world range; after every level the
+ * ranks publish where each (destination, queue) piece of their frame starts and the next sweep pulls its input
+ * straight out of the peers' frames over NVLink (P2P loads); one barrier per level, no collective.  All ranks call
+ * it together.  The bit vectors still have to be OR-combined afterwards.  Communicators: e2i_comm_local (world
+ * handles for the threads of one process) or e2i_comm_shm (one handle per process of one box; `name` is a POSIX
+ * shared-memory name chosen by the launcher, rank 0 creates it; peer device memory is mapped by CUDA IPC). */
+int e2i_navigate_ranged(e2i_ctx *ctx, e2i_comm *comm, const e2i_index *b1, const e2i_index *b2, const e2i_params *p,
+                        e2i_lcpbits **out, e2i_bits **da_out, e2i_stats *st);
+int e2i_comm_local(int world, e2i_comm **out);
+int e2i_comm_shm(const char *name, int rank, int world, e2i_comm **out);
+void e2i_comm_barrier(e2i_comm *c);
+void e2i_comm_free(e2i_comm *c);
 int e2i_or_allreduce(e2i_ctx *ctx, void *const *dev_words, int n_ranks, int rank, uint64_t words32);
 
 #ifdef __cplusplus
