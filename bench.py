@@ -466,7 +466,9 @@ def main():
                        "nodes_per_step": nodes, "leaves_per_step": st["leaves"],
                        "l2": "inputs larger than L2 (index + bitvectors > 126 MB)" if wl["n"] * 0.875 > 126e6 else
                              "index fits L2; every step rebuilds it from the ASCII input",
-                       "parallelism": f"replicated index, {world} traversal shard(s), 1 OR all-reduce" if world > 1 else "single GPU"},
+                       "parallelism": (f"replicated index, traversal sharded over {world} GPUs by "
+                                       + ("subtrees" if os.environ.get("E2I_SHARDING") == "subtree" else "suffix-array position range (records pulled from the peers' frames over NVLink)")
+                                       + ", 1 OR all-reduce of the bit vectors, phase 4 by position range") if world > 1 else "single GPU"},
             "phase_ms": {k: st[k] for k in ("ms_index", "ms_leaves", "ms_nodes", "ms_call", "ms_format", "ms_wall")},
             "wall_ms_per_step": 1e3 * wall_s / args.steps,
             "rank_queries_per_s": (st["rank_leaves"] + st["rank_nodes"] + st["rank_call"]) * args.steps / dev_s,

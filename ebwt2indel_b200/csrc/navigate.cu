@@ -170,8 +170,19 @@ struct Cursor {               // per lane: the entry that holds the lane's curre
     uint32_t s, delta, seg_end, offj;                 // MULTI: segment, source index - position, end of the segment
 };
 
+// entry of a frame that holds global index x: the hints bracket it, a binary search on P finds it -- the
+// entries in between may be thousands of empty ones (a queue without children for a destination)
+__device__ __forceinline__ uint32_t locate_entry(const uint32_t *__restrict__ P, const uint32_t *__restrict__ hint, uint32_t x) {
+    uint32_t lo = __ldg(hint + (x >> 8)), hi = __ldg(hint + (x >> 8) + 1);   // last j in [lo, hi] with P[j] <= x
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi + 1) >> 1;
+        if (__ldg(P + mid) <= x) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+
 __device__ __forceinline__ void cursor_open(const FrameInT<false> &in, Cursor &cur, uint32_t g) {
-    cur.j = __ldg(in.s.hint + (g >> 8));
+    cur.j = locate_entry(in.s.P, in.s.hint, g);
     cur.c = cur.j / in.s.K;
     cur.k = cur.j - cur.c * in.s.K;
     cur.pj = __ldg(in.s.P + cur.j);
@@ -180,12 +191,7 @@ __device__ __forceinline__ void cursor_open(const FrameInT<false> &in, Cursor &c
 
 // move to the entry that holds g (g never decreases, g < P[last])
 __device__ __forceinline__ void cursor_seek(const FrameInT<false> &in, Cursor &cur, uint32_t g) {
-    while (g >= cur.pj1) {
-        ++cur.j;
-        if (++cur.k == in.s.K) { cur.k = 0; ++cur.c; }
-        cur.pj = cur.pj1;
-        cur.pj1 = __ldg(in.s.P + cur.j + 1);
-    }
+    if (g >= cur.pj1) cursor_open(in, cur, g);
 }
 
 __device__ __forceinline__ const uint4 *cursor_record(const FrameInT<false> &in, const Cursor &cur, uint32_t g, int ru) {
@@ -202,10 +208,10 @@ __device__ __forceinline__ void cursor_enter(const FrameInT<true> &in, Cursor &c
     cur.delta = sg.lo - sg.start;
     cur.seg_end = sg.start + sg.len;
     const uint32_t x = g + cur.delta;
-    uint32_t j = __ldg(f.hint + (x >> 8));
-    uint32_t pj = __ldg(f.P + j), pj1 = __ldg(f.P + j + 1);
-    while (x >= pj1) { ++j; pj = pj1; pj1 = __ldg(f.P + j + 1); }
-    cur.j = j; cur.pj = pj; cur.pj1 = pj1;
+    const uint32_t j = locate_entry(f.P, f.hint, x);
+    cur.j = j;
+    cur.pj = __ldg(f.P + j);
+    cur.pj1 = __ldg(f.P + j + 1);
     cur.c = (j / f.K) & 3u;
     cur.k = j % f.K;
     cur.offj = f.off ? __ldg(f.off + j) : 0u;
@@ -215,18 +221,7 @@ __device__ __forceinline__ void cursor_open(const FrameInT<true> &in, Cursor &cu
     cursor_enter(in, cur, g);
 }
 __device__ __forceinline__ void cursor_seek(const FrameInT<true> &in, Cursor &cur, uint32_t g) {
-    if (g >= cur.seg_end) { cursor_enter(in, cur, g); return; }
-    const uint32_t x = g + cur.delta;
-    if (x >= cur.pj1) {
-        const FrameSrc &f = in.src[in.seg[cur.s].src];
-        while (x >= cur.pj1) {
-            ++cur.j;
-            if (++cur.k == f.K) { cur.k = 0; cur.c = (cur.c + 1) & 3u; }
-            cur.pj = cur.pj1;
-            cur.pj1 = __ldg(f.P + cur.j + 1);
-        }
-        cur.offj = f.off ? __ldg(f.off + cur.j) : 0u;
-    }
+    if (g >= cur.seg_end || g + cur.delta >= cur.pj1) cursor_enter(in, cur, g);
 }
 __device__ __forceinline__ const uint4 *cursor_record(const FrameInT<true> &in, const Cursor &cur, uint32_t g, int ru) {
     const FrameSrc &f = in.src[in.seg[cur.s].src];
@@ -1487,8 +1482,11 @@ static int navigate_impl(e2i_ctx *ctx, const e2i_index *b1, const e2i_index *b2,
         mine.small = 0;
         std::vector<LevelInfo> info((size_t)world);
         std::vector<char *> peer_base((size_t)world, nullptr);
+        double t_bar = 0, t_wait = 0, t_host = 0;
+        static const bool debug = std::getenv("E2I_DEBUG") != nullptr;
         for (int level = 0;; ++level) {
             std::memcpy(comm->slot(me), &mine, sizeof mine);
+            const double tb0 = now_ms();
             comm->barrier();                              // every rank has finished the previous sweep and published its frame
             uint64_t all = 0, bound = 0;
             uint32_t err = 0;
@@ -1499,6 +1497,8 @@ static int navigate_impl(e2i_ctx *ctx, const e2i_index *b1, const e2i_index *b2,
                 if (!peer_base[r]) { set_error("cannot map the frame arena of rank %d", r); err |= 1; }
             }
             comm->barrier();                              // everybody has read the slots: they may be rewritten
+            t_bar += now_ms() - tb0;
+            const double th0 = now_ms();
             f_old.reset();                                // the frame of two levels ago is dead on every rank
             f_old = f_prev;
             f_prev.reset();
@@ -1579,6 +1579,8 @@ static int navigate_impl(e2i_ctx *ctx, const e2i_index *b1, const e2i_index *b2,
             E2I_CUDA_TRY(cudaGetLastError());
             ctx->n_launch += 3;
             ctx->n_d2h += sizeof(HostCtl);
+            t_host += now_ms() - th0;
+            const double tw0 = now_ms();
             {
                 volatile unsigned long long *seqp = &hctl->seq;
                 unsigned spins = 0;
@@ -1591,6 +1593,7 @@ static int navigate_impl(e2i_ctx *ctx, const e2i_index *b1, const e2i_index *b2,
                 }
                 std::atomic_thread_fence(std::memory_order_acquire);
             }
+            t_wait += now_ms() - tw0;
             ss.items += n_in;
             ss.sweeps++;
             ss.max_chunk = std::max<uint64_t>(ss.max_chunk, n_in);
@@ -1601,6 +1604,8 @@ static int navigate_impl(e2i_ctx *ctx, const e2i_index *b1, const e2i_index *b2,
             mine.K = fo.K; mine.run_cap = fo.run_cap;
             for (uint32_t i = 0; i <= 4 * fo.D; ++i) mine.qstart[i] = ((volatile uint32_t *)hctl->qstart)[i];
         }
+        if (debug) std::fprintf(stderr, "[e2i] ranged %s pass, rank %d: %llu sweeps, barriers %.1f ms, host %.1f ms, waiting for the sweeps %.1f ms\n",
+                                leaves ? "leaf" : "node", me, (unsigned long long)ss.sweeps, t_bar, t_host, t_wait);
         return E2I_OK;
     };
 

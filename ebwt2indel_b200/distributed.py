@@ -20,6 +20,23 @@ import torch.distributed as dist
 
 
 _pinned = None
+_comm = None            # (world, handle): shared-memory communicator of the position-range traversal, made once per process
+
+
+def shm_comm(api, rank: int, world: int, group=None):
+    """The e2i_comm of this process group: a POSIX shared-memory segment (barrier + publish slots) that the ranks of
+    one box share; rank 0 picks the name and the others learn it through torch.distributed."""
+    global _comm
+    if _comm is not None and _comm[0] == world:
+        return _comm[1]
+    import os
+    import time
+    name = [f"/e2i_{os.getpid()}_{int(time.time() * 1e6) & 0xffffffff:x}" if rank == 0 else None]
+    dist.broadcast_object_list(name, src=0, group=group)
+    h = api.comm_shm(name[0], rank, world)
+    dist.barrier(group=group)
+    _comm = (world, h)
+    return h
 
 
 class _DeviceWords:
@@ -228,7 +245,13 @@ def run_sharded(ctx, api, bwt1, bwt2, da, params, rank: int, world: int, group=N
     dabits = ctx.document_array(da) if da is not None else None
     st = api.Stats()
     lap("index")
-    lcp, da_nav, st = ctx.navigate(b1, b2, params, shard=rank, n_shards=world, stats=st)
+    import os
+    if world > 1 and os.environ.get("E2I_SHARDING", "ranged") != "subtree" and torch.device(device).type == "cuda":
+        # position-range sharding: every rank keeps a dense frontier and pulls its records from the peers' frames
+        # over NVLink (e2i_navigate_ranged); E2I_SHARDING=subtree selects the independent subtree shards
+        lcp, da_nav, st = ctx.navigate_ranged(shm_comm(api, rank, world, group), b1, b2, params, stats=st)
+    else:
+        lcp, da_nav, st = ctx.navigate(b1, b2, params, shard=rank, n_shards=world, stats=st)
     lap("navigate")
     (pt, wt), (pm, wm) = lcp.device_words()
     words = [wrap_device_words(pt, wt, device), wrap_device_words(pm, wm, device)]
