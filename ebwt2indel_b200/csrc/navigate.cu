@@ -104,19 +104,18 @@ struct FrameSrc {
     uint32_t K, run_cap;
 };
 constexpr int kMaxSeg = 4 * kMaxDest;
-struct Segment {                                      // a piece of one source frame in the sweep's input order
+struct Segment {                                      // a contiguous piece of records (own or a peer's memory) of the sweep's input
+    const uint4 *ptr;         // its first record
     uint32_t start, len;      // position in the concatenated input, records
-    uint32_t lo, src;         // first global index in the source frame, source id
 };
 template <bool MULTI> struct FrameInT;
-template <> struct FrameInT<false> {                  // one local frame, read by global index
+template <> struct FrameInT<false> {                  // one local gappy frame, read by global index
     FrameSrc s;
     uint32_t g_lo, g_hi;      // this sweep reads the records [g_lo, g_hi)
 };
-template <> struct FrameInT<true> {                   // pieces of several frames (own and peers'), concatenated in position order
+template <> struct FrameInT<true> {                   // compacted pieces of several ranks' frames, concatenated in position order
     uint32_t g_lo, g_hi;
     uint32_t n_seg, pad;
-    FrameSrc src[kMaxDest];
     Segment seg[kMaxSeg];
 };
 using FrameIn = FrameInT<false>;
@@ -198,34 +197,24 @@ __device__ __forceinline__ const uint4 *cursor_record(const FrameInT<false> &in,
     return in.s.base + (((size_t)cur.c * in.s.K + cur.k) * in.s.run_cap + (g - cur.pj)) * ru;
 }
 
-// MULTI: position g of the concatenated input -> segment -> entry of that segment's source frame
+// MULTI: position g of the concatenated input -> segment (the pieces are plain arrays: frames are compacted
+// per destination before the peers read them)
 __device__ __forceinline__ void cursor_enter(const FrameInT<true> &in, Cursor &cur, uint32_t g) {
     uint32_t s = cur.s;
     while (g >= in.seg[s].start + in.seg[s].len) ++s;
     cur.s = s;
-    const Segment sg = in.seg[s];
-    const FrameSrc &f = in.src[sg.src];
-    cur.delta = sg.lo - sg.start;
-    cur.seg_end = sg.start + sg.len;
-    const uint32_t x = g + cur.delta;
-    const uint32_t j = locate_entry(f.P, f.hint, x);
-    cur.j = j;
-    cur.pj = __ldg(f.P + j);
-    cur.pj1 = __ldg(f.P + j + 1);
-    cur.c = (j / f.K) & 3u;
-    cur.k = j % f.K;
-    cur.offj = f.off ? __ldg(f.off + j) : 0u;
+    cur.delta = in.seg[s].start;
+    cur.seg_end = in.seg[s].start + in.seg[s].len;
 }
 __device__ __forceinline__ void cursor_open(const FrameInT<true> &in, Cursor &cur, uint32_t g) {
     cur.s = 0;
     cursor_enter(in, cur, g);
 }
 __device__ __forceinline__ void cursor_seek(const FrameInT<true> &in, Cursor &cur, uint32_t g) {
-    if (g >= cur.seg_end || g + cur.delta >= cur.pj1) cursor_enter(in, cur, g);
+    if (g >= cur.seg_end) cursor_enter(in, cur, g);
 }
 __device__ __forceinline__ const uint4 *cursor_record(const FrameInT<true> &in, const Cursor &cur, uint32_t g, int ru) {
-    const FrameSrc &f = in.src[in.seg[cur.s].src];
-    return f.base + (((size_t)cur.c * f.K + cur.k) * f.run_cap + cur.offj + (g + cur.delta - cur.pj)) * ru;
+    return in.seg[cur.s].ptr + (size_t)(g - cur.delta) * ru;
 }
 
 // ---- MULTI: children of a run counted per destination (position range) ---------------------------------
@@ -994,6 +983,21 @@ frame_index_kernel(const uint32_t *__restrict__ cnt, const uint32_t *__restrict_
     }
 }
 
+// MULTI: the records of every entry copied to their global index (one warp per entry), so that destination h,
+// queue c is ONE contiguous array [P[(4h+c)K], P[(4h+c+1)K)) that a peer reads with coalesced loads and no metadata
+__global__ void __launch_bounds__(256)
+compact_frame_kernel(const uint4 *__restrict__ base, const uint32_t *__restrict__ cnt, const uint32_t *__restrict__ P,
+                     const uint32_t *__restrict__ off, uint32_t n_entries, uint32_t K, uint32_t run_cap, int ru, uint4 *__restrict__ dst) {
+    const uint32_t e = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (e >= n_entries) return;
+    const uint32_t n = cnt[e] * ru;
+    if (!n) return;
+    const uint32_t h = e / (4 * K), ck = e - h * 4 * K;             // ck = c * K + k: the region
+    const uint4 *src = base + ((size_t)ck * run_cap + off[e]) * ru;
+    uint4 *out = dst + (size_t)P[e] * ru;
+    for (uint32_t i = lane; i < n; i += 32) out[i] = src[i];
+}
+
 // ---------------------------------------------------------------------------------------------
 // Host-side frontier driver
 // ---------------------------------------------------------------------------------------------
@@ -1435,9 +1439,9 @@ static int navigate_impl(e2i_ctx *ctx, const e2i_index *b1, const e2i_index *b2,
     // Every rank's frontier stays as dense as the single-GPU frontier, which is what the subtree deal loses.
     struct LevelInfo {                                  // what a rank publishes after a sweep (one comm slot)
         uint64_t total, maxsz;
-        uint64_t rec_off, p_off, off_off, hint_off;     // the frame inside the rank's arena
-        uint32_t K, run_cap, small, error;
-        uint32_t qstart[4 * kMaxDest + 1];
+        uint64_t rec_off;                               // the compacted records inside the rank's arena
+        uint32_t small, error;
+        uint32_t qstart[4 * kMaxDest + 1];              // record index where (destination h, queue c) starts, total at the end
         void *arena_base;
         cudaIpcMemHandle_t arena_handle;
     };
@@ -1451,32 +1455,24 @@ static int navigate_impl(e2i_ctx *ctx, const e2i_index *b1, const e2i_index *b2,
         std::memset(&mine, 0, sizeof mine);
         mine.arena_base = ctx->arena_mem;
         if (comm->needs_ipc()) E2I_CUDA_TRY(cudaIpcGetMemHandle(&mine.arena_handle, ctx->arena_mem));
-        mine.K = 1; mine.run_cap = 1;
+        const cudaIpcMemHandle_t my_handle = mine.arena_handle;
         char *const abase = static_cast<char *>(ctx->arena_mem);
-        std::shared_ptr<Frame> f_prev, f_old;
-        // level 0: the root lives on rank 0 (its first position is 0), as a frame with one record
+        std::shared_ptr<Frame> f_prev, f_old;           // compacted records of this level (read by everybody) / of the level before
+        // level 0: the root lives on rank 0 (its first position is 0): one record, addressed to (destination 0, queue 0)
         if (me == 0) {
             const int ru_root = leaves ? (two ? 2 : 1) : node_rec_u4(false, two);
-            const FrameLayout lay(1, 1, ru_root, (uint32_t)world);
-            char *mem = static_cast<char *>(ctx->arena.alloc(0, lay.total_bytes));
+            char *mem = static_cast<char *>(ctx->arena.alloc(0, (size_t)ru_root * 16));
             if (!mem) { set_error("frontier arena too small"); return E2I_ERR_MEMORY; }
-            std::vector<uint64_t> host(lay.total_bytes / 8 + 1, 0);
-            uint64_t *rec = host.data();
+            uint64_t rec[12] = {0};
             if (leaves) { rec[0] = 0; rec[1] = b1->F[0]; if (two) { rec[2] = 0; rec[3] = b2->F[0]; } }
             else { pack_wide_host(rec, 0, b1->F, b1->n); if (two) pack_wide_host(rec + 6, 0, b2->F, b2->n); }
-            uint32_t *hp = reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(host.data()) + lay.p_off);
-            const uint32_t ne = 4 * (uint32_t)world;
-            for (uint32_t e = 1; e <= ne; ++e) hp[e] = 1;                  // P = {0, 1, 1, ...}: the record is entry (h=0, c=0, k=0)
-            uint32_t *hh = reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(host.data()) + lay.hint_off);
-            hh[0] = 0; hh[1] = ne - 1;
-            E2I_CUDA_TRY(cudaMemcpyAsync(mem, host.data(), lay.total_bytes, cudaMemcpyHostToDevice, s));
+            E2I_CUDA_TRY(cudaMemcpyAsync(mem, rec, (size_t)ru_root * 16, cudaMemcpyHostToDevice, s));
             E2I_CUDA_TRY(cudaStreamSynchronize(s));
             f_prev = std::make_shared<Frame>();
             f_prev->arena = &ctx->arena; f_prev->side = 0; f_prev->p = mem;
             mine.total = 1;
-            mine.rec_off = (uint64_t)(mem - abase); mine.p_off = mine.rec_off + lay.p_off; mine.off_off = mine.rec_off + lay.off_off;
-            mine.hint_off = mine.rec_off + lay.hint_off;
-            for (uint32_t i = 1; i <= ne; ++i) mine.qstart[i] = 1;
+            mine.rec_off = (uint64_t)(mem - abase);
+            for (uint32_t i = 1; i <= 4 * (uint32_t)world; ++i) mine.qstart[i] = 1;
         }
         mine.maxsz = std::max<uint64_t>(b1->n, two ? b2->n : 0);
         mine.small = 0;
@@ -1484,10 +1480,23 @@ static int navigate_impl(e2i_ctx *ctx, const e2i_index *b1, const e2i_index *b2,
         std::vector<char *> peer_base((size_t)world, nullptr);
         double t_bar = 0, t_wait = 0, t_host = 0;
         static const bool debug = std::getenv("E2I_DEBUG") != nullptr;
+        auto wait_seq = [&](unsigned long long seq) -> int {          // the mapped sequence word of the index kernel
+            volatile unsigned long long *seqp = &hctl->seq;
+            unsigned spins = 0;
+            while (*seqp != seq) {
+                if ((++spins & 0xfffu) == 0) {
+                    const cudaError_t q = cudaStreamQuery(s);
+                    if (q == cudaSuccess) { if (*seqp == seq) break; set_error("traversal sweep finished without publishing its counts"); return E2I_ERR_CUDA; }
+                    if (q != cudaErrorNotReady) { set_error("CUDA error in a traversal sweep: %s", cudaGetErrorString(q)); return E2I_ERR_CUDA; }
+                }
+            }
+            std::atomic_thread_fence(std::memory_order_acquire);
+            return E2I_OK;
+        };
         for (int level = 0;; ++level) {
             std::memcpy(comm->slot(me), &mine, sizeof mine);
             const double tb0 = now_ms();
-            comm->barrier();                              // every rank has finished the previous sweep and published its frame
+            comm->barrier();                              // every rank has finished the previous sweep and published its records
             uint64_t all = 0, bound = 0;
             uint32_t err = 0;
             for (int r = 0; r < world; ++r) {
@@ -1499,50 +1508,46 @@ static int navigate_impl(e2i_ctx *ctx, const e2i_index *b1, const e2i_index *b2,
             comm->barrier();                              // everybody has read the slots: they may be rewritten
             t_bar += now_ms() - tb0;
             const double th0 = now_ms();
-            f_old.reset();                                // the frame of two levels ago is dead on every rank
+            f_old.reset();                                // the records of two levels ago are dead on every rank
             f_old = f_prev;
             f_prev.reset();
             if (err) { if (!mine.error) set_error("position-range traversal failed on another rank"); return E2I_ERR_MEMORY; }
             if (all == 0) break;
-            // my input: for every queue, the pieces the ranks addressed to me, in rank order
+            // my input: for every queue, the pieces the ranks addressed to me, in rank order (= position order)
             FrameInT<true> in;
             std::memset(&in, 0, sizeof in);
+            const bool in_small = !leaves && info[0].small, out_small = !leaves && bound < kSmallLimit;
+            const int ru_in = leaves ? (two ? 2 : 1) : node_rec_u4(in_small, two);
             uint32_t n_in = 0;
             for (int c = 0; c < 4; ++c) {
                 for (int r = 0; r < world; ++r) {
                     const uint32_t lo = info[r].qstart[me * 4 + c], hi = info[r].qstart[me * 4 + c + 1];
                     if (hi <= lo) continue;
                     Segment &sg = in.seg[in.n_seg++];
-                    sg.start = n_in; sg.len = hi - lo; sg.lo = lo; sg.src = (uint32_t)r;
+                    sg.ptr = reinterpret_cast<const uint4 *>(peer_base[r] + info[r].rec_off) + (size_t)lo * ru_in;
+                    sg.start = n_in; sg.len = hi - lo;
                     n_in += hi - lo;
                 }
             }
-            for (int r = 0; r < world; ++r) {
-                FrameSrc &f = in.src[r];
-                f.base = reinterpret_cast<const uint4 *>(peer_base[r] + info[r].rec_off);
-                f.P = reinterpret_cast<const uint32_t *>(peer_base[r] + info[r].p_off);
-                f.off = reinterpret_cast<const uint32_t *>(peer_base[r] + info[r].off_off);
-                f.hint = reinterpret_cast<const uint32_t *>(peer_base[r] + info[r].hint_off);
-                f.K = info[r].K; f.run_cap = info[r].run_cap;
-            }
             in.g_lo = 0; in.g_hi = n_in;
-            const bool in_small = !leaves && info[0].small, out_small = !leaves && bound < kSmallLimit;
             std::memset(&mine, 0, sizeof mine);
             mine.arena_base = ctx->arena_mem;
-            mine.K = 1; mine.run_cap = 1; mine.small = out_small; mine.maxsz = 0;
+            mine.arena_handle = my_handle;
+            mine.small = out_small;
             if (n_in == 0) continue;                      // nothing for me on this level (I still keep the barriers company)
             const int ru_out = leaves ? (two ? 2 : 1) : node_rec_u4(out_small, two);
             const uint32_t run_len = (uint32_t)std::min<uint64_t>(kMaxRun, std::max<uint64_t>(32, (n_in / ((uint64_t)resident_warps * (leaves ? 1 : 4)) + 31) / 32 * 32));
             const FrameLayout lay(n_in, run_len, ru_out, (uint32_t)world);
-            char *mem = static_cast<char *>(ctx->arena.alloc((level + 1) & 1, lay.total_bytes));
+            // the gappy frame is a temporary on top of THIS level's records; the compacted children go to the other end
+            const int side_tmp = level & 1, side_out = (level + 1) & 1;
+            char *mem = static_cast<char *>(ctx->arena.alloc(side_tmp, lay.total_bytes));
             if (!mem) {
                 set_error("frontier memory exhausted in the position-range traversal (arena %llu bytes, level of %u records): raise the frontier budget",
                           (unsigned long long)ctx->arena.size(), n_in);
                 mine.error = 1;
                 continue;                                 // the other ranks learn about it at the next barrier
             }
-            f_prev = std::make_shared<Frame>();
-            f_prev->arena = &ctx->arena; f_prev->side = (level + 1) & 1; f_prev->p = mem;
+            Frame tmp{&ctx->arena, side_tmp, mem};
             FrameOut fo{};
             fo.base = reinterpret_cast<uint4 *>(mem);
             fo.cnt = reinterpret_cast<uint32_t *>(mem + lay.cnt_off);
@@ -1581,28 +1586,32 @@ static int navigate_impl(e2i_ctx *ctx, const e2i_index *b1, const e2i_index *b2,
             ctx->n_d2h += sizeof(HostCtl);
             t_host += now_ms() - th0;
             const double tw0 = now_ms();
-            {
-                volatile unsigned long long *seqp = &hctl->seq;
-                unsigned spins = 0;
-                while (*seqp != seq) {
-                    if ((++spins & 0xfffu) == 0) {
-                        const cudaError_t q = cudaStreamQuery(s);
-                        if (q == cudaSuccess) { if (*seqp == seq) break; set_error("traversal sweep finished without publishing its counts"); return E2I_ERR_CUDA; }
-                        if (q != cudaErrorNotReady) { set_error("CUDA error in a traversal sweep: %s", cudaGetErrorString(q)); return E2I_ERR_CUDA; }
-                    }
-                }
-                std::atomic_thread_fence(std::memory_order_acquire);
-            }
+            E2I_TRY(wait_seq(seq));
             t_wait += now_ms() - tw0;
             ss.items += n_in;
             ss.sweeps++;
             ss.max_chunk = std::max<uint64_t>(ss.max_chunk, n_in);
             mine.total = *(volatile unsigned long long *)&hctl->total;
             mine.maxsz = leaves ? 0 : *(volatile unsigned long long *)&hctl->maxsz;
-            mine.rec_off = (uint64_t)(mem - abase); mine.p_off = mine.rec_off + lay.p_off; mine.off_off = mine.rec_off + lay.off_off;
-            mine.hint_off = mine.rec_off + lay.hint_off;
-            mine.K = fo.K; mine.run_cap = fo.run_cap;
             for (uint32_t i = 0; i <= 4 * fo.D; ++i) mine.qstart[i] = ((volatile uint32_t *)hctl->qstart)[i];
+            if (mine.total) {
+                // compact: every (destination, queue) piece becomes one contiguous array that the peers read directly
+                char *cmem = static_cast<char *>(ctx->arena.alloc(side_out, (size_t)mine.total * ru_out * 16));
+                if (!cmem) {
+                    set_error("frontier memory exhausted in the position-range traversal (arena %llu bytes): raise the frontier budget", (unsigned long long)ctx->arena.size());
+                    mine.error = 1; mine.total = 0;
+                    continue;
+                }
+                f_prev = std::make_shared<Frame>();
+                f_prev->arena = &ctx->arena; f_prev->side = side_out; f_prev->p = cmem;
+                compact_frame_kernel<<<(n_entries + 7) / 8, 256, 0, s>>>(fo.base, fo.cnt, P, off, n_entries, fo.K, fo.run_cap, ru_out, reinterpret_cast<uint4 *>(cmem));
+                E2I_CUDA_TRY(cudaGetLastError());
+                ctx->n_launch++;
+                const double tc0 = now_ms();
+                E2I_CUDA_TRY(cudaStreamSynchronize(s));   // the peers read these records right after the next barrier
+                t_wait += now_ms() - tc0;
+                mine.rec_off = (uint64_t)(cmem - abase);
+            }
         }
         if (debug) std::fprintf(stderr, "[e2i] ranged %s pass, rank %d: %llu sweeps, barriers %.1f ms, host %.1f ms, waiting for the sweeps %.1f ms\n",
                                 leaves ? "leaf" : "node", me, (unsigned long long)ss.sweeps, t_bar, t_host, t_wait);
