@@ -1623,6 +1623,12 @@ static int navigate_impl(e2i_ctx *ctx, const e2i_index *b1, const e2i_index *b2,
     TRYF(cudaMemsetAsync(stripes, 0, stripe_bytes, s));
     TRYF(cudaEventRecord(ctx->ev[0], s));
     SweepStats sl;
+    // With a communicator the LEAF pass is position-range sharded (measured faster than the subtree deal at every N:
+    // small records, no redundant top of the tree); the NODE pass is too only on request (E2I_RANGED_NODES=1): at N = 8
+    // seven of eight records come out of a peer's HBM and the NVLink latency costs more than the sparse frontier
+    // of a subtree shard does (C4, 8 GPUs: 158 ms against 119 ms per rank).
+    const char *rn_env = std::getenv("E2I_RANGED_NODES");
+    const bool ranged_nodes = comm && rn_env && std::strcmp(rn_env, "0") != 0;
     int rc = comm ? run_pass_ranged(true, sl) : run_pass(true, sl);
     if (rc != E2I_OK) return fail(rc);
     TRYF(cudaEventRecord(ctx->ev[1], s));
@@ -1641,7 +1647,7 @@ static int navigate_impl(e2i_ctx *ctx, const e2i_index *b1, const e2i_index *b2,
     TRYF(cudaMemsetAsync(stripes, 0, stripe_bytes, s));
     TRYF(cudaEventRecord(ctx->ev[2], s));
     SweepStats sn;
-    rc = comm ? run_pass_ranged(false, sn) : run_pass(false, sn);
+    rc = ranged_nodes ? run_pass_ranged(false, sn) : run_pass(false, sn);
     if (rc != E2I_OK) return fail(rc);
     TRYF(cudaEventRecord(ctx->ev[3], s));
     rc = sum_stripes(tot);
@@ -1684,7 +1690,7 @@ extern "C" int e2i_navigate_ranged(e2i_ctx *ctx, e2i_comm *comm, const e2i_index
                                    e2i_lcpbits **out, e2i_bits **da_out, e2i_stats *st) {
     if (!comm || comm->world < 1 || comm->world > kMaxDest) { set_error("e2i_navigate_ranged: bad communicator"); return E2I_ERR_ARG; }
     if (comm->world == 1) return navigate_impl(ctx, b1, b2, p, 0, 1, nullptr, out, da_out, st);
-    return navigate_impl(ctx, b1, b2, p, 0, 1, comm, out, da_out, st);
+    return navigate_impl(ctx, b1, b2, p, comm->rank, comm->world, comm, out, da_out, st);
 }
 
 extern "C" int e2i_lcpbits_fetch(e2i_ctx *ctx, const e2i_lcpbits *l, uint64_t *host_thr_words, uint64_t *host_min_words) {

@@ -527,3 +527,15 @@ def test_product_ebwt_builder(gpu_ctx, e2i, tmp_path):
     g = load_golden("m1_default")          # its reads are synth.diploid_reads(6000, 14, 5, 24, 100, seed=11)
     gr = synth.diploid_reads(6000, 14, 5, 24, 100, seed=11)
     assert np.array_equal(gpu_ctx.ebwt_build(gr), g["bwt1"])
+
+
+def test_multi_gpu_ranged_node_pass(e2i, oracle, monkeypatch):
+    """E2I_RANGED_NODES=1: the internal-node pass position-range sharded as well (every rank pulls its records out
+    of the peers' compacted frames); same text and counters as the reference, ranks emulated on one device."""
+    monkeypatch.setenv("E2I_RANGED_NODES", "1")
+    for name in ("m1_default", "m2_default", "m3_flags"):
+        g = load_golden(name)
+        snp, st = e2i.run_multi([0, 0, 0], g["bwt1"], g["bwt2"], g["da"], _case_params(e2i, g))
+        assert snp == g["snp"], name
+        for k, v in g["counters"].items():
+            assert getattr(st, k) == v, (name, k)
