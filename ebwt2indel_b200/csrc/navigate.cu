@@ -533,7 +533,7 @@ template <bool TWO, bool IN_S>
 struct NodeSmem {
     static constexpr int RIN = (IN_S ? 1 : 3) * (TWO ? 2 : 1);    // uint4 per input record
     uint4 stage[kNavWarps][IN_S ? kWarpStage * kBlockU4 : 1];     // staged index blocks, per warp
-    uint4 recbuf[kNavWarps][32 * RIN];                            // records of the next step (slot = lane)
+    uint4 recbuf[kNavWarps][2 * 32 * RIN];                        // records of the next two steps (ring of 2, slot = lane)
     uint32_t need[kNavWarps][IN_S ? 64 : 1];                      // SLOTS staging: block ids wanted by the lanes
     uint64_t mbar[kNavWarps];                                     // completion barrier of the warp's bulk copies
     uint32_t dcnt[kNavWarps][4 * kMaxDest];                       // MULTI: children of the current run per (queue, destination)
@@ -578,6 +578,15 @@ expand_nodes_kernel(const NavArgs a, const __grid_constant__ FrameInT<MULTI> in,
 #pragma unroll
             for (int k = 0; k < RIN; ++k) cp_async16(recbuf + k, rec + k);
         }
+        cp_async_commit();
+        if (g_begin + 32 + lane < g_end) {                // ... and of the second
+            cursor_seek(in, cur, g_begin + 32 + lane);
+            const uint4 *rec = cursor_record(in, cur, g_begin + 32 + lane, RIN);
+#pragma unroll
+            for (int k = 0; k < RIN; ++k) cp_async16(recbuf + 32 * RIN + k, rec + k);
+        }
+        cp_async_commit();
+        uint32_t ring = 0;                                // ring slot of the current step
         uint32_t run_cnt[4] = {0, 0, 0, 0};
         uint4 *region[4];                                 // next free slot of the run's region, per queue
 #pragma unroll
@@ -595,10 +604,13 @@ expand_nodes_kernel(const NavArgs a, const __grid_constant__ FrameInT<MULTI> in,
             const bool active = g < g_end;
             uint64_t base1 = 0, base2 = 0;
             W s1[5] = {0, 0, 0, 0, 0}, s2[5] = {0, 0, 0, 0, 0};
-            cp_async_wait_all();                                            // this lane's own record has landed
+            // copy groups complete in order: all but the newest (the record of the step after this one) are
+            // waited for, so a record has a whole step to arrive -- what remote frames (NVLink) need
+            cp_async_wait_group<1>();                                       // this lane's own record has landed
+            uint4 *rb = recbuf + ring * (32 * RIN);
             if (active) {
-                load_node<IN_S, W>(recbuf, base1, s1);
-                if (TWO) load_node<IN_S, W>(recbuf + RSIDE_IN, base2, s2);
+                load_node<IN_S, W>(rb, base1, s1);
+                if (TWO) load_node<IN_S, W>(rb + RSIDE_IN, base2, s2);
             }
             const uint64_t size1 = (uint64_t)s1[0] + s1[1] + s1[2] + s1[3] + s1[4], size2 = (uint64_t)s2[0] + s2[1] + s2[2] + s2[3] + s2[4];
             max_size = max(max_size, max(size1, size2));
@@ -645,6 +657,16 @@ expand_nodes_kernel(const NavArgs a, const __grid_constant__ FrameInT<MULTI> in,
                     r1.d1 = lb1 - fb1;
                 }
             }
+            cp_async_commit();
+            // the record of the step after the next one goes into the ring slot just consumed
+            if (g + 64 < g_end) {
+                cursor_seek(in, cur, g + 64);
+                const uint4 *rec = cursor_record(in, cur, g + 64, RIN);
+#pragma unroll
+                for (int k = 0; k < RIN; ++k) cp_async16(rb + k, rec + k);
+            }
+            cp_async_commit();
+            ring ^= 1u;
             const uint32_t rpos1 = (uint32_t)base1 & (kBlockSyms - 1), rpos2 = (uint32_t)base2 & (kBlockSyms - 1);
 
             // ---- bit updates on the merged node, while the copies are in flight ----
@@ -653,16 +675,9 @@ expand_nodes_kernel(const NavArgs a, const __grid_constant__ FrameInT<MULTI> in,
                 node_bit_updates<TWO, W>(a, base1 + base2, s1, s2, st);
                 st_lcp += st.lcp; st_min += st.nmin; st_upd += st.upd; st_da += st.da;
             }
-            cp_async_wait_all();
+            cp_async_wait_group<1>();                                       // the staged blocks (and the next step's record)
             if (IN_S && kWindowTma && mode == SRC_WINDOW) { mbar_wait(mbar, mbar_phase); mbar_phase ^= 1u; }
             __syncwarp();                                                   // every lane's copies are visible to the warp
-            // the record of the next step: overlaps with the rank phase below
-            if (g + 32 < g_end) {
-                cursor_seek(in, cur, g + 32);
-                const uint4 *rec = cursor_record(in, cur, g + 32, RIN);
-#pragma unroll
-                for (int k = 0; k < RIN; ++k) cp_async16(recbuf + k, rec + k);
-            }
 
             // ---- ranks -> children; child c is right-maximal iff >= 2 of its 5 gaps are non-empty ----
             ChildSide<W> k1, k2;
