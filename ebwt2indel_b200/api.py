@@ -74,7 +74,7 @@ SYMBOLS = (
     "e2i_fl_batch", "e2i_rank_batch_device", "e2i_da_load", "e2i_da_load_device", "e2i_bits_fetch",
     "e2i_bits_size", "e2i_bits_free", "e2i_navigate", "e2i_navigate_shard", "e2i_lcpbits_fetch",
     "e2i_lcpbits_device", "e2i_bits_device", "e2i_lcpbits_free", "e2i_call", "e2i_calls_count",
-    "e2i_calls_fetch", "e2i_calls_view", "e2i_calls_free", "e2i_snp_format", "e2i_snp_count", "e2i_filter_snp", "e2i_distance", "e2i_buffer_free", "e2i_run",
+    "e2i_calls_fetch", "e2i_calls_view", "e2i_calls_free", "e2i_snp_format", "e2i_snp_format_gpu", "e2i_call_snp", "e2i_snp_count", "e2i_filter_snp", "e2i_distance", "e2i_buffer_free", "e2i_run",
     "e2i_run_device", "e2i_run_files", "e2i_index_build_file", "e2i_da_load_file", "e2i_index_save", "e2i_index_load", "e2i_ebwt_build", "e2i_run_multi", "e2i_enable_peers", "e2i_or_allreduce",
     "e2i_navigate_ranged", "e2i_comm_local", "e2i_comm_shm", "e2i_comm_barrier", "e2i_comm_free",
 )
@@ -139,6 +139,8 @@ def lib():
         "e2i_calls_view": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(u64)]),
         "e2i_calls_free": (None, [vp]),
         "e2i_snp_format": (C.c_int, [vp, vp, vp, u64, PP, C.c_int, u64, C.POINTER(vp), C.POINTER(C.c_size_t), PS]),
+        "e2i_snp_format_gpu": (C.c_int, [vp, vp, vp, vp, u64, PP, C.c_int, u64, C.POINTER(vp), C.POINTER(C.c_size_t), PS]),
+        "e2i_call_snp": (C.c_int, [vp, vp, vp, vp, vp, PP, u64, u64, u64, C.POINTER(vp), C.POINTER(C.c_size_t), PS]),
         "e2i_snp_count": (C.c_int, [vp, vp, vp, u64, PP, C.c_int, C.POINTER(u64)]),
         "e2i_filter_snp": (C.c_int, [C.c_char_p, C.c_size_t, C.c_int32, C.c_int32, C.POINTER(vp), C.POINTER(C.c_size_t)]),
         "e2i_distance": (None, [C.c_char_p, C.c_char_p, C.c_int32, C.c_int32, C.POINTER(C.c_int32)]),
@@ -353,6 +355,29 @@ class Context:
         return LcpBits(self, lh), (Bits(self, dh) if b2 else None), st
 
     # ---- phase 4 ----
+    def call_snp(self, b1, b2, da, lcp, params: Params | None = None, pos_begin: int = 0, pos_end: int = 2 ** 64 - 1,
+                 first_cluster_nr: int = 1, stats: Stats | None = None, copy: bool = True):
+        """Phase 4 + the .snp text of [pos_begin, pos_end), formatted on the device (e2i_call_snp)."""
+        p = params or default_params()
+        st = stats if stats is not None else Stats()
+        out, ln = C.c_void_p(), C.c_size_t()
+        _check(lib().e2i_call_snp(self.h, b1.h, b2.h if b2 else None, da.h if da else None, lcp.h, C.byref(p),
+                                  pos_begin, pos_end, first_cluster_nr, C.byref(out), C.byref(ln), C.byref(st)))
+        text = SnpText(out, ln.value)
+        return (text.tobytes() if copy else text), st
+
+    def snp_format(self, recs, left, right, params: Params, two_samples: bool, first_cluster_nr: int = 1,
+                   stats: Stats | None = None):
+        """snp_format() by the device formatter (e2i_snp_format_gpu): same arguments, same text."""
+        st = stats if stats is not None else Stats()
+        recs = np.ascontiguousarray(recs, dtype=CALL_REC_DTYPE)
+        left = np.ascontiguousarray(left, dtype=np.uint8)
+        right = np.ascontiguousarray(right, dtype=np.uint8)
+        out, ln = C.c_void_p(), C.c_size_t()
+        _check(lib().e2i_snp_format_gpu(self.h, recs.ctypes.data, left.ctypes.data, right.ctypes.data, len(recs), C.byref(params),
+                                        1 if two_samples else 0, first_cluster_nr, C.byref(out), C.byref(ln), C.byref(st)))
+        return SnpText(out, ln.value).tobytes(), st
+
     def call(self, b1, b2, da, lcp, params: Params | None = None, pos_begin: int = 0,
              pos_end: int = 2 ** 64 - 1, stats: Stats | None = None, copy: bool = True):
         """Phase 4 on [pos_begin, pos_end).  Returns (recs, left, right, Stats) as numpy arrays; with

@@ -450,10 +450,19 @@ static int build_da_rank(e2i_ctx *ctx, e2i_bits *da) {
     return E2I_OK;
 }
 
-extern "C" int e2i_call(e2i_ctx *ctx, const e2i_index *b1, const e2i_index *b2, const e2i_bits *da,
-                        const e2i_lcpbits *l, const e2i_params *p, uint64_t pos_begin, uint64_t pos_end,
-                        e2i_calls **out, e2i_stats *st) {
-    if (!ctx || !b1 || !l || !p || !out || !st) { set_error("e2i_call: null argument"); return E2I_ERR_ARG; }
+// Where the text goes when phase 4 formats its records on the device (e2i_call_snp): a malloc'ed host buffer that
+// grows batch by batch; the records themselves then never leave the device.
+struct TextSink {
+    char *buf = nullptr;
+    size_t len = 0, cap = 0;
+    uint64_t next_cluster = 1, events = 0, clusters = 0;
+    double ms = 0;                                      // host wall time spent formatting + copying the text
+};
+
+static int call_impl(e2i_ctx *ctx, const e2i_index *b1, const e2i_index *b2, const e2i_bits *da,
+                     const e2i_lcpbits *l, const e2i_params *p, uint64_t pos_begin, uint64_t pos_end,
+                     e2i_calls **out, TextSink *sink, e2i_stats *st) {
+    if (!ctx || !b1 || !l || !p || (!out && !sink) || !st) { set_error("e2i_call: null argument"); return E2I_ERR_ARG; }
     if (b2 && !da) { set_error("e2i_call: two BWTs need the document array produced by e2i_navigate"); return E2I_ERR_ARG; }
     if (p->k_left < 1 || p->k_left > 255 || p->k_right < 1 || p->k_right > 255) { set_error("e2i_call: k_left and k_right must be in [1,255]"); return E2I_ERR_ARG; }
     if (p->mcov_out < 1) { set_error("e2i_call: mcov_out must be >= 1"); return E2I_ERR_ARG; }
@@ -546,7 +555,7 @@ extern "C" int e2i_call(e2i_ctx *ctx, const e2i_index *b1, const e2i_index *b2, 
     // consensus walks + right contexts + record packing for the candidates gathered so far
     uint64_t n_acc = 0;
     auto flush = [&]() -> int {
-        E2I_TRY(ensure(n_out + n_acc));
+        if (!sink) E2I_TRY(ensure(n_out + n_acc));
         for (uint64_t c0 = 0; c0 < n_acc; c0 += batch_cap) {
             const uint64_t nb = std::min<uint64_t>(batch_cap, n_acc - c0);
             char *o = obase;
@@ -567,11 +576,36 @@ extern "C" int e2i_call(e2i_ctx *ctx, const e2i_index *b1, const e2i_index *b2, 
             right_context_kernel<<<(unsigned)((nb + 127) / 128), 128, 0, s>>>(ab, nb, d_right, d_rlen, d_has, rank_q);
             pack_calls_kernel<<<(unsigned)((nb + 127) / 128), 128, 0, s>>>(ab, nb, d_left, d_support, d_reached, d_rlen, d_has, d_recs);
             E2I_CUDA_TRY(cudaGetLastError());
+            ctx->n_launch += 3;
+            if (sink) {                                   // text on the device: only the characters go to the host
+                E2I_CUDA_TRY(cudaStreamSynchronize(s));   // the walks are phase 4 time, not formatting time
+                const double t0 = now_ms();
+                char *d_text = nullptr;
+                uint64_t tl = 0, cl = 0, ev = 0;
+                E2I_TRY(format_device(ctx, d_recs, d_left, d_right, nb, p, mode != 1, sink->next_cluster, &d_text, &tl, &cl, &ev));
+                if (sink->len + tl + 1 > sink->cap) {
+                    const size_t want = std::max<size_t>(sink->len + tl + 1, sink->cap + sink->cap / 2);
+                    char *nb2 = static_cast<char *>(std::realloc(sink->buf, want));
+                    if (!nb2) { dfree(ctx, d_text); set_error("e2i_call_snp: out of host memory"); return E2I_ERR_MEMORY; }
+                    sink->buf = nb2;
+                    sink->cap = want;
+                }
+                if (tl) E2I_CUDA_TRY(cudaMemcpyAsync(sink->buf + sink->len, d_text, tl, cudaMemcpyDeviceToHost, s));
+                E2I_CUDA_TRY(cudaStreamSynchronize(s));
+                dfree(ctx, d_text);
+                ctx->n_d2h += tl;
+                sink->len += tl;
+                sink->next_cluster += cl;
+                sink->clusters += cl;
+                sink->events += ev;
+                sink->ms += now_ms() - t0;
+                n_out += nb;
+                continue;
+            }
             // the device layout is the final one: three copies straight into the page-locked result arrays
             E2I_CUDA_TRY(cudaMemcpyAsync(calls->recs + n_out, d_recs, nb * sizeof(e2i_call_rec), cudaMemcpyDeviceToHost, s));
             E2I_CUDA_TRY(cudaMemcpyAsync(calls->left + n_out * 8 * kl, d_left, nb * 8 * kl, cudaMemcpyDeviceToHost, s));
             E2I_CUDA_TRY(cudaMemcpyAsync(calls->right + n_out * kr, d_right, nb * kr, cudaMemcpyDeviceToHost, s));
-            ctx->n_launch += 3;
             ctx->n_d2h += nb * rec_bytes;
             E2I_CUDA_TRY(cudaStreamSynchronize(s));
             n_out += nb;
@@ -641,7 +675,38 @@ extern "C" int e2i_call(e2i_ctx *ctx, const e2i_index *b1, const e2i_index *b2, 
     TRYF(cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5]));
     st->ms_call += ms;
 #undef TRYF
+    if (sink) {                                         // the formatting time is reported on its own
+        st->ms_call -= std::min<double>(ms, sink->ms);
+        st->ms_format += sink->ms;
+        st->events += sink->events;
+        st->clusters_out += sink->clusters;
+        delete calls;
+        return E2I_OK;
+    }
     *out = calls;
+    return E2I_OK;
+}
+
+extern "C" int e2i_call(e2i_ctx *ctx, const e2i_index *b1, const e2i_index *b2, const e2i_bits *da,
+                        const e2i_lcpbits *l, const e2i_params *p, uint64_t pos_begin, uint64_t pos_end,
+                        e2i_calls **out, e2i_stats *st) {
+    if (!out) { set_error("e2i_call: null argument"); return E2I_ERR_ARG; }
+    return call_impl(ctx, b1, b2, da, l, p, pos_begin, pos_end, out, nullptr, st);
+}
+
+extern "C" int e2i_call_snp(e2i_ctx *ctx, const e2i_index *b1, const e2i_index *b2, const e2i_bits *da,
+                            const e2i_lcpbits *l, const e2i_params *p, uint64_t pos_begin, uint64_t pos_end,
+                            uint64_t first_cluster_nr, char **snp, size_t *snp_len, e2i_stats *st) {
+    if (!snp || !snp_len) { set_error("e2i_call_snp: null argument"); return E2I_ERR_ARG; }
+    TextSink sink;
+    sink.next_cluster = first_cluster_nr ? first_cluster_nr : 1;
+    const int rc = call_impl(ctx, b1, b2, da, l, p, pos_begin, pos_end, nullptr, &sink, st);
+    if (rc != E2I_OK) { std::free(sink.buf); return rc; }
+    if (!sink.buf) sink.buf = static_cast<char *>(std::malloc(1));
+    if (!sink.buf) { set_error("e2i_call_snp: out of host memory"); return E2I_ERR_MEMORY; }
+    sink.buf[sink.len] = 0;
+    *snp = sink.buf;
+    *snp_len = sink.len;
     return E2I_OK;
 }
 

@@ -155,6 +155,10 @@ inline cudaError_t arena_alloc(e2i_ctx *ctx, size_t bytes, bool ipc) {
     if (e == cudaSuccess) { ctx->arena_bytes = bytes; ctx->arena_ipc = ipc; }
     return e;
 }
+// .snp text of call records that are still in device memory (snp_format.cpp); *d_text is released with dfree
+int format_device(e2i_ctx *ctx, const e2i_call_rec *d_recs, const char *d_left, const char *d_right, uint64_t n_recs,
+                  const e2i_params *p, int two_samples, uint64_t first_cluster_nr,
+                  char **d_text, uint64_t *text_len, uint64_t *clusters, uint64_t *events);
 struct Accounting {            // adds what a call launched / copied to its e2i_stats on scope exit
     e2i_ctx *ctx; e2i_stats *st; uint64_t l0, h0, d0;
     Accounting(e2i_ctx *c, e2i_stats *s) : ctx(c), st(s), l0(c->n_launch), h0(c->n_h2d), d0(c->n_d2h) {}

@@ -155,21 +155,15 @@ namespace {
 int run_with_indexes(e2i_ctx *ctx, e2i_index *b1, e2i_index *b2, e2i_bits *da, const e2i_params *p, char **snp, size_t *snp_len, e2i_stats *st) {
     e2i_bits *da_nav = nullptr;
     e2i_lcpbits *lcp = nullptr;
-    e2i_calls *calls = nullptr;
     const auto w0 = std::chrono::steady_clock::now();
     int rc = e2i_navigate(ctx, b1, b2, p, &lcp, b2 ? &da_nav : nullptr, st);
-    if (rc == E2I_OK) rc = e2i_call(ctx, b1, b2, b2 ? da_nav : da, lcp, p, 0, UINT64_MAX, &calls, st);
-    if (std::getenv("E2I_DEBUG")) {
-        cudaStreamSynchronize(ctx->stream);
-        std::fprintf(stderr, "[e2i] run: %.1f ms of host wall time before formatting (phases: index %.1f leaves %.1f nodes %.1f call %.1f)\n",
+    // phase 4 and the text in one go: the records are classified and printed where they are, in HBM
+    // (st->ms_format: the formatting kernels + the copy of the text)
+    if (rc == E2I_OK) rc = e2i_call_snp(ctx, b1, b2, b2 ? da_nav : da, lcp, p, 0, UINT64_MAX, 1, snp, snp_len, st);
+    if (std::getenv("E2I_DEBUG"))
+        std::fprintf(stderr, "[e2i] run: %.1f ms of host wall time (phases: index %.1f leaves %.1f nodes %.1f call %.1f format %.1f)\n",
                      std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - w0).count(),
-                     st->ms_index, st->ms_leaves, st->ms_nodes, st->ms_call);
-    }
-    const auto w1 = std::chrono::steady_clock::now();
-    if (rc == E2I_OK)
-        rc = e2i_snp_format(calls->recs, calls->left, calls->right, calls->n, p, (b2 || da) ? 1 : 0, 1, snp, snp_len, st);
-    st->ms_format += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - w1).count();
-    e2i_calls_free(calls);
+                     st->ms_index, st->ms_leaves, st->ms_nodes, st->ms_call, st->ms_format);
     e2i_lcpbits_free(lcp);
     e2i_bits_free(da_nav);
     return rc;

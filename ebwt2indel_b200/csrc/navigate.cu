@@ -746,7 +746,7 @@ template <bool TWO>
 struct LeafSmem {
     static constexpr int RU = TWO ? 2 : 1;            // uint4 per record
     uint4 stage[kNavWarps][64 * kBlockU4];            // two blocks per lane
-    uint4 recbuf[kNavWarps][32 * RU];
+    uint4 recbuf[kNavWarps][2 * 32 * RU];             // records of the next two steps (ring of 2, slot = lane)
     uint32_t need[kNavWarps][64];
     uint32_t dcnt[kNavWarps][4 * kMaxDest];           // MULTI: children of the current run per (queue, destination)
 };
@@ -789,6 +789,15 @@ expand_leaves_kernel(const NavArgs a, const __grid_constant__ FrameInT<MULTI> in
 #pragma unroll
             for (int k = 0; k < RU; ++k) cp_async16(recbuf + k, rec + k);
         }
+        cp_async_commit();
+        if (g_begin + 32 + lane < g_end) {
+            cursor_seek(in, cur, g_begin + 32 + lane);
+            const uint4 *rec = cursor_record(in, cur, g_begin + 32 + lane, RU);
+#pragma unroll
+            for (int k = 0; k < RU; ++k) cp_async16(recbuf + 32 * RU + k, rec + k);
+        }
+        cp_async_commit();
+        uint32_t ring = 0;
         uint32_t run_cnt[4] = {0, 0, 0, 0};
         uint32_t dcur[4] = {0, 0, 0, 0};
         uint64_t dbound[4];
@@ -802,9 +811,10 @@ expand_leaves_kernel(const NavArgs a, const __grid_constant__ FrameInT<MULTI> in
             const uint32_t g = g0 + lane;
             const bool active = g < g_end;
             uint64_t f1 = 0, s1 = 0, f2 = 0, s2 = 0;
-            cp_async_wait_all();                           // this lane's own record has landed
+            cp_async_wait_group<1>();                      // this lane's own record has landed (see the node sweep)
+            uint4 *rb = recbuf + ring * (32 * RU);
             if (active) {
-                const ulonglong2 *rec = reinterpret_cast<const ulonglong2 *>(recbuf);
+                const ulonglong2 *rec = reinterpret_cast<const ulonglong2 *>(rb);
                 const ulonglong2 x = rec[0];
                 f1 = x.x; s1 = x.y;
                 if (TWO) { const ulonglong2 z = rec[1]; f2 = z.x; s2 = z.y; }
@@ -829,6 +839,15 @@ expand_leaves_kernel(const NavArgs a, const __grid_constant__ FrameInT<MULTI> in
                     if (blk != ~0u) cp_async16(&stage[stage_slot(slot, k & 1)], src + (size_t)blk * kBlockU4 + (k & 1));
                 }
             }
+            cp_async_commit();
+            if (g + 64 < g_end) {                          // the record of the step after the next one
+                cursor_seek(in, cur, g + 64);
+                const uint4 *rec = cursor_record(in, cur, g + 64, RU);
+#pragma unroll
+                for (int k = 0; k < RU; ++k) cp_async16(rb + k, rec + k);
+            }
+            cp_async_commit();
+            ring ^= 1u;
             if (active && a.write) {
                 // update_LCP_leaf (:344-355) / update_DA (:394-425) at merged coordinates
                 const uint64_t start1 = f1 + f2, start2 = f2 + s1, end = s1 + s2;
@@ -840,14 +859,8 @@ expand_leaves_kernel(const NavArgs a, const __grid_constant__ FrameInT<MULTI> in
                     fill_bits(a.da, start2, end, 0xffffffffu);
                 }
             }
-            cp_async_wait_all();
+            cp_async_wait_group<1>();
             __syncwarp();
-            if (g + 32 < g_end) {
-                cursor_seek(in, cur, g + 32);
-                const uint4 *rec = cursor_record(in, cur, g + 32, RU);
-#pragma unroll
-                for (int k = 0; k < RU; ++k) cp_async16(recbuf + k, rec + k);
-            }
             // next_leaves (dna_bwt.hpp:358-379; two BWTs: ebwt2InDel.cpp:452-472): LF(range) = 2 ranks per BWT
             uint64_t lo1[4] = {0, 0, 0, 0}, hi1[4] = {0, 0, 0, 0}, lo2[4] = {0, 0, 0, 0}, hi2[4] = {0, 0, 0, 0};
             if (active) {

@@ -217,6 +217,18 @@ void e2i_calls_free(e2i_calls *c);
 int e2i_snp_format(const e2i_call_rec *recs, const char *left, const char *right, uint64_t n_recs,
                    const e2i_params *p, int two_samples, uint64_t first_cluster_nr,
                    char **snp, size_t *snp_len, e2i_stats *st);
+/* The same text, produced by the device formatter (one thread per record: measure, number the clusters with a
+ * scan, place the records with a scan, write) from host records -- what e2i_call_snp runs on the records while they
+ * are still in HBM; this entry exists so that the two formatters can be compared on any records. */
+int e2i_snp_format_gpu(e2i_ctx *ctx, const e2i_call_rec *recs, const char *left, const char *right, uint64_t n_recs,
+                       const e2i_params *p, int two_samples, uint64_t first_cluster_nr,
+                       char **snp, size_t *snp_len, e2i_stats *st);
+/* Phase 4 and the .snp text in one call: find_variants + to_file (ebwt2InDel.cpp:1344-1660, 1149-1330) for the
+ * positions [pos_begin, pos_end); the records never leave the device, only the text is copied out (*snp malloc'ed,
+ * e2i_buffer_free).  This is what e2i_run / e2i_run_files / e2i_run_device use. */
+int e2i_call_snp(e2i_ctx *ctx, const e2i_index *b1, const e2i_index *b2, const e2i_bits *da,
+                 const e2i_lcpbits *l, const e2i_params *p, uint64_t pos_begin, uint64_t pos_end,
+                 uint64_t first_cluster_nr, char **snp, size_t *snp_len, e2i_stats *st);
 /* How many cluster numbers the records consume (= what e2i_snp_format adds to clusters_out),
  * without building text: lets every GPU rank learn its first cluster number (distributed.py). */
 int e2i_snp_count(const e2i_call_rec *recs, const char *left, const char *right, uint64_t n_recs,

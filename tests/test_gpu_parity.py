@@ -539,3 +539,81 @@ def test_multi_gpu_ranged_node_pass(e2i, oracle, monkeypatch):
         assert snp == g["snp"], name
         for k, v in g["counters"].items():
             assert getattr(st, k) == v, (name, k)
+
+
+# ---- device formatter (e2i_snp_format_gpu / e2i_call_snp) against the host formatter ---------------
+def _random_call_records(rng, n, kl, kr, alphabet, dtype):
+    """Arbitrary records in the layout of e2i_call_rec: everything the formatter branches on varies."""
+    recs = np.zeros(n, dtype=dtype)
+    recs["begin"] = np.arange(n) * 7
+    recs["end"] = recs["begin"] + 3
+    recs["n0"] = rng.integers(0, 5, n)
+    recs["n1"] = rng.integers(0, 5, n)
+    recs["right_len"] = rng.integers(0, kr + 1, n)
+    recs["has_right"] = rng.random(n) < 0.9
+    recs["support"] = rng.integers(0, 12, (n, 8))
+    letters = np.frombuffer(alphabet, dtype=np.uint8)
+    # contexts that differ in few places, so that SNPs, insertions and deletions all occur
+    base = letters[rng.integers(0, len(letters), (n, 1, kl + 12))]
+    left = np.repeat(base, 8, axis=1)
+    shift = rng.integers(0, 4, (n, 8))
+    out = np.zeros((n, 8, kl), dtype=np.uint8)
+    for s in range(4):
+        m = shift == s
+        out[m] = left[:, :, s:s + kl][m]
+    flip = rng.random((n, 8, kl)) < 0.04
+    out[flip] = letters[rng.integers(0, len(letters), int(flip.sum()))]
+    out[:, :, kl - 1] = letters[rng.integers(0, min(4, len(letters)), (n, 8))]      # the variant character
+    right = letters[rng.integers(0, len(letters), (n, kr))]
+    runs = rng.random(n) < 0.1
+    right[runs] = right[runs][:, :1]                                                    # low-complexity right contexts
+    return recs, np.ascontiguousarray(out).reshape(-1), np.ascontiguousarray(right).reshape(-1)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kl,kr,gap,alphabet", [(31, 30, 10, b"ACGT"), (8, 5, 3, b"ACGT"), (40, 30, 10, b"ACGT"), (31, 30, 0, b"ACGT"),
+                                                (5, 4, 9, b"ACGT"), (31, 30, 10, b"ACGTN#"), (32, 255, 33, b"ACGT"), (1, 1, 1, b"ACGT")])
+@pytest.mark.parametrize("two", [False, True])
+def test_device_formatter_equals_host_formatter(gpu_ctx, e2i, kl, kr, gap, alphabet, two):
+    rng = np.random.default_rng(kl * 1000 + kr + gap + (7 if two else 0))
+    p = e2i.default_params()
+    p.k_left, p.k_right, p.max_gap, p.complexity = kl, kr, gap, min(20, max(1, kr // 2))
+    p.max_snvs = 3
+    recs, left, right = _random_call_records(rng, 20000, kl, kr, alphabet, e2i.CALL_REC_DTYPE)
+    for first in (1, 95, 99990):                        # cluster numbers that cross a power of ten change the layout
+        host, sh = e2i.snp_format(recs, left, right, p, two_samples=two, first_cluster_nr=first)
+        dev, sd = gpu_ctx.snp_format(recs, left, right, p, two_samples=two, first_cluster_nr=first)
+        assert len(host) > 1000
+        assert dev == host
+        assert (sd.events, sd.clusters_out) == (sh.events, sh.clusters_out)
+        assert e2i.snp_count(recs, left, right, p, two) == sd.clusters_out
+    # nothing to print
+    dev, sd = gpu_ctx.snp_format(recs[:0], left[:0], right[:0], p, two_samples=two)
+    assert dev == b"" and sd.clusters_out == 0
+    none = recs.copy()
+    none["has_right"] = 0
+    dev, sd = gpu_ctx.snp_format(none, left, right, p, two_samples=two)
+    assert dev == b"" and sd.clusters_out == 0 and sd.events == 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["m1_default", "m2_default", "m3_default"])
+def test_call_snp_ranges_concatenate_to_golden(gpu_ctx, e2i, name):
+    """Phase 4 + text on the device, range by range with running cluster numbers (what a rank of a sharded run does)."""
+    g = load_golden(name)
+    p = e2i.default_params()
+    b1 = gpu_ctx.index(g["bwt1"])
+    b2 = gpu_ctx.index(g["bwt2"]) if g.get("bwt2") is not None else None
+    da = gpu_ctx.document_array(g["da"]) if g.get("da") is not None else None
+    lcp, da_nav, _ = gpu_ctx.navigate(b1, b2, p)
+    n = len(g["bwt1"]) + (len(g["bwt2"]) if b2 else 0)
+    whole, st = gpu_ctx.call_snp(b1, b2, da_nav if b2 else da, lcp, p)
+    assert whole == g["snp"]
+    assert st.n_clusters == g["counters"]["n_clusters"]
+    cuts = [0, n // 3 + 17, 2 * n // 3 + 5, n]
+    text, first = b"", 1
+    for i in range(3):
+        part, ps = gpu_ctx.call_snp(b1, b2, da_nav if b2 else da, lcp, p, cuts[i], cuts[i + 1], first_cluster_nr=first)
+        text += part
+        first += ps.clusters_out
+    assert text == g["snp"]
