@@ -583,10 +583,12 @@ static int call_impl(e2i_ctx *ctx, const e2i_index *b1, const e2i_index *b2, con
                 char *d_text = nullptr;
                 uint64_t tl = 0, cl = 0, ev = 0;
                 E2I_TRY(format_device(ctx, d_recs, d_left, d_right, nb, p, mode != 1, sink->next_cluster, &d_text, &tl, &cl, &ev));
-                if (sink->len + tl + 1 > sink->cap) {
+                if (sink->len + tl + 1 > sink->cap) {     // page-locked buffer (text_alloc); a second batch moves what is there
                     const size_t want = std::max<size_t>(sink->len + tl + 1, sink->cap + sink->cap / 2);
-                    char *nb2 = static_cast<char *>(std::realloc(sink->buf, want));
-                    if (!nb2) { dfree(ctx, d_text); set_error("e2i_call_snp: out of host memory"); return E2I_ERR_MEMORY; }
+                    char *nb2 = text_alloc(want);
+                    if (!nb2) { dfree(ctx, d_text); set_error("e2i_call_snp: cannot page-lock %llu bytes for the text", (unsigned long long)want); return E2I_ERR_MEMORY; }
+                    if (sink->len) std::memcpy(nb2, sink->buf, sink->len);
+                    if (sink->buf) text_release(sink->buf);
                     sink->buf = nb2;
                     sink->cap = want;
                 }
@@ -701,8 +703,8 @@ extern "C" int e2i_call_snp(e2i_ctx *ctx, const e2i_index *b1, const e2i_index *
     TextSink sink;
     sink.next_cluster = first_cluster_nr ? first_cluster_nr : 1;
     const int rc = call_impl(ctx, b1, b2, da, l, p, pos_begin, pos_end, nullptr, &sink, st);
-    if (rc != E2I_OK) { std::free(sink.buf); return rc; }
-    if (!sink.buf) sink.buf = static_cast<char *>(std::malloc(1));
+    if (rc != E2I_OK) { if (sink.buf) text_release(sink.buf); return rc; }
+    if (!sink.buf) sink.buf = text_alloc(1);
     if (!sink.buf) { set_error("e2i_call_snp: out of host memory"); return E2I_ERR_MEMORY; }
     sink.buf[sink.len] = 0;
     *snp = sink.buf;

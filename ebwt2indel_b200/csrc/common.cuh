@@ -155,6 +155,11 @@ inline cudaError_t arena_alloc(e2i_ctx *ctx, size_t bytes, bool ipc) {
     if (e == cudaSuccess) { ctx->arena_bytes = bytes; ctx->arena_ipc = ipc; }
     return e;
 }
+// Host buffers for the .snp text handed to the caller: page-locked (the text arrives by one DMA copy, no page
+// faults, no staging) and cached process-wide between calls; e2i_buffer_free gives them back (snp_format.cpp).
+char *text_alloc(size_t bytes);
+bool text_release(void *p);              // false: not one of ours
+void text_cache_trim();                  // frees the cached buffers that are not handed out
 // .snp text of call records that are still in device memory (snp_format.cpp); *d_text is released with dfree
 int format_device(e2i_ctx *ctx, const e2i_call_rec *d_recs, const char *d_left, const char *d_right, uint64_t n_recs,
                   const e2i_params *p, int two_samples, uint64_t first_cluster_nr,

@@ -123,6 +123,7 @@ extern "C" void e2i_destroy(e2i_ctx *ctx) {
     cudaFree(ctx->ctl);
     cudaFreeHost(ctx->ctl_host);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    text_cache_trim();
     for (void *r : ctx->ring) if (r) cudaFreeHost(r);
     for (auto &ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);

@@ -37,39 +37,70 @@ struct Piece {               // 16 symbols
 // bit k of the result = least significant bit of byte k of x (x holds 0/1 per byte)
 __device__ __forceinline__ uint32_t gather4(uint32_t x) { return ((x & 0x01010101u) * 0x01020408u) >> 24; }
 
-// 16 symbols at once: four bytes per SIMD-in-register compare (__vcmpeq4 gives 0xff per equal byte)
-__device__ __forceinline__ Piece encode_piece(uint4 v, uint64_t pos0, uint64_t n, uint32_t term) {
+// 0x80 in every byte of the result whose byte of v is zero (exact, no borrow between bytes)
+__device__ __forceinline__ uint32_t zero_bytes(uint32_t v) { return ~(((v & 0x7f7f7f7fu) + 0x7f7f7f7fu) | v) & 0x80808080u; }
+
+// 16 symbols at once, four per 32-bit word, without per-byte compares: the 2-bit code of A,C,G,T is read off bits
+// 1-2 of the ASCII byte (A 0x41, C 0x43, G 0x47, T 0x54: y = bits 2..1 = 0,1,3,2; code = y ^ (y >> 1)), the byte that
+// code stands for is rebuilt and compared with the input in one XOR, and the terminator test (which comes first, as
+// in the reference: a terminator that is one of A,C,G,T stays a terminator) is one more.  ~35 integer operations per
+// word against ~100 for five __vcmpeq4 (emulated on this architecture): the build kernels were issue-bound on them.
+template <bool TAIL>
+__device__ __forceinline__ Piece encode_words(const uint32_t (&w)[4], int valid, uint32_t t4) {
     Piece pc{0, 0, 0, 0, -1};
-    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-    const uint32_t t4 = term * 0x01010101u;
-    const int valid = pos0 + 16 <= n ? 16 : (int)(n - pos0);          // symbols of this piece inside the string
+    uint32_t notok[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-        uint32_t live = 0xffffffffu;                                   // byte mask of the in-range symbols of this word
-        const int k = valid - 4 * q;
-        if (k < 4) live = k <= 0 ? 0u : (0xffffffffu >> (8 * (4 - k)));
-        const uint32_t isX = __vcmpeq4(w[q], t4) & live;                // the terminator test comes first, as in the reference
-        const uint32_t base = live & ~isX;
-        const uint32_t isA = __vcmpeq4(w[q], 0x41414141u) & base, isC = __vcmpeq4(w[q], 0x43434343u) & base,
-                       isG = __vcmpeq4(w[q], 0x47474747u) & base, isT = __vcmpeq4(w[q], 0x54545454u) & base;
-        const uint32_t ok = isA | isC | isG | isT | isX;
-        if (ok != live && pc.bad < 0) pc.bad = 4 * q + ((__ffs((int)(~ok & live)) - 1) >> 3);
-        pc.p0 |= gather4(isC | isT) << (4 * q);
-        pc.p1 |= gather4(isG | isT) << (4 * q);
-        pc.pt |= gather4(isX | ~live) << (4 * q);                       // positions past the end count as terminators: never as A
-        pc.cnt += (uint32_t)__popc(isA & 0x01010101u) | ((uint32_t)__popc(isC & 0x01010101u) << 8) |
-                  ((uint32_t)__popc(isG & 0x01010101u) << 16) | ((uint32_t)__popc(isT & 0x01010101u) << 24);
+        uint32_t live = 0x80808080u;                                   // 0x80 per in-range symbol of this word
+        if (TAIL) {
+            const int k = valid - 4 * q;
+            if (k < 4) live = k <= 0 ? 0u : (0x80808080u >> (8 * (4 - k)));
+        }
+        const uint32_t y = (w[q] >> 1) & 0x03030303u;
+        const uint32_t hi = (y >> 1) & 0x01010101u, lo = (y ^ hi) & 0x01010101u;       // code = lo | hi << 1
+        const uint32_t expect = 0x41414141u + lo * 2u + hi * 6u + (lo & hi) * 11u;      // +2 C, +6 G, +19 T
+        const uint32_t isX = zero_bytes(w[q] ^ t4) & live;
+        const uint32_t base = zero_bytes(w[q] ^ expect) & live & ~isX;                  // A,C,G,T that are not the terminator
+        notok[q] = live & ~(base | isX);                                                // 0x80 per forbidden symbol
+        const uint32_t b1 = base >> 7;                                                  // 0x01 per byte
+        pc.p0 |= ((( lo & b1) * 0x01020408u) >> 24) << (4 * q);
+        pc.p1 |= ((( hi & b1) * 0x01020408u) >> 24) << (4 * q);
+        // positions past the end count as terminators: never as A
+        pc.pt |= ((((isX | (TAIL ? ~live & 0x80808080u : 0u)) >> 7) * 0x01020408u) >> 24) << (4 * q);
     }
+    if (notok[0] | notok[1] | notok[2] | notok[3]) {                   // rare: where is the first forbidden symbol
+        for (int q = 3; q >= 0; --q) if (notok[q]) pc.bad = 4 * q + ((__ffs((int)notok[q]) - 1) >> 3);
+    }
+    // counts from the planes: outside A,C,G,T both plane bits are zero and the terminator bit tells them from A
+    const uint32_t a = ~(pc.p0 | pc.p1 | pc.pt) & 0xffffu;
+    pc.cnt = (uint32_t)__popc(a) | ((uint32_t)__popc(pc.p0 & ~pc.p1) << 8) | ((uint32_t)__popc(pc.p1 & ~pc.p0) << 16) |
+             ((uint32_t)__popc(pc.p0 & pc.p1) << 24);
     return pc;
+}
+
+__device__ __noinline__ Piece encode_tail(uint4 v, int valid, uint32_t t4) {      // the last piece of the string: out of line
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    return encode_words<true>(w, valid, t4);
+}
+
+__device__ __forceinline__ Piece encode_piece(uint4 v, uint64_t pos0, uint64_t n, uint32_t term) {
+    const uint32_t t4 = term * 0x01010101u;
+    if (pos0 + 16 > n) return encode_tail(v, (int)(n - pos0), t4);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    return encode_words<false>(w, 16, t4);
+}
+
+__device__ __noinline__ uint4 load_tail(const uint8_t *ascii, uint64_t pos0, uint64_t n) {
+    uint32_t w[4] = {0, 0, 0, 0};
+    for (int j = 0; j < 16; ++j)
+        if (pos0 + j < n) w[j >> 2] |= (uint32_t)ascii[pos0 + j] << (8 * (j & 3));
+    return make_uint4(w[0], w[1], w[2], w[3]);
 }
 
 __device__ __forceinline__ uint4 load_piece(const uint8_t *ascii, uint64_t pos0, uint64_t n) {
     // 16-byte aligned vector load when the whole piece is inside the buffer, bytewise tail otherwise
     if (pos0 + 16 <= n) return __ldg(reinterpret_cast<const uint4 *>(ascii + pos0));
-    uint32_t w[4] = {0, 0, 0, 0};
-    for (int j = 0; j < 16; ++j)
-        if (pos0 + j < n) w[j >> 2] |= (uint32_t)ascii[pos0 + j] << (8 * (j & 3));
-    return make_uint4(w[0], w[1], w[2], w[3]);
+    return load_tail(ascii, pos0, n);
 }
 
 constexpr int kBuildThreads = 256;
@@ -161,58 +192,100 @@ scan_tiles_kernel(const uint4 *__restrict__ tile_cnt, uint64_t n_tiles, ulonglon
     if (threadIdx.x < 4) totals[threadIdx.x] = s_carry[threadIdx.x];
 }
 
-// Kernel 3: pack one tile (256 blocks of 64 symbols) per CTA iteration.
+// Packing of ONE tile (256 blocks of 64 symbols) by a CTA of 256 threads: encode 4 pieces per thread into shared
+// memory, scan the per-block totals, write the 512 uint4 of the tile coalesced.  `rel` = counts of A,C,G,T before the
+// tile relative to its superblock start (< 2^16 each).  Returns the tile's totals (4 x 16 bit, every thread).
+struct TileSmem {
+    uint16_t plane[3][kPiecesPerTile];
+    uint32_t cnt[kPiecesPerTile];
+    unsigned long long mid[kTileBlocks];                  // counts before the middle of each block, 4 x 16 bit, tile-relative
+    unsigned long long wsum[kBuildThreads / 32];
+};
+
+__device__ __forceinline__ unsigned long long widen_counts(uint32_t c) {
+    return (unsigned long long)(c & 0xffu) | ((unsigned long long)((c >> 8) & 0xffu) << 16) |
+           ((unsigned long long)((c >> 16) & 0xffu) << 32) | ((unsigned long long)(c >> 24) << 48);
+}
+
+__device__ __forceinline__ unsigned long long pack_one_tile(TileSmem &sm, const uint8_t *__restrict__ ascii, uint64_t n, uint32_t term, uint64_t tile,
+                                                            const uint32_t (&rel)[4], uint4 *__restrict__ blocks, unsigned long long *bad_pos) {
+    static_assert(kTileBlocks == kBuildThreads, "one thread per block in the per-block scan");
+#pragma unroll
+    for (int it = 0; it < kPiecesPerThread; ++it) {
+        const int piece = it * kBuildThreads + threadIdx.x;
+        const uint64_t pos0 = (tile << kTileShift) + (uint64_t)piece * 16;
+        Piece pc{0, 0, 0xffffu, 0, -1};                                   // past the end: terminator bits, no counts
+        if (pos0 < n) pc = encode_piece(load_piece(ascii, pos0, n), pos0, n, term);
+        if (bad_pos && pc.bad >= 0) atomicMin(bad_pos, (unsigned long long)(pos0 + pc.bad));
+        sm.plane[0][piece] = (uint16_t)pc.p0;
+        sm.plane[1][piece] = (uint16_t)pc.p1;
+        sm.plane[2][piece] = (uint16_t)pc.pt;
+        sm.cnt[piece] = pc.cnt;
+    }
+    __syncthreads();
+    // per-block totals (4 pieces each) and their exclusive scan over the 256 blocks of the tile
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint4 c4 = reinterpret_cast<const uint4 *>(sm.cnt)[threadIdx.x];
+    const unsigned long long half = widen_counts(c4.x) + widen_counts(c4.y);
+    const unsigned long long mine = half + widen_counts(c4.z) + widen_counts(c4.w);
+    unsigned long long incl = mine;
+#pragma unroll
+    for (int s = 1; s < 32; s <<= 1) {
+        const unsigned long long y = __shfl_up_sync(0xffffffffu, incl, s);
+        if (lane >= s) incl += y;
+    }
+    if (lane == 31) sm.wsum[warp] = incl;
+    __syncthreads();
+    unsigned long long off = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < kBuildThreads / 32; ++w) {
+        const unsigned long long v = sm.wsum[w];
+        if (w < warp) off += v;
+        total += v;                                                   // <= 16384 per field
+    }
+    sm.mid[threadIdx.x] = off + incl - mine + half;                   // 16-bit fields: a tile has 16384 symbols
+    __syncthreads();
+    // 256 blocks x 2 uint4 = 512 uint4 per tile, written coalesced
+    uint4 *out = blocks + (tile << (kTileShift - kBlockShift)) * kBlockU4;
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+        const int q = it * kBuildThreads + threadIdx.x;
+        const int blk = q >> 1, part = q & 1;
+        uint4 v;
+        if (part == 0) {
+            const unsigned long long e = sm.mid[blk];
+            const uint16_t *pl = sm.plane[0] + blk * 4;
+            // counts before the middle of the block, relative to the superblock start (< 2^16)
+            v.x = (rel[0] + (uint32_t)(e & 0xffff)) | ((rel[1] + (uint32_t)((e >> 16) & 0xffff)) << 16);
+            v.y = (rel[2] + (uint32_t)((e >> 32) & 0xffff)) | ((rel[3] + (uint32_t)(e >> 48)) << 16);
+            v.z = pl[0] | ((uint32_t)pl[1] << 16);
+            v.w = pl[2] | ((uint32_t)pl[3] << 16);
+        } else {
+            const uint16_t *pb = sm.plane[1] + blk * 4, *pt = sm.plane[2] + blk * 4;
+            v.x = pb[0] | ((uint32_t)pb[1] << 16);
+            v.y = pb[2] | ((uint32_t)pb[3] << 16);
+            v.z = pt[0] | ((uint32_t)pt[1] << 16);
+            v.w = pt[2] | ((uint32_t)pt[3] << 16);
+        }
+        out[q] = v;
+    }
+    __syncthreads();
+    return total;
+}
+
+// Kernel 3 (slice-wise build): pack tiles whose prefix counts are known.
 __global__ void __launch_bounds__(kBuildThreads)
 pack_tiles_kernel(const uint8_t *__restrict__ ascii, uint64_t n, uint32_t term, uint64_t tile0, uint64_t n_tiles,
                   const ulonglong4 *__restrict__ tile_prefix, const ulonglong4 base,
                   const unsigned long long *__restrict__ super_in, uint4 *__restrict__ blocks,
                   unsigned long long *__restrict__ super) {
     // Packs global tiles tile0 .. tile0 + n_tiles - 1 (`ascii` points at position tile0 << kTileShift);
-    // tile_prefix is local to the slice and `base` holds the counts before it.  Whole-string build:
-    // tile0 = 0, base = 0, super_in = nullptr (superblock entries are written here).  Slice build:
-    // super_in = the complete table of absolute counts at the superblock starts.
-    static_assert(kTileBlocks == kBuildThreads, "one thread per block in the per-block scan");
+    // tile_prefix is local to the slice and `base` holds the counts before it.  super_in = the complete table of
+    // absolute counts at the superblock starts (nullptr: the slice starts at 0 and the entries are written here).
     ascii -= tile0 << kTileShift;
-    __shared__ uint16_t s_plane[3][kPiecesPerTile];
-    __shared__ uint32_t s_cnt[kPiecesPerTile];
-    __shared__ unsigned long long s_mid[kTileBlocks];                 // counts before the middle of each block, 4 x 16 bit, tile-relative
-    __shared__ unsigned long long s_wsum[kBuildThreads / 32];
-    auto widen = [](uint32_t c) {
-        return (unsigned long long)(c & 0xffu) | ((unsigned long long)((c >> 8) & 0xffu) << 16) |
-               ((unsigned long long)((c >> 16) & 0xffu) << 32) | ((unsigned long long)(c >> 24) << 48);
-    };
+    __shared__ __align__(16) TileSmem sm;
     for (uint64_t lt = blockIdx.x; lt < n_tiles; lt += gridDim.x) {
         const uint64_t tile = tile0 + lt;
-#pragma unroll
-        for (int it = 0; it < kPiecesPerThread; ++it) {
-            const int piece = it * kBuildThreads + threadIdx.x;
-            const uint64_t pos0 = (tile << kTileShift) + (uint64_t)piece * 16;
-            Piece pc{0, 0, 0xffffu, 0, -1};                                   // past the end: terminator bits, no counts
-            if (pos0 < n) pc = encode_piece(load_piece(ascii, pos0, n), pos0, n, term);
-            s_plane[0][piece] = (uint16_t)pc.p0;
-            s_plane[1][piece] = (uint16_t)pc.p1;
-            s_plane[2][piece] = (uint16_t)pc.pt;
-            s_cnt[piece] = pc.cnt;
-        }
-        __syncthreads();
-        // per-block totals (4 pieces each) and their exclusive scan over the 256 blocks of the tile
-        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-        const unsigned long long half = widen(s_cnt[threadIdx.x * 4]) + widen(s_cnt[threadIdx.x * 4 + 1]);
-        const unsigned long long mine = half + widen(s_cnt[threadIdx.x * 4 + 2]) + widen(s_cnt[threadIdx.x * 4 + 3]);
-        unsigned long long incl = mine;
-#pragma unroll
-        for (int s = 1; s < 32; s <<= 1) {
-            const unsigned long long y = __shfl_up_sync(0xffffffffu, incl, s);
-            if (lane >= s) incl += y;
-        }
-        if (lane == 31) s_wsum[warp] = incl;
-        __syncthreads();
-        {
-            unsigned long long off = 0;
-            for (int w = 0; w < warp; ++w) off += s_wsum[w];
-            s_mid[threadIdx.x] = off + incl - mine + half;           // 16-bit fields: a tile has 16384 symbols
-        }
-        __syncthreads();
         ulonglong4 tp = tile_prefix[lt], sp;
         tp.x += base.x; tp.y += base.y; tp.z += base.z; tp.w += base.w;       // absolute counts before the tile
         if (super_in) {
@@ -225,31 +298,32 @@ pack_tiles_kernel(const uint8_t *__restrict__ ascii, uint64_t n, uint32_t term, 
                 s[0] = tp.x; s[1] = tp.y; s[2] = tp.z; s[3] = tp.w;
             }
         }
-        // 256 blocks x 2 uint4 = 512 uint4 per tile, written coalesced
-        uint4 *out = blocks + (tile << (kTileShift - kBlockShift)) * kBlockU4;
-#pragma unroll
-        for (int it = 0; it < 2; ++it) {
-            const int q = it * kBuildThreads + threadIdx.x;
-            const int blk = q >> 1, part = q & 1;
-            uint4 v;
-            if (part == 0) {
-                const unsigned long long e = s_mid[blk];
-                const uint16_t *pl = s_plane[0] + blk * 4;
-                // counts before the middle of the block, relative to the superblock start (< 2^16)
-                v.x = ((uint32_t)(tp.x - sp.x) + (uint32_t)(e & 0xffff)) | (((uint32_t)(tp.y - sp.y) + (uint32_t)((e >> 16) & 0xffff)) << 16);
-                v.y = ((uint32_t)(tp.z - sp.z) + (uint32_t)((e >> 32) & 0xffff)) | (((uint32_t)(tp.w - sp.w) + (uint32_t)(e >> 48)) << 16);
-                v.z = pl[0] | ((uint32_t)pl[1] << 16);
-                v.w = pl[2] | ((uint32_t)pl[3] << 16);
-            } else {
-                const uint16_t *pb = s_plane[1] + blk * 4, *pt = s_plane[2] + blk * 4;
-                v.x = pb[0] | ((uint32_t)pb[1] << 16);
-                v.y = pb[2] | ((uint32_t)pb[3] << 16);
-                v.z = pt[0] | ((uint32_t)pt[1] << 16);
-                v.w = pt[2] | ((uint32_t)pt[3] << 16);
-            }
-            out[q] = v;
+        const uint32_t rel[4] = {(uint32_t)(tp.x - sp.x), (uint32_t)(tp.y - sp.y), (uint32_t)(tp.z - sp.z), (uint32_t)(tp.w - sp.w)};
+        pack_one_tile(sm, ascii, n, term, tile, rel, blocks, nullptr);
+    }
+}
+
+// One-pass build (whole-string and streamed builds): a CTA packs a whole SUPERBLOCK (4 tiles), so the block
+// counters -- which are relative to the superblock start -- need no prefix from anywhere else; the totals of the
+// superblocks are scanned afterwards into the (tiny) table of absolute counts.  The ASCII text is read ONCE and
+// the forbidden-symbol check rides along.  `ascii` is addressed with global positions and is valid in
+// [first byte of superblock sb0, end): a streamed build passes the device copy of ONE chunk, shifted.
+__global__ void __launch_bounds__(kBuildThreads)
+pack_super_kernel(const uint8_t *__restrict__ ascii, uint64_t end, uint32_t term, uint64_t sb0, uint64_t n_sb, uint64_t n_tiles_total,
+                  uint4 *__restrict__ blocks, uint4 *__restrict__ sb_tot, unsigned long long *bad_pos) {
+    __shared__ __align__(16) TileSmem sm;
+    for (uint64_t sb = sb0 + blockIdx.x; sb < sb0 + n_sb; sb += gridDim.x) {
+        uint32_t rel[4] = {0, 0, 0, 0};
+        for (uint64_t t = 0; t < (1ull << kSuperTileShift); ++t) {
+            const uint64_t tile = (sb << kSuperTileShift) + t;
+            if (tile >= n_tiles_total) break;
+            const unsigned long long tot = pack_one_tile(sm, ascii, end, term, tile, rel, blocks, bad_pos);
+            rel[0] += (uint32_t)(tot & 0xffff);
+            rel[1] += (uint32_t)((tot >> 16) & 0xffff);
+            rel[2] += (uint32_t)((tot >> 32) & 0xffff);
+            rel[3] += (uint32_t)(tot >> 48);
         }
-        __syncthreads();
+        if (threadIdx.x == 0) sb_tot[sb] = make_uint4(rel[0], rel[1], rel[2], rel[3]);
     }
 }
 
@@ -303,18 +377,18 @@ using namespace e2i;
 // =================================================================================================
 // C ABI
 // =================================================================================================
-// ---- whole-string build in three steps, so that the counting pass can follow the data as it arrives ----
+// ---- whole-string build: superblocks are packed as their bytes become available (all at once for a resident
+//      string, chunk by chunk behind the copies of a streamed one), then the superblock totals are scanned ----
 namespace {
 struct IndexBuild {
     e2i_index *ix = nullptr;
-    uint4 *tile_cnt = nullptr;
-    ulonglong4 *tile_prefix = nullptr;
+    uint4 *sb_tot = nullptr;               // A,C,G,T totals of every superblock
     unsigned long long *scal = nullptr;    // [0..3] totals, [4] position of the first forbidden symbol
-    uint64_t n_tiles = 0;
+    uint64_t n_tiles = 0, n_sb = 0, packed_sb = 0;
 };
 
 void index_abort(e2i_ctx *ctx, IndexBuild &b) {
-    dfree(ctx, b.tile_cnt); dfree(ctx, b.tile_prefix); dfree(ctx, b.scal);
+    dfree(ctx, b.sb_tot); dfree(ctx, b.scal);
     e2i_index_free(b.ix);
     b = IndexBuild();
 }
@@ -329,15 +403,14 @@ int index_begin(e2i_ctx *ctx, uint64_t n, uint8_t term, IndexBuild &b) {
     ix->n_blocks = n / kBlockSyms + 1;                       // rank(n) must be addressable (dna_string.hpp:62)
     b.n_tiles = (ix->n_blocks + kTileBlocks - 1) / kTileBlocks;
     ix->n_super = (n >> kSuperShift) + 1;
+    b.n_sb = ix->n_super;                                    // = ceil(n_tiles / tiles per superblock)
     const size_t blk_bytes = b.n_tiles * kTileBlocks * kBlockU4 * sizeof(uint4);
     ix->bytes = blk_bytes + ix->n_super * 32;
     const unsigned long long init[5] = {0, 0, 0, 0, ~0ull};
     cudaError_t e = dmalloc(ctx, &ix->blocks, blk_bytes);
     if (e == cudaSuccess) e = dmalloc(ctx, &ix->super, ix->n_super * 32);
-    if (e == cudaSuccess) e = dmalloc(ctx, &b.tile_cnt, b.n_tiles * sizeof(uint4));
-    if (e == cudaSuccess) e = dmalloc(ctx, &b.tile_prefix, b.n_tiles * sizeof(ulonglong4));
+    if (e == cudaSuccess) e = dmalloc(ctx, &b.sb_tot, b.n_sb * sizeof(uint4));
     if (e == cudaSuccess) e = dmalloc(ctx, &b.scal, 5 * sizeof(unsigned long long));
-    if (e == cudaSuccess) e = cudaMemsetAsync(b.tile_cnt, 0, b.n_tiles * sizeof(uint4), s);   // the last tile may hold no symbol
     if (e == cudaSuccess) e = cudaMemcpyAsync(b.scal, init, sizeof init, cudaMemcpyHostToDevice, s);
     if (e == cudaSuccess) e = cudaStreamSynchronize(s);      // `init` lives on this stack frame
     if (e != cudaSuccess) { set_error("index build: %s", cudaGetErrorString(e)); cudaGetLastError(); index_abort(ctx, b); return E2I_ERR_CUDA; }
@@ -345,29 +418,33 @@ int index_begin(e2i_ctx *ctx, uint64_t n, uint8_t term, IndexBuild &b) {
     return E2I_OK;
 }
 
-// count the symbols of tiles [tile0, tile0 + nt); dev_ascii = the string's first byte, valid up to position `end`
-int index_count(e2i_ctx *ctx, IndexBuild &b, const uint8_t *dev_ascii, uint64_t tile0, uint64_t nt, uint64_t end) {
-    if (!nt) return E2I_OK;
-    const int grid = (int)std::min<uint64_t>(nt, (uint64_t)ctx->sm_count * 16);
-    count_tiles_kernel<<<grid, kBuildThreads, 0, ctx->stream>>>(dev_ascii + (tile0 << kTileShift), end, b.ix->term, tile0, nt, b.tile_cnt + tile0, b.scal + 4);
+// pack superblocks [sb0, sb0 + nsb); `ascii` is addressed with global positions and holds the bytes of these
+// superblocks up to position `end` (the superblocks of a chunk: the chunk's device copy, shifted)
+int index_pack(e2i_ctx *ctx, IndexBuild &b, const uint8_t *ascii, uint64_t sb0, uint64_t nsb, uint64_t end) {
+    if (!nsb) return E2I_OK;
+    const int grid = (int)std::min<uint64_t>(nsb, (uint64_t)ctx->sm_count * 8);
+    pack_super_kernel<<<grid, kBuildThreads, 0, ctx->stream>>>(ascii, end, b.ix->term, sb0, nsb, b.n_tiles, b.ix->blocks, b.sb_tot, b.scal + 4);
     E2I_CUDA_TRY(cudaGetLastError());
     ctx->n_launch++;
+    b.packed_sb = sb0 + nsb;
     return E2I_OK;
 }
 
-int index_finish(e2i_ctx *ctx, IndexBuild &b, const uint8_t *dev_ascii, e2i_index **out, uint64_t *bad_pos) {
+int index_finish(e2i_ctx *ctx, IndexBuild &b, e2i_index **out, uint64_t *bad_pos) {
     cudaStream_t s = ctx->stream;
     e2i_index *ix = b.ix;
-    const int grid = (int)std::min<uint64_t>(b.n_tiles, (uint64_t)ctx->sm_count * 16);
-    scan_tiles_kernel<<<1, kScanThreads, 0, s>>>(b.tile_cnt, b.n_tiles, b.tile_prefix, b.scal);
-    pack_tiles_kernel<<<grid, kBuildThreads, 0, s>>>(dev_ascii, ix->n, ix->term, 0, b.n_tiles, b.tile_prefix, make_ulonglong4(0, 0, 0, 0), nullptr,
-                                                     ix->blocks, reinterpret_cast<unsigned long long *>(ix->super));
+    if (b.packed_sb < b.n_sb) {                              // only superblocks without a byte can be left (empty string)
+        if ((b.packed_sb << kSuperShift) < ix->n) { set_error("index build: the input ended early"); index_abort(ctx, b); return E2I_ERR_ARG; }
+        const int rc = index_pack(ctx, b, nullptr, b.packed_sb, b.n_sb - b.packed_sb, ix->n);
+        if (rc != E2I_OK) { index_abort(ctx, b); return rc; }
+    }
+    scan_tiles_kernel<<<1, kScanThreads, 0, s>>>(b.sb_tot, b.n_sb, reinterpret_cast<ulonglong4 *>(ix->super), b.scal);
     unsigned long long res[5];
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaMemcpyAsync(res, b.scal, sizeof res, cudaMemcpyDeviceToHost, s);
     if (e == cudaSuccess) e = cudaStreamSynchronize(s);
     if (e != cudaSuccess) { set_error("index build: %s", cudaGetErrorString(e)); index_abort(ctx, b); return E2I_ERR_CUDA; }
-    ctx->n_launch += 2;
+    ctx->n_launch += 1;
     ctx->n_d2h += sizeof res;
     if (res[4] != ~0ull) {
         if (bad_pos) *bad_pos = res[4];
@@ -381,7 +458,7 @@ int index_finish(e2i_ctx *ctx, IndexBuild &b, const uint8_t *dev_ascii, e2i_inde
     ix->F[1] = ix->F[0] + res[0];
     ix->F[2] = ix->F[1] + res[1];
     ix->F[3] = ix->F[2] + res[2];
-    dfree(ctx, b.tile_cnt); dfree(ctx, b.tile_prefix); dfree(ctx, b.scal);
+    dfree(ctx, b.sb_tot); dfree(ctx, b.scal);
     *out = ix;
     b = IndexBuild();
     return E2I_OK;
@@ -395,9 +472,9 @@ extern "C" int e2i_index_build_device(e2i_ctx *ctx, const uint8_t *dev_ascii, ui
     E2I_CUDA_TRY(cudaSetDevice(ctx->device));
     IndexBuild b;
     E2I_TRY(index_begin(ctx, n, term, b));
-    const int rc = index_count(ctx, b, dev_ascii, 0, (n + kTileSyms - 1) >> kTileShift, n);
+    const int rc = index_pack(ctx, b, dev_ascii, 0, b.n_sb, n);
     if (rc != E2I_OK) { index_abort(ctx, b); return rc; }
-    return index_finish(ctx, b, dev_ascii, out, bad_pos);
+    return index_finish(ctx, b, out, bad_pos);
 }
 
 // ---- slice-wise construction (multi-GPU): every rank packs the blocks of one tile-aligned slice ----
@@ -536,28 +613,46 @@ extern "C" int e2i_index_device(const e2i_index *ix, void **dev_blocks, uint64_t
 //      page-locked buffers, so disk reads, PCIe copies and the counting kernels overlap.  Replaces the
 //      byte-at-a-time loop of dna_string.hpp:82-101. ---------------------------------------------------
 namespace {
-constexpr uint64_t kChunk = 64ull << 20;                  // multiple of the tile size
+constexpr uint64_t kChunk = 64ull << 20;                  // multiple of the superblock size
+static_assert(kChunk % (1ull << kSuperShift) == 0, "chunks must end on superblock boundaries");
 constexpr int kRing = 4;
 
-struct Uploader {                                           // H2D of consecutive chunks + counting behind them
+struct Uploader {                                           // H2D of consecutive chunks into a small device ring + packing behind them
     e2i_ctx *ctx;
     IndexBuild *b;
-    uint8_t *dev;
     uint64_t n, off = 0;
-    cudaEvent_t ev[kRing] = {};
+    uint8_t *ring = nullptr;                                // kRing chunk buffers in device memory: the ASCII text never sits in HBM as a whole
+    cudaEvent_t ev[kRing] = {}, packed[kRing] = {};
     int k = 0;
-    int init() { for (auto &e : ev) E2I_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); return E2I_OK; }
-    ~Uploader() { for (auto &e : ev) if (e) cudaEventDestroy(e); }
+    int init() {
+        for (auto &e : ev) E2I_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        for (auto &e : packed) E2I_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        E2I_CUDA_TRY(dmalloc(ctx, &ring, (size_t)kRing * kChunk));
+        // the copy stream must not run ahead of the allocations made on the compute stream
+        E2I_CUDA_TRY(cudaEventRecord(ev[0], ctx->stream));
+        E2I_CUDA_TRY(cudaStreamWaitEvent(ctx->copy_stream, ev[0], 0));
+        return E2I_OK;
+    }
+    ~Uploader() {
+        for (auto &e : ev) if (e) cudaEventDestroy(e);
+        for (auto &e : packed) if (e) cudaEventDestroy(e);
+        dfree(ctx, ring);                                   // stream-ordered: after the last packing kernel
+    }
     // host must stay valid until event `slot` (returned) has completed
     int push(const uint8_t *host, uint64_t len, int *slot) {
-        const int sl = k++ % kRing;
-        E2I_CUDA_TRY(cudaMemcpyAsync(dev + off, host, len, cudaMemcpyHostToDevice, ctx->copy_stream));
+        const int sl = k % kRing;
+        uint8_t *dst = ring + (size_t)sl * kChunk;
+        if (k >= kRing) E2I_CUDA_TRY(cudaStreamWaitEvent(ctx->copy_stream, packed[sl], 0));   // the kernel that read this buffer is done
+        ++k;
+        E2I_CUDA_TRY(cudaMemcpyAsync(dst, host, len, cudaMemcpyHostToDevice, ctx->copy_stream));
         E2I_CUDA_TRY(cudaEventRecord(ev[sl], ctx->copy_stream));
         E2I_CUDA_TRY(cudaStreamWaitEvent(ctx->stream, ev[sl], 0));
         ctx->n_h2d += len;
-        // chunks are tile-aligned except the last: count the tiles this chunk completes
-        const uint64_t t0 = off >> kTileShift, t1 = (off + len + kTileSyms - 1) >> kTileShift;
-        E2I_TRY(index_count(ctx, *b, dev, t0, t1 - t0, off + len));
+        // chunks are superblock-aligned except the last, which also owns what follows the string's end
+        const bool last = off + len >= n;
+        const uint64_t sb0 = off >> kSuperShift, sb1 = last ? b->n_sb : (off + len) >> kSuperShift;
+        E2I_TRY(index_pack(ctx, *b, dst - off, sb0, sb1 - sb0, off + len));
+        E2I_CUDA_TRY(cudaEventRecord(packed[sl], ctx->stream));
         off += len;
         if (slot) *slot = sl;
         return E2I_OK;
@@ -569,26 +664,23 @@ extern "C" int e2i_index_build(e2i_ctx *ctx, const uint8_t *host_ascii, uint64_t
                                e2i_index **out, uint64_t *bad_pos) {
     if (!ctx || !out || (n && !host_ascii)) { set_error("e2i_index_build: null argument"); return E2I_ERR_ARG; }
     E2I_CUDA_TRY(cudaSetDevice(ctx->device));
-    uint8_t *d = nullptr;
-    E2I_CUDA_TRY(dmalloc(ctx, &d, n + 16));
     IndexBuild b;
     int rc = index_begin(ctx, n, term, b);
-    if (rc != E2I_OK) { dfree(ctx, d); return rc; }
-    // the copy stream must not run ahead of the allocations made on the compute stream
-    Uploader up{ctx, &b, d, n};
-    rc = up.init();
-    cudaEvent_t t0 = nullptr, t1 = nullptr;
-    if (rc == E2I_OK && (cudaEventCreate(&t0) != cudaSuccess || cudaEventCreate(&t1) != cudaSuccess)) rc = E2I_ERR_CUDA;
-    if (rc == E2I_OK && cudaEventRecord(up.ev[0], ctx->stream) == cudaSuccess) cudaStreamWaitEvent(ctx->copy_stream, up.ev[0], 0);
-    if (rc == E2I_OK) cudaEventRecord(t0, ctx->copy_stream);
-    for (uint64_t off = 0; rc == E2I_OK && off < n; off += kChunk) rc = up.push(host_ascii + off, std::min(kChunk, n - off), nullptr);
-    if (rc == E2I_OK) cudaEventRecord(t1, ctx->copy_stream);
-    if (rc == E2I_OK) rc = index_finish(ctx, b, d, out, bad_pos); else index_abort(ctx, b);
-    if (t0 && t1 && rc == E2I_OK) { float ms = 0; if (cudaEventElapsedTime(&ms, t0, t1) == cudaSuccess) ctx->last_h2d_ms = ms; }
-    if (t0) cudaEventDestroy(t0);
-    if (t1) cudaEventDestroy(t1);
-    cudaStreamSynchronize(ctx->copy_stream);
-    dfree(ctx, d);
+    if (rc != E2I_OK) return rc;
+    {
+        Uploader up{ctx, &b, n};
+        rc = up.init();
+        cudaEvent_t t0 = nullptr, t1 = nullptr;
+        if (rc == E2I_OK && (cudaEventCreate(&t0) != cudaSuccess || cudaEventCreate(&t1) != cudaSuccess)) rc = E2I_ERR_CUDA;
+        if (rc == E2I_OK) cudaEventRecord(t0, ctx->copy_stream);
+        for (uint64_t off = 0; rc == E2I_OK && off < n; off += kChunk) rc = up.push(host_ascii + off, std::min(kChunk, n - off), nullptr);
+        if (rc == E2I_OK) cudaEventRecord(t1, ctx->copy_stream);
+        if (rc == E2I_OK) rc = index_finish(ctx, b, out, bad_pos); else index_abort(ctx, b);
+        if (t0 && t1 && rc == E2I_OK) { float ms = 0; if (cudaEventElapsedTime(&ms, t0, t1) == cudaSuccess) ctx->last_h2d_ms = ms; }
+        if (t0) cudaEventDestroy(t0);
+        if (t1) cudaEventDestroy(t1);
+        cudaStreamSynchronize(ctx->copy_stream);
+    }
     return rc;
 }
 
@@ -673,29 +765,27 @@ extern "C" int e2i_index_build_file(e2i_ctx *ctx, const char *path, uint8_t term
     FileStream fs;
     E2I_TRY(fs.open(ctx, path, 0));
     const uint64_t n = fs.total;
-    uint8_t *d = nullptr;
-    E2I_CUDA_TRY(dmalloc(ctx, &d, n + 16));
     IndexBuild b;
     int rc = index_begin(ctx, n, term, b);
-    if (rc != E2I_OK) { dfree(ctx, d); return rc; }
-    Uploader up{ctx, &b, d, n};
-    rc = up.init();
-    if (rc == E2I_OK && cudaEventRecord(up.ev[0], ctx->stream) == cudaSuccess) cudaStreamWaitEvent(ctx->copy_stream, up.ev[0], 0);
-    const uint64_t n_chunks = (n + kChunk - 1) / kChunk;
-    std::vector<int> slot_of(n_chunks, 0);
-    for (uint64_t c = 0; rc == E2I_OK && c < n_chunks; ++c) {
-        const uint8_t *p;
-        uint64_t l;
-        if (!fs.next(c, &p, &l)) { set_error("read error on %s", path); rc = E2I_ERR_IO; break; }
-        int sl = 0;
-        rc = up.push(p, l, &sl);
-        slot_of[c] = sl;
-        // the buffer of chunk c - (kRing - 2) is free once its copy has completed
-        if (rc == E2I_OK && c + 2 >= (uint64_t)kRing) { cudaEventSynchronize(up.ev[slot_of[c + 2 - kRing]]); fs.release(); }
+    if (rc != E2I_OK) return rc;
+    {
+        Uploader up{ctx, &b, n};
+        rc = up.init();
+        const uint64_t n_chunks = (n + kChunk - 1) / kChunk;
+        std::vector<int> slot_of(n_chunks, 0);
+        for (uint64_t c = 0; rc == E2I_OK && c < n_chunks; ++c) {
+            const uint8_t *p;
+            uint64_t l;
+            if (!fs.next(c, &p, &l)) { set_error("read error on %s", path); rc = E2I_ERR_IO; break; }
+            int sl = 0;
+            rc = up.push(p, l, &sl);
+            slot_of[c] = sl;
+            // the buffer of chunk c - (kRing - 2) is free once its copy has completed
+            if (rc == E2I_OK && c + 2 >= (uint64_t)kRing) { cudaEventSynchronize(up.ev[slot_of[c + 2 - kRing]]); fs.release(); }
+        }
+        cudaStreamSynchronize(ctx->copy_stream);
+        if (rc == E2I_OK) rc = index_finish(ctx, b, out, bad_pos); else index_abort(ctx, b);
     }
-    cudaStreamSynchronize(ctx->copy_stream);
-    if (rc == E2I_OK) rc = index_finish(ctx, b, d, out, bad_pos); else index_abort(ctx, b);
-    dfree(ctx, d);
     return rc;
 }
 

@@ -468,14 +468,57 @@ int e2i::format_device(e2i_ctx *ctx, const e2i_call_rec *d_recs, const char *d_l
     return E2I_OK;
 }
 
-// host text buffer of exactly the text's size, filled by one copy
+// ---- page-locked text buffers, cached process-wide ---------------------------------------------
+namespace {
+struct TextBlock { char *p; size_t cap; bool used; };
+std::mutex g_text_mutex;
+std::vector<TextBlock> g_text_blocks;
+constexpr size_t kTextCached = 3;                       // buffers kept when they come back
+}  // namespace
+
+char *e2i::text_alloc(size_t bytes) {
+    std::lock_guard<std::mutex> hold(g_text_mutex);
+    TextBlock *best = nullptr;
+    for (auto &b : g_text_blocks) if (!b.used && b.cap >= bytes && (!best || b.cap < best->cap)) best = &b;
+    if (best) { best->used = true; return best->p; }
+    const size_t cap = std::max<size_t>(bytes + bytes / 8, 1u << 20);
+    void *p = nullptr;
+    if (cudaMallocHost(&p, cap) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    g_text_blocks.push_back({static_cast<char *>(p), cap, true});
+    return static_cast<char *>(p);
+}
+
+bool e2i::text_release(void *p) {
+    std::lock_guard<std::mutex> hold(g_text_mutex);
+    for (size_t i = 0; i < g_text_blocks.size(); ++i) {
+        if (g_text_blocks[i].p != p) continue;
+        g_text_blocks[i].used = false;
+        size_t idle = 0, smallest = i;
+        for (size_t k = 0; k < g_text_blocks.size(); ++k)
+            if (!g_text_blocks[k].used) { ++idle; if (g_text_blocks[k].cap < g_text_blocks[smallest].cap) smallest = k; }
+        if (idle > kTextCached) {                       // keep the large ones
+            cudaFreeHost(g_text_blocks[smallest].p);
+            g_text_blocks.erase(g_text_blocks.begin() + (long)smallest);
+        }
+        return true;
+    }
+    return false;
+}
+
+void e2i::text_cache_trim() {
+    std::lock_guard<std::mutex> hold(g_text_mutex);
+    for (size_t i = g_text_blocks.size(); i-- > 0;)
+        if (!g_text_blocks[i].used) { cudaFreeHost(g_text_blocks[i].p); g_text_blocks.erase(g_text_blocks.begin() + (long)i); }
+}
+
+// host text buffer filled by one copy
 static int text_to_host(e2i_ctx *ctx, char *d_text, uint64_t len, char **snp, size_t *snp_len) {
-    char *buf = static_cast<char *>(std::malloc(len + 1));
+    char *buf = e2i::text_alloc(len + 1);
     if (!buf) { e2i::dfree(ctx, d_text); e2i::set_error("out of host memory (%llu bytes of .snp text)", (unsigned long long)len); return E2I_ERR_MEMORY; }
     if (len) {
         cudaError_t e = cudaMemcpyAsync(buf, d_text, len, cudaMemcpyDeviceToHost, ctx->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-        if (e != cudaSuccess) { std::free(buf); e2i::dfree(ctx, d_text); e2i::set_error("CUDA error copying the .snp text: %s", cudaGetErrorString(e)); return E2I_ERR_CUDA; }
+        if (e != cudaSuccess) { e2i::text_release(buf); e2i::dfree(ctx, d_text); e2i::set_error("CUDA error copying the .snp text: %s", cudaGetErrorString(e)); return E2I_ERR_CUDA; }
         ctx->n_d2h += len;
     }
     e2i::dfree(ctx, d_text);
@@ -657,4 +700,6 @@ extern "C" int e2i_filter_snp(const char *snp, size_t len, int32_t m, int32_t M,
     return E2I_OK;
 }
 
-extern "C" void e2i_buffer_free(void *p) { std::free(p); }
+extern "C" void e2i_buffer_free(void *p) {
+    if (p && !e2i::text_release(p)) std::free(p);
+}

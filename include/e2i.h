@@ -224,8 +224,8 @@ int e2i_snp_format_gpu(e2i_ctx *ctx, const e2i_call_rec *recs, const char *left,
                        const e2i_params *p, int two_samples, uint64_t first_cluster_nr,
                        char **snp, size_t *snp_len, e2i_stats *st);
 /* Phase 4 and the .snp text in one call: find_variants + to_file (ebwt2InDel.cpp:1344-1660, 1149-1330) for the
- * positions [pos_begin, pos_end); the records never leave the device, only the text is copied out (*snp malloc'ed,
- * e2i_buffer_free).  This is what e2i_run / e2i_run_files / e2i_run_device use. */
+ * positions [pos_begin, pos_end); the records never leave the device, only the text is copied out (*snp is a
+ * page-locked buffer owned by the library's cache: give it back with e2i_buffer_free).  This is what e2i_run / e2i_run_files / e2i_run_device use. */
 int e2i_call_snp(e2i_ctx *ctx, const e2i_index *b1, const e2i_index *b2, const e2i_bits *da,
                  const e2i_lcpbits *l, const e2i_params *p, uint64_t pos_begin, uint64_t pos_end,
                  uint64_t first_cluster_nr, char **snp, size_t *snp_len, e2i_stats *st);

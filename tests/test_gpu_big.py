@@ -76,6 +76,7 @@ def test_rank_access_beyond_2_32_positions(gpu_ctx):
     for off in range(0, n, step):
         k = min(step, n - off)
         bwt[off:off + k] = lut[torch.randint(0, 256, (k,), device=dev, generator=g)]
+    torch.cuda.synchronize()              # the library works on its own stream: torch's fill must have finished
     ix = gpu_ctx.index(bwt)
     rng = np.random.default_rng(11)
     pos = np.unique(np.concatenate([rng.integers(0, n + 1, 200_000), [0, 1, n - 1, n, 1 << 32, (1 << 32) - 1, (1 << 32) + 1,
