@@ -509,6 +509,27 @@ __device__ __forceinline__ void bulk_copy_g2s(void *smem, const void *gmem, uint
 // generic-proxy reads of the staging buffer (previous step) are ordered before the async-proxy writes that follow
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// MULTI (position-range sharding): the records of a step are a stretch of at most 32 consecutive entries of the
+// concatenated input -- plain arrays in the frames of the ranks (most of them behind NVLink).  ONE lane fetches the
+// step with bulk copies (one per segment the stretch touches, almost always one: 512 bytes for 32 SMALL records)
+// that complete on an mbarrier of their own, so the records of the next kRecRing steps are in flight while the
+// warp works -- independent of the ordered cp.async groups of the index staging, which capped the LDGSTS prefetch
+// at one step (a round trip to a peer is several steps long).
+constexpr int kRecRing = 4;
+__device__ __forceinline__ void fetch_records_bulk(const FrameInT<true> &in, uint32_t &seg, uint32_t g0, uint32_t g_end, int ru,
+                                                   uint4 *slot, uint64_t *bar) {
+    uint32_t cnt = min(32u, g_end - g0), g = g0;
+    fence_proxy_async();                                  // the warp's reads of this slot (generic proxy) are over
+    mbar_expect_tx(bar, cnt * (uint32_t)ru * 16u);
+    while (cnt) {
+        while (g >= in.seg[seg].start + in.seg[seg].len) ++seg;
+        const uint32_t take = min(cnt, in.seg[seg].start + in.seg[seg].len - g);
+        bulk_copy_g2s(slot + (size_t)(g - g0) * ru, in.seg[seg].ptr + (size_t)(g - in.seg[seg].start) * ru, take * (uint32_t)ru * 16u, bar);
+        g += take;
+        cnt -= take;
+    }
+}
+
 // position of this lane's children inside the step (before[c]) and the step's totals (tot[c])
 __device__ __forceinline__ uint32_t warp_child_slots(const bool (&valid)[4], int lane, uint32_t (&before)[4], uint32_t (&tot)[4]) {
     uint32_t vm = 0;
@@ -529,11 +550,13 @@ __device__ __forceinline__ uint32_t warp_child_slots(const bool (&valid)[4], int
 //   its 4 KB of shared memory by asynchronous copies, overlapped with the bit updates of the step
 //   -> ranks -> children written straight to the run's own region of the output frame.
 // ---------------------------------------------------------------------------------------------
-template <bool TWO, bool IN_S>
+template <bool TWO, bool IN_S, bool MULTI>
 struct NodeSmem {
     static constexpr int RIN = (IN_S ? 1 : 3) * (TWO ? 2 : 1);    // uint4 per input record
+    static constexpr int RING = MULTI && IN_S ? kRecRing : 2;     // steps of records in flight (WIDE records: 2, they are few)
     uint4 stage[kNavWarps][IN_S ? kWarpStage * kBlockU4 : 1];     // staged index blocks, per warp
-    uint4 recbuf[kNavWarps][2 * 32 * RIN];                        // records of the next two steps (ring of 2, slot = lane)
+    uint4 recbuf[kNavWarps][RING * 32 * RIN];                     // records of the next steps (ring, slot = lane)
+    uint64_t rbar[kNavWarps][kRecRing];                           // MULTI: completion barriers of the record ring
     uint32_t need[kNavWarps][IN_S ? 64 : 1];                      // SLOTS staging: block ids wanted by the lanes
     uint64_t mbar[kNavWarps];                                     // completion barrier of the warp's bulk copies
     uint32_t dcnt[kNavWarps][4 * kMaxDest];                       // MULTI: children of the current run per (queue, destination)
@@ -542,8 +565,9 @@ struct NodeSmem {
 template <bool TWO, bool IN_S, bool OUT_S, bool MULTI>
 __global__ void __launch_bounds__(kNavThreads, IN_S ? (TWO ? kPairCtas : kNodeCtas) : 1)
 expand_nodes_kernel(const NavArgs a, const __grid_constant__ FrameInT<MULTI> in, const FrameOut out) {
-    using SM = NodeSmem<TWO, IN_S>;
+    using SM = NodeSmem<TWO, IN_S, MULTI>;
     using W = typename std::conditional<IN_S, uint32_t, uint64_t>::type;
+    constexpr int RING = SM::RING;
     constexpr int RIN = SM::RIN, RSIDE_IN = IN_S ? 1 : 3, RSIDE_OUT = OUT_S ? 1 : 3, ROUT = RSIDE_OUT * (TWO ? 2 : 1);
     constexpr int STAGE = TWO ? kWarpStage / 2 : kWarpStage;               // blocks staged per BWT
     __shared__ __align__(1024) SM sm;
@@ -558,6 +582,11 @@ expand_nodes_kernel(const NavArgs a, const __grid_constant__ FrameInT<MULTI> in,
         if (lane == 0) mbar_init(mbar, 1);
         __syncwarp();
     }
+    uint32_t it = 0;                                      // MULTI: steps this warp has taken (ring slot it % RING, parity of its barrier)
+    if (MULTI) {
+        if (lane == 0) for (int d = 0; d < RING; ++d) mbar_init(&sm.rbar[warp][d], 1);
+        __syncwarp();
+    }
 
     uint32_t st_lcp = 0, st_min = 0, st_rank = 0, st_upd = 0, st_da = 0;
     uint64_t max_size = 0;
@@ -570,22 +599,33 @@ expand_nodes_kernel(const NavArgs a, const __grid_constant__ FrameInT<MULTI> in,
         if (lane == 0) next_run = gridDim.x * kNavWarps + atomicAdd(&a.sweep->ticket, 1u);   // its latency hides behind this run
         const uint32_t g_begin = in.g_lo + run * out.run_cap, g_end = min(in.g_hi, g_begin + out.run_cap);
         Cursor cur;
-        cursor_open(in, cur, g_begin);
-        // the record of the first step
-        if (g_begin + lane < g_end) {
-            cursor_seek(in, cur, g_begin + lane);
-            const uint4 *rec = cursor_record(in, cur, g_begin + lane, RIN);
+        uint32_t seg = 0;                                 // MULTI: segment cursor of the lane that fetches
+        if constexpr (MULTI) {
+            __syncwarp();                                 // every lane is done with the previous run's records
+            if (lane == 0) {
 #pragma unroll
-            for (int k = 0; k < RIN; ++k) cp_async16(recbuf + k, rec + k);
-        }
-        cp_async_commit();
-        if (g_begin + 32 + lane < g_end) {                // ... and of the second
-            cursor_seek(in, cur, g_begin + 32 + lane);
-            const uint4 *rec = cursor_record(in, cur, g_begin + 32 + lane, RIN);
+                for (int d = 0; d < RING; ++d)
+                    if (g_begin + 32u * d < g_end)
+                        fetch_records_bulk(in, seg, g_begin + 32u * d, g_end, RIN, sm.recbuf[warp] + ((it + d) % RING) * (32 * RIN), &sm.rbar[warp][(it + d) % RING]);
+            }
+        } else {
+            cursor_open(in, cur, g_begin);
+            // the record of the first step
+            if (g_begin + lane < g_end) {
+                cursor_seek(in, cur, g_begin + lane);
+                const uint4 *rec = cursor_record(in, cur, g_begin + lane, RIN);
 #pragma unroll
-            for (int k = 0; k < RIN; ++k) cp_async16(recbuf + 32 * RIN + k, rec + k);
+                for (int k = 0; k < RIN; ++k) cp_async16(recbuf + k, rec + k);
+            }
+            cp_async_commit();
+            if (g_begin + 32 + lane < g_end) {            // ... and of the second
+                cursor_seek(in, cur, g_begin + 32 + lane);
+                const uint4 *rec = cursor_record(in, cur, g_begin + 32 + lane, RIN);
+#pragma unroll
+                for (int k = 0; k < RIN; ++k) cp_async16(recbuf + 32 * RIN + k, rec + k);
+            }
+            cp_async_commit();
         }
-        cp_async_commit();
         uint32_t ring = 0;                                // ring slot of the current step
         uint32_t run_cnt[4] = {0, 0, 0, 0};
         uint4 *region[4];                                 // next free slot of the run's region, per queue
@@ -606,11 +646,23 @@ expand_nodes_kernel(const NavArgs a, const __grid_constant__ FrameInT<MULTI> in,
             W s1[5] = {0, 0, 0, 0, 0}, s2[5] = {0, 0, 0, 0, 0};
             // copy groups complete in order: all but the newest (the record of the step after this one) are
             // waited for, so a record has a whole step to arrive -- what remote frames (NVLink) need
-            cp_async_wait_group<1>();                                       // this lane's own record has landed
-            uint4 *rb = recbuf + ring * (32 * RIN);
+            uint4 *rb;
+            if constexpr (MULTI) {
+                mbar_wait(&sm.rbar[warp][it % RING], (it / RING) & 1u);     // the step's records have landed
+                rb = recbuf + (it % RING) * (32 * RIN);
+            } else {
+                cp_async_wait_group<1>();                                   // this lane's own record has landed
+                rb = recbuf + ring * (32 * RIN);
+            }
             if (active) {
                 load_node<IN_S, W>(rb, base1, s1);
                 if (TWO) load_node<IN_S, W>(rb + RSIDE_IN, base2, s2);
+            }
+            if constexpr (MULTI) {                                          // the slot just read takes the step RING ahead
+                __syncwarp();
+                if (lane == 0 && g0 + 32u * RING < g_end)
+                    fetch_records_bulk(in, seg, g0 + 32u * RING, g_end, RIN, sm.recbuf[warp] + (it % RING) * (32 * RIN), &sm.rbar[warp][it % RING]);
+                ++it;
             }
             const uint64_t size1 = (uint64_t)s1[0] + s1[1] + s1[2] + s1[3] + s1[4], size2 = (uint64_t)s2[0] + s2[1] + s2[2] + s2[3] + s2[4];
             max_size = max(max_size, max(size1, size2));
@@ -659,11 +711,13 @@ expand_nodes_kernel(const NavArgs a, const __grid_constant__ FrameInT<MULTI> in,
             }
             cp_async_commit();
             // the record of the step after the next one goes into the ring slot just consumed
-            if (g + 64 < g_end) {
-                cursor_seek(in, cur, g + 64);
-                const uint4 *rec = cursor_record(in, cur, g + 64, RIN);
+            if constexpr (!MULTI) {
+                if (g + 64 < g_end) {
+                    cursor_seek(in, cur, g + 64);
+                    const uint4 *rec = cursor_record(in, cur, g + 64, RIN);
 #pragma unroll
-                for (int k = 0; k < RIN; ++k) cp_async16(rb + k, rec + k);
+                    for (int k = 0; k < RIN; ++k) cp_async16(rb + k, rec + k);
+                }
             }
             cp_async_commit();
             ring ^= 1u;
@@ -742,11 +796,13 @@ expand_nodes_kernel(const NavArgs a, const __grid_constant__ FrameInT<MULTI> in,
 // {first, second} (a pair: 32 bytes).  Same warp-per-run structure.  Leaves are sparse in position
 // space: the two blocks of a leaf are staged per lane (SLOTS).
 // ---------------------------------------------------------------------------------------------
-template <bool TWO>
+template <bool TWO, bool MULTI>
 struct LeafSmem {
     static constexpr int RU = TWO ? 2 : 1;            // uint4 per record
+    static constexpr int RING = MULTI ? kRecRing : 2; // steps of records in flight
     uint4 stage[kNavWarps][64 * kBlockU4];            // two blocks per lane
-    uint4 recbuf[kNavWarps][2 * 32 * RU];             // records of the next two steps (ring of 2, slot = lane)
+    uint4 recbuf[kNavWarps][RING * 32 * RU];          // records of the next steps (ring, slot = lane)
+    uint64_t rbar[kNavWarps][kRecRing];               // MULTI: completion barriers of the record ring
     uint32_t need[kNavWarps][64];
     uint32_t dcnt[kNavWarps][4 * kMaxDest];           // MULTI: children of the current run per (queue, destination)
 };
@@ -764,13 +820,18 @@ __device__ __forceinline__ void rank_slot(const DevIndex &ix, const uint4 *stage
 template <bool TWO, bool MULTI>
 __global__ void __launch_bounds__(kNavThreads, TWO ? kPairCtas : kNodeCtas)
 expand_leaves_kernel(const NavArgs a, const __grid_constant__ FrameInT<MULTI> in, const FrameOut out) {
-    constexpr int RU = TWO ? 2 : 1;
-    __shared__ __align__(1024) LeafSmem<TWO> sm;
+    constexpr int RU = TWO ? 2 : 1, RING = LeafSmem<TWO, MULTI>::RING;
+    __shared__ __align__(1024) LeafSmem<TWO, MULTI> sm;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint4 *stage = sm.stage[warp];
     uint4 *recbuf = sm.recbuf[warp] + lane * RU;
     uint32_t *need = sm.need[warp];
 
+    uint32_t it = 0;                                  // MULTI: steps this warp has taken (see the node sweep)
+    if (MULTI) {
+        if (lane == 0) for (int d = 0; d < RING; ++d) mbar_init(&sm.rbar[warp][d], 1);
+        __syncwarp();
+    }
     unsigned long long st_lcp = 0, st_da = 0;
     uint32_t st_rank = 0;
     // the first run of a warp is its own index (no atomic: small sweeps never touch the ticket), the
@@ -782,21 +843,32 @@ expand_leaves_kernel(const NavArgs a, const __grid_constant__ FrameInT<MULTI> in
         if (lane == 0) next_run = gridDim.x * kNavWarps + atomicAdd(&a.sweep->ticket, 1u);   // its latency hides behind this run
         const uint32_t g_begin = in.g_lo + run * out.run_cap, g_end = min(in.g_hi, g_begin + out.run_cap);
         Cursor cur;
-        cursor_open(in, cur, g_begin);
-        if (g_begin + lane < g_end) {
-            cursor_seek(in, cur, g_begin + lane);
-            const uint4 *rec = cursor_record(in, cur, g_begin + lane, RU);
+        uint32_t seg = 0;
+        if constexpr (MULTI) {
+            __syncwarp();
+            if (lane == 0) {
 #pragma unroll
-            for (int k = 0; k < RU; ++k) cp_async16(recbuf + k, rec + k);
-        }
-        cp_async_commit();
-        if (g_begin + 32 + lane < g_end) {
-            cursor_seek(in, cur, g_begin + 32 + lane);
-            const uint4 *rec = cursor_record(in, cur, g_begin + 32 + lane, RU);
+                for (int d = 0; d < RING; ++d)
+                    if (g_begin + 32u * d < g_end)
+                        fetch_records_bulk(in, seg, g_begin + 32u * d, g_end, RU, sm.recbuf[warp] + ((it + d) % RING) * (32 * RU), &sm.rbar[warp][(it + d) % RING]);
+            }
+        } else {
+            cursor_open(in, cur, g_begin);
+            if (g_begin + lane < g_end) {
+                cursor_seek(in, cur, g_begin + lane);
+                const uint4 *rec = cursor_record(in, cur, g_begin + lane, RU);
 #pragma unroll
-            for (int k = 0; k < RU; ++k) cp_async16(recbuf + 32 * RU + k, rec + k);
+                for (int k = 0; k < RU; ++k) cp_async16(recbuf + k, rec + k);
+            }
+            cp_async_commit();
+            if (g_begin + 32 + lane < g_end) {
+                cursor_seek(in, cur, g_begin + 32 + lane);
+                const uint4 *rec = cursor_record(in, cur, g_begin + 32 + lane, RU);
+#pragma unroll
+                for (int k = 0; k < RU; ++k) cp_async16(recbuf + 32 * RU + k, rec + k);
+            }
+            cp_async_commit();
         }
-        cp_async_commit();
         uint32_t ring = 0;
         uint32_t run_cnt[4] = {0, 0, 0, 0};
         uint32_t dcur[4] = {0, 0, 0, 0};
@@ -811,13 +883,25 @@ expand_leaves_kernel(const NavArgs a, const __grid_constant__ FrameInT<MULTI> in
             const uint32_t g = g0 + lane;
             const bool active = g < g_end;
             uint64_t f1 = 0, s1 = 0, f2 = 0, s2 = 0;
-            cp_async_wait_group<1>();                      // this lane's own record has landed (see the node sweep)
-            uint4 *rb = recbuf + ring * (32 * RU);
+            uint4 *rb;
+            if constexpr (MULTI) {
+                mbar_wait(&sm.rbar[warp][it % RING], (it / RING) & 1u);
+                rb = recbuf + (it % RING) * (32 * RU);
+            } else {
+                cp_async_wait_group<1>();                  // this lane's own record has landed (see the node sweep)
+                rb = recbuf + ring * (32 * RU);
+            }
             if (active) {
                 const ulonglong2 *rec = reinterpret_cast<const ulonglong2 *>(rb);
                 const ulonglong2 x = rec[0];
                 f1 = x.x; s1 = x.y;
                 if (TWO) { const ulonglong2 z = rec[1]; f2 = z.x; s2 = z.y; }
+            }
+            if constexpr (MULTI) {
+                __syncwarp();
+                if (lane == 0 && g0 + 32u * RING < g_end)
+                    fetch_records_bulk(in, seg, g0 + 32u * RING, g_end, RU, sm.recbuf[warp] + (it % RING) * (32 * RU), &sm.rbar[warp][it % RING]);
+                ++it;
             }
             // the (up to) two index blocks this leaf (pair) needs: slots 2 lane, 2 lane + 1 (TWO: one BWT each,
             // the second boundary of a side reads HBM unless it shares the block of the first)
@@ -840,11 +924,13 @@ expand_leaves_kernel(const NavArgs a, const __grid_constant__ FrameInT<MULTI> in
                 }
             }
             cp_async_commit();
-            if (g + 64 < g_end) {                          // the record of the step after the next one
-                cursor_seek(in, cur, g + 64);
-                const uint4 *rec = cursor_record(in, cur, g + 64, RU);
+            if constexpr (!MULTI) {
+                if (g + 64 < g_end) {                      // the record of the step after the next one
+                    cursor_seek(in, cur, g + 64);
+                    const uint4 *rec = cursor_record(in, cur, g + 64, RU);
 #pragma unroll
-                for (int k = 0; k < RU; ++k) cp_async16(rb + k, rec + k);
+                    for (int k = 0; k < RU; ++k) cp_async16(rb + k, rec + k);
+                }
             }
             cp_async_commit();
             ring ^= 1u;
@@ -983,7 +1069,7 @@ frame_index_kernel(const uint32_t *__restrict__ cnt, const uint32_t *__restrict_
         P[j] = (uint32_t)p;
         // every multiple of 256 inside [p, p + c) starts a hint
         for (unsigned long long t = (p + 255) >> 8; (t << 8) < p + c; ++t) hint[t] = j;
-        if (D > 1) {                                      // slots of the region taken by the destinations before this one
+        if (off) {                                        // ranged sweeps: slots of the region taken by the destinations before this one
             const uint32_t h = j / (4 * K), ck = j - h * 4 * K;
             uint32_t o = 0;
             for (uint32_t hh = 0; hh < h; ++hh) o += cnt[(size_t)hh * 4 * K + ck];
@@ -1054,7 +1140,7 @@ struct Frame {
 struct FrameLayout {
     uint32_t K, run_cap, D;
     size_t rec_bytes, cnt_off, gsum_off, p_off, off_off, hint_off, total_bytes;
-    FrameLayout(uint64_t n_in, uint32_t run, int ru_out, uint32_t dests = 1) {
+    FrameLayout(uint64_t n_in, uint32_t run, int ru_out, uint32_t dests = 1, bool ranged = false) {
         auto pad = [](size_t b) { return (b + 255) & ~(size_t)255; };
         run_cap = run;
         D = dests;
@@ -1065,7 +1151,7 @@ struct FrameLayout {
         gsum_off = cnt_off + pad(ne * 4);
         p_off = gsum_off + pad((ne / 256 + 1) * 4);
         off_off = p_off + pad((ne + 1) * 4);
-        hint_off = off_off + pad(D > 1 ? ne * 4 : 0);
+        hint_off = off_off + pad(D > 1 || ranged ? ne * 4 : 0);       // `off`: only the ranged sweeps compact their frames
         total_bytes = hint_off + pad(((size_t)4 * K * run_cap / 256 + 2) * 4);
     }
 };
@@ -1565,7 +1651,7 @@ static int navigate_impl(e2i_ctx *ctx, const e2i_index *b1, const e2i_index *b2,
             if (n_in == 0) continue;                      // nothing for me on this level (I still keep the barriers company)
             const int ru_out = leaves ? (two ? 2 : 1) : node_rec_u4(out_small, two);
             const uint32_t run_len = (uint32_t)std::min<uint64_t>(kMaxRun, std::max<uint64_t>(32, (n_in / ((uint64_t)resident_warps * (leaves ? 1 : 4)) + 31) / 32 * 32));
-            const FrameLayout lay(n_in, run_len, ru_out, (uint32_t)world);
+            const FrameLayout lay(n_in, run_len, ru_out, (uint32_t)world, true);
             // the gappy frame is a temporary on top of THIS level's records; the compacted children go to the other end
             const int side_tmp = level & 1, side_out = (level + 1) & 1;
             char *mem = static_cast<char *>(ctx->arena.alloc(side_tmp, lay.total_bytes));
@@ -1717,7 +1803,8 @@ extern "C" int e2i_navigate(e2i_ctx *ctx, const e2i_index *b1, const e2i_index *
 extern "C" int e2i_navigate_ranged(e2i_ctx *ctx, e2i_comm *comm, const e2i_index *b1, const e2i_index *b2, const e2i_params *p,
                                    e2i_lcpbits **out, e2i_bits **da_out, e2i_stats *st) {
     if (!comm || comm->world < 1 || comm->world > kMaxDest) { set_error("e2i_navigate_ranged: bad communicator"); return E2I_ERR_ARG; }
-    if (comm->world == 1) return navigate_impl(ctx, b1, b2, p, 0, 1, nullptr, out, da_out, st);
+    // one rank: the plain traversal (E2I_RANGED_FORCE=1 keeps the ranged machinery, to measure what it costs by itself)
+    if (comm->world == 1 && !std::getenv("E2I_RANGED_FORCE")) return navigate_impl(ctx, b1, b2, p, 0, 1, nullptr, out, da_out, st);
     return navigate_impl(ctx, b1, b2, p, comm->rank, comm->world, comm, out, da_out, st);
 }
 
