@@ -74,7 +74,7 @@ SYMBOLS = (
     "e2i_fl_batch", "e2i_rank_batch_device", "e2i_da_load", "e2i_da_load_device", "e2i_bits_fetch",
     "e2i_bits_size", "e2i_bits_free", "e2i_navigate", "e2i_navigate_shard", "e2i_lcpbits_fetch",
     "e2i_lcpbits_device", "e2i_bits_device", "e2i_lcpbits_free", "e2i_call", "e2i_calls_count",
-    "e2i_calls_fetch", "e2i_calls_view", "e2i_calls_free", "e2i_snp_format", "e2i_snp_format_gpu", "e2i_call_snp", "e2i_snp_count", "e2i_filter_snp", "e2i_distance", "e2i_buffer_free", "e2i_run",
+    "e2i_calls_fetch", "e2i_calls_view", "e2i_calls_free", "e2i_snp_format", "e2i_snp_format_gpu", "e2i_call_snp", "e2i_call_device", "e2i_calls_clusters", "e2i_calls_snp", "e2i_calls_snp_device", "e2i_device_free", "e2i_snp_count", "e2i_filter_snp", "e2i_distance", "e2i_buffer_free", "e2i_run",
     "e2i_run_device", "e2i_run_files", "e2i_index_build_file", "e2i_da_load_file", "e2i_index_save", "e2i_index_load", "e2i_ebwt_build", "e2i_run_multi", "e2i_enable_peers", "e2i_or_allreduce",
     "e2i_navigate_ranged", "e2i_comm_local", "e2i_comm_shm", "e2i_comm_barrier", "e2i_comm_free",
 )
@@ -141,6 +141,11 @@ def lib():
         "e2i_snp_format": (C.c_int, [vp, vp, vp, u64, PP, C.c_int, u64, C.POINTER(vp), C.POINTER(C.c_size_t), PS]),
         "e2i_snp_format_gpu": (C.c_int, [vp, vp, vp, vp, u64, PP, C.c_int, u64, C.POINTER(vp), C.POINTER(C.c_size_t), PS]),
         "e2i_call_snp": (C.c_int, [vp, vp, vp, vp, vp, PP, u64, u64, u64, C.POINTER(vp), C.POINTER(C.c_size_t), PS]),
+        "e2i_call_device": (C.c_int, [vp, vp, vp, vp, vp, PP, u64, u64, C.POINTER(vp), PS]),
+        "e2i_calls_clusters": (C.c_int, [vp, PP, C.POINTER(u64)]),
+        "e2i_calls_snp": (C.c_int, [vp, PP, u64, C.POINTER(vp), C.POINTER(C.c_size_t), PS]),
+        "e2i_calls_snp_device": (C.c_int, [vp, PP, u64, C.POINTER(vp), C.POINTER(u64), PS]),
+        "e2i_device_free": (None, [vp, vp]),
         "e2i_snp_count": (C.c_int, [vp, vp, vp, u64, PP, C.c_int, C.POINTER(u64)]),
         "e2i_filter_snp": (C.c_int, [C.c_char_p, C.c_size_t, C.c_int32, C.c_int32, C.POINTER(vp), C.POINTER(C.c_size_t)]),
         "e2i_distance": (None, [C.c_char_p, C.c_char_p, C.c_int32, C.c_int32, C.POINTER(C.c_int32)]),
@@ -366,6 +371,16 @@ class Context:
         text = SnpText(out, ln.value)
         return (text.tobytes() if copy else text), st
 
+    def call_device(self, b1, b2, da, lcp, params: Params | None = None, pos_begin: int = 0,
+                    pos_end: int = 2 ** 64 - 1, stats: Stats | None = None) -> "DeviceCalls":
+        """Phase 4 on [pos_begin, pos_end) with the records left in HBM (e2i_call_device)."""
+        p = params or default_params()
+        st = stats if stats is not None else Stats()
+        ch = C.c_void_p()
+        _check(lib().e2i_call_device(self.h, b1.h, b2.h if b2 else None, da.h if da else None, lcp.h, C.byref(p),
+                                     pos_begin, pos_end, C.byref(ch), C.byref(st)))
+        return DeviceCalls(self, ch, p, st)
+
     def snp_format(self, recs, left, right, params: Params, two_samples: bool, first_cluster_nr: int = 1,
                    stats: Stats | None = None):
         """snp_format() by the device formatter (e2i_snp_format_gpu): same arguments, same text."""
@@ -514,6 +529,46 @@ def snp_format(recs: np.ndarray, left: np.ndarray, right: np.ndarray, params: Pa
                                 1 if two_samples else 0, first_cluster_nr, C.byref(out), C.byref(ln), C.byref(st)))
     text = SnpText(out, ln.value)
     return (text.tobytes() if copy else text), st
+
+
+class DeviceCalls:
+    """Call records of one position range, resident in HBM (Context.call_device)."""
+
+    def __init__(self, ctx: Context, h, params: Params, stats: Stats):
+        self.ctx, self.h, self.params, self.stats = ctx, h, params, stats
+
+    def __len__(self):
+        return int(lib().e2i_calls_count(self.h))
+
+    def clusters(self) -> int:
+        """Cluster numbers the range consumes (device pass, no text)."""
+        out = C.c_uint64(0)
+        _check(lib().e2i_calls_clusters(self.h, C.byref(self.params), C.byref(out)))
+        return int(out.value)
+
+    def snp(self, first_cluster_nr: int = 1, copy: bool = True):
+        out, ln = C.c_void_p(), C.c_size_t()
+        _check(lib().e2i_calls_snp(self.h, C.byref(self.params), first_cluster_nr, C.byref(out), C.byref(ln), C.byref(self.stats)))
+        text = SnpText(out, ln.value)
+        return text.tobytes() if copy else text
+
+    def snp_device(self, first_cluster_nr: int = 1):
+        """(device pointer, length) of the text, left in device memory; release with free_device()."""
+        out, ln = C.c_void_p(), C.c_uint64(0)
+        _check(lib().e2i_calls_snp_device(self.h, C.byref(self.params), first_cluster_nr, C.byref(out), C.byref(ln), C.byref(self.stats)))
+        return out, int(ln.value)
+
+    def free_device(self, ptr):
+        if ptr and self.ctx.h:
+            lib().e2i_device_free(self.ctx.h, ptr)
+
+    def close(self):
+        if getattr(self, "h", None) and _lib is not None:
+            _lib.e2i_calls_free(self.h)
+        self.h = None
+
+    def __del__(self):
+        self.close()
 
 
 class Index:

@@ -450,6 +450,8 @@ static int build_da_rank(e2i_ctx *ctx, e2i_bits *da) {
     return E2I_OK;
 }
 
+extern "C" void e2i_calls_free(e2i_calls *c);
+
 // Where the text goes when phase 4 formats its records on the device (e2i_call_snp): a malloc'ed host buffer that
 // grows batch by batch; the records themselves then never leave the device.
 struct TextSink {
@@ -461,7 +463,7 @@ struct TextSink {
 
 static int call_impl(e2i_ctx *ctx, const e2i_index *b1, const e2i_index *b2, const e2i_bits *da,
                      const e2i_lcpbits *l, const e2i_params *p, uint64_t pos_begin, uint64_t pos_end,
-                     e2i_calls **out, TextSink *sink, e2i_stats *st) {
+                     e2i_calls **out, TextSink *sink, bool keep_device, e2i_stats *st) {
     if (!ctx || !b1 || !l || !p || (!out && !sink) || !st) { set_error("e2i_call: null argument"); return E2I_ERR_ARG; }
     if (b2 && !da) { set_error("e2i_call: two BWTs need the document array produced by e2i_navigate"); return E2I_ERR_ARG; }
     if (p->k_left < 1 || p->k_left > 255 || p->k_right < 1 || p->k_right > 255) { set_error("e2i_call: k_left and k_right must be in [1,255]"); return E2I_ERR_ARG; }
@@ -479,6 +481,7 @@ static int call_impl(e2i_ctx *ctx, const e2i_index *b1, const e2i_index *b2, con
     calls->ctx = ctx;
     calls->k_left = p->k_left;
     calls->k_right = p->k_right;
+    calls->two_samples = mode != 1;
 
     CallArgs a{};
     a.ix1 = b1->dev();
@@ -508,7 +511,7 @@ static int call_impl(e2i_ctx *ctx, const e2i_index *b1, const e2i_index *b2, con
     const uint64_t cand_cap = (ctx->arena_bytes / 4) / sizeof(Candidate);
     char *const obase = abase + 8192 + ((cand_cap * sizeof(Candidate) + 255) & ~(size_t)255);
     const uint64_t batch_cap = (uint64_t)((abase + ctx->arena_bytes - obase) / out_per);
-    auto fail = [&](int rc) { delete calls; return rc; };
+    auto fail = [&](int rc) { e2i_calls_free(calls); return rc; };
 #define TRYF(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { set_error("CUDA error %s at %s:%d: %s", cudaGetErrorName(_e), __FILE__, __LINE__, cudaGetErrorString(_e)); return fail(E2I_ERR_CUDA); } } while (0)
     TRYF(cudaMemsetAsync(rank_q, 0, 64 * 8, s));
     TRYF(cudaEventRecord(ctx->ev[4], s));
@@ -555,7 +558,24 @@ static int call_impl(e2i_ctx *ctx, const e2i_index *b1, const e2i_index *b2, con
     // consensus walks + right contexts + record packing for the candidates gathered so far
     uint64_t n_acc = 0;
     auto flush = [&]() -> int {
-        if (!sink) E2I_TRY(ensure(n_out + n_acc));
+        if (!sink && !keep_device) E2I_TRY(ensure(n_out + n_acc));
+        if (keep_device && n_out + n_acc > calls->d_cap) {           // device arrays, grown by moving (one batch is the rule)
+            const uint64_t ncap = std::max<uint64_t>(n_out + n_acc, 2 * calls->d_cap);
+            const size_t o_left = (ncap * sizeof(e2i_call_rec) + 255) & ~(size_t)255, o_right = o_left + ((ncap * 8 * kl + 255) & ~(size_t)255);
+            char *nb = nullptr;
+            if (dmalloc(ctx, &nb, o_right + ncap * kr + 256) != cudaSuccess) { cudaGetLastError(); set_error("e2i_call_device: out of device memory for %llu records", (unsigned long long)ncap); return E2I_ERR_MEMORY; }
+            if (n_out) {
+                E2I_CUDA_TRY(cudaMemcpyAsync(nb, calls->d_recs, n_out * sizeof(e2i_call_rec), cudaMemcpyDeviceToDevice, s));
+                E2I_CUDA_TRY(cudaMemcpyAsync(nb + o_left, calls->d_left, n_out * 8 * kl, cudaMemcpyDeviceToDevice, s));
+                E2I_CUDA_TRY(cudaMemcpyAsync(nb + o_right, calls->d_right, n_out * kr, cudaMemcpyDeviceToDevice, s));
+            }
+            dfree(ctx, calls->d_block);
+            calls->d_block = nb;
+            calls->d_recs = reinterpret_cast<e2i_call_rec *>(nb);
+            calls->d_left = nb + o_left;
+            calls->d_right = nb + o_right;
+            calls->d_cap = ncap;
+        }
         for (uint64_t c0 = 0; c0 < n_acc; c0 += batch_cap) {
             const uint64_t nb = std::min<uint64_t>(batch_cap, n_acc - c0);
             char *o = obase;
@@ -601,6 +621,14 @@ static int call_impl(e2i_ctx *ctx, const e2i_index *b1, const e2i_index *b2, con
                 sink->clusters += cl;
                 sink->events += ev;
                 sink->ms += now_ms() - t0;
+                n_out += nb;
+                continue;
+            }
+            if (keep_device) {                            // the records stay in HBM for e2i_calls_snp
+                E2I_CUDA_TRY(cudaMemcpyAsync(calls->d_recs + n_out, d_recs, nb * sizeof(e2i_call_rec), cudaMemcpyDeviceToDevice, s));
+                E2I_CUDA_TRY(cudaMemcpyAsync(calls->d_left + n_out * 8 * kl, d_left, nb * 8 * kl, cudaMemcpyDeviceToDevice, s));
+                E2I_CUDA_TRY(cudaMemcpyAsync(calls->d_right + n_out * kr, d_right, nb * kr, cudaMemcpyDeviceToDevice, s));
+                E2I_CUDA_TRY(cudaStreamSynchronize(s));
                 n_out += nb;
                 continue;
             }
@@ -693,7 +721,69 @@ extern "C" int e2i_call(e2i_ctx *ctx, const e2i_index *b1, const e2i_index *b2, 
                         const e2i_lcpbits *l, const e2i_params *p, uint64_t pos_begin, uint64_t pos_end,
                         e2i_calls **out, e2i_stats *st) {
     if (!out) { set_error("e2i_call: null argument"); return E2I_ERR_ARG; }
-    return call_impl(ctx, b1, b2, da, l, p, pos_begin, pos_end, out, nullptr, st);
+    return call_impl(ctx, b1, b2, da, l, p, pos_begin, pos_end, out, nullptr, false, st);
+}
+
+extern "C" int e2i_call_device(e2i_ctx *ctx, const e2i_index *b1, const e2i_index *b2, const e2i_bits *da,
+                               const e2i_lcpbits *l, const e2i_params *p, uint64_t pos_begin, uint64_t pos_end,
+                               e2i_calls **out, e2i_stats *st) {
+    if (!out) { set_error("e2i_call_device: null argument"); return E2I_ERR_ARG; }
+    return call_impl(ctx, b1, b2, da, l, p, pos_begin, pos_end, out, nullptr, true, st);
+}
+
+static int calls_format(const e2i_calls *c, const e2i_params *p, uint64_t first, bool want_text, char **d_text, uint64_t *len,
+                        uint64_t *clusters, uint64_t *events) {
+    if (!c || !p) { set_error("e2i_calls_snp: null argument"); return E2I_ERR_ARG; }
+    if (c->n && !c->d_recs) { set_error("e2i_calls_snp: the records are not on the device (use e2i_call_device)"); return E2I_ERR_ARG; }
+    if (p->k_left != c->k_left || p->k_right != c->k_right) { set_error("e2i_calls_snp: k_left / k_right differ from the ones the records were made with"); return E2I_ERR_ARG; }
+    E2I_CUDA_TRY(cudaSetDevice(c->ctx->device));
+    return format_device(c->ctx, c->d_recs, c->d_left, c->d_right, c->n, p, c->two_samples, first ? first : 1, d_text, len, clusters, events, want_text);
+}
+
+extern "C" int e2i_calls_clusters(const e2i_calls *c, const e2i_params *p, uint64_t *clusters) {
+    if (!clusters) { set_error("e2i_calls_clusters: null argument"); return E2I_ERR_ARG; }
+    char *d_text = nullptr;
+    uint64_t len = 0, ev = 0;
+    return calls_format(c, p, 1, false, &d_text, &len, clusters, &ev);
+}
+
+extern "C" int e2i_calls_snp_device(const e2i_calls *c, const e2i_params *p, uint64_t first_cluster_nr, void **dev_text, uint64_t *len,
+                                    e2i_stats *st) {
+    if (!c || !dev_text || !len) { set_error("e2i_calls_snp_device: null argument"); return E2I_ERR_ARG; }
+    char *d_text = nullptr;
+    uint64_t cl = 0, ev = 0;
+    Accounting acct(c->ctx, st);
+    E2I_TRY(calls_format(c, p, first_cluster_nr, true, &d_text, len, &cl, &ev));
+    E2I_CUDA_TRY(cudaStreamSynchronize(c->ctx->stream));       // the caller reads the text on a stream of its own
+    *dev_text = d_text;
+    if (st) { st->events += ev; st->clusters_out += cl; }
+    return E2I_OK;
+}
+
+extern "C" void e2i_device_free(e2i_ctx *ctx, void *p) {
+    if (ctx && p) { cudaSetDevice(ctx->device); dfree(ctx, p); }
+}
+
+extern "C" int e2i_calls_snp(const e2i_calls *c, const e2i_params *p, uint64_t first_cluster_nr, char **snp, size_t *snp_len, e2i_stats *st) {
+    if (!snp || !snp_len) { set_error("e2i_calls_snp: null argument"); return E2I_ERR_ARG; }
+    void *d_text = nullptr;
+    uint64_t len = 0;
+    E2I_TRY(e2i_calls_snp_device(c, p, first_cluster_nr, &d_text, &len, st));
+    e2i_ctx *ctx = c->ctx;
+    char *buf = text_alloc(len + 1);
+    if (!buf) { dfree(ctx, d_text); set_error("e2i_calls_snp: cannot page-lock %llu bytes for the text", (unsigned long long)len); return E2I_ERR_MEMORY; }
+    if (len) {
+        cudaError_t e = cudaMemcpyAsync(buf, d_text, len, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) { text_release(buf); dfree(ctx, d_text); set_error("CUDA error copying the .snp text: %s", cudaGetErrorString(e)); return E2I_ERR_CUDA; }
+        ctx->n_d2h += len;
+        if (st) st->d2h_bytes += len;
+    }
+    dfree(ctx, d_text);
+    buf[len] = 0;
+    *snp = buf;
+    *snp_len = (size_t)len;
+    return E2I_OK;
 }
 
 extern "C" int e2i_call_snp(e2i_ctx *ctx, const e2i_index *b1, const e2i_index *b2, const e2i_bits *da,
@@ -702,7 +792,7 @@ extern "C" int e2i_call_snp(e2i_ctx *ctx, const e2i_index *b1, const e2i_index *
     if (!snp || !snp_len) { set_error("e2i_call_snp: null argument"); return E2I_ERR_ARG; }
     TextSink sink;
     sink.next_cluster = first_cluster_nr ? first_cluster_nr : 1;
-    const int rc = call_impl(ctx, b1, b2, da, l, p, pos_begin, pos_end, nullptr, &sink, st);
+    const int rc = call_impl(ctx, b1, b2, da, l, p, pos_begin, pos_end, nullptr, &sink, false, st);
     if (rc != E2I_OK) { if (sink.buf) text_release(sink.buf); return rc; }
     if (!sink.buf) sink.buf = text_alloc(1);
     if (!sink.buf) { set_error("e2i_call_snp: out of host memory"); return E2I_ERR_MEMORY; }
@@ -717,6 +807,7 @@ extern "C" uint64_t e2i_calls_count(const e2i_calls *c) { return c ? c->n : 0; }
 extern "C" int e2i_calls_fetch(const e2i_calls *c, e2i_call_rec *host_recs, char *host_left, char *host_right,
                                uint64_t cap, uint64_t *n) {
     if (!c || !n) { set_error("e2i_calls_fetch: null argument"); return E2I_ERR_ARG; }
+    if (c->n && !c->recs) { set_error("e2i_calls_fetch: the records are on the device (e2i_call_device): format them with e2i_calls_snp"); return E2I_ERR_ARG; }
     if (c->gen != c->ctx->pinned_gen) { set_error("e2i_calls_fetch: stale handle (a later e2i_call on this context reused the staging buffer)"); return E2I_ERR_ARG; }
     const uint64_t k = std::min<uint64_t>(cap, c->n);
     if (k && (!host_recs || !host_left || !host_right)) { set_error("e2i_calls_fetch: null buffer"); return E2I_ERR_ARG; }
@@ -731,9 +822,13 @@ extern "C" int e2i_calls_fetch(const e2i_calls *c, e2i_call_rec *host_recs, char
 
 extern "C" int e2i_calls_view(const e2i_calls *c, const e2i_call_rec **recs, const char **left, const char **right, uint64_t *n) {
     if (!c || !recs || !left || !right || !n) { set_error("e2i_calls_view: null argument"); return E2I_ERR_ARG; }
+    if (c->n && !c->recs) { set_error("e2i_calls_view: the records are on the device (e2i_call_device): format them with e2i_calls_snp"); return E2I_ERR_ARG; }
     if (c->gen != c->ctx->pinned_gen) { set_error("e2i_calls_view: stale handle (a later e2i_call on this context reused the staging buffer)"); return E2I_ERR_ARG; }
     *recs = c->recs; *left = c->left; *right = c->right; *n = c->n;
     return E2I_OK;
 }
 
-extern "C" void e2i_calls_free(e2i_calls *c) { delete c; }
+extern "C" void e2i_calls_free(e2i_calls *c) {
+    if (c && c->d_block) { cudaSetDevice(c->ctx->device); dfree(c->ctx, c->d_block); }
+    delete c;
+}

@@ -163,7 +163,7 @@ void text_cache_trim();                  // frees the cached buffers that are no
 // .snp text of call records that are still in device memory (snp_format.cpp); *d_text is released with dfree
 int format_device(e2i_ctx *ctx, const e2i_call_rec *d_recs, const char *d_left, const char *d_right, uint64_t n_recs,
                   const e2i_params *p, int two_samples, uint64_t first_cluster_nr,
-                  char **d_text, uint64_t *text_len, uint64_t *clusters, uint64_t *events);
+                  char **d_text, uint64_t *text_len, uint64_t *clusters, uint64_t *events, bool want_text = true);
 struct Accounting {            // adds what a call launched / copied to its e2i_stats on scope exit
     e2i_ctx *ctx; e2i_stats *st; uint64_t l0, h0, d0;
     Accounting(e2i_ctx *c, e2i_stats *s) : ctx(c), st(s), l0(c->n_launch), h0(c->n_h2d), d0(c->n_d2h) {}
@@ -214,10 +214,16 @@ struct e2i_lcpbits {
 // bounce): a handle is valid until the next e2i_call on the same context (checked by `gen`).
 struct e2i_calls {
     e2i_ctx *ctx = nullptr;
-    e2i_call_rec *recs = nullptr;
+    e2i_call_rec *recs = nullptr;                       // page-locked host arrays (e2i_call) ...
     char *left = nullptr, *right = nullptr;
     uint64_t n = 0, gen = 0;
     int k_left = 0, k_right = 0;
+    // ... or device arrays (e2i_call_device): [recs | left | right] in one pool block with room for d_cap records
+    char *d_block = nullptr;
+    e2i_call_rec *d_recs = nullptr;
+    char *d_left = nullptr, *d_right = nullptr;
+    uint64_t d_cap = 0;
+    int two_samples = 0;
 };
 
 #ifdef __CUDACC__

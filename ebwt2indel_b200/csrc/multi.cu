@@ -153,7 +153,7 @@ struct MultiShared {
     std::vector<e2i_bits *> da_nav, da;
     // call + format
     std::vector<uint64_t> clusters;
-    std::vector<char *> text;
+    char *final_text = nullptr;          // the whole .snp text (page-locked, text_alloc): every rank copies its piece in
     std::vector<size_t> text_len;
     std::vector<e2i_stats> st;
     bool any_failed() const { for (int r : rc) if (r != E2I_OK) return true; return false; }
@@ -275,7 +275,6 @@ extern "C" int e2i_run_multi(const int *devices, int n_devices, const uint8_t *h
     sh.da_nav.assign(world, nullptr);
     sh.da.assign(world, nullptr);
     sh.clusters.assign(world, 0);
-    sh.text.assign(world, nullptr);
     sh.text_len.assign(world, 0);
     sh.st.resize(world);
     for (auto &s : sh.st) std::memset(&s, 0, sizeof s);
@@ -396,24 +395,38 @@ extern "C" int e2i_run_multi(const int *devices, int n_devices, const uint8_t *h
         bar.wait();                                      // the combined vectors are everywhere
         // ---- 4. phase 4 on this GPU's suffix-array range, text per range ----
         e2i_calls *calls = nullptr;
-        const e2i_call_rec *recs = nullptr;
-        const char *left = nullptr, *right = nullptr;
-        uint64_t n_recs = 0;
-        const int two_samples = (two || host_da) ? 1 : 0;
         if (!sh.any_failed()) {
             const uint64_t lo = (uint64_t)((unsigned __int128)n * rank / world), hi = (uint64_t)((unsigned __int128)n * (rank + 1) / world);
-            STEP(e2i_call(ctx, sh.ix[0][rank], two ? sh.ix[1][rank] : nullptr, two ? sh.da_nav[rank] : sh.da[rank], sh.lcp[rank], p, lo, hi, &calls, &st));
-            STEP(e2i_calls_view(calls, &recs, &left, &right, &n_recs));
-            STEP(e2i_snp_count(recs, left, right, n_recs, p, two_samples, &sh.clusters[rank]));
+            // the records stay in HBM: counted and printed there once the first cluster number of the range is known
+            STEP(e2i_call_device(ctx, sh.ix[0][rank], two ? sh.ix[1][rank] : nullptr, two ? sh.da_nav[rank] : sh.da[rank], sh.lcp[rank], p, lo, hi, &calls, &st));
+            STEP(e2i_calls_clusters(calls, p, &sh.clusters[rank]));
         }
         bar.wait();                                      // every range knows how many cluster numbers it consumes
+        void *d_text = nullptr;
         if (!sh.any_failed()) {
-            uint64_t first = 1;
+            uint64_t first = 1, len = 0;
             for (int r = 0; r < rank; ++r) first += sh.clusters[r];
             const auto t0 = std::chrono::steady_clock::now();
-            STEP(e2i_snp_format(recs, left, right, n_recs, p, two_samples, first, &sh.text[rank], &sh.text_len[rank], &st));
+            STEP(e2i_calls_snp_device(calls, p, first, &d_text, &len, &st));
+            sh.text_len[rank] = (size_t)len;
             st.ms_format += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
         }
+        bar.wait();                                      // every range knows the length of its text
+        if (rank == 0 && !sh.any_failed()) {             // one page-locked buffer for the whole text
+            size_t total = 0;
+            for (int r = 0; r < world; ++r) total += sh.text_len[r];
+            sh.final_text = text_alloc(total + 1);
+            if (!sh.final_text) { set_error("cannot page-lock %llu bytes for the .snp text", (unsigned long long)total); fail(E2I_ERR_MEMORY); }
+            else sh.final_text[total] = 0;
+        }
+        bar.wait();
+        if (!sh.any_failed() && sh.text_len[rank]) {     // every GPU copies its piece to its place
+            size_t off = 0;
+            for (int r = 0; r < rank; ++r) off += sh.text_len[r];
+            CUDA_STEP(cudaMemcpy(sh.final_text + off, d_text, sh.text_len[rank], cudaMemcpyDeviceToHost));
+            st.d2h_bytes += sh.text_len[rank];
+        }
+        e2i_device_free(ctx, d_text);
         e2i_calls_free(calls);
         e2i_lcpbits_free(sh.lcp[rank]);
         e2i_bits_free(sh.da_nav[rank]);
@@ -435,17 +448,11 @@ extern "C" int e2i_run_multi(const int *devices, int n_devices, const uint8_t *h
     if (rc == E2I_OK) {
         size_t total = 0;
         for (int r = 0; r < world; ++r) total += sh.text_len[r];
-        char *buf = static_cast<char *>(std::malloc(total + 1));
-        if (!buf) { set_error("e2i_run_multi: out of host memory"); rc = E2I_ERR_MEMORY; }
-        else {
-            size_t off = 0;
-            for (int r = 0; r < world; ++r) { if (sh.text_len[r]) std::memcpy(buf + off, sh.text[r], sh.text_len[r]); off += sh.text_len[r]; }
-            buf[total] = 0;
-            *snp = buf;
-            *snp_len = total;
-        }
+        *snp = sh.final_text;
+        *snp_len = total;
+    } else if (sh.final_text) {
+        text_release(sh.final_text);
     }
-    for (int r = 0; r < world; ++r) e2i_buffer_free(sh.text[r]);
     // counters: every unit of work is done by exactly one rank -> sums; phase times -> max over ranks
     e2i_stats &o = *st_out;
     for (int r = 0; r < world; ++r) {

@@ -1360,6 +1360,8 @@ static int navigate_impl(e2i_ctx *ctx, const e2i_index *b1, const e2i_index *b2,
     cudaStream_t s = ctx->stream;
     const bool two = b2 != nullptr;
     const uint64_t n = b1->n + (two ? b2->n : 0);
+    const bool dbg_time = std::getenv("E2I_DEBUG") != nullptr;
+    const double t_enter = now_ms();
 
     e2i_lcpbits *l = new e2i_lcpbits();
     l->ctx = ctx;
@@ -1733,6 +1735,8 @@ static int navigate_impl(e2i_ctx *ctx, const e2i_index *b1, const e2i_index *b2,
     };
 
     unsigned long long tot[C_NCOUNTERS];
+    double t_setup = 0;
+    if (dbg_time) { cudaStreamSynchronize(s); t_setup = now_ms() - t_enter; }
     // ---- Phase 2: leaves ----
     TRYF(cudaMemsetAsync(stripes, 0, stripe_bytes, s));
     TRYF(cudaEventRecord(ctx->ev[0], s));
@@ -1778,6 +1782,7 @@ static int navigate_impl(e2i_ctx *ctx, const e2i_index *b1, const e2i_index *b2,
         std::fprintf(stderr, "[e2i] leaves: %llu sweeps, alloc %.2f ms, sync %.2f ms (max %.2f), kernels %.2f + index %.2f ms | nodes: %llu sweeps, alloc %.2f ms, sync %.2f ms (max %.2f), kernels %.2f + index %.2f ms\n",
                      (unsigned long long)sl.sweeps, sl.ms_alloc, sl.ms_sync, sl.ms_max_sync, sl.ms_sweep, sl.ms_index,
                      (unsigned long long)sn.sweeps, sn.ms_alloc, sn.ms_sync, sn.ms_max_sync, sn.ms_sweep, sn.ms_index);
+    if (dbg_time) std::fprintf(stderr, "[e2i] navigate: setup (bit vectors, arena) %.1f ms, %.1f ms of host wall time in all\n", t_setup, now_ms() - t_enter);
     float ms = 0;
     TRYF(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
     st->ms_leaves += ms;

@@ -415,7 +415,7 @@ uint64_t count_range(const e2i_call_rec *recs, const char *left, const char *rig
 // text in device memory (*d_text, to be released with dfree; nullptr when the records print nothing).
 int e2i::format_device(e2i_ctx *ctx, const e2i_call_rec *d_recs, const char *d_left, const char *d_right, uint64_t n_recs,
                        const e2i_params *p, int two_samples, uint64_t first_cluster_nr,
-                       char **d_text, uint64_t *text_len, uint64_t *clusters, uint64_t *events) {
+                       char **d_text, uint64_t *text_len, uint64_t *clusters, uint64_t *events, bool want_text) {
     *d_text = nullptr;
     *text_len = *clusters = *events = 0;
     if (n_recs == 0) return E2I_OK;
@@ -451,7 +451,7 @@ int e2i::format_device(e2i_ctx *ctx, const e2i_call_rec *d_recs, const char *d_l
     TRYF(cudaStreamSynchronize(s));
     ctx->n_launch += 5;
     ctx->n_d2h += sizeof h;
-    if (h[0]) {
+    if (h[0] && want_text) {
         char *text = nullptr;
         if (dmalloc(ctx, &text, h[0]) != cudaSuccess) { cudaGetLastError(); set_error("format_device: out of device memory (%llu bytes of text)", h[0]); return fail(E2I_ERR_MEMORY); }
         snp_write_kernel<<<grid, kFmtThreads, 0, s>>>(d_recs, d_left, d_right, n, *p, two_samples, cpre, first_cluster_nr, off, len, text);

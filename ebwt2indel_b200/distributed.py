@@ -145,12 +145,42 @@ def format_sharded(api, recs, left, right, params, two_samples: bool, rank: int,
     return gather_bytes(txt.view(), rank, world, device, group), int(ev[0]), sum(counts)
 
 
+class _DeviceBytes:
+    """Zero-copy view of `n` bytes at a raw device pointer (CUDA array interface)."""
+
+    def __init__(self, ptr: int, n: int):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "|u1", "data": (int(ptr), False), "version": 2, "strides": None}
+
+
+def format_sharded_device(calls, rank: int, world: int, device, group=None):
+    """format_sharded for records that stayed in HBM (Context.call_device): the cluster numbers a range consumes are
+    counted on the device, exchanged, the text is written on the device from the rank's true first number and gathered
+    over NVLink without touching the host; rank 0 copies the whole text out once."""
+    mine = torch.tensor([calls.clusters()], dtype=torch.int64, device=device)
+    allc = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(allc, mine, group=group)
+    counts = [int(t[0]) for t in allc]
+    ev0 = int(calls.stats.events)
+    ptr, ln = calls.snp_device(1 + sum(counts[:rank]))
+    try:
+        ev = torch.tensor([int(calls.stats.events) - ev0], dtype=torch.int64, device=device)
+        dist.all_reduce(ev, op=dist.ReduceOp.SUM, group=group)
+        piece = torch.as_tensor(_DeviceBytes(ptr.value, ln), device=device) if ln else torch.empty(0, dtype=torch.uint8, device=device)
+        out = gather_bytes(piece, rank, world, device, group)
+    finally:
+        torch.cuda.synchronize(device)
+        calls.free_device(ptr)
+    return out, int(ev[0]), sum(counts)
+
+
 def gather_bytes(view, rank: int, world: int, device, group=None):
     """Concatenation of every rank's bytes on rank 0 (rank order) as a uint8 numpy array.
     Sizes are exchanged first; then ONE gather collective of pieces padded to the largest size (NCCL over
     NVLink on GPUs, gloo on CPU) and one copy per piece into a page-locked host buffer kept across calls."""
     global _pinned
-    view = memoryview(view).cast("B") if len(view) else memoryview(b"")
+    on_device = isinstance(view, torch.Tensor)          # a piece that is already in device memory
+    if not on_device:
+        view = memoryview(view).cast("B") if len(view) else memoryview(b"")
     size = torch.tensor([len(view)], dtype=torch.int64, device=device)
     sizes = [torch.zeros_like(size) for _ in range(world)]
     dist.all_gather(sizes, size, group=group)
@@ -159,7 +189,7 @@ def gather_bytes(view, rank: int, world: int, device, group=None):
     pad = max(max(sizes), 1)
     mine = torch.empty(pad, dtype=torch.uint8, device=device)
     if len(view):
-        mine[:len(view)].copy_(torch.from_numpy(np.frombuffer(view, dtype=np.uint8)), non_blocking=True)
+        mine[:len(view)].copy_(view if on_device else torch.from_numpy(np.frombuffer(view, dtype=np.uint8)), non_blocking=True)
     parts = [torch.empty(pad, dtype=torch.uint8, device=device) for _ in range(world)] if rank == 0 else None
     dist.gather(mine, parts, dst=0, group=group)
     if rank != 0:
@@ -268,8 +298,12 @@ def run_sharded(ctx, api, bwt1, bwt2, da, params, rank: int, world: int, group=N
     lap("or_reduce")
     n = b1.n + (b2.n if b2 is not None else 0)
     cuts = position_cuts(n, world)
-    recs, left, right, st = ctx.call(b1, b2, da_nav if b2 is not None else dabits, lcp, params,
-                                     cuts[rank], cuts[rank + 1], stats=st, copy=False)
+    on_gpu = torch.device(device).type == "cuda"
+    if on_gpu:      # the records stay in HBM and are printed there
+        calls = ctx.call_device(b1, b2, da_nav if b2 is not None else dabits, lcp, params, cuts[rank], cuts[rank + 1], stats=st)
+    else:
+        recs, left, right, st = ctx.call(b1, b2, da_nav if b2 is not None else dabits, lcp, params,
+                                         cuts[rank], cuts[rank + 1], stats=st, copy=False)
     lap("call")
     stats = reduce_stats(st.as_dict(), device, group)
     lap("reduce_stats")
@@ -277,8 +311,12 @@ def run_sharded(ctx, api, bwt1, bwt2, da, params, rank: int, world: int, group=N
     # the SUM all-reduce above is an OR only under that condition, so a violated deal fails loudly here.
     if stats["lcp_values"] != n or (b2 is not None and stats["da_values"] != n):
         raise RuntimeError(f"sharded traversal wrote {stats['lcp_values']} LCP values for {n} positions: the shards disagree on the deal")
-    snp, events, clusters = format_sharded(api, recs, left, right, params, (b2 is not None or da is not None),
-                                           rank, world, device, group)
+    if on_gpu:
+        snp, events, clusters = format_sharded_device(calls, rank, world, device, group)
+        calls.close()
+    else:
+        snp, events, clusters = format_sharded(api, recs, left, right, params, (b2 is not None or da is not None),
+                                               rank, world, device, group)
     lap("format+gather")
     stats["events"], stats["clusters_out"] = events, clusters
     stats["host_ms"] = tm

@@ -229,6 +229,19 @@ int e2i_snp_format_gpu(e2i_ctx *ctx, const e2i_call_rec *recs, const char *left,
 int e2i_call_snp(e2i_ctx *ctx, const e2i_index *b1, const e2i_index *b2, const e2i_bits *da,
                  const e2i_lcpbits *l, const e2i_params *p, uint64_t pos_begin, uint64_t pos_end,
                  uint64_t first_cluster_nr, char **snp, size_t *snp_len, e2i_stats *st);
+/* Phase 4 with the records left in HBM (no host copy): for callers that number the clusters of several position
+ * ranges consecutively (one range per GPU).  e2i_calls_count works on the handle; the records are turned into text by
+ *   e2i_calls_clusters   - how many cluster numbers the range consumes (device pass, no text)
+ *   e2i_calls_snp        - the text from a given first cluster number (*snp: e2i_buffer_free)
+ *   e2i_calls_snp_device - the same text left in device memory (for a gather over NVLink; e2i_device_free) */
+int e2i_call_device(e2i_ctx *ctx, const e2i_index *b1, const e2i_index *b2, const e2i_bits *da,
+                    const e2i_lcpbits *l, const e2i_params *p, uint64_t pos_begin, uint64_t pos_end,
+                    e2i_calls **out, e2i_stats *st);
+int e2i_calls_clusters(const e2i_calls *c, const e2i_params *p, uint64_t *clusters);
+int e2i_calls_snp(const e2i_calls *c, const e2i_params *p, uint64_t first_cluster_nr, char **snp, size_t *snp_len, e2i_stats *st);
+int e2i_calls_snp_device(const e2i_calls *c, const e2i_params *p, uint64_t first_cluster_nr, void **dev_text, uint64_t *len,
+                         e2i_stats *st);
+void e2i_device_free(e2i_ctx *ctx, void *p);
 /* How many cluster numbers the records consume (= what e2i_snp_format adds to clusters_out),
  * without building text: lets every GPU rank learn its first cluster number (distributed.py). */
 int e2i_snp_count(const e2i_call_rec *recs, const char *left, const char *right, uint64_t n_recs,

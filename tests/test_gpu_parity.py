@@ -617,3 +617,43 @@ def test_call_snp_ranges_concatenate_to_golden(gpu_ctx, e2i, name):
         text += part
         first += ps.clusters_out
     assert text == g["snp"]
+
+
+@pytest.mark.parametrize("name", ["m1_default", "m2_default", "m3_default"])
+def test_device_resident_calls_number_ranges_consecutively(gpu_ctx, e2i, name):
+    """e2i_call_device: the records stay in HBM; counted there, then printed from each range's true first cluster
+    number (the protocol of the multi-GPU drivers).  The host copy of the text and the device copy agree."""
+    import torch
+    g = load_golden(name)
+    p = e2i.default_params()
+    b1 = gpu_ctx.index(g["bwt1"])
+    b2 = gpu_ctx.index(g["bwt2"]) if g.get("bwt2") is not None else None
+    da = gpu_ctx.document_array(g["da"]) if g.get("da") is not None else None
+    lcp, da_nav, _ = gpu_ctx.navigate(b1, b2, p)
+    n = len(g["bwt1"]) + (len(g["bwt2"]) if b2 else 0)
+    cuts = [0, n // 4 + 3, n // 4 + 3, 2 * n // 3 + 5, n]                 # one empty range
+    parts = [gpu_ctx.call_device(b1, b2, da_nav if b2 else da, lcp, p, cuts[i], cuts[i + 1]) for i in range(4)]
+    counts = [c.clusters() for c in parts]
+    host_view = gpu_ctx.call(b1, b2, da_nav if b2 else da, lcp, p)
+    assert sum(len(c) for c in parts) == len(host_view[0])
+    assert sum(counts) == e2i.snp_count(host_view[0], host_view[1], host_view[2], p, b2 is not None or da is not None)
+    text = b""
+    for i, c in enumerate(parts):
+        first = 1 + sum(counts[:i])
+        piece = c.snp(first)
+        ptr, ln = c.snp_device(first)
+        try:
+            assert ln == len(piece)
+            if ln:
+                from ebwt2indel_b200.distributed import _DeviceBytes
+                dev = torch.as_tensor(_DeviceBytes(ptr.value, ln), device="cuda:0")
+                assert bytes(dev.cpu().numpy()) == piece
+        finally:
+            c.free_device(ptr)
+        text += piece
+    assert text == g["snp"]
+    with pytest.raises(e2i.E2iError):
+        lib_view = e2i.lib().e2i_calls_view          # the records of a device handle cannot be viewed on the host
+        import ctypes as C
+        pr, pl, pt, nn = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_uint64()
+        e2i._check(lib_view(parts[0].h, C.byref(pr), C.byref(pl), C.byref(pt), C.byref(nn))) if len(parts[0]) else e2i._check(3)
