@@ -275,9 +275,15 @@ extern "C" int e2i_run_files(e2i_ctx *ctx, const char *path_bwt1, const char *pa
     if (rc == E2I_ERR_SYMBOL && bad_pos) { bad_pos[0] = bad; bad_pos[1] = (uint64_t)which; }
     if (n1_out) *n1_out = b1 ? b1->n : 0;
     if (n2_out) *n2_out = b2 ? b2->n : 0;
+    const auto w1 = std::chrono::steady_clock::now();
     if (rc == E2I_OK) rc = run_with_indexes(ctx, b1, b2, da, p, snp, snp_len, st);
+    const auto w2 = std::chrono::steady_clock::now();
     e2i_bits_free(da); e2i_index_free(b1); e2i_index_free(b2);
     st->ms_wall += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - w0).count();
+    if (std::getenv("E2I_DEBUG"))
+        std::fprintf(stderr, "[e2i] run_files: ingest + index %.1f ms, traversal + calls + text %.1f ms, frees %.1f ms (host wall)\n",
+                     std::chrono::duration<double, std::milli>(w1 - w0).count(), std::chrono::duration<double, std::milli>(w2 - w1).count(),
+                     std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - w2).count());
     return rc;
 }
 

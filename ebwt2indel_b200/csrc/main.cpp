@@ -172,6 +172,9 @@ int main(int argc, char **argv) {
     uint64_t frontier_bytes = 0;
     if (const char *fb = std::getenv("E2I_FRONTIER_BYTES")) frontier_bytes = strtoull(fb, nullptr, 10);
     e2i_ctx *ctx = nullptr;
+    const bool dbg = std::getenv("E2I_DEBUG") != nullptr;
+    const auto t_start = std::chrono::steady_clock::now();
+    auto since = [&](std::chrono::steady_clock::time_point a) { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - a).count(); };
     if (!multi) {
         if (devices.size() == 1) device = devices[0];
         if (e2i_create(device, &ctx) != E2I_OK) {
@@ -181,6 +184,7 @@ int main(int argc, char **argv) {
         if (frontier_bytes) e2i_set_frontier_budget(ctx, frontier_bytes);
     }
 
+    if (dbg) std::fprintf(stderr, "[e2i] cli: context created after %.1f ms\n", since(t_start));
     const bool two = !input2.empty(), with_da = !input_da.empty();
     cout << (two ? "Phase 1/4: loading and indexing eBWTs ... " : "Phase 1/4: loading and indexing eBWT ... ") << std::flush;
     const auto t0 = std::chrono::steady_clock::now();
@@ -245,12 +249,14 @@ int main(int argc, char **argv) {
     cout << "Phase 4/4: detecting SNPs and indels." << endl;
     cout << "Output events will be stored in " << output << endl;
 
+    if (dbg) std::fprintf(stderr, "[e2i] cli: results ready after %.1f ms\n", since(t_start));
     FILE *f = std::fopen(output.c_str(), "wb");
     if (!f || (snp_len && std::fwrite(snp, 1, snp_len, f) != snp_len)) {
         cout << "Error: could not write " << output << endl;
         return 2;
     }
     std::fclose(f);
+    if (dbg) std::fprintf(stderr, "[e2i] cli: output written after %.1f ms\n", since(t_start));
 
     const double avg = st.n_clusters ? double(st.clust_size) / double(st.n_clusters) : 0.0 / 0.0;
     cout << endl << "Done." << endl << "Analyzed " << st.n_clusters << " clusters." << endl
@@ -274,5 +280,6 @@ int main(int argc, char **argv) {
     e2i_host_free(b2);
     e2i_host_free(da);
     e2i_destroy(ctx);
+    if (dbg) std::fprintf(stderr, "[e2i] cli: context destroyed after %.1f ms\n", since(t_start));
     return 0;
 }
