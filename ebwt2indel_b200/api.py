@@ -176,6 +176,14 @@ def lib():
     return L
 
 
+def _await_producer(t):
+    """The library works on the context's own stream.  A torch CUDA tensor handed in may still be being written by
+    kernels queued on torch's current stream: wait for them (a no-op when the stream is idle)."""
+    if hasattr(t, "is_cuda") and t.is_cuda:
+        import torch
+        torch.cuda.current_stream(t.device).synchronize()
+
+
 def _check(rc: int):
     if rc != E2I_OK:
         raise E2iError(rc, lib().e2i_last_error().decode(errors="replace"))
@@ -269,6 +277,7 @@ class Context:
         """bwt: numpy uint8 array / bytes (host) or a torch CUDA uint8 tensor (device, 16-byte aligned)."""
         h, bad = C.c_void_p(), C.c_uint64(0)
         if hasattr(bwt, "data_ptr") and bwt.is_cuda:
+            _await_producer(bwt)
             rc = lib().e2i_index_build_device(self.h, bwt.data_ptr(), bwt.numel(), term, C.byref(h), C.byref(bad))
         else:
             keep, ptr = _host_u8(np.frombuffer(bwt, dtype=np.uint8) if isinstance(bwt, (bytes, bytearray)) else bwt)
@@ -335,6 +344,7 @@ class Context:
     def document_array(self, da) -> "Bits":
         h = C.c_void_p()
         if hasattr(da, "data_ptr") and da.is_cuda:
+            _await_producer(da)
             _check(lib().e2i_da_load_device(self.h, da.data_ptr(), da.numel(), C.byref(h)))
         else:
             keep, ptr = _host_u8(da)
@@ -438,6 +448,8 @@ class Context:
         p = params or default_params()
         st = stats if stats is not None else Stats()
         on_dev = hasattr(bwt1, "is_cuda") and bwt1.is_cuda
+        if on_dev:
+            _await_producer(bwt1)
         keep = []
 
         def arg(x):
