@@ -608,7 +608,7 @@ static int call_impl(e2i_ctx *ctx, const e2i_index *b1, const e2i_index *b2, con
                     char *nb2 = text_alloc(want);
                     if (!nb2) { dfree(ctx, d_text); set_error("e2i_call_snp: cannot page-lock %llu bytes for the text", (unsigned long long)want); return E2I_ERR_MEMORY; }
                     if (sink->len) std::memcpy(nb2, sink->buf, sink->len);
-                    if (sink->buf) text_release(sink->buf);
+                    e2i_buffer_free(sink->buf);
                     sink->buf = nb2;
                     sink->cap = want;
                 }
@@ -775,7 +775,7 @@ extern "C" int e2i_calls_snp(const e2i_calls *c, const e2i_params *p, uint64_t f
     if (len) {
         cudaError_t e = cudaMemcpyAsync(buf, d_text, len, cudaMemcpyDeviceToHost, ctx->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-        if (e != cudaSuccess) { text_release(buf); dfree(ctx, d_text); set_error("CUDA error copying the .snp text: %s", cudaGetErrorString(e)); return E2I_ERR_CUDA; }
+        if (e != cudaSuccess) { e2i_buffer_free(buf); dfree(ctx, d_text); set_error("CUDA error copying the .snp text: %s", cudaGetErrorString(e)); return E2I_ERR_CUDA; }
         ctx->n_d2h += len;
         if (st) st->d2h_bytes += len;
     }
@@ -793,7 +793,7 @@ extern "C" int e2i_call_snp(e2i_ctx *ctx, const e2i_index *b1, const e2i_index *
     TextSink sink;
     sink.next_cluster = first_cluster_nr ? first_cluster_nr : 1;
     const int rc = call_impl(ctx, b1, b2, da, l, p, pos_begin, pos_end, nullptr, &sink, false, st);
-    if (rc != E2I_OK) { if (sink.buf) text_release(sink.buf); return rc; }
+    if (rc != E2I_OK) { e2i_buffer_free(sink.buf); return rc; }
     if (!sink.buf) sink.buf = text_alloc(1);
     if (!sink.buf) { set_error("e2i_call_snp: out of host memory"); return E2I_ERR_MEMORY; }
     sink.buf[sink.len] = 0;

@@ -157,7 +157,7 @@ inline cudaError_t arena_alloc(e2i_ctx *ctx, size_t bytes, bool ipc) {
 }
 // Host buffers for the .snp text handed to the caller: page-locked (the text arrives by one DMA copy, no page
 // faults, no staging) and cached process-wide between calls; e2i_buffer_free gives them back (snp_format.cpp).
-char *text_alloc(size_t bytes);
+char *text_alloc(size_t bytes);          // ordinary malloc memory when nothing can be page-locked any more; nullptr: out of memory
 bool text_release(void *p);              // false: not one of ours
 void text_cache_trim();                  // frees the cached buffers that are not handed out
 // .snp text of call records that are still in device memory (snp_format.cpp); *d_text is released with dfree

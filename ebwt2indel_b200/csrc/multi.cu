@@ -451,7 +451,7 @@ extern "C" int e2i_run_multi(const int *devices, int n_devices, const uint8_t *h
         *snp = sh.final_text;
         *snp_len = total;
     } else if (sh.final_text) {
-        text_release(sh.final_text);
+        e2i_buffer_free(sh.final_text);
     }
     // counters: every unit of work is done by exactly one rank -> sums; phase times -> max over ranks
     e2i_stats &o = *st_out;

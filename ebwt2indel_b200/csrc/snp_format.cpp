@@ -483,7 +483,10 @@ char *e2i::text_alloc(size_t bytes) {
     if (best) { best->used = true; return best->p; }
     const size_t cap = std::max<size_t>(bytes + bytes / 8, 1u << 20);
     void *p = nullptr;
-    if (cudaMallocHost(&p, cap) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    if (cudaMallocHost(&p, cap) != cudaSuccess) {       // no page-locked memory left: an ordinary buffer (the copy is staged by the driver)
+        cudaGetLastError();
+        return static_cast<char *>(std::malloc(bytes ? bytes : 1));
+    }
     g_text_blocks.push_back({static_cast<char *>(p), cap, true});
     return static_cast<char *>(p);
 }
@@ -511,6 +514,8 @@ void e2i::text_cache_trim() {
         if (!g_text_blocks[i].used) { cudaFreeHost(g_text_blocks[i].p); g_text_blocks.erase(g_text_blocks.begin() + (long)i); }
 }
 
+extern "C" void e2i_buffer_free(void *p);
+
 // host text buffer filled by one copy
 static int text_to_host(e2i_ctx *ctx, char *d_text, uint64_t len, char **snp, size_t *snp_len) {
     char *buf = e2i::text_alloc(len + 1);
@@ -518,7 +523,7 @@ static int text_to_host(e2i_ctx *ctx, char *d_text, uint64_t len, char **snp, si
     if (len) {
         cudaError_t e = cudaMemcpyAsync(buf, d_text, len, cudaMemcpyDeviceToHost, ctx->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-        if (e != cudaSuccess) { e2i::text_release(buf); e2i::dfree(ctx, d_text); e2i::set_error("CUDA error copying the .snp text: %s", cudaGetErrorString(e)); return E2I_ERR_CUDA; }
+        if (e != cudaSuccess) { e2i_buffer_free(buf); e2i::dfree(ctx, d_text); e2i::set_error("CUDA error copying the .snp text: %s", cudaGetErrorString(e)); return E2I_ERR_CUDA; }
         ctx->n_d2h += len;
     }
     e2i::dfree(ctx, d_text);
